@@ -1,0 +1,48 @@
+"""Shared test helpers: golden-fixture access and the compact-array comparison."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STRIDE = 31          # must match tests/golden/make_golden.py
+NAMES = ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias",
+         "fc2_2.weight", "fc2_2.bias", "fc3.weight", "fc3.bias"]
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def check_compact(g, key, arr, atol, what=""):
+    """Compare `arr` with a golden entry stored whole or as subsample+checksums."""
+    arr = np.asarray(arr)
+    if key in g.files:
+        ref = g[key]
+        assert ref.shape == arr.shape, (key, ref.shape, arr.shape)
+        err = np.abs(ref.astype(np.float64) - arr.astype(np.float64)).max() if arr.size else 0.0
+        assert err <= atol, "%s %s: max abs err %.3e > %.1e" % (what, key, err, atol)
+        return err
+    sub, chk = g[key + "__sub"], g[key + "__chk"]
+    flat = arr.reshape(-1)
+    assert flat.size == int(chk[2]), (key, flat.size, chk[2])
+    err = np.abs(sub.astype(np.float64) - flat[::STRIDE].astype(np.float64)).max()
+    assert err <= atol, "%s %s: subsample max abs err %.3e > %.1e" % (what, key, err, atol)
+    s = flat.astype(np.float64).sum()
+    assert abs(s - chk[0]) <= atol * flat.size, "%s %s: checksum %.6e vs %.6e" % (what, key, s, chk[0])
+    return err
+
+
+def regen_init(seed, obs_dim, act_dim, n_atoms):
+    """Initial actor/critic weights of a train_*.npz fixture, regenerated from its
+    seed with the oracle's RNG-parity initialisers (global DDPG is built first:
+    actor, actor_target, critic, ... -- ddpg.py:56-64)."""
+    import random
+    from oracle import d4pg_oracle as O
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    a = O.init_actor(obs_dim, act_dim)
+    O.init_actor(obs_dim, act_dim)               # actor_target consumes the RNG too
+    c = O.init_critic(obs_dim, act_dim, n_atoms)
+    return a, c
