@@ -23,6 +23,8 @@ def test_projection_random_vs_reproject2():
         p = torch.softmax(torch.from_numpy(rng.randn(B, 51).astype(np.float32) * 3), 1).numpy()
         r = (-60 * rng.rand(B)) if trial % 2 else -rng.randint(0, 3, B).astype(np.float64)
         done = np.zeros(B, bool) if trial < 4 else (rng.rand(B) < 0.3)
+        if trial == 5:
+            r = -40 * rng.rand(B)      # terminal rows all non-integer, unclamped (no H6 mix)
         m_ref = d.reproject2(p, r, done)
         m = O.project_live(p, r, done, -50.0, 0.0, 51, 0.99)
         assert np.array_equal(m, m_ref)
