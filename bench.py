@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- learner gradient-steps/sec of the D4PG hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of ddpg.py
+
+Workload (config.workload = "c2"): |s|=17 |a|=6, 51 atoms, batch 256 per GPU, prioritized
+replay capacity 2^20 per GPU (full), fp32.  One step = everything DDPG.train() does
+(ddpg.py:200-255).  Weak scaling: every rank owns a replay shard and a 256-row minibatch; one
+NCCL all-reduce of the flat gradient per step.  `value` counts batch-256 gradient steps over all
+ranks per second (N x iterations/s).
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = {
+    "c2": dict(obs=17, act=6, atoms=51, batch=256, cap=1 << 20, v_min=-50.0, v_max=0.0, n_steps=1, proj="reference"),
+    "c3": dict(obs=376, act=17, atoms=51, batch=1024, cap=1000000, v_min=-50.0, v_max=0.0, n_steps=1, proj="reference"),
+    "c5": dict(obs=17, act=6, atoms=101, batch=4096, cap=1 << 20, v_min=-150.0, v_max=150.0, n_steps=5, proj="nstep"),
+}
+H = 256
+METRIC = "learner grad-steps/sec (batch 256, 51 atoms)"
+
+
+def algorithmic(cfg):
+    """FLOPs and bytes per gradient step."""
+    S, A, N, B, cap = cfg["obs"], cfg["act"], cfg["atoms"], cfg["batch"], cfg["cap"]
+    log2cap = int(np.ceil(np.log2(cap)))
+    Pa = S * H + H + 2 * (H * H + H) + H * A + A
+    Pc = S * H + H + (H + A) * H + H + H * H + H + H * N + N
+    mac_a = S * H + 2 * H * H + H * A
+    mac_c = S * H + (H + A) * H + H * H + H * N
+    flops = 2 * B * (4 * mac_a + 6 * mac_c)
+    gemm_bytes = (3 * Pa + 5 * Pc) * 4
+    byts = (B * (2 * S + A + 2) * 4 + B * log2cap * 4 + B * (1 + log2cap) * 2 * 2 * 4 + 3 * B * N * 4
+            + 7 * (Pa + Pc) * 4 + 3 * (Pa + Pc) * 4 + gemm_bytes)
+    return dict(P=Pa + Pc, flops=flops, bytes=byts, gemm_bytes=gemm_bytes)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf=p.get("bf16_tflops_sustained", p.get("bf16_tflops")), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def synth(cfg, n, seed):
+    """SURVEY.md section 8d synthetic transitions (fp32-representable)."""
+    rng = np.random.RandomState(seed)
+    S, A = cfg["obs"], cfg["act"]
+    return (rng.randn(n, S).astype(np.float32), rng.uniform(-1, 1, (n, A)).astype(np.float32),
+            (-3.0 * rng.rand(n)).astype(np.float32).astype(np.float64), rng.randn(n, S).astype(np.float32),
+            np.zeros(n, dtype=bool))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's DDPG.train (the reference itself is Python and
+# cannot travel to the GPU box; oracle/ is pinned bit-exact to it, see oracle/__init__.py)
+# ------------------------------------------------------------------------------------------
+def cpu_arm(cfg, steps, warmup, budget_s=25.0):
+    import torch
+    from oracle import d4pg_oracle as O
+    info = {"type": "categorical", "v_min": cfg["v_min"], "v_max": cfg["v_max"], "n_atoms": cfg["atoms"]}
+    B, cap = cfg["batch"], cfg["cap"]
+    ncores = len(os.sched_getaffinity(0))
+    best = None
+    for threads in sorted({1, ncores}):
+        torch.set_num_threads(threads)
+        torch.manual_seed(0); random.seed(0)
+        lo = O.LearnerOracle(cfg["obs"], cfg["act"], info, n_steps=cfg["n_steps"],
+                             projection="live" if cfg["proj"] == "reference" else "nstep")
+        ob = O.PrioritizedReplayOracle(cap, 0.6, cfg["obs"], cfg["act"])
+        ob.add_batch(*synth(cfg, cap, 0))
+        sched = O.LinearScheduleOracle(100000, 1.0, 0.4)
+
+        def one():
+            us = [random.random() for _ in range(B)]
+            batch = ob.sample(B, sched.value(), us)
+            out = lo.train_step(*batch[:5])
+            ob.update_priorities(batch[6], out["prio"])
+        for _ in range(warmup):
+            one()
+        t0 = time.perf_counter()
+        done = 0
+        while done < steps and (time.perf_counter() - t0) < budget_s / 2:
+            one()
+            done += 1
+        dt = time.perf_counter() - t0
+        rate = done / dt
+        if best is None or rate > best["value"]:
+            best = dict(value=rate, cores=threads, done=done, dt=dt)
+    return best
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CFG[args.config]
+    r = cpu_arm(cfg, args.steps, args.warmup)
+    sample = "%d oracle steps of workload %s (buffer full, capacity %d), torch threads=%d" % (
+        r["done"], args.config, cfg["cap"], r["cores"])
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": r["done"], "warmup": args.warmup, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.config, "batch": cfg["batch"], "obs_dim": cfg["obs"], "act_dim": cfg["act"],
+                       "n_atoms": cfg["atoms"], "replay_capacity": cfg["cap"]},
+            "cpu_baseline": {"value": r["value"], "unit": "steps/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def gpu_main(args):
+    import torch
+    import d4pg_b200 as d4pg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = d4pg.dist.Comm()
+    cfg = CFG[args.config]
+    info = {"type": "categorical", "v_min": cfg["v_min"], "v_max": cfg["v_max"], "n_atoms": cfg["atoms"]}
+    B, cap = cfg["batch"], cfg["cap"]
+
+    def make(sampling):
+        torch.manual_seed(0); random.seed(0)            # identical replicas on every rank
+        dd = d4pg.DDPG(cfg["obs"], cfg["act"], memory_size=cap, batch_size=B, critic_dist_info=info,
+                       n_steps=cfg["n_steps"], projection=cfg["proj"], sampling=sampling, philox_seed=1234 + rank,
+                       comm=comm)
+        dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
+                                   d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
+        dd.replayBuffer.add_batch(*synth(cfg, cap, seed=rank))     # this rank's shard, resident in HBM
+        return dd
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: inputs resident in HBM, device-side sampling, CUDA-graph replay -------------
+    dd = make("device")
+    for _ in range(max(args.warmup, 3)):
+        dd.train()
+    stream = dd._learner.stream
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    for _ in range(args.steps):
+        dd.train()
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    sampler.stop_flag = True
+    kernels = dd.kernels_per_step()
+    lc, la = dd.last_losses()
+    assert np.isfinite(lc) and np.isfinite(la)
+    ms_per_step = ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # ---- per-launch device times (eager step, CUDA events on the launching stream) -----------
+    prof = {}
+    for _ in range(5):
+        for name, t in dd.profile_step():
+            prof.setdefault(name, []).append(t)
+    alg = algorithmic(cfg)
+    pk = peaks()
+    gemm_ms = [t for t in prof.get("gemm_batch_launch", [])]
+    n_gemm = len(gemm_ms) // 5 if gemm_ms else 0
+    gemm_avg_ms = float(np.mean(gemm_ms)) if gemm_ms else None
+    roofline = None
+    if gemm_avg_ms:
+        ach = alg["gemm_bytes"] / n_gemm / (gemm_avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("gemm_ffma_kernel_dram_bytes_per_launch")
+        roofline = {"kernel": "gemm_ffma_kernel (MLP fwd/bwd levels, %d launches/step)" % n_gemm, "bound": "hbm",
+                    "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
+                    "peak_source": pk["src"], "avg_launch_us": gemm_avg_ms * 1e3,
+                    "flops_frac_of_bf16_peak": alg["flops"] / n_gemm / (gemm_avg_ms * 1e-3) / 1e12 / pk["tf"]}
+    step_roof = {"hbm_frac": alg["bytes"] / (ms_per_step * 1e-3) / 1e9 / pk["hbm"],
+                 "tensor_frac": alg["flops"] / (ms_per_step * 1e-3) / 1e12 / pk["tf"],
+                 "algorithmic_bytes": alg["bytes"], "algorithmic_flops": alg["flops"]}
+    launch_breakdown = {k: round(float(np.mean(v)) * 1e3 * (len(v) // 5), 2) for k, v in prof.items()}   # us/step
+    del dd
+
+    # ---- e2e: public API with host buffers: per step H2D of new transitions + uniforms, D2H loss
+    dd = make("reference")
+    n_new = B
+    S, A_, R, S2, D = synth(cfg, n_new * 8, seed=100 + rank)
+    pin = [torch.from_numpy(x).pin_memory() for x in (S, A_, R, S2, D)]
+    h2d = B * 8 + n_new * ((2 * cfg["obs"] + cfg["act"]) * 4 + 8 + 1)
+    d2h = 16
+
+    def e2e_step(i):
+        lo = (i % 8) * n_new
+        dd.replayBuffer.add_batch(*[p[lo:lo + n_new] for p in pin])      # H2D from pinned host memory
+        dd.train()                                                        # host MT19937 uniforms -> H2D
+        return dd.last_losses()                                           # D2H + sync
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    ev1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+    e2e_value = world * args.steps / (e2e_ms * 1e-3)
+    del dd
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_arm(cfg, 200, 3, budget_s=24.0)
+        cpu = {"value": r["value"], "unit": "steps/s", "cores": r["cores"], "kind": "port",
+               "sample": "%d oracle steps (restatement of ddpg.py:200-255 + PER, pinned to the reference), workload %s, "
+                         "buffer full; host has %d cores, best of torch threads {1,%d}" % (
+                             r["done"], args.config, len(os.sched_getaffinity(0)), len(os.sched_getaffinity(0)))}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.config, "batch_per_gpu": B, "global_batch": B * world, "obs_dim": cfg["obs"],
+                           "act_dim": cfg["act"], "n_atoms": cfg["atoms"], "replay_capacity_per_gpu": cap,
+                           "parallelism": "dp%d" % world, "precision": "fp32 FFMA",
+                           "l2": "inputs larger than L2: replay store %.0f MB + trees %.0f MB per GPU, rows sampled at "
+                                 "random; parameters (%.1f MB) are L2-resident by design" % (
+                                     cap * ((2 * cfg["obs"] + cfg["act"]) * 4 + 9) / 1e6, 16 * cap / 1e6 * 1.05, alg["P"] * 16 / 1e6)},
+                "clocks": sampler.summary(), "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                                                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": kernels * args.steps, "kernels_per_step": kernels,
+                "roofline": roofline, "roofline_step": step_roof, "launch_us_per_step": launch_breakdown,
+                "cpu_baseline": cpu, "losses": [lc, la]}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CFG))
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_main(args)
+    else:
+        gpu_main(args)
+
+
+if __name__ == "__main__":
+    main()

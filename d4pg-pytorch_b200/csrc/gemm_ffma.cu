@@ -1,0 +1,151 @@
+// Exact-fp32 grouped GEMM for the actor/critic MLP layers (precision mode 0).
+//
+// Replaces the ATen/MKL nn.Linear forward calls of models.py:33-40,77-83 and their autograd
+// backward (ddpg.py:230,242).  One launch runs up to 8 independent layer problems (the actor,
+// critic and target networks advance in lock-step through the step's dependency levels), each
+// tiled 32x32 so a 256x256x256 layer spreads over 64 CTAs: at batch 256 the whole step is
+// latency-bound, so small tiles on many SMs beat big tiles on few.  Accumulation is plain FFMA
+// in k order, i.e. a true fp32 dot product (needed for the 1e-5 parity of config 2).
+#include "gemm_ffma.cuh"
+
+namespace d4pg {
+
+constexpr int BM = 32, BN = 32, KC = 128;
+constexpr int LDS_A = BM + 2;   // even (float2 reads), 2-way conflicts at worst on transposed stores
+constexpr int LDS_B = BN + 2;
+constexpr int GEMM_THREADS = 256;
+
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_ffma_kernel(const __grid_constant__ GemmBatch batch) {
+  __shared__ __align__(16) float As[KC * LDS_A];
+  __shared__ __align__(16) float Bs[KC * LDS_B];
+
+  // locate problem and tile
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
+    if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
+  const GemmProblem& P = batch.p[pi];
+  const int tile = blockIdx.x - P.tile_begin;
+  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+  const int m0 = tm * BM, n0 = tn * BN;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc00 = 0.f, acc01 = 0.f, acc10 = 0.f, acc11 = 0.f;
+  float colsum = 0.f;                       // DW: bias gradient, threads < BM of the tn==0 tiles
+  const bool want_bias_grad = (P.mode == GEMM_DW) && (P.bias_grad != nullptr) && (tn == 0);
+
+  for (int k0 = 0; k0 < P.K; k0 += KC) {
+    const int kc = min(KC, P.K - k0);
+    // ---- stage A[kk][i] ------------------------------------------------------------------
+    if (P.mode == GEMM_DW) {          // A(i,k) = dZ[k*lda + i]: i fastest
+      for (int e = tid; e < kc * BM; e += GEMM_THREADS) {
+        const int kk = e / BM, i = e - kk * BM;
+        const int gi = m0 + i;
+        As[kk * LDS_A + i] = (gi < P.M) ? __ldg(P.A + size_t(k0 + kk) * P.lda + gi) : 0.f;
+      }
+    } else {                          // A(i,k) = A[i*lda + k] (k fastest), optional concat
+      for (int e = tid; e < kc * BM; e += GEMM_THREADS) {
+        const int i = e / kc, kk = e - i * kc;
+        const int gi = m0 + i, gk = k0 + kk;
+        float v = 0.f;
+        if (gi < P.M) v = (gk < P.K1) ? __ldg(P.A + size_t(gi) * P.lda + gk)
+                                      : __ldg(P.A2 + size_t(gi) * P.lda2 + (gk - P.K1));
+        As[kk * LDS_A + i] = v;
+      }
+    }
+    // ---- stage B[kk][j] ------------------------------------------------------------------
+    if (P.mode == GEMM_FWD) {         // B(k,j) = W[j*ldb + k]: k fastest
+      for (int e = tid; e < kc * BN; e += GEMM_THREADS) {
+        const int j = e / kc, kk = e - j * kc;
+        const int gj = n0 + j;
+        Bs[kk * LDS_B + j] = (gj < P.N) ? __ldg(P.Bm + size_t(gj) * P.ldb + k0 + kk) : 0.f;
+      }
+    } else {                          // B(k,j) = B[k*ldb + j]: j fastest
+      for (int e = tid; e < kc * BN; e += GEMM_THREADS) {
+        const int kk = e / BN, j = e - kk * BN;
+        const int gj = n0 + j;
+        Bs[kk * LDS_B + j] = (gj < P.N) ? __ldg(P.Bm + size_t(k0 + kk) * P.ldb + gj) : 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- 2x2 register tile, k order --------------------------------------------------------
+#pragma unroll 8
+    for (int kk = 0; kk < kc; ++kk) {
+      const float2 a = *reinterpret_cast<const float2*>(&As[kk * LDS_A + ty * 2]);
+      const float2 b = *reinterpret_cast<const float2*>(&Bs[kk * LDS_B + tx * 2]);
+      acc00 = fmaf(a.x, b.x, acc00); acc01 = fmaf(a.x, b.y, acc01);
+      acc10 = fmaf(a.y, b.x, acc10); acc11 = fmaf(a.y, b.y, acc11);
+    }
+    if (want_bias_grad && tid < BM) {
+      for (int kk = 0; kk < kc; ++kk) colsum += As[kk * LDS_A + tid];
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ------------------------------------------------------------------------------
+  float v[2][2] = {{acc00, acc01}, {acc10, acc11}};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int gi = m0 + ty * 2 + r;
+    if (gi >= P.M) continue;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int gj = n0 + tx * 2 + c;
+      if (gj >= P.N) continue;
+      float x = v[r][c];
+      switch (P.epi) {
+        case EPI_BIAS: x += __ldg(P.bias + gj); break;
+        case EPI_BIAS_RELU: x = fmaxf(x + __ldg(P.bias + gj), 0.f); break;
+        case EPI_BIAS_TANH: x = tanhf(x + __ldg(P.bias + gj)); break;
+        case EPI_RELU_MASK: x = (__ldg(P.aux + size_t(gi) * P.ldaux + gj) > 0.f) ? x : 0.f; break;
+        case EPI_TANH_MASK: { const float t = __ldg(P.aux + size_t(gi) * P.ldaux + gj); x *= (1.f - t * t); } break;
+        default: break;
+      }
+      P.C[size_t(gi) * P.ldc + gj] = x;
+    }
+  }
+  if (want_bias_grad && tid < BM && m0 + tid < P.M) P.bias_grad[m0 + tid] = colsum;
+}
+
+// ---- host side -------------------------------------------------------------------------------
+GemmProblem gemm_fwd(const float* X, int ldx, const float* X2, int ldx2, int K1, const float* W, int ldw,
+                     const float* bias, float* Y, int ldy, int M, int N, int K, int epi) {
+  GemmProblem p{};
+  p.A = X; p.lda = ldx; p.A2 = X2 ? X2 : X; p.lda2 = X2 ? ldx2 : ldx; p.K1 = X2 ? K1 : K;
+  p.Bm = W; p.ldb = ldw; p.bias = bias; p.C = Y; p.ldc = ldy; p.M = M; p.N = N; p.K = K;
+  p.mode = GEMM_FWD; p.epi = epi;
+  return p;
+}
+GemmProblem gemm_dx(const float* dZ, int lddz, const float* W, int ldw, float* dX, int lddx,
+                    int M, int N_in, int K_out, int epi, const float* aux, int ldaux) {
+  GemmProblem p{};
+  p.A = dZ; p.lda = lddz; p.A2 = dZ; p.lda2 = lddz; p.K1 = K_out;
+  p.Bm = W; p.ldb = ldw; p.C = dX; p.ldc = lddx; p.M = M; p.N = N_in; p.K = K_out;
+  p.mode = GEMM_DX; p.epi = epi; p.aux = aux; p.ldaux = ldaux;
+  return p;
+}
+GemmProblem gemm_dw(const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw,
+                    float* db, int N_out, int K_in, int M_batch) {
+  GemmProblem p{};
+  p.A = dZ; p.lda = lddz; p.A2 = dZ; p.lda2 = lddz; p.K1 = M_batch;
+  p.Bm = X; p.ldb = ldx; p.C = dW; p.ldc = lddw; p.bias_grad = db;
+  p.M = N_out; p.N = K_in; p.K = M_batch;
+  p.mode = GEMM_DW; p.epi = EPI_NONE;
+  return p;
+}
+void gemm_batch_begin(GemmBatch& b) { b.n = 0; b.total_tiles = 0; }
+void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
+  GemmProblem p = pin;
+  p.tiles_m = cdiv(p.M, BM); p.tiles_n = cdiv(p.N, BN); p.tile_begin = b.total_tiles;
+  b.total_tiles += p.tiles_m * p.tiles_n;
+  b.p[b.n++] = p;
+}
+int gemm_batch_launch(const GemmBatch& b, cudaStream_t st) {
+  D4PG_REQUIRE(b.n > 0 && b.n <= GEMM_MAX_PROBLEMS, D4PG_EINVAL, "gemm_batch_launch: %d problems", b.n);
+  gemm_ffma_kernel<<<b.total_tiles, GEMM_THREADS, 0, st>>>(b);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+}  // namespace d4pg

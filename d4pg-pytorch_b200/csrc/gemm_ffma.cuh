@@ -1,0 +1,45 @@
+// Grouped small-GEMM launcher (exact-fp32 FFMA path) used by the MLP forward/backward.
+#pragma once
+#include "common.cuh"
+
+namespace d4pg {
+
+enum GemmMode {
+  GEMM_FWD = 0,   // C[M,N] = A[M,K] . W[N,K]^T (+bias, act)      models.py:33-40,77-83
+  GEMM_DX = 1,    // C[M,N] = dZ[M,K] . W[K,N]    (* act')         autograd of the above, ddpg.py:230,242
+  GEMM_DW = 2     // C[M,N] = dZ[K,M]^T . X[K,N]  (+ column sums -> bias grad)
+};
+enum GemmEpi {
+  EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_TANH = 3,
+  EPI_RELU_MASK = 4,   // C *= (aux > 0)
+  EPI_TANH_MASK = 5    // C *= (1 - aux^2)
+};
+
+struct GemmProblem {
+  const float* A; const float* A2; const float* Bm; const float* bias; const float* aux;
+  float* C; float* bias_grad;
+  int M, N, K, K1;
+  int lda, lda2, ldb, ldc, ldaux;
+  int mode, epi;
+  int tiles_m, tiles_n, tile_begin;
+};
+
+constexpr int GEMM_MAX_PROBLEMS = 8;
+struct GemmBatch {
+  GemmProblem p[GEMM_MAX_PROBLEMS];
+  int n;
+  int total_tiles;
+};
+
+// host helpers ---------------------------------------------------------------------------
+GemmProblem gemm_fwd(const float* X, int ldx, const float* X2, int ldx2, int K1, const float* W, int ldw,
+                     const float* bias, float* Y, int ldy, int M, int N, int K, int epi);
+GemmProblem gemm_dx(const float* dZ, int lddz, const float* W, int ldw, float* dX, int lddx,
+                    int M, int N_in, int K_out, int epi, const float* aux, int ldaux);
+GemmProblem gemm_dw(const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw,
+                    float* db, int N_out, int K_in, int M_batch);
+void gemm_batch_begin(GemmBatch& b);
+void gemm_batch_add(GemmBatch& b, const GemmProblem& p);
+int gemm_batch_launch(const GemmBatch& b, cudaStream_t st);
+
+}  // namespace d4pg

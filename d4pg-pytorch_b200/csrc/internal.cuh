@@ -1,0 +1,29 @@
+// Cross-translation-unit internals of libd4pg_sm100.so (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+struct d4pg_replay;
+struct d4pg_comm;
+
+namespace d4pg {
+
+struct HeadsArgs {
+  const float* target_logits; const float* q_logits; const float* pi_logits;
+  const double* rewards; const uint8_t* dones;
+  int B, N; int flags;
+  double v_min, v_max, delta, discount, prio_eps;
+  float grad_scale;
+  float* m; int32_t* bins_l; int32_t* bins_u; float* target_probs; float* q_probs;
+  float* loss_rows; float* td; float* prio; float* dlogits_q; float* pi_rows; float* dlogits_pi;
+};
+int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st);
+
+// sample for the learner: per-step scalars come from device memory (graph replay safe)
+int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
+                   uint64_t seed, const int64_t* counter_ptr, const float* beta_ptr,
+                   int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
+                   cudaStream_t st);
+int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st);
+int comm_allreduce(d4pg_comm* c, float* buf, int64_t n, cudaStream_t st);
+
+}  // namespace d4pg

@@ -1,0 +1,359 @@
+// The learner: one DDPG.train() body (ddpg.py:200-255) as a fixed sequence of launches,
+// captured once into a CUDA graph and replayed.  No host synchronisation inside a step; every
+// per-step scalar (Adam bias corrections, PER beta, Philox counter) lives in device memory and
+// is advanced by a one-thread clock kernel so the captured graph never needs patching.
+//
+// Step order (reference line -> launch):
+//   ddpg.py:202  sample                       -> sample_gather_kernel (tree descent + row gather)
+//   ddpg.py:205-208 target/online forwards    -> 7 grouped-GEMM levels (actor_target, critic_target,
+//                                                critic, actor and critic(s, actor(s)) in lock-step)
+//   ddpg.py:214-222 projection, CE loss, td   -> heads_kernel (also the policy head of ddpg.py:236-238)
+//   ddpg.py:229-231 critic backward           -> grouped dX / dW levels (shared with the policy pass)
+//   ddpg.py:236-243 policy backward           -> uses the PRE-update critic weights:
+//                                                both backward passes run before any Adam update
+//   ddpg.py:232,244,247,250 Adam x2, sync, Polyak -> one fused adam_polyak_kernel (2 segments)
+//   ddpg.py:252-255 update_priorities         -> tree_write_kernel<TREE_UPDATE>
+#include "common.cuh"
+#include "gemm_ffma.cuh"
+#include "adam.cuh"
+#include <string.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "internal.cuh"
+
+namespace d4pg {
+
+struct Workspace {
+  // batch
+  float *s, *a, *s2; double* r; uint8_t* done;
+  // activations: [0]=actor_target [1]=critic_target [2]=critic [3]=actor [4]=critic on policy action
+  float *h1[5], *h2[5], *h3[5], *out[5];
+  // heads
+  float *m, *q_probs, *target_probs, *dlogits_q, *dlogits_pi, *loss_rows, *pi_rows;
+  // backward
+  float *c_dz22, *c_dz2, *c_dz1, *p_dz22, *p_dz2, *a_dz3, *a_dz22, *a_dh2, *a_dz1;
+  LearnerClock* clock;
+  int64_t total;
+};
+
+static Workspace carve(float* base, int B, int S, int A, int N) {
+  Workspace w{};
+  int64_t off = 0;
+  auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
+  const int H = D4PG_HIDDEN;
+  w.s = take(int64_t(B) * S); w.a = take(int64_t(B) * A); w.s2 = take(int64_t(B) * S);
+  w.r = reinterpret_cast<double*>(take(int64_t(B) * 2));
+  w.done = reinterpret_cast<uint8_t*>(take((B + 3) / 4));
+  for (int k = 0; k < 5; ++k) {
+    if (k != 4) w.h1[k] = take(int64_t(B) * H);
+    w.h2[k] = take(int64_t(B) * H); w.h3[k] = take(int64_t(B) * H);
+  }
+  w.out[0] = take(int64_t(B) * A); w.out[3] = take(int64_t(B) * A);
+  w.out[1] = take(int64_t(B) * N); w.out[2] = take(int64_t(B) * N); w.out[4] = take(int64_t(B) * N);
+  w.m = take(int64_t(B) * N); w.q_probs = take(int64_t(B) * N); w.target_probs = take(int64_t(B) * N);
+  w.dlogits_q = take(int64_t(B) * N); w.dlogits_pi = take(int64_t(B) * N);
+  w.loss_rows = take(B); w.pi_rows = take(B);
+  w.c_dz22 = take(int64_t(B) * H); w.c_dz2 = take(int64_t(B) * H); w.c_dz1 = take(int64_t(B) * H);
+  w.p_dz22 = take(int64_t(B) * H); w.p_dz2 = take(int64_t(B) * H);
+  w.a_dz3 = take(int64_t(B) * A); w.a_dz22 = take(int64_t(B) * H); w.a_dh2 = take(int64_t(B) * H);
+  w.a_dz1 = take(int64_t(B) * H);
+  w.clock = reinterpret_cast<LearnerClock*>(take(sizeof(LearnerClock) / 4 + 4));
+  w.total = off;
+  return w;
+}
+}  // namespace d4pg
+
+using namespace d4pg;
+
+struct d4pg_learner {
+  d4pg_learner_config_t cfg;
+  d4pg_learner_buffers_t buf;
+  d4pg_replay* replay;
+  d4pg_comm* comm;
+  Workspace ws;
+  NetDims da, dc;
+  cudaGraphExec_t graph_exec;
+  bool graph_ready;
+  int64_t steps_done;
+  int kernels_per_step;
+  // profiling (d4pg_learner_profile_step): CUDA-event pair around every launch of an eager step
+  bool profiling;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> ev_name;
+};
+
+static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
+  const d4pg_learner_config_t& c = L->cfg;
+  const d4pg_learner_buffers_t& b = L->buf;
+  Workspace& w = L->ws;
+  const NetDims& da = L->da; const NetDims& dc = L->dc;
+  const int B = c.batch, S = c.obs_dim, A = c.act_dim, N = c.n_atoms, H = D4PG_HIDDEN;
+  int rc; int nk = 0;
+#define RUN(expr)                                                                          \
+  do {                                                                                     \
+    if (L->profiling) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);    \
+      cudaEventRecord(e0, st); rc = (expr); cudaEventRecord(e1, st);                       \
+      L->ev.push_back(e0); L->ev.push_back(e1);                                            \
+      std::string nm(#expr); L->ev_name.push_back(nm.substr(0, nm.find('('))); }           \
+    else rc = (expr);                                                                      \
+    if (rc) return rc;                                                                     \
+    ++nk;                                                                                  \
+  } while (0)
+
+  // 0. clock: Adam step count / bias corrections, PER beta, Philox counter
+  ClockArgs ca{w.clock, c.lr_actor, c.lr_critic, c.beta1, c.beta2, c.per_beta0, c.per_beta_final,
+               c.per_beta_iters > 0 ? c.per_beta_iters : 1};
+  RUN(launch_clock(ca, st));
+
+  // 1. sample + gather (ddpg.py:187-197)
+  RUN(learner_sample(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
+                     (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
+                     c.philox_seed, &w.clock->steps_done, &w.clock->beta,
+                     b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, st));
+
+  const float* Wa = b.actor; const float* Wat = b.actor_target; const float* Wc = b.critic; const float* Wct = b.critic_target;
+  GemmBatch g;
+  // 2. forward level 1: fc1 of actor_target(s'), critic_target(s'), critic(s), actor(s)
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_fwd(w.s2, S, nullptr, 0, 0, Wat + da.w_off[0], S, Wat + da.b_off[0], w.h1[0], H, B, H, S, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.s2, S, nullptr, 0, 0, Wct + dc.w_off[0], S, Wct + dc.b_off[0], w.h1[1], H, B, H, S, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.s, S, nullptr, 0, 0, Wc + dc.w_off[0], S, Wc + dc.b_off[0], w.h1[2], H, B, H, S, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.s, S, nullptr, 0, 0, Wa + da.w_off[0], S, Wa + da.b_off[0], w.h1[3], H, B, H, S, EPI_BIAS_RELU));
+  RUN(gemm_batch_launch(g, st));
+  // level 2: fc2 (actor: no activation, models.py:36; critic: cat(h1, a) + relu, models.py:80)
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_fwd(w.h1[0], H, nullptr, 0, 0, Wat + da.w_off[1], H, Wat + da.b_off[1], w.h2[0], H, B, H, H, EPI_BIAS));
+  gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.a, A, H, Wc + dc.w_off[1], H + A, Wc + dc.b_off[1], w.h2[2], H, B, H, H + A, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h1[3], H, nullptr, 0, 0, Wa + da.w_off[1], H, Wa + da.b_off[1], w.h2[3], H, B, H, H, EPI_BIAS));
+  RUN(gemm_batch_launch(g, st));
+  // level 3: fc2_2 + relu
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_fwd(w.h2[0], H, nullptr, 0, 0, Wat + da.w_off[2], H, Wat + da.b_off[2], w.h3[0], H, B, H, H, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h2[2], H, nullptr, 0, 0, Wc + dc.w_off[2], H, Wc + dc.b_off[2], w.h3[2], H, B, H, H, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h2[3], H, nullptr, 0, 0, Wa + da.w_off[2], H, Wa + da.b_off[2], w.h3[3], H, B, H, H, EPI_BIAS_RELU));
+  RUN(gemm_batch_launch(g, st));
+  // level 4: fc3 (actor: tanh; critic: logits)
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_fwd(w.h3[0], H, nullptr, 0, 0, Wat + da.w_off[3], H, Wat + da.b_off[3], w.out[0], A, B, A, H, EPI_BIAS_TANH));
+  gemm_batch_add(g, gemm_fwd(w.h3[2], H, nullptr, 0, 0, Wc + dc.w_off[3], H, Wc + dc.b_off[3], w.out[2], N, B, N, H, EPI_BIAS));
+  gemm_batch_add(g, gemm_fwd(w.h3[3], H, nullptr, 0, 0, Wa + da.w_off[3], H, Wa + da.b_off[3], w.out[3], A, B, A, H, EPI_BIAS_TANH));
+  RUN(gemm_batch_launch(g, st));
+  // level 5: critic_target.fc2([h1t, a_t(s')]) and critic.fc2([h1, actor(s)]) (h1 of the critic is reused)
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_fwd(w.h1[1], H, w.out[0], A, H, Wct + dc.w_off[1], H + A, Wct + dc.b_off[1], w.h2[1], H, B, H, H + A, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.out[3], A, H, Wc + dc.w_off[1], H + A, Wc + dc.b_off[1], w.h2[4], H, B, H, H + A, EPI_BIAS_RELU));
+  RUN(gemm_batch_launch(g, st));
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_fwd(w.h2[1], H, nullptr, 0, 0, Wct + dc.w_off[2], H, Wct + dc.b_off[2], w.h3[1], H, B, H, H, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h2[4], H, nullptr, 0, 0, Wc + dc.w_off[2], H, Wc + dc.b_off[2], w.h3[4], H, B, H, H, EPI_BIAS_RELU));
+  RUN(gemm_batch_launch(g, st));
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_fwd(w.h3[1], H, nullptr, 0, 0, Wct + dc.w_off[3], H, Wct + dc.b_off[3], w.out[1], N, B, N, H, EPI_BIAS));
+  gemm_batch_add(g, gemm_fwd(w.h3[4], H, nullptr, 0, 0, Wc + dc.w_off[3], H, Wc + dc.b_off[3], w.out[4], N, B, N, H, EPI_BIAS));
+  RUN(gemm_batch_launch(g, st));
+
+  // 3. heads: softmaxes, projection, CE loss, td, priorities, logit gradients (ddpg.py:214-222,236-238)
+  HeadsArgs ha{};
+  ha.target_logits = w.out[1]; ha.q_logits = w.out[2]; ha.pi_logits = w.out[4];
+  ha.rewards = w.r; ha.dones = w.done; ha.B = B; ha.N = N; ha.flags = 0;
+  ha.v_min = c.v_min; ha.v_max = c.v_max; ha.delta = (c.v_max - c.v_min) / double(N - 1);
+  // live projection discounts with gamma even for n_steps>1; mode 1 uses gamma**n (ddpg.py:24)
+  ha.discount = (c.proj_mode == 1) ? pow(c.gamma, double(c.n_steps)) : c.gamma; ha.prio_eps = c.prio_eps;
+  ha.grad_scale = 1.0f / (float(B) * float(c.world_size > 1 ? c.world_size : 1));
+  ha.m = w.m; ha.target_probs = w.target_probs; ha.q_probs = w.q_probs;
+  ha.loss_rows = w.loss_rows; ha.td = b.td; ha.prio = b.prio; ha.dlogits_q = w.dlogits_q;
+  ha.pi_rows = w.pi_rows; ha.dlogits_pi = w.dlogits_pi;
+  RUN(launch_heads(ha, c.proj_mode, st));
+
+  // 4. priorities into the trees (ddpg.py:252-255); independent of the backward pass
+  if (c.prioritized) RUN(launch_tree_update(L->replay, B, b.idx, b.prio, st));
+
+  float* Ga = b.grad_actor; float* Gc = b.grad_critic;
+  // 5. backward.  "c_" = critic-loss pass, "p_" = policy pass through the critic, "a_" = actor.
+  // level B1: through critic.fc3
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_dx(w.dlogits_q, N, Wc + dc.w_off[3], H, w.c_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[2], H));
+  gemm_batch_add(g, gemm_dx(w.dlogits_pi, N, Wc + dc.w_off[3], H, w.p_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[4], H));
+  gemm_batch_add(g, gemm_dw(w.dlogits_q, N, w.h3[2], H, Gc + dc.w_off[3], H, Gc + dc.b_off[3], N, H, B));
+  RUN(gemm_batch_launch(g, st));
+  // level B2: through critic.fc2_2
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_dx(w.c_dz22, H, Wc + dc.w_off[2], H, w.c_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[2], H));
+  gemm_batch_add(g, gemm_dx(w.p_dz22, H, Wc + dc.w_off[2], H, w.p_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[4], H));
+  gemm_batch_add(g, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], H, Gc + dc.b_off[2], H, H, B));
+  RUN(gemm_batch_launch(g, st));
+  // level B3: through critic.fc2: dh1 (critic loss), d action (policy, tanh' folded in), dW2 = [dz2^T h1 | dz2^T a]
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_dx(w.c_dz2, H, Wc + dc.w_off[1], H + A, w.c_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[2], H));
+  gemm_batch_add(g, gemm_dx(w.p_dz2, H, Wc + dc.w_off[1] + H, H + A, w.a_dz3, A, B, A, H, EPI_TANH_MASK, w.out[3], A));
+  gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], H + A, Gc + dc.b_off[1], H, H, B));
+  gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.a, A, Gc + dc.w_off[1] + H, H + A, nullptr, H, A, B));
+  RUN(gemm_batch_launch(g, st));
+  // level B4: critic.fc1 weights; actor.fc3
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_dw(w.c_dz1, H, w.s, S, Gc + dc.w_off[0], S, Gc + dc.b_off[0], H, S, B));
+  gemm_batch_add(g, gemm_dx(w.a_dz3, A, Wa + da.w_off[3], H, w.a_dz22, H, B, H, A, EPI_RELU_MASK, w.h3[3], H));
+  gemm_batch_add(g, gemm_dw(w.a_dz3, A, w.h3[3], H, Ga + da.w_off[3], H, Ga + da.b_off[3], A, H, B));
+  RUN(gemm_batch_launch(g, st));
+  // level B5: actor.fc2_2 (its input h2 has no activation -> plain dX)
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_dx(w.a_dz22, H, Wa + da.w_off[2], H, w.a_dh2, H, B, H, H, EPI_NONE, nullptr, 0));
+  gemm_batch_add(g, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], H, Ga + da.b_off[2], H, H, B));
+  RUN(gemm_batch_launch(g, st));
+  // level B6: actor.fc2
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_dx(w.a_dh2, H, Wa + da.w_off[1], H, w.a_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[3], H));
+  gemm_batch_add(g, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], H, Ga + da.b_off[1], H, H, B));
+  RUN(gemm_batch_launch(g, st));
+  // level B7: actor.fc1
+  gemm_batch_begin(g);
+  gemm_batch_add(g, gemm_dw(w.a_dz1, H, w.s, S, Ga + da.w_off[0], S, Ga + da.b_off[0], H, S, B));
+  RUN(gemm_batch_launch(g, st));
+
+  // 6. data-parallel gradient exchange: ONE all-reduce over the flat [P_a + P_c] buffer
+  if (c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
+
+  // 7. Adam (actor + critic), sync (identity), Polyak -- one launch, two segments
+  AdamArgs aa{};
+  aa.seg[0] = AdamSeg{b.actor, Ga, b.adam_m_actor, b.adam_v_actor, b.actor_target, da.total, 0.f, 0};
+  aa.seg[1] = AdamSeg{b.critic, Gc, b.adam_m_critic, b.adam_v_critic, b.critic_target, dc.total, 0.f, 1};
+  aa.nseg = 2;
+  aa.w1 = float(1.0 - c.beta1); aa.w2 = float(1.0 - c.beta2); aa.beta2 = float(c.beta2); aa.eps = float(c.adam_eps);
+  aa.tau = float(c.tau); aa.one_minus_tau = float(1.0 - c.tau); aa.grad_scale = 1.0f; aa.clock = w.clock;
+  RUN(launch_adam(aa, st));
+
+  // 8. reported scalars
+  RUN(launch_loss_reduce(w.loss_rows, w.pi_rows, B, 1.0f / float(B), b.losses, st));
+#undef RUN
+  L->kernels_per_step = nk;
+  return D4PG_OK;
+}
+
+extern "C" int64_t d4pg_learner_workspace_floats(const d4pg_learner_config_t* cfg) {
+  if (!cfg) return -1;
+  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms).total;
+}
+
+extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d4pg_learner_buffers_t* buf,
+                                       d4pg_replay_t* replay, d4pg_comm_t* comm, d4pg_learner_t** out) {
+  D4PG_REQUIRE(cfg && buf && replay && out, D4PG_EINVAL, "d4pg_learner_create: null argument");
+  D4PG_REQUIRE(cfg->batch > 0 && cfg->obs_dim > 0 && cfg->act_dim > 0, D4PG_EINVAL, "d4pg_learner_create: bad dims");
+  D4PG_REQUIRE(cfg->n_atoms >= 2 && cfg->n_atoms <= D4PG_MAX_ATOMS, D4PG_EINVAL, "d4pg_learner_create: n_atoms must be in [2,%d]", D4PG_MAX_ATOMS);
+  D4PG_REQUIRE(cfg->v_max > cfg->v_min, D4PG_EINVAL, "d4pg_learner_create: v_max <= v_min");
+  D4PG_REQUIRE(cfg->proj_mode == 0 || cfg->proj_mode == 1, D4PG_EINVAL, "d4pg_learner_create: proj_mode must be 0/1");
+  D4PG_REQUIRE(cfg->precision == 0, D4PG_ENOTSUP, "d4pg_learner_create: precision %d not available in this build", cfg->precision);
+  D4PG_REQUIRE(cfg->world_size <= 1 || comm, D4PG_EINVAL, "d4pg_learner_create: world_size>1 needs a communicator");
+  D4PG_REQUIRE(buf->actor && buf->actor_target && buf->critic && buf->critic_target && buf->grad_actor && buf->grad_critic &&
+               buf->adam_m_actor && buf->adam_v_actor && buf->adam_m_critic && buf->adam_v_critic &&
+               buf->idx && buf->prio && buf->td && buf->losses && buf->workspace, D4PG_EINVAL,
+               "d4pg_learner_create: null device buffer");
+  d4pg_learner* L = new (std::nothrow) d4pg_learner();
+  D4PG_REQUIRE(L, D4PG_EINVAL, "d4pg_learner_create: out of host memory");
+  L->cfg = *cfg; L->buf = *buf; L->replay = replay; L->comm = comm;
+  L->da = actor_dims(cfg->obs_dim, cfg->act_dim);
+  L->dc = critic_dims(cfg->obs_dim, cfg->act_dim, cfg->n_atoms);
+  if (buf->grad_critic != buf->grad_actor + L->da.total) {
+    set_error("d4pg_learner_create: grad_critic must equal grad_actor + P_a (one flat gradient buffer)");
+    delete L; return D4PG_EINVAL;
+  }
+  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms);
+  L->graph_exec = nullptr; L->graph_ready = false; L->steps_done = 0; L->kernels_per_step = 0;
+  L->profiling = false;
+  cudaError_t e = cudaMemset(L->ws.clock, 0, sizeof(LearnerClock));
+  if (e != cudaSuccess) { set_error("d4pg_learner_create: %s", cudaGetErrorString(e)); delete L; return D4PG_ECUDA; }
+  *out = L;
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
+  if (!L) return D4PG_OK;
+  if (L->graph_exec) cudaGraphExecDestroy(L->graph_exec);
+  delete L;
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_learner_step(d4pg_learner_t* L, d4pg_stream_t stream) {
+  D4PG_REQUIRE(L, D4PG_EINVAL, "d4pg_learner_step: null handle");
+  cudaStream_t st = as_stream(stream);
+  if (!L->cfg.use_graph) {
+    int rc = enqueue_step(L, st);
+    if (rc == D4PG_OK) ++L->steps_done;
+    return rc;
+  }
+  if (!L->graph_ready) {
+    D4PG_REQUIRE(st != nullptr, D4PG_EINVAL, "d4pg_learner_step: graph capture needs a non-default stream");
+    cudaGraph_t graph = nullptr;
+    D4PG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_step(L, st);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != D4PG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { set_error("d4pg_learner_step: end capture: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
+    e = cudaGraphInstantiate(&L->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { set_error("d4pg_learner_step: instantiate: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
+    L->graph_ready = true;
+  }
+  D4PG_CUDA_OK(cudaGraphLaunch(L->graph_exec, st));
+  ++L->steps_done;
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t stream, int32_t max_launches,
+                                             float* ms_out, char* names_out, int32_t name_stride, int32_t* n_out) {
+  D4PG_REQUIRE(L && ms_out && n_out && max_launches > 0, D4PG_EINVAL, "d4pg_learner_profile_step: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  L->profiling = true; L->ev.clear(); L->ev_name.clear();
+  int rc = enqueue_step(L, st);
+  L->profiling = false;
+  if (rc == D4PG_OK) ++L->steps_done;
+  cudaError_t e = cudaStreamSynchronize(st);
+  const int n = int(L->ev_name.size());
+  *n_out = n < max_launches ? n : max_launches;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, L->ev[2 * i], L->ev[2 * i + 1]);
+    if (i < max_launches) {
+      ms_out[i] = ms;
+      if (names_out && name_stride > 1) {
+        strncpy(names_out + size_t(i) * name_stride, L->ev_name[i].c_str(), name_stride - 1);
+        names_out[size_t(i) * name_stride + name_stride - 1] = 0;
+      }
+    }
+    cudaEventDestroy(L->ev[2 * i]); cudaEventDestroy(L->ev[2 * i + 1]);
+  }
+  L->ev.clear(); L->ev_name.clear();
+  if (e != cudaSuccess) { set_error("d4pg_learner_profile_step: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
+  return rc;
+}
+
+extern "C" int64_t d4pg_learner_steps_done(const d4pg_learner_t* L) { return L ? L->steps_done : -1; }
+extern "C" int32_t d4pg_learner_kernels_per_step(const d4pg_learner_t* L) { return L ? L->kernels_per_step : -1; }
+
+extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_step, int64_t beta_t, d4pg_stream_t stream) {
+  D4PG_REQUIRE(L && adam_step >= 0 && beta_t >= 0, D4PG_EINVAL, "d4pg_learner_set_counters: bad arguments");
+  LearnerClock c{};
+  c.adam_step = adam_step; c.beta_t = beta_t; c.steps_done = adam_step;
+  D4PG_CUDA_OK(cudaMemcpyAsync(L->ws.clock, &c, sizeof(c), cudaMemcpyHostToDevice, as_stream(stream)));
+  D4PG_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_learner_tensor(d4pg_learner_t* L, const char* name, void** ptr, int64_t* count) {
+  D4PG_REQUIRE(L && name && ptr && count, D4PG_EINVAL, "d4pg_learner_tensor: null argument");
+  const Workspace& w = L->ws;
+  const int64_t B = L->cfg.batch, S = L->cfg.obs_dim, A = L->cfg.act_dim, N = L->cfg.n_atoms;
+  struct E { const char* n; void* p; int64_t c; };
+  const E table[] = {
+      {"s", w.s, B * S}, {"a", w.a, B * A}, {"r", w.r, B}, {"s2", w.s2, B * S}, {"done", w.done, B},
+      {"target_logits", w.out[1], B * N}, {"q_logits", w.out[2], B * N}, {"pi_logits", w.out[4], B * N},
+      {"m", w.m, B * N}, {"q_probs", w.q_probs, B * N}, {"target_probs", w.target_probs, B * N},
+      {"dlogits_q", w.dlogits_q, B * N}, {"dlogits_pi", w.dlogits_pi, B * N},
+      {"actor_out", w.out[3], B * A}, {"actor_target_out", w.out[0], B * A},
+      {"loss_rows", w.loss_rows, B}, {"pi_rows", w.pi_rows, B}};
+  for (const E& e : table)
+    if (strcmp(e.n, name) == 0) { *ptr = e.p; *count = e.c; return D4PG_OK; }
+  set_error("d4pg_learner_tensor: unknown tensor '%s'", name);
+  return D4PG_EINVAL;
+}

@@ -1,0 +1,509 @@
+// GPU-resident prioritized replay: fp32 sum/min segment trees + SoA transition storage.
+//
+// Replaces (reference, relative to /root/reference):
+//   prioritized_replay_memory.py:33-113   SegmentTree (__setitem__, reduce, _reduce_helper)
+//   prioritized_replay_memory.py:114-162  SumSegmentTree.sum/find_prefixsum_idx, MinSegmentTree.min
+//   prioritized_replay_memory.py:164-222  ReplayBuffer.add/_encode_sample
+//   prioritized_replay_memory.py:224-335  PrioritizedReplayBuffer.add/_sample_proportional/sample/
+//                                         update_priorities
+//   replay_memory.py:14-19,61-80          Replay.add / Replay.sample (gather only)
+//
+// Tree layout is the reference's: root at 1, leaves at [cap, 2cap), V[i] = op(V[2i], V[2i+1]).
+// Node dtype is fp32 -- what the reference's Python evaluates to under NumPy 2.
+// Everything is HBM/L2 pointer chasing + row gathers: no tensor-core work here.
+#include "internal.cuh"
+#include <new>
+#include <algorithm>
+
+struct d4pg_replay {
+  int64_t size, cap; int log2cap;
+  int obs_dim, act_dim;
+  double alpha; float alpha_f32;
+  float* sum; float* mn;
+  float* obs; float* act; double* rew; float* obs2; uint8_t* done;
+  int32_t* scratch; float* state;
+  int64_t len, next_idx;
+  int pristine;
+};
+
+namespace d4pg {
+
+// Device-resident bookkeeping (lives in the caller's `state` buffer, 32 bytes).  Kernels read
+// len / pristine from here so a captured CUDA graph stays valid while add() keeps filling.
+struct ReplayState {
+  float max_priority;      // PrioritizedReplayBuffer._max_priority, :249,335
+  int32_t pristine;        // 1 until the first update_priorities (tree still "all Python floats")
+  int64_t len;             // len(self._storage)
+  int64_t next_idx;        // self._next_idx
+  int64_t reserved;
+};
+static_assert(sizeof(ReplayState) == 32, "ReplayState must fit the 8-float state buffer");
+
+// leaf = priority ** alpha with np.float32 ** float semantics: powf(p, (float)alpha).  glibc's
+// powf is correctly rounded in all but vanishing cases, so we evaluate in fp64 and round once.
+__device__ __forceinline__ float pow_alpha(float p, float alpha_f32) {
+  if (p == 1.0f) return 1.0f;
+  return __double2float_rn(pow(double(p), double(alpha_f32)));
+}
+
+// SumSegmentTree.sum(0, end+1): reduce over leaves [0, end] with _reduce_helper's association
+// (prioritized_replay_memory.py:61-96): V[left] + (V[left'] + (... + V[last])), fp32.
+__device__ float prefix_sum_ref(const float* __restrict__ V, int64_t cap, int64_t e) {
+  float terms[40];
+  int n = 0;
+  int64_t node = 1, lo = 0, hi = cap - 1;
+  while (true) {
+    if (e == hi) { terms[n++] = __ldcg(V + node); break; }
+    int64_t mid = (lo + hi) >> 1;
+    if (e <= mid) { node = 2 * node; hi = mid; }
+    else { terms[n++] = __ldcg(V + 2 * node); node = 2 * node + 1; lo = mid + 1; }
+  }
+  float acc = terms[n - 1];
+  for (int i = n - 2; i >= 0; --i) acc = __fadd_rn(terms[i], acc);
+  return acc;
+}
+__device__ float prefix_min_ref(const float* __restrict__ V, int64_t cap, int64_t e) {
+  float acc = INFINITY;
+  int64_t node = 1, lo = 0, hi = cap - 1;
+  while (true) {
+    if (e == hi) { acc = fminf(acc, __ldcg(V + node)); break; }
+    int64_t mid = (lo + hi) >> 1;
+    if (e <= mid) { node = 2 * node; hi = mid; }
+    else { acc = fminf(acc, __ldcg(V + 2 * node)); node = 2 * node + 1; lo = mid + 1; }
+  }
+  return acc;
+}
+
+struct SampleArgs {
+  const float* sum; const float* mn; int64_t cap; const ReplayState* state;
+  const double* uniforms; uint64_t seed, counter; float beta;
+  const int64_t* counter_ptr;       // optional device counter added to `counter` (graph replay)
+  const float* beta_ptr;            // optional device beta (graph replay)
+  const float* obs; const float* act; const double* rew; const float* obs2; const uint8_t* done;
+  int obs_dim, act_dim; int B;
+  const int32_t* idx_in;            // gather-only mode when non-null
+  int uniform_mode;                 // 1: idx = floor(u*len) (device-side uniform replay, with replacement)
+  int32_t* idx; float* weights;
+  float* s; float* a; double* r; float* s2; uint8_t* d;
+};
+
+constexpr int SAMPLE_ROWS = 32;      // rows per CTA
+constexpr int SAMPLE_THREADS = 256;
+
+// _sample_proportional (:258-265) + IS weights (:303-311) + _encode_sample (:189-199), fused.
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const SampleArgs a) {
+  __shared__ int32_t idx_s[SAMPLE_ROWS];
+  const int row0 = blockIdx.x * SAMPLE_ROWS;
+  const int nrows = min(SAMPLE_ROWS, a.B - row0);
+  const int t = threadIdx.x;
+  if (t < nrows) {
+    const int row = row0 + t;
+    int32_t leaf_idx;
+    if (a.idx_in) {
+      leaf_idx = a.idx_in[row];
+    } else {
+      const int64_t len = a.state->len;
+      const float total = a.uniform_mode ? 0.f : prefix_sum_ref(a.sum, a.cap, len - 2);   // sum(0, len-1)
+      const uint64_t ctr = a.counter + (a.counter_ptr ? uint64_t(*a.counter_ptr) : 0ull);
+      const double u = a.uniforms ? a.uniforms[row] : Philox::uniform53(a.seed, ctr, uint32_t(row));
+      int64_t i = 1;
+      if (a.uniform_mode) {
+        int64_t pick = int64_t(u * double(len));
+        i = a.cap + (pick < len ? pick : len - 1);
+      } else if (a.state->pristine) {
+        // tree of Python floats: mass and the descent are fp64 (all node values are integers)
+        double mass = __dmul_rn(u, double(total));
+        while (i < a.cap) {
+          const double left = double(__ldcg(a.sum + 2 * i));
+          if (left > mass) i = 2 * i;                                 // strict, :144
+          else { mass = __dsub_rn(mass, left); i = 2 * i + 1; }
+        }
+      } else {
+        float mass = __fmul_rn(__double2float_rn(u), total);          // weak float * np.float32
+        while (i < a.cap) {
+          const float left = __ldcg(a.sum + 2 * i);
+          if (left > mass) i = 2 * i;
+          else { mass = __fsub_rn(mass, left); i = 2 * i + 1; }
+        }
+      }
+      leaf_idx = int32_t(i - a.cap);
+      if (a.weights && !a.uniform_mode) {
+        const float tot = __ldcg(a.sum + 1);
+        const float pmin = __fdiv_rn(__ldcg(a.mn + 1), tot);
+        const float n = float(len);
+        const float beta = a.beta_ptr ? *a.beta_ptr : a.beta;
+        const float maxw = __double2float_rn(pow(double(__fmul_rn(pmin, n)), double(-beta)));
+        const float ps = __fdiv_rn(__ldcg(a.sum + a.cap + leaf_idx), tot);
+        const float w = __double2float_rn(pow(double(__fmul_rn(ps, n)), double(-beta)));
+        a.weights[row] = __fdiv_rn(w, maxw);
+      }
+    }
+    idx_s[t] = leaf_idx;
+    if (a.idx) a.idx[row] = leaf_idx;
+    if (a.r) a.r[row] = a.rew[leaf_idx];
+    if (a.d) a.d[row] = a.done[leaf_idx];
+  }
+  __syncthreads();
+  // coalesced row gathers: consecutive threads walk consecutive features of one transition
+  const int od = a.obs_dim, ad = a.act_dim;
+  for (int e = t; e < nrows * od; e += SAMPLE_THREADS) {
+    const int rr = e / od, c = e - rr * od;
+    const size_t src = size_t(idx_s[rr]) * od + c, dst = size_t(row0 + rr) * od + c;
+    a.s[dst] = __ldg(a.obs + src);
+    a.s2[dst] = __ldg(a.obs2 + src);
+  }
+  for (int e = t; e < nrows * ad; e += SAMPLE_THREADS) {
+    const int rr = e / ad, c = e - rr * ad;
+    a.a[size_t(row0 + rr) * ad + c] = __ldg(a.act + size_t(idx_s[rr]) * ad + c);
+  }
+}
+
+// ---- leaf writes + level-synchronous parent recompute, one CTA ---------------------------
+// update_priorities (:315-335) is a sequential Python loop; its final state equals "write all
+// leaves (last writer wins on duplicates), then recompute every touched ancestor bottom-up",
+// because each node's last recompute sees its children's final values.
+enum { TREE_UPDATE = 0, TREE_SET = 1, TREE_ADD = 2 };
+struct TreeArgs {
+  float* sum; float* mn; int64_t cap; int log2cap; int64_t size;
+  int n; const int32_t* idx; const float* v0; const float* v1;   // UPDATE: v0=prio; SET: v0=sum vals, v1=min vals
+  int64_t ring_start;                                              // ADD: positions (ring_start+i) % size
+  float alpha_f32; int32_t* scratch; ReplayState* state;
+};
+constexpr int TREE_THREADS = 1024;
+
+template <int MODE>
+__global__ void __launch_bounds__(TREE_THREADS) tree_write_kernel(const TreeArgs a) {
+  __shared__ float red[32];
+  const int t = threadIdx.x;
+  auto pos = [&](int i) -> int64_t {
+    return MODE == TREE_ADD ? (a.ring_start + i) % a.size : int64_t(a.idx[i]);
+  };
+  if (MODE != TREE_ADD) {
+    for (int i = t; i < a.n; i += TREE_THREADS) atomicMax(a.scratch + pos(i), i);
+    __syncthreads();
+  }
+  float local_max = 0.f;
+  const float add_leaf = (MODE == TREE_ADD) ? pow_alpha(a.state->max_priority, a.alpha_f32) : 0.f;  // :255-256
+  for (int i = t; i < a.n; i += TREE_THREADS) {
+    const int64_t p = pos(i);
+    if (MODE == TREE_ADD || a.scratch[p] == i) {
+      float ls, lm;
+      if (MODE == TREE_UPDATE) { ls = lm = pow_alpha(a.v0[i], a.alpha_f32); }
+      else if (MODE == TREE_SET) { ls = a.v0[i]; lm = a.v1[i]; }
+      else { ls = lm = add_leaf; }
+      a.sum[a.cap + p] = ls;
+      a.mn[a.cap + p] = lm;
+    }
+    if (MODE == TREE_UPDATE) local_max = fmaxf(local_max, a.v0[i]);
+  }
+  if (MODE == TREE_UPDATE) {                                       // _max_priority, :335
+    local_max = warp_max(local_max);
+    if ((t & 31) == 0) red[t >> 5] = local_max;
+    __syncthreads();
+    if (t < 32) {
+      float v = warp_max(red[t]);
+      if (t == 0) {
+        if (v > a.state->max_priority) a.state->max_priority = v;
+        a.state->pristine = 0;
+      }
+    }
+  }
+  __syncthreads();
+  if (MODE != TREE_ADD)
+    for (int i = t; i < a.n; i += TREE_THREADS) a.scratch[pos(i)] = -1;
+  for (int lvl = 1; lvl <= a.log2cap; ++lvl) {
+    __syncthreads();
+    for (int i = t; i < a.n; i += TREE_THREADS) {
+      const int64_t node = (a.cap + pos(i)) >> lvl;
+      const float l = __ldcg(a.sum + 2 * node), r = __ldcg(a.sum + 2 * node + 1);
+      a.sum[node] = __fadd_rn(l, r);
+      a.mn[node] = fminf(__ldcg(a.mn + 2 * node), __ldcg(a.mn + 2 * node + 1));
+    }
+  }
+}
+
+// bulk path for large adds: grid-wide leaf fill, then one launch per level
+__global__ void leaf_fill_kernel(float* sum, float* mn, int64_t cap, int64_t size, int64_t ring_start,
+                                 int64_t n, const ReplayState* state, float alpha_f32) {
+  const float leaf = pow_alpha(state->max_priority, alpha_f32);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t p = (ring_start + i) % size;
+    sum[cap + p] = leaf; mn[cap + p] = leaf;
+  }
+}
+__global__ void level_rebuild_kernel(float* sum, float* mn, int64_t first, int64_t count) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t node = first + i;
+    sum[node] = __fadd_rn(sum[2 * node], sum[2 * node + 1]);
+    mn[node] = fminf(mn[2 * node], mn[2 * node + 1]);
+  }
+}
+
+// ring insert of n rows from device staging buffers (ReplayBuffer.add, :180-187)
+__global__ void ring_write_kernel(float* obs, float* act, double* rew, float* obs2, uint8_t* done,
+                                  const float* s, const float* a, const double* r, const float* s2,
+                                  const uint8_t* d, int64_t n, int obs_dim, int act_dim,
+                                  int64_t size, int64_t ring_start, ReplayState* state,
+                                  int64_t new_len, int64_t new_next) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x, t0 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (t0 == 0) { state->len = new_len; state->next_idx = new_next; }
+  for (int64_t e = t0; e < n * obs_dim; e += stride) {
+    const int64_t i = e / obs_dim, c = e - i * obs_dim, p = (ring_start + i) % size;
+    obs[p * obs_dim + c] = s[e];
+    obs2[p * obs_dim + c] = s2[e];
+  }
+  for (int64_t e = t0; e < n * act_dim; e += stride) {
+    const int64_t i = e / act_dim, c = e - i * act_dim, p = (ring_start + i) % size;
+    act[p * act_dim + c] = a[e];
+  }
+  for (int64_t i = t0; i < n; i += stride) {
+    const int64_t p = (ring_start + i) % size;
+    rew[p] = r[i]; done[p] = d[i];
+  }
+}
+
+__global__ void tree_init_kernel(float* sum, float* mn, int32_t* scratch, ReplayState* state, int64_t cap) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t t0 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  for (int64_t i = t0; i < 2 * cap; i += stride) {
+    sum[i] = 0.f; mn[i] = INFINITY;                                  // neutral elements, :116-120,152-156
+    if (i < cap) scratch[i] = -1;
+  }
+  if (t0 == 0) {
+    state->max_priority = 1.0f;                                      // :249
+    state->pristine = 1; state->len = 0; state->next_idx = 0; state->reserved = 0;
+  }
+}
+
+__global__ void state_set_kernel(ReplayState* state, int64_t len, int64_t next_idx, int pristine) {
+  state->len = len; state->next_idx = next_idx; state->pristine = pristine;
+}
+
+// SegmentTree.reduce(start, end+1) for an arbitrary range with _reduce_helper's association
+// (:61-96): after the first split the left part is a suffix query (left-nested from the deepest
+// node up) and the right part a prefix query (right-nested); IS_SUM selects + or min.
+template <bool IS_SUM>
+__device__ float range_reduce_ref(const float* __restrict__ V, int64_t cap, int64_t s, int64_t e) {
+  auto op = [](float a, float b) { return IS_SUM ? __fadd_rn(a, b) : fminf(a, b); };
+  int64_t node = 1, lo = 0, hi = cap - 1;
+  while (true) {                                   // descend while the range sits in one child
+    if (s == lo && e == hi) return __ldcg(V + node);
+    const int64_t mid = (lo + hi) >> 1;
+    if (e <= mid) { node = 2 * node; hi = mid; }
+    else if (s > mid) { node = 2 * node + 1; lo = mid + 1; }
+    else break;
+  }
+  const int64_t mid = (lo + hi) >> 1;
+  // left: suffix [s, mid] of node 2*node
+  float terms[40]; int n = 0;
+  int64_t nd = 2 * node, l2 = lo, h2 = mid;
+  while (s != l2) {
+    const int64_t m2 = (l2 + h2) >> 1;
+    if (s > m2) { nd = 2 * nd + 1; l2 = m2 + 1; }
+    else { terms[n++] = __ldcg(V + 2 * nd + 1); nd = 2 * nd; h2 = m2; }
+  }
+  float left = __ldcg(V + nd);
+  for (int i = n - 1; i >= 0; --i) left = op(left, terms[i]);
+  // right: prefix [mid+1, e] of node 2*node+1
+  n = 0; nd = 2 * node + 1; l2 = mid + 1; h2 = hi;
+  while (e != h2) {
+    const int64_t m2 = (l2 + h2) >> 1;
+    if (e <= m2) { nd = 2 * nd; h2 = m2; }
+    else { terms[n++] = __ldcg(V + 2 * nd); nd = 2 * nd + 1; l2 = m2 + 1; }
+  }
+  float right = __ldcg(V + nd);
+  for (int i = n - 1; i >= 0; --i) right = op(terms[i], right);
+  return op(left, right);
+}
+
+__global__ void reduce_kernel(const float* sum, const float* mn, int64_t cap, int64_t s, int64_t e, float* out) {
+  if (threadIdx.x == 0) { out[0] = range_reduce_ref<true>(sum, cap, s, e); out[1] = range_reduce_ref<false>(mn, cap, s, e); }
+}
+
+// SumSegmentTree.find_prefixsum_idx (:126-149) for caller-supplied masses (fp32 descent)
+__global__ void find_prefix_kernel(const float* sum, int64_t cap, int n, const double* masses, int32_t* idx) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  float mass = __double2float_rn(masses[t]);
+  int64_t i = 1;
+  while (i < cap) {
+    const float left = __ldcg(sum + 2 * i);
+    if (left > mass) i = 2 * i;
+    else { mass = __fsub_rn(mass, left); i = 2 * i + 1; }
+  }
+  idx[t] = int32_t(i - cap);
+}
+
+int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
+  a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.state = reinterpret_cast<const ReplayState*>(h->state);
+  a.obs = h->obs; a.act = h->act; a.rew = h->rew; a.obs2 = h->obs2; a.done = h->done;
+  a.obs_dim = h->obs_dim; a.act_dim = h->act_dim;
+  sample_gather_kernel<<<cdiv(a.B, SAMPLE_ROWS), SAMPLE_THREADS, 0, st>>>(a);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
+                   uint64_t seed, const int64_t* counter_ptr, const float* beta_ptr,
+                   int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
+                   cudaStream_t st) {
+  SampleArgs sa{};
+  sa.uniforms = uniforms; sa.seed = seed; sa.counter = 0; sa.counter_ptr = counter_ptr;
+  sa.beta = 1.f; sa.beta_ptr = beta_ptr; sa.B = B; sa.idx = idx; sa.weights = prioritized ? weights : nullptr;
+  sa.s = s; sa.a = a; sa.r = r; sa.s2 = s2; sa.d = d;
+  if (!prioritized) { sa.idx_in = positions; sa.uniform_mode = positions ? 0 : 1; }
+  return launch_sample(h, sa, st);
+}
+
+int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st) {
+  TreeArgs a{};
+  a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.log2cap = h->log2cap; a.size = h->size;
+  a.n = B; a.idx = idx; a.v0 = prio; a.alpha_f32 = h->alpha_f32; a.scratch = h->scratch; a.state = reinterpret_cast<ReplayState*>(h->state);
+  tree_write_kernel<TREE_UPDATE><<<1, TREE_THREADS, 0, st>>>(a);
+  D4PG_LAUNCH_OK();
+  h->pristine = 0;
+  return D4PG_OK;
+}
+
+}  // namespace d4pg
+
+using namespace d4pg;
+
+extern "C" int32_t d4pg_replay_capacity(int64_t size, int64_t* cap_out) {
+  D4PG_REQUIRE(size > 0 && cap_out, D4PG_EINVAL, "d4pg_replay_capacity: bad arguments");
+  int64_t cap = 1;
+  while (cap < size) cap *= 2;                                       // :243-245
+  *cap_out = cap;
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_replay_create(int64_t size, int32_t obs_dim, int32_t act_dim, double alpha,
+                                      float* sum_tree, float* min_tree,
+                                      float* obs, float* act, double* rew, float* obs2, uint8_t* done,
+                                      int32_t* scratch, float* state, d4pg_stream_t stream, d4pg_replay_t** out) {
+  D4PG_REQUIRE(out && size > 0 && size < (int64_t(1) << 30), D4PG_EINVAL, "d4pg_replay_create: size out of range");
+  D4PG_REQUIRE(obs_dim > 0 && act_dim > 0, D4PG_EINVAL, "d4pg_replay_create: dims must be positive");
+  D4PG_REQUIRE(alpha >= 0, D4PG_EINVAL, "d4pg_replay_create: alpha must be >= 0");                      // :240
+  D4PG_REQUIRE(sum_tree && min_tree && obs && act && rew && obs2 && done && scratch && state, D4PG_EINVAL,
+               "d4pg_replay_create: null buffer");
+  d4pg_replay* h = new (std::nothrow) d4pg_replay();
+  D4PG_REQUIRE(h, D4PG_EINVAL, "d4pg_replay_create: out of host memory");
+  h->size = size; d4pg_replay_capacity(size, &h->cap);
+  h->log2cap = 0; while ((int64_t(1) << h->log2cap) < h->cap) ++h->log2cap;
+  h->obs_dim = obs_dim; h->act_dim = act_dim; h->alpha = alpha; h->alpha_f32 = float(alpha);
+  h->sum = sum_tree; h->mn = min_tree; h->obs = obs; h->act = act; h->rew = rew; h->obs2 = obs2; h->done = done;
+  h->scratch = scratch; h->state = state; h->len = 0; h->next_idx = 0; h->pristine = 1;
+  tree_init_kernel<<<296, 256, 0, as_stream(stream)>>>(h->sum, h->mn, h->scratch,
+                                                        reinterpret_cast<ReplayState*>(h->state), h->cap);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("d4pg_replay_create: %s", cudaGetErrorString(e)); delete h; return D4PG_ECUDA; }
+  *out = h;
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_replay_destroy(d4pg_replay_t* h) { delete h; return D4PG_OK; }
+extern "C" int64_t d4pg_replay_len(const d4pg_replay_t* h) { return h ? h->len : -1; }
+extern "C" int64_t d4pg_replay_next_idx(const d4pg_replay_t* h) { return h ? h->next_idx : -1; }
+
+extern "C" int32_t d4pg_replay_set_len(d4pg_replay_t* h, int64_t len, int64_t next_idx, int32_t pristine) {
+  D4PG_REQUIRE(h && len >= 0 && len <= h->size && next_idx >= 0 && next_idx < h->size, D4PG_EINVAL,
+               "d4pg_replay_set_len: out of range");
+  h->len = len; h->next_idx = next_idx; h->pristine = pristine ? 1 : 0;
+  state_set_kernel<<<1, 1>>>(reinterpret_cast<ReplayState*>(h->state), len, next_idx, h->pristine);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_replay_add(d4pg_replay_t* h, int64_t n, const float* obs, const float* act,
+                                   const double* rew, const float* obs2, const uint8_t* done,
+                                   int32_t prioritized, d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && obs && act && rew && obs2 && done, D4PG_EINVAL, "d4pg_replay_add: null argument");
+  D4PG_REQUIRE(n > 0 && n <= h->size, D4PG_EINVAL, "d4pg_replay_add: need 0 < n <= size (n=%lld)", (long long)n);
+  cudaStream_t st = as_stream(stream);
+  const int64_t start = h->next_idx;
+  const int64_t new_len = std::min<int64_t>(h->size, std::max<int64_t>(h->len, start + n));
+  const int64_t new_next = (start + n) % h->size;
+  const int blocks = int(std::min<int64_t>(148 * 4, (n * h->obs_dim + 255) / 256));
+  ring_write_kernel<<<blocks, 256, 0, st>>>(h->obs, h->act, h->rew, h->obs2, h->done, obs, act, rew, obs2, done,
+                                             n, h->obs_dim, h->act_dim, h->size, start,
+                                             reinterpret_cast<ReplayState*>(h->state), new_len, new_next);
+  D4PG_LAUNCH_OK();
+  if (prioritized) {
+    if (n <= 4096) {
+      TreeArgs a{};
+      a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.log2cap = h->log2cap; a.size = h->size;
+      a.n = int(n); a.ring_start = start; a.alpha_f32 = h->alpha_f32; a.scratch = h->scratch; a.state = reinterpret_cast<ReplayState*>(h->state);
+      tree_write_kernel<TREE_ADD><<<1, TREE_THREADS, 0, st>>>(a);
+      D4PG_LAUNCH_OK();
+    } else {
+      leaf_fill_kernel<<<296, 256, 0, st>>>(h->sum, h->mn, h->cap, h->size, start, n,
+                                            reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);
+      D4PG_LAUNCH_OK();
+      for (int64_t c = h->cap / 2; c >= 1; c /= 2) {
+        const int b = int(std::min<int64_t>(296, (c + 255) / 256));
+        level_rebuild_kernel<<<b, 256, 0, st>>>(h->sum, h->mn, c, c);
+        D4PG_LAUNCH_OK();
+      }
+    }
+  }
+  h->len = new_len;
+  h->next_idx = new_next;
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_replay_sample(d4pg_replay_t* h, int32_t B, const double* uniforms,
+                                      uint64_t philox_seed, uint64_t philox_counter, double beta,
+                                      int32_t* idx, float* weights,
+                                      float* s, float* a, double* r, float* s2, uint8_t* done,
+                                      d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && B > 0 && idx && s && a && r && s2 && done, D4PG_EINVAL, "d4pg_replay_sample: null/empty argument");
+  D4PG_REQUIRE(h->len >= 2, D4PG_ESTATE, "d4pg_replay_sample: needs at least 2 stored transitions (sum(0,len-1))");
+  D4PG_REQUIRE(beta > 0, D4PG_EINVAL, "d4pg_replay_sample: beta must be > 0");                           // :299
+  SampleArgs sa{};
+  sa.uniforms = uniforms; sa.seed = philox_seed; sa.counter = philox_counter; sa.beta = float(beta);
+  sa.B = B; sa.idx = idx; sa.weights = weights; sa.s = s; sa.a = a; sa.r = r; sa.s2 = s2; sa.d = done;
+  return launch_sample(h, sa, as_stream(stream));
+}
+
+extern "C" int32_t d4pg_replay_gather(d4pg_replay_t* h, int32_t B, const int32_t* idx,
+                                      float* s, float* a, double* r, float* s2, uint8_t* done, d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && B > 0 && idx && s && a && r && s2 && done, D4PG_EINVAL, "d4pg_replay_gather: null/empty argument");
+  SampleArgs sa{};
+  sa.B = B; sa.idx_in = idx; sa.s = s; sa.a = a; sa.r = r; sa.s2 = s2; sa.d = done;
+  return launch_sample(h, sa, as_stream(stream));
+}
+
+extern "C" int32_t d4pg_replay_update_priorities(d4pg_replay_t* h, int32_t B, const int32_t* idx,
+                                                 const float* prio, d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && B > 0 && idx && prio, D4PG_EINVAL, "d4pg_replay_update_priorities: null/empty argument");
+  return launch_tree_update(h, B, idx, prio, as_stream(stream));
+}
+
+extern "C" int32_t d4pg_replay_set_leaves(d4pg_replay_t* h, int32_t n, const int32_t* idx, const float* sum_vals,
+                                          const float* min_vals, d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && n > 0 && idx && sum_vals && min_vals, D4PG_EINVAL, "d4pg_replay_set_leaves: null/empty argument");
+  TreeArgs a{};
+  a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.log2cap = h->log2cap; a.size = h->size;
+  a.n = n; a.idx = idx; a.v0 = sum_vals; a.v1 = min_vals; a.scratch = h->scratch; a.state = reinterpret_cast<ReplayState*>(h->state);
+  tree_write_kernel<TREE_SET><<<1, TREE_THREADS, 0, as_stream(stream)>>>(a);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_replay_reduce(d4pg_replay_t* h, int64_t start, int64_t end, float* out, d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && out, D4PG_EINVAL, "d4pg_replay_reduce: null argument");
+  if (end <= 0) end += h->cap;                                        // :91-94 (None / negative end)
+  D4PG_REQUIRE(start >= 0 && start < end && end <= h->cap, D4PG_EINVAL, "d4pg_replay_reduce: bad range [%lld,%lld)",
+               (long long)start, (long long)end);
+  reduce_kernel<<<1, 32, 0, as_stream(stream)>>>(h->sum, h->mn, h->cap, start, end - 1, out);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_replay_find_prefixsum(d4pg_replay_t* h, int32_t n, const double* masses, int32_t* idx,
+                                              d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && n > 0 && masses && idx, D4PG_EINVAL, "d4pg_replay_find_prefixsum: null/empty argument");
+  find_prefix_kernel<<<cdiv(n, 128), 128, 0, as_stream(stream)>>>(h->sum, h->cap, n, masses, idx);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}

@@ -1,0 +1,172 @@
+"""Full DDPG.train() steps on the GPU vs the golden fixtures (reference outputs) and the oracle.
+Tolerances: sampled indices and atom bins bit-exact; probabilities, losses, gradients,
+post-step parameters within 1e-5 (fp32), as BASELINE.json's north_star states."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import d4pg_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _build(d4pg, g, use_graph, sampling="reference"):
+    obs_dim, act_dim, N, B, mem, n_fill, per, steps = [int(x) for x in g["meta"]]
+    v_min, v_max = [float(x) for x in g["dist"]]
+    info = {"type": "categorical", "v_min": v_min, "v_max": v_max, "n_atoms": N}
+    seed = int(g["seed"])
+    torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
+    kw = dict(memory_size=mem, batch_size=B, critic_dist_info=info, prioritized_replay=bool(per),
+              use_graph=use_graph, sampling=sampling)
+    glob = d4pg.DDPG(obs_dim, act_dim, **kw)               # main.py:382-385
+    oa = d4pg.SharedAdam(glob.actor.parameters(), lr=1e-3)
+    oc = d4pg.SharedAdam(glob.critic.parameters(), lr=1e-3)
+    loc = d4pg.DDPG(obs_dim, act_dim, **kw)                # main.py:187-195
+    loc.assign_global_optimizer(oa, oc)
+    loc.sync_local_global(glob)
+    loc.hard_update()
+    for k in H.NAMES:   # same seed -> same initial weights as the reference run
+        H.check_compact(g, "init_actor_" + k, loc.actor.state_dict()[k].cpu().numpy(), 0.0)
+        H.check_compact(g, "init_critic_" + k, loc.critic.state_dict()[k].cpu().numpy(), 0.0)
+    for i in range(n_fill):
+        loc.replayBuffer.add(g["S"][i], g["A"][i], float(g["R"][i]), g["S2"][i], bool(g["D"][i]))
+    return glob, loc, oa, oc, (obs_dim, act_dim, N, B, mem, n_fill, per, steps, v_min, v_max)
+
+
+@pytest.mark.parametrize("tag", ["per_c2", "per_part", "uniform_c1"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_steps_vs_reference_golden(tag, use_graph):
+    import d4pg_b200 as d4pg
+    g = H.load("train_%s.npz" % tag)
+    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph)
+    obs_dim, act_dim, N, B, mem, n_fill, per, steps, v_min, v_max = meta
+    for t in range(steps):
+        random.seed(9000 + t)                       # same generator state as the reference run
+        loc.train(glob)
+        info = loc.last_batch_info()
+        idx = info["idx"].cpu().numpy()
+        assert np.array_equal(idx, g["idx_%d" % t]), "sampled indices differ at step %d" % t
+        lc, la = loc.last_losses()
+        assert abs(lc - float(g["loss_critic_%d" % t])) <= TOL
+        assert abs(la - float(g["loss_actor_%d" % t])) <= TOL * max(1.0, abs(la))
+        tp = loc.debug_tensor("target_probs", (B, N)).cpu().numpy()
+        m = loc.debug_tensor("m", (B, N)).cpu().numpy()
+        q = loc.debug_tensor("q_probs", (B, N)).cpu().numpy()
+        assert np.abs(tp - g["target_probs_%d" % t]).max() <= TOL
+        assert np.abs(m - g["m_%d" % t]).max() <= TOL
+        assert np.abs(q - g["q_%d" % t]).max() <= TOL
+        # gathered batch is bit-exact
+        r = loc.debug_tensor("r", None, torch.float64).cpu().numpy()
+        assert np.array_equal(r, g["R"][idx])
+        s = loc.debug_tensor("s", (B, obs_dim)).cpu().numpy()
+        assert np.array_equal(s, g["S"][idx])
+        if per:
+            assert np.abs(info["prio"].cpu().numpy() - g["prio_%d" % t]).max() <= TOL
+            tree = loc.replayBuffer._it_sum.values().astype(np.float64)
+            assert np.abs(tree - g["tree_sum_%d" % t]).max() <= 1e-4 * max(1.0, np.abs(g["tree_sum_%d" % t]).max() * 1e-2)
+        ga = loc.actor.flat_grads().cpu().numpy()
+        gc = loc.critic.flat_grads().cpu().numpy()
+        for name, net, flat in (("actor", loc.actor, ga), ("critic", loc.critic, gc)):
+            for i, k in enumerate(H.NAMES):
+                off, n = net._offsets[i], net._sizes[i]
+                H.check_compact(g, "g_%s_%s_%d" % (name, k, t), flat[off:off + n], TOL)
+                H.check_compact(g, "%s_%s_%d" % (name, k, t), net.state_dict()[k].cpu().numpy().reshape(-1), TOL)
+        # local == global (ddpg.py:247)
+        assert torch.equal(loc.actor.flat_params(), glob.actor.flat_params())
+    t = steps - 1
+    for k in H.NAMES:
+        H.check_compact(g, "actor_target_%s_%d" % (k, t), loc.actor_target.state_dict()[k].cpu().numpy().reshape(-1), TOL)
+        H.check_compact(g, "critic_target_%s_%d" % (k, t), loc.critic_target.state_dict()[k].cpu().numpy().reshape(-1), TOL)
+    for (k, _), i in zip(loc.actor.named_parameters(), range(8)):
+        pass
+    ma, va = oa.moments(glob.actor)
+    mc, vc = oc.moments(glob.critic)
+    for i, k in enumerate(H.NAMES):
+        off, n = loc.actor._offsets[i], loc.actor._sizes[i]
+        H.check_compact(g, "adam_m_actor_%s_%d" % (k, t), ma.cpu().numpy()[off:off + n], 1e-6)
+        off, n = loc.critic._offsets[i], loc.critic._sizes[i]
+        H.check_compact(g, "adam_v_critic_%s_%d" % (k, t), vc.cpu().numpy()[off:off + n], 1e-6)
+    assert loc.kernels_per_step() > 0
+
+
+def test_config2_full_size_vs_oracle():
+    """Config 2 (|s|=17,|a|=6,51 atoms,B=256), 2 steps vs the oracle at full batch size."""
+    import d4pg_b200 as d4pg
+    B, mem, n_fill = 256, 4096, 4096
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": 51}
+    torch.manual_seed(3); np.random.seed(3); random.seed(3)
+    dd = d4pg.DDPG(17, 6, memory_size=mem, batch_size=B, critic_dist_info=info)
+    oa = d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3)
+    oc = d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3)
+    dd.assign_global_optimizer(oa, oc)
+    rng = np.random.RandomState(4)
+    S = rng.randn(n_fill, 17).astype(np.float32); A = rng.uniform(-1, 1, (n_fill, 6)).astype(np.float32)
+    R = (-3 * rng.rand(n_fill)).astype(np.float32).astype(np.float64); S2 = rng.randn(n_fill, 17).astype(np.float32)
+    D = rng.rand(n_fill) < 0.05
+    dd.replayBuffer.add_batch(S, A, R, S2, D)
+    lo = O.LearnerOracle(17, 6, info, actor_w={k: v.cpu().clone() for k, v in dd.actor.state_dict().items()},
+                         critic_w={k: v.cpu().clone() for k, v in dd.critic.state_dict().items()})
+    ob = O.PrioritizedReplayOracle(mem, 0.6, 17, 6)
+    ob.add_batch(S, A, R, S2, D)
+    sched = O.LinearScheduleOracle(100000, 1.0, 0.4)
+    for t in range(2):
+        random.seed(50 + t)
+        st = random.getstate(); us = [random.random() for _ in range(B)]; random.setstate(st)
+        dd.train(dd)
+        batch = ob.sample(B, sched.value(), us)
+        assert np.array_equal(dd.last_batch_info()["idx"].cpu().numpy(), batch[6])
+        out = lo.train_step(*batch[:5])
+        ob.update_priorities(batch[6], out["prio"])
+        lc, la = dd.last_losses()
+        assert abs(lc - float(out["loss_critic"])) <= TOL and abs(la - float(out["loss_actor"])) <= TOL * abs(la)
+        assert np.abs(dd.critic.flat_grads().cpu().numpy()[:dd.critic._sizes[0]] -
+                      out["grads_critic"]["fc1.weight"].numpy().reshape(-1)).max() <= TOL
+        for k in H.NAMES:
+            assert (dd.actor.state_dict()[k].cpu() - lo.actor[k]).abs().max().item() <= TOL
+            assert (dd.critic.state_dict()[k].cpu() - lo.critic[k]).abs().max().item() <= TOL
+            assert (dd.critic_target.state_dict()[k].cpu() - lo.critic_target[k]).abs().max().item() <= TOL
+
+
+def test_device_sampling_mode_runs_and_is_deterministic():
+    import d4pg_b200 as d4pg
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": 51}
+    outs = []
+    for rep in range(2):
+        torch.manual_seed(1)
+        dd = d4pg.DDPG(17, 6, memory_size=2048, batch_size=64, critic_dist_info=info, sampling="device", philox_seed=9)
+        dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters()), d4pg.SharedAdam(dd.critic.parameters()))
+        rng = np.random.RandomState(0)
+        dd.replayBuffer.add_batch(rng.randn(2048, 17), rng.uniform(-1, 1, (2048, 6)), -rng.rand(2048), rng.randn(2048, 17),
+                                  np.zeros(2048, bool))
+        for _ in range(5):
+            dd.train()
+        outs.append((dd.last_batch_info()["idx"].cpu().numpy().copy(), dd.last_losses(), dd.actor.flat_params().cpu().clone()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1] and torch.equal(outs[0][2], outs[1][2])
+    assert len(np.unique(outs[0][0])) > 32
+
+
+def test_nstep_projection_learner_mode():
+    import d4pg_b200 as d4pg
+    info = {"type": "categorical", "v_min": -150.0, "v_max": 150.0, "n_atoms": 101}
+    torch.manual_seed(2); random.seed(2)
+    B = 128
+    dd = d4pg.DDPG(17, 6, memory_size=1024, batch_size=B, critic_dist_info=info, n_steps=5, projection="nstep")
+    dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters()), d4pg.SharedAdam(dd.critic.parameters()))
+    rng = np.random.RandomState(5)
+    S = rng.randn(1024, 17).astype(np.float32); A = rng.uniform(-1, 1, (1024, 6)).astype(np.float32)
+    R = (40 * (rng.rand(1024) - 0.5)); S2 = rng.randn(1024, 17).astype(np.float32); D = rng.rand(1024) < 0.05
+    dd.replayBuffer.add_batch(S, A, R, S2, D)
+    lo = O.LearnerOracle(17, 6, info, n_steps=5, projection="nstep",
+                         actor_w={k: v.cpu().clone() for k, v in dd.actor.state_dict().items()},
+                         critic_w={k: v.cpu().clone() for k, v in dd.critic.state_dict().items()})
+    dd.train()
+    idx = dd.last_batch_info()["idx"].cpu().numpy()
+    out = lo.train_step(S[idx], A[idx], R[idx], S2[idx], D[idx])
+    m = dd.debug_tensor("m", (B, 101)).cpu().numpy()
+    assert np.abs(m - out["m"]).max() <= TOL
+    lc, la = dd.last_losses()
+    assert abs(lc - float(out["loss_critic"])) <= TOL
