@@ -14,7 +14,31 @@
 
 namespace d4pg {
 
+// mean over the batch of the per-row loss terms (ddpg.py:217 `.mean()`, ddpg.py:238 `.mean()`),
+// fixed-order single-block reduction so the reported scalars are run-to-run deterministic.
+__device__ void loss_reduce_block(const float* loss_rows, const float* pi_rows, int B, float inv_count, float* out) {
+  __shared__ float red[2][8];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) { a += loss_rows[i]; if (pi_rows) b += pi_rows[i]; }
+  a = warp_sum(a); b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sa = 0.f, sb = 0.f;
+    for (int w = 0; w < 8; ++w) { sa += red[0][w]; sb += red[1][w]; }
+    out[0] = sa * inv_count; out[1] = sb * inv_count;
+  }
+}
+
 __global__ void __launch_bounds__(256) adam_polyak_kernel(const AdamArgs a) {
+  if (int(blockIdx.y) == a.nseg) {
+    // tail slice: reported losses + advance the base counters for the NEXT step (nobody in this
+    // kernel reads them: the derived scalars were written by the step's first kernel)
+    if (blockIdx.x != 0) return;
+    if (a.loss_out) loss_reduce_block(a.loss_rows, a.pi_rows, a.B, a.inv_count, a.loss_out);
+    if (threadIdx.x == 0 && a.clock) { a.clock->adam_step += 1; a.clock->beta_t += 1; a.clock->steps_done += 1; }
+    return;
+  }
   const AdamSeg& s = a.seg[blockIdx.y];
   const float nss = (a.clock && s.clock_slot >= 0) ? a.clock->neg_step_size[s.clock_slot] : s.neg_step_size;
   const float bc2s = a.clock ? a.clock->bc2_sqrt : a.bc2_sqrt;
@@ -48,51 +72,8 @@ int launch_adam(const AdamArgs& a, cudaStream_t st) {
   int blocks = int((nmax / 4 + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  adam_polyak_kernel<<<dim3(blocks, a.nseg), 256, 0, st>>>(a);
-  D4PG_LAUNCH_OK();
-  return D4PG_OK;
-}
-
-// One thread: advance Adam's step count and the PER beta schedule
-// (prioritized_replay_memory.py:25-29: value() uses t, then t += 1).
-__global__ void clock_kernel(const ClockArgs a) {
-  LearnerClock* c = a.clock;
-  c->adam_step += 1;
-  const double step = double(c->adam_step);
-  const double bc1 = 1.0 - pow(a.beta1, step);
-  const double bc2 = 1.0 - pow(a.beta2, step);
-  c->neg_step_size[0] = float(-(a.lr_actor / bc1));
-  c->neg_step_size[1] = float(-(a.lr_critic / bc1));
-  c->bc2_sqrt = float(sqrt(bc2));
-  const double frac = fmin(double(c->beta_t) / double(a.per_beta_iters), 1.0);
-  c->beta = float(a.per_beta0 + frac * (a.per_beta_final - a.per_beta0));
-  c->beta_t += 1;
-  c->steps_done += 1;
-}
-int launch_clock(const ClockArgs& a, cudaStream_t st) {
-  clock_kernel<<<1, 1, 0, st>>>(a);
-  D4PG_LAUNCH_OK();
-  return D4PG_OK;
-}
-
-// mean over the batch of the per-row loss terms (ddpg.py:217 `.mean()`, ddpg.py:238 `.mean()`),
-// fixed-order single-block reduction so the reported scalars are run-to-run deterministic.
-__global__ void __launch_bounds__(256) loss_reduce_kernel(const float* loss_rows, const float* pi_rows, int B,
-                                                          float inv_count, float* out) {
-  __shared__ float red[2][8];
-  float a = 0.f, b = 0.f;
-  for (int i = threadIdx.x; i < B; i += 256) { a += loss_rows[i]; if (pi_rows) b += pi_rows[i]; }
-  a = warp_sum(a); b = warp_sum(b);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float sa = 0.f, sb = 0.f;
-    for (int w = 0; w < 8; ++w) { sa += red[0][w]; sb += red[1][w]; }
-    out[0] = sa * inv_count; out[1] = sb * inv_count;
-  }
-}
-int launch_loss_reduce(const float* loss_rows, const float* pi_rows, int B, float inv_count, float* out, cudaStream_t st) {
-  loss_reduce_kernel<<<1, 256, 0, st>>>(loss_rows, pi_rows, B, inv_count, out);
+  const int tail = (a.clock || a.loss_out) ? 1 : 0;
+  adam_polyak_kernel<<<dim3(blocks, a.nseg + tail), 256, 0, st>>>(a);
   D4PG_LAUNCH_OK();
   return D4PG_OK;
 }
@@ -114,7 +95,7 @@ extern "C" int32_t d4pg_adam_polyak(float* p, const float* g, float* m, float* v
   a.nseg = 1;
   a.w1 = float(1.0 - beta1); a.w2 = float(1.0 - beta2); a.beta2 = float(beta2); a.eps = float(eps);
   a.bc2_sqrt = float(sqrt(bc2)); a.tau = float(tau); a.one_minus_tau = float(1.0 - tau);
-  a.grad_scale = grad_scale; a.clock = nullptr;
+  a.grad_scale = grad_scale; a.clock = nullptr; a.loss_out = nullptr;
   return launch_adam(a, as_stream(stream));
 }
 

@@ -6,14 +6,36 @@ namespace d4pg {
 
 // Per-step scalars produced on the device so a captured CUDA graph needs no host patching.
 struct LearnerClock {
-  int64_t adam_step;     // post-increment count used by this step's Adam (state['step'])
+  // base counters: read by the step's FIRST kernel (sample), advanced by its LAST (adam)
+  int64_t adam_step;     // completed Adam steps (state['step'] before this step)
   int64_t beta_t;        // LinearSchedule.t
   int64_t steps_done;    // Philox counter / bookkeeping
+  // derived per-step scalars: written by the sample kernel, read by later kernels of the step
   float beta;            // PER beta for this step's IS weights
   float neg_step_size[2];   // -(lr/bc1) for actor, critic
   float bc2_sqrt;        // sqrt(1 - beta2^step)
   float pad;
 };
+
+struct ClockParams {
+  double lr_actor, lr_critic, beta1, beta2;
+  double per_beta0, per_beta_final; int64_t per_beta_iters;
+};
+
+// executed by ONE thread of the step's first kernel
+__device__ __forceinline__ void clock_derive(LearnerClock* c, const ClockParams& a) {
+  const double step = double(c->adam_step + 1);                      // post-increment step count
+  const double bc1 = 1.0 - pow(a.beta1, step);
+  const double bc2 = 1.0 - pow(a.beta2, step);
+  c->neg_step_size[0] = float(-(a.lr_actor / bc1));
+  c->neg_step_size[1] = float(-(a.lr_critic / bc1));
+  c->bc2_sqrt = float(sqrt(bc2));
+}
+// LinearSchedule.value() for clock t (prioritized_replay_memory.py:25-29)
+__device__ __forceinline__ float clock_beta(const LearnerClock* c, const ClockParams& a) {
+  const double frac = fmin(double(c->beta_t) / double(a.per_beta_iters), 1.0);
+  return float(a.per_beta0 + frac * (a.per_beta_final - a.per_beta0));
+}
 
 struct AdamSeg {
   float* p; const float* g; float* m; float* v; float* target; int64_t n;
@@ -22,16 +44,11 @@ struct AdamSeg {
 struct AdamArgs {
   AdamSeg seg[2]; int nseg;
   float w1, w2, beta2, eps, bc2_sqrt, tau, one_minus_tau, grad_scale;
-  const LearnerClock* clock;                  // optional
+  LearnerClock* clock;                        // optional (learner): scalars in, counters advanced
+  // fused tail (learner): deterministic batch means of the per-row losses -> out[0], out[1]
+  const float* loss_rows; const float* pi_rows; int B; float inv_count; float* loss_out;
 };
 int launch_adam(const AdamArgs& a, cudaStream_t st);
 
-struct ClockArgs {
-  LearnerClock* clock;
-  double lr_actor, lr_critic, beta1, beta2;
-  double per_beta0, per_beta_final; int64_t per_beta_iters;
-};
-int launch_clock(const ClockArgs& a, cudaStream_t st);
-int launch_loss_reduce(const float* loss_rows, const float* pi_rows, int B, float inv_count, float* out, cudaStream_t st);
 
 }  // namespace d4pg

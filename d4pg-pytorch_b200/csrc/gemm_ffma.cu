@@ -10,14 +10,55 @@
 
 namespace d4pg {
 
-constexpr int BM = 32, BN = 32, KC = 128;
-constexpr int LDS_A = BM + 2;   // even (float2 reads), 2-way conflicts at worst on transposed stores
+constexpr int BM = 32, BN = 32, KC = 64;
+constexpr int LDS_A = BM + 2;   // even (float2 reads); transposed stores are at worst 2-way conflicted
 constexpr int LDS_B = BN + 2;
 constexpr int GEMM_THREADS = 256;
+constexpr int PER_THREAD = BM * KC / GEMM_THREADS;   // 8 staged elements per thread per operand per chunk
 
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_ffma_kernel(const __grid_constant__ GemmBatch batch) {
-  __shared__ __align__(16) float As[KC * LDS_A];
-  __shared__ __align__(16) float Bs[KC * LDS_B];
+// Stage one K-chunk of both operands global -> registers.  All 16 loads of a thread are issued
+// back to back (fully unrolled, predicated) so one chunk costs ONE L2 round trip, and the next
+// chunk's loads are in flight while the current one is being multiplied.
+__device__ __forceinline__ void load_chunk(const GemmProblem& P, int m0, int n0, int k0, int tid,
+                                           float (&ra)[PER_THREAD], float (&rb)[PER_THREAD]) {
+#pragma unroll
+  for (int r = 0; r < PER_THREAD; ++r) {
+    const int e = tid + r * GEMM_THREADS;
+    float va = 0.f, vb = 0.f;
+    if (P.mode == GEMM_DW) {                       // A(i,k) = dZ[k*lda + i]: i fastest
+      const int kk = e / BM, i = e % BM, gi = m0 + i, gk = k0 + kk;
+      if (gi < P.M && gk < P.K) va = __ldg(P.A + size_t(gk) * P.lda + gi);
+    } else {                                       // A(i,k) = A[i*lda + k]: k fastest (+ concat)
+      const int i = e / KC, kk = e % KC, gi = m0 + i, gk = k0 + kk;
+      if (gi < P.M && gk < P.K)
+        va = (gk < P.K1) ? __ldg(P.A + size_t(gi) * P.lda + gk) : __ldg(P.A2 + size_t(gi) * P.lda2 + (gk - P.K1));
+    }
+    if (P.mode == GEMM_FWD) {                      // B(k,j) = W[j*ldb + k]: k fastest
+      const int j = e / KC, kk = e % KC, gj = n0 + j, gk = k0 + kk;
+      if (gj < P.N && gk < P.K) vb = __ldg(P.Bm + size_t(gj) * P.ldb + gk);
+    } else {                                       // B(k,j) = B[k*ldb + j]: j fastest
+      const int kk = e / BN, j = e % BN, gj = n0 + j, gk = k0 + kk;
+      if (gj < P.N && gk < P.K) vb = __ldg(P.Bm + size_t(gk) * P.ldb + gj);
+    }
+    ra[r] = va; rb[r] = vb;
+  }
+}
+
+__device__ __forceinline__ void store_chunk(const GemmProblem& P, int tid, float* __restrict__ As, float* __restrict__ Bs,
+                                            const float (&ra)[PER_THREAD], const float (&rb)[PER_THREAD]) {
+#pragma unroll
+  for (int r = 0; r < PER_THREAD; ++r) {
+    const int e = tid + r * GEMM_THREADS;
+    if (P.mode == GEMM_DW) As[(e / BM) * LDS_A + (e % BM)] = ra[r];
+    else As[(e % KC) * LDS_A + (e / KC)] = ra[r];
+    if (P.mode == GEMM_FWD) Bs[(e % KC) * LDS_B + (e / KC)] = rb[r];
+    else Bs[(e / BN) * LDS_B + (e % BN)] = rb[r];
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid_constant__ GemmBatch batch) {
+  __shared__ __align__(16) float As[2][KC * LDS_A];
+  __shared__ __align__(16) float Bs[2][KC * LDS_B];
 
   // locate problem and tile
   int pi = 0;
@@ -35,51 +76,28 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_ffma_kernel(const __grid_co
   float colsum = 0.f;                       // DW: bias gradient, threads < BM of the tn==0 tiles
   const bool want_bias_grad = (P.mode == GEMM_DW) && (P.bias_grad != nullptr) && (tn == 0);
 
-  for (int k0 = 0; k0 < P.K; k0 += KC) {
-    const int kc = min(KC, P.K - k0);
-    // ---- stage A[kk][i] ------------------------------------------------------------------
-    if (P.mode == GEMM_DW) {          // A(i,k) = dZ[k*lda + i]: i fastest
-      for (int e = tid; e < kc * BM; e += GEMM_THREADS) {
-        const int kk = e / BM, i = e - kk * BM;
-        const int gi = m0 + i;
-        As[kk * LDS_A + i] = (gi < P.M) ? __ldg(P.A + size_t(k0 + kk) * P.lda + gi) : 0.f;
-      }
-    } else {                          // A(i,k) = A[i*lda + k] (k fastest), optional concat
-      for (int e = tid; e < kc * BM; e += GEMM_THREADS) {
-        const int i = e / kc, kk = e - i * kc;
-        const int gi = m0 + i, gk = k0 + kk;
-        float v = 0.f;
-        if (gi < P.M) v = (gk < P.K1) ? __ldg(P.A + size_t(gi) * P.lda + gk)
-                                      : __ldg(P.A2 + size_t(gi) * P.lda2 + (gk - P.K1));
-        As[kk * LDS_A + i] = v;
-      }
-    }
-    // ---- stage B[kk][j] ------------------------------------------------------------------
-    if (P.mode == GEMM_FWD) {         // B(k,j) = W[j*ldb + k]: k fastest
-      for (int e = tid; e < kc * BN; e += GEMM_THREADS) {
-        const int j = e / kc, kk = e - j * kc;
-        const int gj = n0 + j;
-        Bs[kk * LDS_B + j] = (gj < P.N) ? __ldg(P.Bm + size_t(gj) * P.ldb + k0 + kk) : 0.f;
-      }
-    } else {                          // B(k,j) = B[k*ldb + j]: j fastest
-      for (int e = tid; e < kc * BN; e += GEMM_THREADS) {
-        const int kk = e / BN, j = e - kk * BN;
-        const int gj = n0 + j;
-        Bs[kk * LDS_B + j] = (gj < P.N) ? __ldg(P.Bm + size_t(k0 + kk) * P.ldb + gj) : 0.f;
-      }
-    }
-    __syncthreads();
-    // ---- 2x2 register tile, k order --------------------------------------------------------
-#pragma unroll 8
-    for (int kk = 0; kk < kc; ++kk) {
-      const float2 a = *reinterpret_cast<const float2*>(&As[kk * LDS_A + ty * 2]);
-      const float2 b = *reinterpret_cast<const float2*>(&Bs[kk * LDS_B + tx * 2]);
+  float ra[PER_THREAD], rb[PER_THREAD];
+  const int nchunks = (P.K + KC - 1) / KC;
+  load_chunk(P, m0, n0, 0, tid, ra, rb);
+  store_chunk(P, tid, As[0], Bs[0], ra, rb);
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunks) load_chunk(P, m0, n0, (c + 1) * KC, tid, ra, rb);     // in flight during the FMAs
+    const float* __restrict__ as = As[cur];
+    const float* __restrict__ bs = Bs[cur];
+#pragma unroll 16
+    for (int kk = 0; kk < KC; ++kk) {                                           // zero-padded past K
+      const float2 a = *reinterpret_cast<const float2*>(&as[kk * LDS_A + ty * 2]);
+      const float2 b = *reinterpret_cast<const float2*>(&bs[kk * LDS_B + tx * 2]);
       acc00 = fmaf(a.x, b.x, acc00); acc01 = fmaf(a.x, b.y, acc01);
       acc10 = fmaf(a.y, b.x, acc10); acc11 = fmaf(a.y, b.y, acc11);
     }
     if (want_bias_grad && tid < BM) {
-      for (int kk = 0; kk < kc; ++kk) colsum += As[kk * LDS_A + tid];
+#pragma unroll 8
+      for (int kk = 0; kk < KC; ++kk) colsum += as[kk * LDS_A + tid];
     }
+    if (c + 1 < nchunks) store_chunk(P, tid, As[cur ^ 1], Bs[cur ^ 1], ra, rb);
     __syncthreads();
   }
 

@@ -1,6 +1,7 @@
 // Cross-translation-unit internals of libd4pg_sm100.so (not part of the C ABI).
 #pragma once
 #include "common.cuh"
+#include "adam.cuh"
 
 struct d4pg_replay;
 struct d4pg_comm;
@@ -20,7 +21,7 @@ int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st);
 
 // sample for the learner: per-step scalars come from device memory (graph replay safe)
 int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
-                   uint64_t seed, const int64_t* counter_ptr, const float* beta_ptr,
+                   uint64_t seed, LearnerClock* clock, const ClockParams& cp,
                    int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
                    cudaStream_t st);
 int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st);

@@ -79,10 +79,14 @@ struct d4pg_learner {
   int64_t steps_done;
   int kernels_per_step;
   // profiling (d4pg_learner_profile_step): CUDA-event pair around every launch of an eager step
+  cudaStream_t side; cudaEvent_t ev_fork, ev_join;
   bool profiling;
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> ev_name;
 };
+
+// idempotent launches (pure functions of their inputs) are repeated in profile mode
+constexpr int PROFILE_REPS = 16;
 
 static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   const d4pg_learner_config_t& c = L->cfg;
@@ -94,7 +98,10 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 #define RUN(expr)                                                                          \
   do {                                                                                     \
     if (L->profiling) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);    \
-      cudaEventRecord(e0, st); rc = (expr); cudaEventRecord(e1, st);                       \
+      std::string nm0(#expr); const bool rep = nm0.rfind("gemm_batch_launch", 0) == 0 || nm0.rfind("launch_heads", 0) == 0; \
+      cudaEventRecord(e0, st); rc = (expr);                                                \
+      for (int _r = 1; rep && _r < PROFILE_REPS && rc == 0; ++_r) rc = (expr);             \
+      cudaEventRecord(e1, st);                                                             \
       L->ev.push_back(e0); L->ev.push_back(e1);                                            \
       std::string nm(#expr); L->ev_name.push_back(nm.substr(0, nm.find('('))); }           \
     else rc = (expr);                                                                      \
@@ -102,15 +109,13 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
     ++nk;                                                                                  \
   } while (0)
 
-  // 0. clock: Adam step count / bias corrections, PER beta, Philox counter
-  ClockArgs ca{w.clock, c.lr_actor, c.lr_critic, c.beta1, c.beta2, c.per_beta0, c.per_beta_final,
-               c.per_beta_iters > 0 ? c.per_beta_iters : 1};
-  RUN(launch_clock(ca, st));
-
-  // 1. sample + gather (ddpg.py:187-197)
+  // 1. sample + gather (ddpg.py:187-197).  The same kernel derives this step's device-side
+  //    scalars (Adam bias corrections, PER beta, Philox counter) from the learner clock.
+  ClockParams cp{c.lr_actor, c.lr_critic, c.beta1, c.beta2, c.per_beta0, c.per_beta_final,
+                 c.per_beta_iters > 0 ? c.per_beta_iters : 1};
   RUN(learner_sample(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
                      (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
-                     c.philox_seed, &w.clock->steps_done, &w.clock->beta,
+                     c.philox_seed, w.clock, cp,
                      b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, st));
 
   const float* Wa = b.actor; const float* Wat = b.actor_target; const float* Wc = b.critic; const float* Wct = b.critic_target;
@@ -167,8 +172,14 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   ha.pi_rows = w.pi_rows; ha.dlogits_pi = w.dlogits_pi;
   RUN(launch_heads(ha, c.proj_mode, st));
 
-  // 4. priorities into the trees (ddpg.py:252-255); independent of the backward pass
-  if (c.prioritized) RUN(launch_tree_update(L->replay, B, b.idx, b.prio, st));
+  // 4. priorities into the trees (ddpg.py:252-255): independent of the backward pass, so it runs
+  //    on a forked branch (side stream -> parallel graph branch) and joins before the step ends
+  if (c.prioritized) {
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_fork, st));
+    D4PG_CUDA_OK(cudaStreamWaitEvent(L->side, L->ev_fork, 0));
+    RUN(launch_tree_update(L->replay, B, b.idx, b.prio, L->side));
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_join, L->side));
+  }
 
   float* Ga = b.grad_actor; float* Gc = b.grad_critic;
   // 5. backward.  "c_" = critic-loss pass, "p_" = policy pass through the critic, "a_" = actor.
@@ -222,10 +233,10 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   aa.nseg = 2;
   aa.w1 = float(1.0 - c.beta1); aa.w2 = float(1.0 - c.beta2); aa.beta2 = float(c.beta2); aa.eps = float(c.adam_eps);
   aa.tau = float(c.tau); aa.one_minus_tau = float(1.0 - c.tau); aa.grad_scale = 1.0f; aa.clock = w.clock;
+  // tail slice of the same launch: reported batch-mean losses + advance the device clock
+  aa.loss_rows = w.loss_rows; aa.pi_rows = w.pi_rows; aa.B = B; aa.inv_count = 1.0f / float(B); aa.loss_out = b.losses;
   RUN(launch_adam(aa, st));
-
-  // 8. reported scalars
-  RUN(launch_loss_reduce(w.loss_rows, w.pi_rows, B, 1.0f / float(B), b.losses, st));
+  if (c.prioritized) D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join, 0));
 #undef RUN
   L->kernels_per_step = nk;
   return D4PG_OK;
@@ -261,6 +272,11 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms);
   L->graph_exec = nullptr; L->graph_ready = false; L->steps_done = 0; L->kernels_per_step = 0;
   L->profiling = false;
+  if (cudaStreamCreateWithFlags(&L->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("d4pg_learner_create: stream/event creation failed"); delete L; return D4PG_ECUDA;
+  }
   cudaError_t e = cudaMemset(L->ws.clock, 0, sizeof(LearnerClock));
   if (e != cudaSuccess) { set_error("d4pg_learner_create: %s", cudaGetErrorString(e)); delete L; return D4PG_ECUDA; }
   *out = L;
@@ -270,6 +286,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
 extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   if (!L) return D4PG_OK;
   if (L->graph_exec) cudaGraphExecDestroy(L->graph_exec);
+  cudaEventDestroy(L->ev_fork); cudaEventDestroy(L->ev_join); cudaStreamDestroy(L->side);
   delete L;
   return D4PG_OK;
 }
@@ -314,6 +331,7 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
   for (int i = 0; i < n; ++i) {
     float ms = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, L->ev[2 * i], L->ev[2 * i + 1]);
+    if (L->ev_name[i] == "gemm_batch_launch" || L->ev_name[i] == "launch_heads") ms /= float(PROFILE_REPS);
     if (i < max_launches) {
       ms_out[i] = ms;
       if (names_out && name_stride > 1) {

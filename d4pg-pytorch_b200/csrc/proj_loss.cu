@@ -22,17 +22,18 @@ constexpr int HEAD_WARPS = 4;
 
 // softmax of one row held as 4 values per lane (atom k = lane + 32*t); fp32, max-subtracted,
 // exp then divide (models.py:83 -> torch softmax).
-__device__ __forceinline__ void row_softmax(const float* __restrict__ logits, int N, int lane, float (&p)[4],
+template <int NT>
+__device__ __forceinline__ void row_softmax(const float* __restrict__ logits, int N, int lane, float (&p)[NT],
                                             bool already_probs = false) {
   if (already_probs) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { int k = lane + 32 * t; p[t] = (k < N) ? __ldg(logits + k) : 0.f; }
+    for (int t = 0; t < NT; ++t) { int k = lane + 32 * t; p[t] = (k < N) ? __ldg(logits + k) : 0.f; }
     return;
   }
-  float x[4];
+  float x[NT];
   float mx = -INFINITY;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < NT; ++t) {
     int k = lane + 32 * t;
     x[t] = (k < N) ? __ldg(logits + k) : -INFINITY;
     mx = fmaxf(mx, x[t]);
@@ -40,17 +41,17 @@ __device__ __forceinline__ void row_softmax(const float* __restrict__ logits, in
   mx = warp_max(mx);
   float s = 0.f;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < NT; ++t) {
     int k = lane + 32 * t;
     p[t] = (k < N) ? expf(x[t] - mx) : 0.f;
     s += p[t];
   }
   s = warp_sum(s);
 #pragma unroll
-  for (int t = 0; t < 4; ++t) p[t] = p[t] / s;
+  for (int t = 0; t < NT; ++t) p[t] = p[t] / s;
 }
 
-template <int MODE>
+template <int MODE, int NT>
 __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs a) {
   __shared__ float  p_s[HEAD_WARPS][D4PG_MAX_ATOMS];
   __shared__ int    l_s[HEAD_WARPS][D4PG_MAX_ATOMS];
@@ -65,12 +66,14 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
   const size_t ro = size_t(row) * N;
 
   // ---- target distribution ------------------------------------------------------------
-  float p[4];
+  float p[NT];
   row_softmax(a.target_logits + ro, N, lane, p, (a.flags & D4PG_PROJ_TARGET_IS_PROBS) != 0);
   const double r = a.rewards[row];
   const bool done = a.dones[row] != 0;
 
-  float mk[4] = {0.f, 0.f, 0.f, 0.f};
+  float mk[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) mk[t] = 0.f;
 
   if (MODE == 0 && done) {
     // ddpg.py:165-181: zero the row, Dirac at clip(r); weights cast f64 -> f32
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
     float wl = (l == u) ? 1.0f : __double2float_rn(__dsub_rn(uf, b));
     float wu = __double2float_rn(__dsub_rn(b, lf));
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < NT; ++t) {
       int k = lane + 32 * t;
       if (k < N) {
         if (k == l) mk[t] = wl;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
   } else {
     // per-atom bins and weights in fp64 (ddpg.py:155-158 / ddpg.py:129-134)
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < NT; ++t) {
       int j = lane + 32 * t;
       if (j < N) {
         double zj = __dadd_rn(a.v_min, __dmul_rn(double(j), a.delta));
@@ -122,12 +125,14 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
     __syncwarp();
     // ordered per-bin accumulation (gather form: lane owns output bins, visits atoms in order)
     if (MODE == 0) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc[t] = 0.f;
       for (int j = 0; j < N; ++j) {
         const int l = l_s[warp][j], u = u_s[warp][j];
         const double pj = double(p_s[warp][j]);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < NT; ++t) {
           const int k = lane + 32 * t;
           if (k == l) {
             // eq: f32+f32 add; ne: f32 + (f64 product) in f64, rounded to f32
@@ -139,31 +144,33 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
         }
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) mk[t] = acc[t];
+      for (int t = 0; t < NT; ++t) mk[t] = acc[t];
     } else {
-      double acc[4] = {0., 0., 0., 0.};
+      double acc[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc[t] = 0.;
       for (int j = 0; j < N; ++j) {
         const int l = l_s[warp][j], u = u_s[warp][j];
         const double pj = double(p_s[warp][j]);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < NT; ++t) {
           const int k = lane + 32 * t;
           if (k == l) acc[t] = __dadd_rn(acc[t], __dmul_rn(pj, wl_s[warp][j]));
           if (k == u) acc[t] = __dadd_rn(acc[t], __dmul_rn(pj, wu_s[warp][j]));
         }
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) mk[t] = __double2float_rn(acc[t]);
+      for (int t = 0; t < NT; ++t) mk[t] = __double2float_rn(acc[t]);
     }
   }
 
   // ---- online critic: CE loss, TD proxy, priority, d loss / d logits -------------------
-  float q[4];
+  float q[NT];
   row_softmax(a.q_logits + ro, N, lane, q, (a.flags & D4PG_PROJ_Q_IS_PROBS) != 0);
   float ce = 0.f, mq = 0.f, sq = 0.f;
-  float gq[4];
+  float gq[NT];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < NT; ++t) {
     int k = lane + 32 * t;
     gq[t] = 0.f;
     if (k < N) {
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
   }
   ce = warp_sum(ce); mq = warp_sum(mq); sq = warp_sum(sq);
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < NT; ++t) {
     int k = lane + 32 * t;
     if (k < N) {
       if (a.m) a.m[ro + k] = mk[t];
@@ -194,19 +201,19 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
 
   // ---- policy head: -E_q[z] and its logit gradient --------------------------------------
   if (a.pi_logits) {
-    float qp[4];
+    float qp[NT];
     row_softmax(a.pi_logits + ro, N, lane, qp);
     float ez = 0.f;
-    float z[4];
+    float z[NT];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < NT; ++t) {
       int k = lane + 32 * t;
       z[t] = (k < N) ? float(__dadd_rn(a.v_min, __dmul_rn(double(k), a.delta))) : 0.f;  // ddpg.py:47,238
       ez += qp[t] * z[t];
     }
     ez = warp_sum(ez);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < NT; ++t) {
       int k = lane + 32 * t;
       if (k < N && a.dlogits_pi) a.dlogits_pi[ro + k] = -a.grad_scale * qp[t] * (z[t] - ez);
     }
@@ -216,8 +223,14 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
 
 int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st) {
   dim3 grid(cdiv(a.B, HEAD_WARPS)), block(HEAD_WARPS * 32);
-  if (mode == 0) heads_kernel<0><<<grid, block, 0, st>>>(a);
-  else heads_kernel<1><<<grid, block, 0, st>>>(a);
+  // NT = atom slots per lane: 2 covers N<=64 (51 atoms), 4 covers N<=128 (101 atoms)
+  if (a.N <= 64) {
+    if (mode == 0) heads_kernel<0, 2><<<grid, block, 0, st>>>(a);
+    else heads_kernel<1, 2><<<grid, block, 0, st>>>(a);
+  } else {
+    if (mode == 0) heads_kernel<0, 4><<<grid, block, 0, st>>>(a);
+    else heads_kernel<1, 4><<<grid, block, 0, st>>>(a);
+  }
   D4PG_LAUNCH_OK();
   return D4PG_OK;
 }

@@ -12,6 +12,7 @@
 // Node dtype is fp32 -- what the reference's Python evaluates to under NumPy 2.
 // Everything is HBM/L2 pointer chasing + row gathers: no tensor-core work here.
 #include "internal.cuh"
+#include "adam.cuh"
 #include <new>
 #include <algorithm>
 
@@ -49,15 +50,20 @@ __device__ __forceinline__ float pow_alpha(float p, float alpha_f32) {
 // SumSegmentTree.sum(0, end+1): reduce over leaves [0, end] with _reduce_helper's association
 // (prioritized_replay_memory.py:61-96): V[left] + (V[left'] + (... + V[last])), fp32.
 __device__ float prefix_sum_ref(const float* __restrict__ V, int64_t cap, int64_t e) {
-  float terms[40];
+  // the node cover depends only on (cap, e): collect the addresses first so the loads are
+  // independent and overlap (one L2 round trip instead of log2(cap) dependent ones)
+  int64_t nodes[40];
   int n = 0;
   int64_t node = 1, lo = 0, hi = cap - 1;
   while (true) {
-    if (e == hi) { terms[n++] = __ldcg(V + node); break; }
+    if (e == hi) { nodes[n++] = node; break; }
     int64_t mid = (lo + hi) >> 1;
     if (e <= mid) { node = 2 * node; hi = mid; }
-    else { terms[n++] = __ldcg(V + 2 * node); node = 2 * node + 1; lo = mid + 1; }
+    else { nodes[n++] = 2 * node; node = 2 * node + 1; lo = mid + 1; }
   }
+  float terms[40];
+#pragma unroll 8
+  for (int i = 0; i < n; ++i) terms[i] = __ldcg(V + nodes[i]);
   float acc = terms[n - 1];
   for (int i = n - 2; i >= 0; --i) acc = __fadd_rn(terms[i], acc);
   return acc;
@@ -77,8 +83,8 @@ __device__ float prefix_min_ref(const float* __restrict__ V, int64_t cap, int64_
 struct SampleArgs {
   const float* sum; const float* mn; int64_t cap; const ReplayState* state;
   const double* uniforms; uint64_t seed, counter; float beta;
-  const int64_t* counter_ptr;       // optional device counter added to `counter` (graph replay)
-  const float* beta_ptr;            // optional device beta (graph replay)
+  LearnerClock* clock;              // optional (learner): Philox counter / beta from the device clock;
+  ClockParams clock_params;         //   block 0 also derives this step's Adam scalars into it
   const float* obs; const float* act; const double* rew; const float* obs2; const uint8_t* done;
   int obs_dim, act_dim; int B;
   const int32_t* idx_in;            // gather-only mode when non-null
@@ -96,6 +102,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const Sam
   const int row0 = blockIdx.x * SAMPLE_ROWS;
   const int nrows = min(SAMPLE_ROWS, a.B - row0);
   const int t = threadIdx.x;
+  if (a.clock && blockIdx.x == 0 && t == SAMPLE_THREADS - 1) {
+    clock_derive(a.clock, a.clock_params);
+    a.clock->beta = clock_beta(a.clock, a.clock_params);
+  }
   if (t < nrows) {
     const int row = row0 + t;
     int32_t leaf_idx;
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const Sam
     } else {
       const int64_t len = a.state->len;
       const float total = a.uniform_mode ? 0.f : prefix_sum_ref(a.sum, a.cap, len - 2);   // sum(0, len-1)
-      const uint64_t ctr = a.counter + (a.counter_ptr ? uint64_t(*a.counter_ptr) : 0ull);
+      const uint64_t ctr = a.counter + (a.clock ? uint64_t(a.clock->steps_done) : 0ull);
       const double u = a.uniforms ? a.uniforms[row] : Philox::uniform53(a.seed, ctr, uint32_t(row));
       int64_t i = 1;
       if (a.uniform_mode) {
@@ -131,7 +141,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const Sam
         const float tot = __ldcg(a.sum + 1);
         const float pmin = __fdiv_rn(__ldcg(a.mn + 1), tot);
         const float n = float(len);
-        const float beta = a.beta_ptr ? *a.beta_ptr : a.beta;
+        const float beta = a.clock ? clock_beta(a.clock, a.clock_params) : a.beta;
         const float maxw = __double2float_rn(pow(double(__fmul_rn(pmin, n)), double(-beta)));
         const float ps = __fdiv_rn(__ldcg(a.sum + a.cap + leaf_idx), tot);
         const float w = __double2float_rn(pow(double(__fmul_rn(ps, n)), double(-beta)));
@@ -344,12 +354,12 @@ int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
 }
 
 int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
-                   uint64_t seed, const int64_t* counter_ptr, const float* beta_ptr,
+                   uint64_t seed, LearnerClock* clock, const ClockParams& cp,
                    int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
                    cudaStream_t st) {
   SampleArgs sa{};
-  sa.uniforms = uniforms; sa.seed = seed; sa.counter = 0; sa.counter_ptr = counter_ptr;
-  sa.beta = 1.f; sa.beta_ptr = beta_ptr; sa.B = B; sa.idx = idx; sa.weights = prioritized ? weights : nullptr;
+  sa.uniforms = uniforms; sa.seed = seed; sa.counter = 0; sa.clock = clock; sa.clock_params = cp;
+  sa.beta = 1.f; sa.B = B; sa.idx = idx; sa.weights = prioritized ? weights : nullptr;
   sa.s = s; sa.a = a; sa.r = r; sa.s2 = s2; sa.d = d;
   if (!prioritized) { sa.idx_in = positions; sa.uniform_mode = positions ? 0 : 1; }
   return launch_sample(h, sa, st);

@@ -109,7 +109,11 @@ def test_heads_losses_and_gradients(d4pg):
         done = rng.rand(B) < 0.1
         v_min, v_max = (-50.0, 0.0)
         dev = "cuda"
-        t = lambda x, dt=None: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+        keep = []
+
+        def t(x):
+            keep.append(torch.from_numpy(np.ascontiguousarray(x)).to(dev))
+            return keep[-1]
         outs = {k: torch.empty(B, N, dtype=torch.float32, device=dev) for k in ("m", "tp", "qp", "dq", "dpi")}
         rows = {k: torch.empty(B, dtype=torch.float32, device=dev) for k in ("loss", "td", "prio", "pi")}
         _lib.check(_lib.lib().d4pg_proj_loss(_lib.ptr(t(tl)), _lib.ptr(t(ql)), _lib.ptr(t(pl)), _lib.ptr(t(r)),
