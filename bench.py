@@ -201,8 +201,7 @@ def gpu_main(args):
 
     # ---- value: inputs resident in HBM, device-side sampling, CUDA-graph replay -------------
     dd = make("device")
-    for _ in range(max(args.warmup, 3)):
-        dd.train()
+    dd.train_n(max(args.warmup, 3))
     stream = dd._learner.stream
     sampler = ClockSampler(local)
     barrier()
@@ -210,8 +209,7 @@ def gpu_main(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
-    for _ in range(args.steps):
-        dd.train()
+    dd.train_n(args.steps)                          # K graph replays, no host work in between
     with torch.cuda.stream(stream):
         e1.record(stream)
     barrier()

@@ -91,6 +91,7 @@ _PROTOS = {
     "d4pg_learner_create": (C.c_int32, [C.POINTER(LearnerConfig), C.POINTER(LearnerBuffers), _P, _P, C.POINTER(_P)]),
     "d4pg_learner_destroy": (C.c_int32, [_P]),
     "d4pg_learner_step": (C.c_int32, [_P, _P]),
+    "d4pg_learner_run": (C.c_int32, [_P, C.c_int32, _P]),
     "d4pg_learner_tensor": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "d4pg_learner_profile_step": (C.c_int32, [_P, _P, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "d4pg_learner_steps_done": (C.c_int64, [_P]),

@@ -317,6 +317,15 @@ extern "C" int32_t d4pg_learner_step(d4pg_learner_t* L, d4pg_stream_t stream) {
   return D4PG_OK;
 }
 
+extern "C" int32_t d4pg_learner_run(d4pg_learner_t* L, int32_t n_steps, d4pg_stream_t stream) {
+  D4PG_REQUIRE(L && n_steps > 0, D4PG_EINVAL, "d4pg_learner_run: bad arguments");
+  for (int i = 0; i < n_steps; ++i) {
+    int rc = d4pg_learner_step(L, stream);
+    if (rc) return rc;
+  }
+  return D4PG_OK;
+}
+
 extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t stream, int32_t max_launches,
                                              float* ms_out, char* names_out, int32_t name_stride, int32_t* n_out) {
   D4PG_REQUIRE(L && ms_out && n_out && max_launches > 0, D4PG_EINVAL, "d4pg_learner_profile_step: bad arguments");

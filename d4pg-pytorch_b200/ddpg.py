@@ -301,6 +301,22 @@ class DDPG:
         for opt in (self.optimizer_global_actor, self.optimizer_global_critic):
             opt.step_count += 1
 
+    def train_n(self, n, global_model=None):
+        """`n` gradient steps in one C call (device-side sampling only): the learner's CUDA graph is
+        replayed back to back with no Python in between."""
+        if self.sampling != "device":
+            raise _lib.D4PGError("train_n needs sampling='device' (host-drawn uniforms are per-step inputs)")
+        g = global_model if global_model is not None else self
+        L = self._get_learner(g)
+        self.replayBuffer._store.flush()
+        L.stream.wait_stream(torch.cuda.current_stream())
+        _lib.check(_lib.lib().d4pg_learner_run(L.handle, int(n), C.c_void_p(L.stream.cuda_stream)), "d4pg_learner_run")
+        torch.cuda.current_stream().wait_stream(L.stream)
+        if self.prioritized_replay:
+            self.beta_schedule.t += n
+        for opt in (self.optimizer_global_actor, self.optimizer_global_critic):
+            opt.step_count += n
+
     def last_losses(self):
         """(critic_loss, actor_loss) of the most recent train() -- synchronises on the result."""
         L = self._learner

@@ -224,6 +224,9 @@ int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d4pg_learner
 int32_t d4pg_learner_destroy(d4pg_learner_t* h);
 /* One gradient step.  Everything is stream-ordered; results land in buf->losses etc. */
 int32_t d4pg_learner_step(d4pg_learner_t* h, d4pg_stream_t stream);
+/* n_steps back-to-back gradient steps without returning to the caller in between (device-side
+ * sampling keeps advancing; caller-supplied uniforms/positions would be reused). */
+int32_t d4pg_learner_run(d4pg_learner_t* h, int32_t n_steps, d4pg_stream_t stream);
 /* Named intermediate (for parity tests): returns device pointer + element count.
  * names: "s","a","r","s2","done","target_logits","q_logits","pi_logits","m","q_probs",
  *        "target_probs","dlogits_q","dlogits_pi","actor_out","loss_rows","pi_rows" */

@@ -243,7 +243,8 @@ def find_prefixsum_idx(values, capacity, mass):
         if left > mass:                                           # strict, :144
             i = 2 * i
         else:
-            mass = mass - left if isinstance(mass, float) else F32(mass - left)
+            # pristine reference tree: Python-float nodes -> the subtraction stays f64
+            mass = (mass - float(left)) if isinstance(mass, float) else F32(mass - left)
             i = 2 * i + 1
     return i - capacity
 

@@ -14,12 +14,32 @@ def load(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
+def check_params(g, key, arr, atol=1e-5, outlier_atol=2e-4, outlier_frac=2e-3):
+    """Post-Adam parameters / targets / moments.  Adam divides by sqrt(v)+eps, so an element whose
+    gradient is ~0 by cancellation turns a 1e-10 gradient difference (any fp32 summation-order
+    change, e.g. a different BLAS) into a difference of up to ~lr in the parameter.  Gradients are
+    held to 1e-5 absolute elsewhere; here: all but `outlier_frac` of the elements within `atol`,
+    every element within `outlier_atol` (= 0.2*lr)."""
+    arr = np.asarray(arr).reshape(-1)
+    if key in g.files:
+        ref, mine = g[key].reshape(-1), arr
+    else:
+        ref, mine = g[key + "__sub"], arr[::STRIDE]
+        assert arr.size == int(g[key + "__chk"][2])
+    err = np.abs(ref.astype(np.float64) - mine.astype(np.float64))
+    assert err.max() <= outlier_atol, "%s: max abs err %.3e > %.1e" % (key, err.max(), outlier_atol)
+    bad = float((err > atol).mean())
+    assert bad <= outlier_frac, "%s: %.4f of elements differ by more than %.1e" % (key, bad, atol)
+    return err.max()
+
+
 def check_compact(g, key, arr, atol, what=""):
     """Compare `arr` with a golden entry stored whole or as subsample+checksums."""
     arr = np.asarray(arr)
     if key in g.files:
         ref = g[key]
-        assert ref.shape == arr.shape, (key, ref.shape, arr.shape)
+        assert ref.size == arr.size, (key, ref.shape, arr.shape)
+        ref, arr = ref.reshape(-1), arr.reshape(-1)
         err = np.abs(ref.astype(np.float64) - arr.astype(np.float64)).max() if arr.size else 0.0
         assert err <= atol, "%s %s: max abs err %.3e > %.1e" % (what, key, err, atol)
         return err

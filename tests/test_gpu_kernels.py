@@ -159,7 +159,8 @@ def test_tree_golden_indices_bit_exact(d4pg, name):
         assert np.array_equal(np.array(out[6]), g[name + "_idx"][k]), (name, k)
         np.testing.assert_allclose(out[5], g[name + "_w"][k], rtol=1e-5)
         # gathered rows are the stored rows
-        assert np.array_equal(out[0][:, 0].astype(np.int64) % size, np.array(out[6]))
+        if k <= 3:      # (after round 3 seven zero rows are added, see below)
+            assert np.array_equal(out[0][:, 0].astype(np.int64) % size, np.array(out[6]))
         buf.update_priorities(g[name + "_upd_idx"][k], g[name + "_upd_prio"][k])
         s = buf._it_sum.values().astype(np.float64)
         gs = g["%s_sum_r%d" % (name, k + 1)]
@@ -236,11 +237,12 @@ def test_tree_full_size_capacity_1m(d4pg):
 def test_segment_tree_api(d4pg):
     t = d4pg.SumSegmentTree(16)
     o = O.SegmentTree32(16, "sum")
+    om = O.SegmentTree32(16, "min")
     mt = d4pg.MinSegmentTree(16)
     rng = np.random.RandomState(2)
     for i in range(13):
         v = float(np.float32(rng.rand()))
-        t[i] = v; mt[i] = v; o.set(i, v)
+        t[i] = v; mt[i] = v; o.set(i, v); om.set(i, v)
     assert t[5] == o.get(5)
     assert np.float32(t.sum()) == o.root()
     for s, e in ((0, 13), (0, 12), (3, 11), (7, 8), (5, 16), (1, 2)):
@@ -256,7 +258,7 @@ def test_segment_tree_api(d4pg):
                 return helper(start, end, 2 * node + 1, mid + 1, ne)
             return np.float32(helper(start, mid, 2 * node, ns, mid) + helper(mid + 1, end, 2 * node + 1, mid + 1, ne))
         assert np.float32(t.sum(s, e)) == helper(s, e - 1, 1, 0, 15), (s, e)
-        assert np.float32(mt.min(s, e)) == np.float32(min(ref_tree[16 + s:16 + e]))
+        assert np.float32(mt.min(s, e)) == np.float32(om.value[16 + s:16 + e].min())
     total = float(t.sum())
     for frac in (0.0, 0.3, 0.77, 0.999):
         assert t.find_prefixsum_idx(frac * total) == O.find_prefixsum_idx(o.value, 16, np.float32(frac * total))

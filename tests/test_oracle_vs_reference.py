@@ -77,3 +77,27 @@ def test_five_train_steps_vs_live_reference():
                              (lo.actor_target, l.actor_target), (lo.critic_target, l.critic_target)):
             for k, v in theirs.state_dict().items():
                 assert torch.equal(mine[k], v), (t, k)
+
+
+def test_pristine_tree_sampling_is_f64_at_scale():
+    """Before any update_priorities the reference tree holds Python floats: mass = u*sum and the
+    descent run in f64.  Needs a buffer large enough that f32 rounding of the mass would matter."""
+    ref = ref_shim.load()
+    size = 1 << 16
+    buf = ref.prioritized_replay_memory.PrioritizedReplayBuffer(size, alpha=0.6)
+    z = np.zeros(1, np.float32)
+    for i in range(size - 3):
+        buf.add(z, z, 0.0, z, False)
+    ob = O.PrioritizedReplayOracle(size, 0.6, 1, 1)
+    ob.add_batch(np.zeros((size - 3, 1), np.float32), np.zeros((size - 3, 1), np.float32), np.zeros(size - 3),
+                 np.zeros((size - 3, 1), np.float32), np.zeros(size - 3, bool))
+    random.seed(5)
+    st = random.getstate()
+    us = [random.random() for _ in range(2000)]
+    random.setstate(st)
+    idx_ref = buf._sample_proportional(2000)
+    idx = ob.sample_indices(us)
+    assert list(idx) == idx_ref
+    f32_idx = [O.find_prefixsum_idx(ob.sum.value, ob.capacity, np.float32(np.float32(u) * ob.sum.reduce_prefix(ob.length - 2)))
+               for u in us]
+    assert f32_idx != idx_ref          # the f32 rule really is different at this size
