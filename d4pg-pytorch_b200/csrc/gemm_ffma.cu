@@ -11,9 +11,11 @@
 namespace d4pg {
 
 constexpr int BM = 32, BN = 32, KC = 64;
-constexpr int LDS_A = BM + 2;   // even (float2 reads); transposed stores are at worst 2-way conflicted
-constexpr int LDS_B = BN + 2;
+constexpr int LDS_A = BM + 4;   // multiple of 4 (float4 reads)
+constexpr int LDS_B = BN + 4;
 constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_WARPS = GEMM_THREADS / 32;
+constexpr int KW = KC / GEMM_WARPS;                  // k values per warp per chunk (intra-CTA split-K)
 constexpr int PER_THREAD = BM * KC / GEMM_THREADS;   // 8 staged elements per thread per operand per chunk
 
 // Stage one K-chunk of both operands global -> registers.  All 16 loads of a thread are issued
@@ -56,11 +58,18 @@ __device__ __forceinline__ void store_chunk(const GemmProblem& P, int tid, float
   }
 }
 
+// Per-CTA structure (ncu of the first version showed 2 warps/scheduler stalled on LDS->FFMA
+// dependencies, IPC 0.38): the 8 warps now split K inside the CTA.  Each warp owns the whole
+// 32x32 tile for 1/8 of every K-chunk with an 8x4 register tile per lane (32 independent FFMAs
+// per 3 LDS.128), and the 8 partial tiles are summed through shared memory in fixed warp order
+// (deterministic).  Per-warp serial instruction count drops ~3x, which is what bounds a
+// latency-bound 256^3 layer at batch 256.
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid_constant__ GemmBatch batch) {
-  __shared__ __align__(16) float As[2][KC * LDS_A];
-  __shared__ __align__(16) float Bs[2][KC * LDS_B];
+  __shared__ __align__(16) float smem[2 * KC * LDS_A + 2 * KC * LDS_B];
+  float* As0 = smem;                      // [2][KC*LDS_A]
+  float* Bs0 = smem + 2 * KC * LDS_A;     // [2][KC*LDS_B]
+  static_assert(2 * KC * LDS_A + 2 * KC * LDS_B >= GEMM_WARPS * BM * BN, "partial-tile buffer must fit");
 
-  // locate problem and tile
   int pi = 0;
 #pragma unroll
   for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
@@ -69,49 +78,71 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid
   const int tile = blockIdx.x - P.tile_begin;
   const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
   const int m0 = tm * BM, n0 = tn * BN;
-  const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = (lane >> 3) * 8, c0 = (lane & 7) * 4;      // lane's 8x4 sub-tile
 
-  float acc00 = 0.f, acc01 = 0.f, acc10 = 0.f, acc11 = 0.f;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float colsum = 0.f;                       // DW: bias gradient, threads < BM of the tn==0 tiles
   const bool want_bias_grad = (P.mode == GEMM_DW) && (P.bias_grad != nullptr) && (tn == 0);
 
   float ra[PER_THREAD], rb[PER_THREAD];
   const int nchunks = (P.K + KC - 1) / KC;
   load_chunk(P, m0, n0, 0, tid, ra, rb);
-  store_chunk(P, tid, As[0], Bs[0], ra, rb);
+  store_chunk(P, tid, As0, Bs0, ra, rb);
   __syncthreads();
   for (int c = 0; c < nchunks; ++c) {
     const int cur = c & 1;
     if (c + 1 < nchunks) load_chunk(P, m0, n0, (c + 1) * KC, tid, ra, rb);     // in flight during the FMAs
-    const float* __restrict__ as = As[cur];
-    const float* __restrict__ bs = Bs[cur];
-#pragma unroll 16
-    for (int kk = 0; kk < KC; ++kk) {                                           // zero-padded past K
-      const float2 a = *reinterpret_cast<const float2*>(&as[kk * LDS_A + ty * 2]);
-      const float2 b = *reinterpret_cast<const float2*>(&bs[kk * LDS_B + tx * 2]);
-      acc00 = fmaf(a.x, b.x, acc00); acc01 = fmaf(a.x, b.y, acc01);
-      acc10 = fmaf(a.y, b.x, acc10); acc11 = fmaf(a.y, b.y, acc11);
+    const float* __restrict__ as = As0 + cur * KC * LDS_A;
+    const float* __restrict__ bs = Bs0 + cur * KC * LDS_B;
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {                                              // zero-padded past K
+      const int kk = warp * KW + k;
+      const float4 a0 = *reinterpret_cast<const float4*>(&as[kk * LDS_A + r0]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&as[kk * LDS_A + r0 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&bs[kk * LDS_B + c0]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     if (want_bias_grad && tid < BM) {
 #pragma unroll 8
       for (int kk = 0; kk < KC; ++kk) colsum += as[kk * LDS_A + tid];
     }
-    if (c + 1 < nchunks) store_chunk(P, tid, As[cur ^ 1], Bs[cur ^ 1], ra, rb);
+    if (c + 1 < nchunks) store_chunk(P, tid, As0 + (cur ^ 1) * KC * LDS_A, Bs0 + (cur ^ 1) * KC * LDS_B, ra, rb);
     __syncthreads();
   }
 
+  // ---- cross-warp reduction of the 8 partial tiles (fixed order w = 0..7) ---------------------
+  float* red = smem;                        // [GEMM_WARPS][BM][BN]
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(&red[(warp * BM + r0 + i) * BN + c0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  __syncthreads();
+  const int orow = tid >> 3, ocol = (tid & 7) * 4;          // thread's 4 outputs
+  float4 sum = *reinterpret_cast<const float4*>(&red[orow * BN + ocol]);
+#pragma unroll
+  for (int w = 1; w < GEMM_WARPS; ++w) {
+    const float4 t = *reinterpret_cast<const float4*>(&red[(w * BM + orow) * BN + ocol]);
+    sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+  }
+
   // ---- epilogue ------------------------------------------------------------------------------
-  float v[2][2] = {{acc00, acc01}, {acc10, acc11}};
+  const int gi = m0 + orow;
+  if (gi < P.M) {
+    const float v[4] = {sum.x, sum.y, sum.z, sum.w};
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int gi = m0 + ty * 2 + r;
-    if (gi >= P.M) continue;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int gj = n0 + tx * 2 + c;
+    for (int cc = 0; cc < 4; ++cc) {
+      const int gj = n0 + ocol + cc;
       if (gj >= P.N) continue;
-      float x = v[r][c];
+      float x = v[cc];
       switch (P.epi) {
         case EPI_BIAS: x += __ldg(P.bias + gj); break;
         case EPI_BIAS_RELU: x = fmaxf(x + __ldg(P.bias + gj), 0.f); break;

