@@ -18,66 +18,133 @@ constexpr int GEMM_WARPS = GEMM_THREADS / 32;
 constexpr int KW = KC / GEMM_WARPS;                  // k values per warp per chunk (intra-CTA split-K)
 constexpr int PER_THREAD = BM * KC / GEMM_THREADS;   // 8 staged elements per thread per operand per chunk
 
-// Stage one K-chunk of both operands global -> registers.  All 16 loads of a thread are issued
-// back to back (fully unrolled, predicated) so one chunk costs ONE L2 round trip, and the next
-// chunk's loads are in flight while the current one is being multiplied.
-__device__ __forceinline__ void load_chunk(const GemmProblem& P, int m0, int n0, int k0, int tid,
-                                           float (&ra)[PER_THREAD], float (&rb)[PER_THREAD]) {
+// ---- operand staging ---------------------------------------------------------------------------
+// Two source shapes, each with a 128-bit fast path (ncu of the first version: 42 % of all issued
+// instructions were address arithmetic / predicate / constant-bank loads of the scalar staging):
+//   K-contiguous  src[row*ld + k]  (rows = tile dim): thread reads 2 float4 along k
+//   row-contiguous src[k*ld + col] (cols = tile dim): thread reads 2 float4 along the tile dim
+// Everything is read into registers first (all loads of a chunk in flight together), then
+// written to the k-major smem tiles As[kk][i] / Bs[kk][j].
+template <bool VEC>
+__device__ __forceinline__ void load_kcontig(const float* __restrict__ src, int ld, int row0, int nrows, int k0, int K,
+                                             int tid, float (&r)[PER_THREAD]) {
+  if (VEC) {
 #pragma unroll
-  for (int r = 0; r < PER_THREAD; ++r) {
-    const int e = tid + r * GEMM_THREADS;
-    float va = 0.f, vb = 0.f;
-    if (P.mode == GEMM_DW) {                       // A(i,k) = dZ[k*lda + i]: i fastest
-      const int kk = e / BM, i = e % BM, gi = m0 + i, gk = k0 + kk;
-      if (gi < P.M && gk < P.K) va = __ldg(P.A + size_t(gk) * P.lda + gi);
-    } else {                                       // A(i,k) = A[i*lda + k]: k fastest (+ concat)
-      const int i = e / KC, kk = e % KC, gi = m0 + i, gk = k0 + kk;
-      if (gi < P.M && gk < P.K)
-        va = (gk < P.K1) ? __ldg(P.A + size_t(gi) * P.lda + gk) : __ldg(P.A2 + size_t(gi) * P.lda2 + (gk - P.K1));
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * GEMM_THREADS, row = e >> 4, k = k0 + ((e & 15) << 2);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + row < nrows && k < K) v = __ldg(reinterpret_cast<const float4*>(src + size_t(row0 + row) * ld + k));
+      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
     }
-    if (P.mode == GEMM_FWD) {                      // B(k,j) = W[j*ldb + k]: k fastest
-      const int j = e / KC, kk = e % KC, gj = n0 + j, gk = k0 + kk;
-      if (gj < P.N && gk < P.K) vb = __ldg(P.Bm + size_t(gj) * P.ldb + gk);
-    } else {                                       // B(k,j) = B[k*ldb + j]: j fastest
-      const int kk = e / BN, j = e % BN, gj = n0 + j, gk = k0 + kk;
-      if (gj < P.N && gk < P.K) vb = __ldg(P.Bm + size_t(gk) * P.ldb + gj);
+  } else {
+#pragma unroll
+    for (int q = 0; q < PER_THREAD; ++q) {
+      const int e = tid + q * GEMM_THREADS, row = e >> 6, k = k0 + (e & 63);
+      r[q] = (row0 + row < nrows && k < K) ? __ldg(src + size_t(row0 + row) * ld + k) : 0.f;
     }
-    ra[r] = va; rb[r] = vb;
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void store_kcontig(float* __restrict__ dst, int lds, int tid, const float (&r)[PER_THREAD]) {
+  if (VEC) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * GEMM_THREADS, row = e >> 4, kk = (e & 15) << 2;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[(kk + c) * lds + row] = r[4 * q + c];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < PER_THREAD; ++q) {
+      const int e = tid + q * GEMM_THREADS;
+      dst[(e & 63) * lds + (e >> 6)] = r[q];
+    }
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void load_rowcontig(const float* __restrict__ src, int ld, int col0, int ncols, int k0, int K,
+                                               int tid, float (&r)[PER_THREAD]) {
+  if (VEC) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * GEMM_THREADS, kk = e >> 3, col = col0 + ((e & 7) << 2);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + kk < K && col < ncols) v = __ldg(reinterpret_cast<const float4*>(src + size_t(k0 + kk) * ld + col));
+      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < PER_THREAD; ++q) {
+      const int e = tid + q * GEMM_THREADS, kk = e >> 5, col = col0 + (e & 31);
+      r[q] = (k0 + kk < K && col < ncols) ? __ldg(src + size_t(k0 + kk) * ld + col) : 0.f;
+    }
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void store_rowcontig(float* __restrict__ dst, int lds, int tid, const float (&r)[PER_THREAD]) {
+  if (VEC) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * GEMM_THREADS, kk = e >> 3, col = (e & 7) << 2;
+      *reinterpret_cast<float4*>(&dst[kk * lds + col]) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < PER_THREAD; ++q) {
+      const int e = tid + q * GEMM_THREADS;
+      dst[(e >> 5) * lds + (e & 31)] = r[q];
+    }
   }
 }
 
-__device__ __forceinline__ void store_chunk(const GemmProblem& P, int tid, float* __restrict__ As, float* __restrict__ Bs,
-                                            const float (&ra)[PER_THREAD], const float (&rb)[PER_THREAD]) {
-#pragma unroll
-  for (int r = 0; r < PER_THREAD; ++r) {
-    const int e = tid + r * GEMM_THREADS;
-    if (P.mode == GEMM_DW) As[(e / BM) * LDS_A + (e % BM)] = ra[r];
-    else As[(e % KC) * LDS_A + (e / KC)] = ra[r];
-    if (P.mode == GEMM_FWD) Bs[(e % KC) * LDS_B + (e / KC)] = rb[r];
-    else Bs[(e / BN) * LDS_B + (e % BN)] = rb[r];
+struct Operand { const float* p; int ld; bool vec; };
+
+// A-operand source for chunk k0: FWD may switch to the concatenated second source (k >= K1)
+template <int MODE>
+__device__ __forceinline__ void load_A(const GemmProblem& P, int m0, int k0, int tid, float (&ra)[PER_THREAD], bool& vec) {
+  if (MODE == GEMM_DW) {               // A(i,k) = dZ[k*lda + i]
+    vec = (P.flags & 1) != 0;
+    if (vec) load_rowcontig<true>(P.A, P.lda, m0, P.M, k0, P.K, tid, ra);
+    else load_rowcontig<false>(P.A, P.lda, m0, P.M, k0, P.K, tid, ra);
+  } else if (k0 >= P.K1) {             // concatenated tail (critic fc2's action columns): scalar
+    vec = false;
+    load_kcontig<false>(P.A2, P.lda2, m0, P.M, k0 - P.K1, P.K - P.K1, tid, ra);
+  } else {
+    vec = (P.flags & 1) != 0;
+    if (vec) load_kcontig<true>(P.A, P.lda, m0, P.M, k0, P.K1, tid, ra);
+    else load_kcontig<false>(P.A, P.lda, m0, P.M, k0, P.K1, tid, ra);
   }
 }
+template <int MODE>
+__device__ __forceinline__ void store_A(float* As, int tid, const float (&ra)[PER_THREAD], bool vec) {
+  if (MODE == GEMM_DW) { if (vec) store_rowcontig<true>(As, LDS_A, tid, ra); else store_rowcontig<false>(As, LDS_A, tid, ra); }
+  else { if (vec) store_kcontig<true>(As, LDS_A, tid, ra); else store_kcontig<false>(As, LDS_A, tid, ra); }
+}
+template <int MODE>
+__device__ __forceinline__ void load_B(const GemmProblem& P, int n0, int k0, int tid, float (&rb)[PER_THREAD]) {
+  const bool vec = (P.flags & 2) != 0;
+  if (MODE == GEMM_FWD) {              // B(k,j) = W[j*ldb + k]
+    if (vec) load_kcontig<true>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
+    else load_kcontig<false>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
+  } else {                             // B(k,j) = B[k*ldb + j]
+    if (vec) load_rowcontig<true>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
+    else load_rowcontig<false>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void store_B(const GemmProblem& P, float* Bs, int tid, const float (&rb)[PER_THREAD]) {
+  const bool vec = (P.flags & 2) != 0;
+  if (MODE == GEMM_FWD) { if (vec) store_kcontig<true>(Bs, LDS_B, tid, rb); else store_kcontig<false>(Bs, LDS_B, tid, rb); }
+  else { if (vec) store_rowcontig<true>(Bs, LDS_B, tid, rb); else store_rowcontig<false>(Bs, LDS_B, tid, rb); }
+}
 
-// Per-CTA structure (ncu of the first version showed 2 warps/scheduler stalled on LDS->FFMA
-// dependencies, IPC 0.38): the 8 warps now split K inside the CTA.  Each warp owns the whole
-// 32x32 tile for 1/8 of every K-chunk with an 8x4 register tile per lane (32 independent FFMAs
-// per 3 LDS.128), and the 8 partial tiles are summed through shared memory in fixed warp order
-// (deterministic).  Per-warp serial instruction count drops ~3x, which is what bounds a
-// latency-bound 256^3 layer at batch 256.
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid_constant__ GemmBatch batch) {
-  __shared__ __align__(16) float smem[2 * KC * LDS_A + 2 * KC * LDS_B];
+// One 32x32 output tile.  The 8 warps split K inside the CTA: each warp owns the whole tile for
+// 1/8 of every K-chunk with an 8x4 register tile per lane (32 independent FFMAs per 3 LDS.128);
+// the 8 partial tiles are summed through shared memory in fixed warp order (deterministic).
+template <int MODE>
+__device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int m0, int n0, int tn) {
   float* As0 = smem;                      // [2][KC*LDS_A]
   float* Bs0 = smem + 2 * KC * LDS_A;     // [2][KC*LDS_B]
-  static_assert(2 * KC * LDS_A + 2 * KC * LDS_B >= GEMM_WARPS * BM * BN, "partial-tile buffer must fit");
-
-  int pi = 0;
-#pragma unroll
-  for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
-    if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
-  const GemmProblem& P = batch.p[pi];
-  const int tile = blockIdx.x - P.tile_begin;
-  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
-  const int m0 = tm * BM, n0 = tn * BN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = (lane >> 3) * 8, c0 = (lane & 7) * 4;      // lane's 8x4 sub-tile
 
@@ -87,16 +154,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float colsum = 0.f;                       // DW: bias gradient, threads < BM of the tn==0 tiles
-  const bool want_bias_grad = (P.mode == GEMM_DW) && (P.bias_grad != nullptr) && (tn == 0);
+  const bool want_bias_grad = (MODE == GEMM_DW) && (P.bias_grad != nullptr) && (tn == 0);
 
   float ra[PER_THREAD], rb[PER_THREAD];
+  bool avec;
   const int nchunks = (P.K + KC - 1) / KC;
-  load_chunk(P, m0, n0, 0, tid, ra, rb);
-  store_chunk(P, tid, As0, Bs0, ra, rb);
+  load_A<MODE>(P, m0, 0, tid, ra, avec);
+  load_B<MODE>(P, n0, 0, tid, rb);
+  store_A<MODE>(As0, tid, ra, avec);
+  store_B<MODE>(P, Bs0, tid, rb);
   __syncthreads();
   for (int c = 0; c < nchunks; ++c) {
     const int cur = c & 1;
-    if (c + 1 < nchunks) load_chunk(P, m0, n0, (c + 1) * KC, tid, ra, rb);     // in flight during the FMAs
+    if (c + 1 < nchunks) {                                                      // in flight during the FMAs
+      load_A<MODE>(P, m0, (c + 1) * KC, tid, ra, avec);
+      load_B<MODE>(P, n0, (c + 1) * KC, tid, rb);
+    }
     const float* __restrict__ as = As0 + cur * KC * LDS_A;
     const float* __restrict__ bs = Bs0 + cur * KC * LDS_B;
 #pragma unroll
@@ -116,7 +189,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid
 #pragma unroll 8
       for (int kk = 0; kk < KC; ++kk) colsum += as[kk * LDS_A + tid];
     }
-    if (c + 1 < nchunks) store_chunk(P, tid, As0 + (cur ^ 1) * KC * LDS_A, Bs0 + (cur ^ 1) * KC * LDS_B, ra, rb);
+    if (c + 1 < nchunks) {
+      store_A<MODE>(As0 + (cur ^ 1) * KC * LDS_A, tid, ra, avec);
+      store_B<MODE>(P, Bs0 + (cur ^ 1) * KC * LDS_B, tid, rb);
+    }
     __syncthreads();
   }
 
@@ -157,6 +233,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid
   if (want_bias_grad && tid < BM && m0 + tid < P.M) P.bias_grad[m0 + tid] = colsum;
 }
 
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid_constant__ GemmBatch batch) {
+  __shared__ __align__(16) float smem[2 * KC * LDS_A + 2 * KC * LDS_B];
+  static_assert(2 * KC * LDS_A + 2 * KC * LDS_B >= GEMM_WARPS * BM * BN, "partial-tile buffer must fit");
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
+    if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
+  const GemmProblem P = batch.p[pi];        // one copy into registers (no constant-bank reads in the loops)
+  const int tile = blockIdx.x - P.tile_begin;
+  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+  if (P.mode == GEMM_FWD) gemm_tile<GEMM_FWD>(P, smem, tm * BM, tn * BN, tn);
+  else if (P.mode == GEMM_DX) gemm_tile<GEMM_DX>(P, smem, tm * BM, tn * BN, tn);
+  else gemm_tile<GEMM_DW>(P, smem, tm * BM, tn * BN, tn);
+}
+
 // ---- host side -------------------------------------------------------------------------------
 GemmProblem gemm_fwd(const float* X, int ldx, const float* X2, int ldx2, int K1, const float* W, int ldw,
                      const float* bias, float* Y, int ldy, int M, int N, int K, int epi) {
@@ -184,14 +275,25 @@ GemmProblem gemm_dw(const float* dZ, int lddz, const float* X, int ldx, float* d
   return p;
 }
 void gemm_batch_begin(GemmBatch& b) { b.n = 0; b.total_tiles = 0; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
   GemmProblem p = pin;
+  // 128-bit staging is legal when rows start 16-B aligned and the contiguous extent is a multiple of 4
+  bool avec, bvec;
+  if (p.mode == GEMM_DW) avec = aligned16(p.A) && p.lda % 4 == 0 && p.M % 4 == 0;
+  else avec = aligned16(p.A) && p.lda % 4 == 0 && p.K1 % 4 == 0;
+  if (p.mode == GEMM_FWD) bvec = aligned16(p.Bm) && p.ldb % 4 == 0 && p.K % 4 == 0;
+  else bvec = aligned16(p.Bm) && p.ldb % 4 == 0 && p.N % 4 == 0;
+  p.flags = (avec ? 1 : 0) | (bvec ? 2 : 0);
   p.tiles_m = cdiv(p.M, BM); p.tiles_n = cdiv(p.N, BN); p.tile_begin = b.total_tiles;
   b.total_tiles += p.tiles_m * p.tiles_n;
   b.p[b.n++] = p;
 }
 int gemm_batch_launch(const GemmBatch& b, cudaStream_t st) {
   D4PG_REQUIRE(b.n > 0 && b.n <= GEMM_MAX_PROBLEMS, D4PG_EINVAL, "gemm_batch_launch: %d problems", b.n);
+  for (int i = 0; i < b.n; ++i)     // a concatenated input must switch source on a K-chunk boundary
+    D4PG_REQUIRE(b.p[i].mode != GEMM_FWD || b.p[i].K1 == b.p[i].K || b.p[i].K1 % KC == 0, D4PG_ENOTSUP,
+                 "gemm_batch_launch: concat split K1=%d must be a multiple of %d", b.p[i].K1, KC);
   gemm_ffma_kernel<<<b.total_tiles, GEMM_THREADS, 0, st>>>(b);
   D4PG_LAUNCH_OK();
   return D4PG_OK;

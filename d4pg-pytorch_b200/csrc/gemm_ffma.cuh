@@ -20,7 +20,7 @@ struct GemmProblem {
   float* C; float* bias_grad;
   int M, N, K, K1;
   int lda, lda2, ldb, ldc, ldaux;
-  int mode, epi;
+  int mode, epi, flags;
   int tiles_m, tiles_n, tile_begin;
 };
 
