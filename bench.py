@@ -178,7 +178,7 @@ def gpu_main(args):
         torch.manual_seed(0); random.seed(0)            # identical replicas on every rank
         dd = d4pg.DDPG(cfg["obs"], cfg["act"], memory_size=cap, batch_size=B, critic_dist_info=info,
                        n_steps=cfg["n_steps"], projection=cfg["proj"], sampling=sampling, philox_seed=1234 + rank,
-                       comm=comm)
+                       comm=comm, precision=args.precision)
         dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
                                    d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
         dd.replayBuffer.add_batch(*synth(cfg, cap, seed=rank))     # this rank's shard, resident in HBM
@@ -228,7 +228,7 @@ def gpu_main(args):
             prof.setdefault(name, []).append(t)
     alg = algorithmic(cfg)
     pk = peaks()
-    gemm_ms = [t for t in prof.get("gemm_batch_launch", [])]
+    gemm_ms = [t for t in prof.get("gemm_launch", [])]
     n_gemm = len(gemm_ms) // 5 if gemm_ms else 0
     gemm_avg_ms = float(np.mean(gemm_ms)) if gemm_ms else None
     roofline = None
@@ -238,7 +238,7 @@ def gpu_main(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("gemm_ffma_kernel_dram_bytes_per_launch")
-        roofline = {"kernel": "gemm_ffma_kernel (MLP fwd/bwd levels, %d launches/step)" % n_gemm, "bound": "hbm",
+        roofline = {"kernel": "%s (MLP fwd/bwd levels, %d launches/step)" % ("gemm_ffma_kernel" if args.precision == "fp32" else "gemm_tc_kernel", n_gemm), "bound": "hbm",
                     "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
                     "peak_source": pk["src"], "avg_launch_us": gemm_avg_ms * 1e3,
                     "flops_frac_of_bf16_peak": alg["flops"] / n_gemm / (gemm_avg_ms * 1e-3) / 1e12 / pk["tf"]}
@@ -289,7 +289,8 @@ def gpu_main(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.config, "batch_per_gpu": B, "global_batch": B * world, "obs_dim": cfg["obs"],
                            "act_dim": cfg["act"], "n_atoms": cfg["atoms"], "replay_capacity_per_gpu": cap,
-                           "parallelism": "dp%d" % world, "precision": "fp32 FFMA",
+                           "parallelism": "dp%d" % world,
+                           "precision": {"fp32": "fp32 FFMA", "tf32x3": "3xTF32 tcgen05 (fp32-accurate)", "tf32": "TF32 tcgen05"}[args.precision],
                            "l2": "inputs larger than L2: replay store %.0f MB + trees %.0f MB per GPU, rows sampled at "
                                  "random; parameters (%.1f MB) are L2-resident by design" % (
                                      cap * ((2 * cfg["obs"] + cfg["act"]) * 4 + 9) / 1e6, 16 * cap / 1e6 * 1.05, alg["P"] * 16 / 1e6)},
@@ -312,6 +313,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CFG))
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)

@@ -91,7 +91,7 @@ extern "C" int32_t d4pg_actor_forward(const float* params, int32_t obs_dim, int3
                                       const float* s, int32_t B, float* action, float* workspace,
                                       int32_t precision, d4pg_stream_t stream) {
   D4PG_REQUIRE(params && s && action && workspace && B > 0, D4PG_EINVAL, "d4pg_actor_forward: null/empty argument");
-  D4PG_REQUIRE(precision == 0, D4PG_ENOTSUP, "d4pg_actor_forward: precision %d not available in this build", precision);
+  D4PG_REQUIRE(precision >= 0 && precision <= 2, D4PG_ENOTSUP, "d4pg_actor_forward: unknown precision %d", precision);
   const NetDims d = actor_dims(obs_dim, act_dim);
   const int H = D4PG_HIDDEN;
   float* h1 = workspace; float* h2 = h1 + size_t(B) * H; float* h3 = h2 + size_t(B) * H;
@@ -103,7 +103,7 @@ extern "C" int32_t d4pg_actor_forward(const float* params, int32_t obs_dim, int3
     GemmBatch b; gemm_batch_begin(b);
     gemm_batch_add(b, gemm_fwd(X[l], d.in[l], nullptr, 0, 0, params + d.w_off[l], d.in[l], params + d.b_off[l],
                                Y[l], d.out[l], B, d.out[l], d.in[l], epi[l]));
-    int rc = gemm_batch_launch(b, st);
+    int rc = gemm_launch(b, precision, st);
     if (rc) return rc;
   }
   return D4PG_OK;
@@ -114,7 +114,7 @@ extern "C" int32_t d4pg_critic_forward(const float* params, int32_t obs_dim, int
                                        const float* s, const float* a, int32_t B, float* probs, float* logits,
                                        float* workspace, int32_t precision, d4pg_stream_t stream) {
   D4PG_REQUIRE(params && s && a && workspace && B > 0 && (probs || logits), D4PG_EINVAL, "d4pg_critic_forward: null/empty argument");
-  D4PG_REQUIRE(precision == 0, D4PG_ENOTSUP, "d4pg_critic_forward: precision %d not available in this build", precision);
+  D4PG_REQUIRE(precision >= 0 && precision <= 2, D4PG_ENOTSUP, "d4pg_critic_forward: unknown precision %d", precision);
   D4PG_REQUIRE(n_atoms >= 2 && n_atoms <= D4PG_MAX_ATOMS, D4PG_EINVAL, "d4pg_critic_forward: n_atoms out of range");
   const NetDims d = critic_dims(obs_dim, act_dim, n_atoms);
   const int H = D4PG_HIDDEN;
@@ -126,16 +126,16 @@ extern "C" int32_t d4pg_critic_forward(const float* params, int32_t obs_dim, int
   GemmBatch b;
   gemm_batch_begin(b);
   gemm_batch_add(b, gemm_fwd(s, obs_dim, nullptr, 0, 0, params + d.w_off[0], d.in[0], params + d.b_off[0], h1, H, B, H, obs_dim, EPI_BIAS_RELU));
-  if ((rc = gemm_batch_launch(b, st))) return rc;
+  if ((rc = gemm_launch(b, precision, st))) return rc;
   gemm_batch_begin(b);
   gemm_batch_add(b, gemm_fwd(h1, H, a, act_dim, H, params + d.w_off[1], d.in[1], params + d.b_off[1], h2, H, B, H, H + act_dim, EPI_BIAS_RELU));
-  if ((rc = gemm_batch_launch(b, st))) return rc;
+  if ((rc = gemm_launch(b, precision, st))) return rc;
   gemm_batch_begin(b);
   gemm_batch_add(b, gemm_fwd(h2, H, nullptr, 0, 0, params + d.w_off[2], H, params + d.b_off[2], h3, H, B, H, H, EPI_BIAS_RELU));
-  if ((rc = gemm_batch_launch(b, st))) return rc;
+  if ((rc = gemm_launch(b, precision, st))) return rc;
   gemm_batch_begin(b);
   gemm_batch_add(b, gemm_fwd(h3, H, nullptr, 0, 0, params + d.w_off[3], H, params + d.b_off[3], z, n_atoms, B, n_atoms, H, EPI_BIAS));
-  if ((rc = gemm_batch_launch(b, st))) return rc;
+  if ((rc = gemm_launch(b, precision, st))) return rc;
   if (probs) {
     softmax_rows_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(z, probs, B, n_atoms);
     D4PG_LAUNCH_OK();

@@ -289,6 +289,19 @@ void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
   b.total_tiles += p.tiles_m * p.tiles_n;
   b.p[b.n++] = p;
 }
+void gemm_batch_retile(GemmBatch& b, int bm, int bn) {
+  b.total_tiles = 0;
+  for (int i = 0; i < b.n; ++i) {
+    GemmProblem& p = b.p[i];
+    p.tiles_m = cdiv(p.M, bm); p.tiles_n = cdiv(p.N, bn); p.tile_begin = b.total_tiles;
+    b.total_tiles += p.tiles_m * p.tiles_n;
+  }
+}
+int gemm_launch(GemmBatch& b, int precision, cudaStream_t st) {
+  if (precision == 0) return gemm_batch_launch(b, st);
+  gemm_batch_retile(b, 128, 32);
+  return gemm_tc_batch_launch(b, precision == 1 ? 3 : 1, st);
+}
 int gemm_batch_launch(const GemmBatch& b, cudaStream_t st) {
   D4PG_REQUIRE(b.n > 0 && b.n <= GEMM_MAX_PROBLEMS, D4PG_EINVAL, "gemm_batch_launch: %d problems", b.n);
   for (int i = 0; i < b.n; ++i)     // a concatenated input must switch source on a K-chunk boundary

@@ -40,6 +40,10 @@ GemmProblem gemm_dw(const float* dZ, int lddz, const float* X, int ldx, float* d
                     float* db, int N_out, int K_in, int M_batch);
 void gemm_batch_begin(GemmBatch& b);
 void gemm_batch_add(GemmBatch& b, const GemmProblem& p);
-int gemm_batch_launch(const GemmBatch& b, cudaStream_t st);
+int gemm_batch_launch(const GemmBatch& b, cudaStream_t st);                    // exact fp32 FFMA (32x32 tiles)
+void gemm_batch_retile(GemmBatch& b, int bm, int bn);
+int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st);      // tcgen05 (128x32 tiles)
+// precision: 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = 1xTF32 tcgen05
+int gemm_launch(GemmBatch& b, int precision, cudaStream_t st);
 
 }  // namespace d4pg

@@ -1,0 +1,228 @@
+// Tensor-core grouped GEMM for the actor/critic MLP layers (precision modes 1 = 3xTF32, 2 = 1xTF32).
+//
+// Same problem descriptors and epilogues as gemm_ffma.cu (models.py:33-40,77-83 forward, autograd
+// backward of ddpg.py:230,242), but the contraction runs on the 5th-generation tensor cores:
+//   * one CTA = one 128 x 32 output tile; fp32 accumulator in TMEM (32 columns x 128 lanes),
+//   * operands staged per 32-deep K chunk into the canonical SWIZZLE_128B UMMA layouts
+//     (all K-major: sources that are contiguous along the tile dim are transposed while staged),
+//   * 3xTF32: every fp32 operand is split into hi = tf32(x) and lo = tf32(x - hi) while it is
+//     staged; D += Ah*Bh + Ah*Bl + Al*Bh gives ~2^-21 relative accuracy, enough for the 1e-5
+//     parity bar of config 2 (a single-pass TF32 or BF16 product is not),
+//   * a single elected thread issues tcgen05.mma; tcgen05.commit -> mbarrier releases the smem
+//     stage (2-stage ring: staging of chunk c+1 overlaps the MMAs of chunk c),
+//   * epilogue: tcgen05.ld (one TMEM lane = one output row per thread), bias / ReLU / tanh /
+//     activation-derivative masks fused, 128-B row segments stored straight to global.
+#include "gemm_ffma.cuh"
+#include "tc_common.cuh"
+
+namespace d4pg {
+
+using namespace tc;
+
+constexpr int TC_BM = 128, TC_BN = 32, TC_KC = 32;
+constexpr int TC_THREADS = 128;
+constexpr uint32_t A_BYTES = TC_BM * 128;          // one K-chunk of A (hi or lo): 128 rows x 128 B
+constexpr uint32_t B_BYTES = TC_BN * 128;          // one K-chunk of B: 32 rows x 128 B
+constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo for both operands
+constexpr int TC_STAGES = 2;
+constexpr uint32_t TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*alignment slack*/;
+
+// ---- staging into SWIZZLE_128B layouts with the hi/lo split ---------------------------------------
+__device__ __forceinline__ void put_split(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float x) {
+  const float h = tf32_hi(x);
+  *reinterpret_cast<float*>(hi_base + off) = h;
+  *reinterpret_cast<float*>(lo_base + off) = tf32_lo(x, h);
+}
+__device__ __forceinline__ void put_split4(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v) {
+  float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  float4 l = make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
+  *reinterpret_cast<float4*>(hi_base + off) = h;
+  *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+// K-major block: rows = M/N index, 32 k per row.  src(row, k) = src[row*ld + k].
+template <int ROWS>
+__device__ __forceinline__ void stage_kmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int ld, bool vec,
+                                             int row0, int nrows, int k0, int K, int tid) {
+  if (vec) {
+    // 8 float4 per row; a 16-B chunk keeps its position inside the 128-B row up to the XOR swizzle
+#pragma unroll 4
+    for (int e = tid; e < ROWS * 8; e += TC_THREADS) {
+      const int r = e >> 3, q = e & 7, k = k0 + (q << 2);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < nrows && k < K) v = __ldg(reinterpret_cast<const float4*>(src + size_t(row0 + r) * ld + k));
+      put_split4(hi, lo, sw128_kmajor_off(r, q << 2), v);
+    }
+  } else {
+#pragma unroll 4
+    for (int e = tid; e < ROWS * 32; e += TC_THREADS) {
+      const int r = e >> 5, kk = e & 31, k = k0 + kk;
+      const float x = (row0 + r < nrows && k < K) ? __ldg(src + size_t(row0 + r) * ld + k) : 0.f;
+      put_split(hi, lo, sw128_kmajor_off(r, kk), x);
+    }
+  }
+}
+// Transposing stage: the source is contiguous along the tile dim (src(k, col) = src[k*ld + col], as in
+// dX's W[nout, kin] and dW's dZ[b, nout] / X[b, kin]); it is read coalesced along `col` and written
+// into the SAME K-major layout with (row = col, k).  Keeping every operand K-major means a single
+// UMMA descriptor form (validated by tests/probe/tc_probe.cu); tf32 MN-major operands would need the
+// SWIZZLE_128B_BASE32B layout instead.
+template <int COLS>
+__device__ __forceinline__ void stage_transposed(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int ld, bool vec,
+                                                 int col0, int ncols, int k0, int K, int tid) {
+  if (vec) {
+#pragma unroll 4
+    for (int e = tid; e < 32 * (COLS / 4); e += TC_THREADS) {
+      const int kk = e / (COLS / 4), col = (e % (COLS / 4)) << 2;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + kk < K && col0 + col < ncols) v = __ldg(reinterpret_cast<const float4*>(src + size_t(k0 + kk) * ld + col0 + col));
+      put_split(hi, lo, sw128_kmajor_off(col, kk), v.x);
+      put_split(hi, lo, sw128_kmajor_off(col + 1, kk), v.y);
+      put_split(hi, lo, sw128_kmajor_off(col + 2, kk), v.z);
+      put_split(hi, lo, sw128_kmajor_off(col + 3, kk), v.w);
+    }
+  } else {
+#pragma unroll 4
+    for (int e = tid; e < 32 * COLS; e += TC_THREADS) {
+      const int kk = e / COLS, col = e % COLS;
+      const float x = (k0 + kk < K && col0 + col < ncols) ? __ldg(src + size_t(k0 + kk) * ld + col0 + col) : 0.f;
+      put_split(hi, lo, sw128_kmajor_off(col, kk), x);
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void tc_tile(const GemmProblem& P, uint8_t* smem, uint64_t* bars, uint32_t tmem_d,
+                                        int m0, int n0, int tn, int passes) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr bool A_T = (MODE == GEMM_DW);       // source contiguous along the tile dim -> transposing stage
+  constexpr bool B_T = (MODE != GEMM_FWD);
+  const uint32_t idesc = make_idesc(FMT_TF32, false, false, TC_BM, TC_BN);
+  const bool avec = (P.flags & 1) != 0, bvec = (P.flags & 2) != 0;
+  const int nchunks = (P.K + TC_KC - 1) / TC_KC;
+  uint64_t* empty = bars;            // [TC_STAGES]  MMAs that read a stage have completed
+  uint64_t* done = bars + TC_STAGES;  // all MMAs of the tile have completed
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % TC_STAGES;
+    uint8_t* Ahi = smem + st * STAGE_BYTES;
+    uint8_t* Alo = Ahi + A_BYTES;
+    uint8_t* Bhi = Alo + A_BYTES;
+    uint8_t* Blo = Bhi + B_BYTES;
+    if (c >= TC_STAGES) mbar_wait(&empty[st], ((c / TC_STAGES) - 1) & 1);     // stage free again
+    const int k0 = c * TC_KC;
+    // ---- A -------------------------------------------------------------------------------------
+    if (A_T) {
+      stage_transposed<TC_BM>(Ahi, Alo, P.A, P.lda, avec, m0, P.M, k0, P.K, tid);       // dZ[k*lda + m]
+    } else if (k0 >= P.K1) {
+      stage_kmajor<TC_BM>(Ahi, Alo, P.A2, P.lda2, false, m0, P.M, k0 - P.K1, P.K - P.K1, tid);   // concat tail
+    } else {
+      stage_kmajor<TC_BM>(Ahi, Alo, P.A, P.lda, avec, m0, P.M, k0, P.K1, tid);
+    }
+    // ---- B -------------------------------------------------------------------------------------
+    if (B_T) stage_transposed<TC_BN>(Bhi, Blo, P.Bm, P.ldb, bvec, n0, P.N, k0, P.K, tid);  // B[k*ldb + n]
+    else stage_kmajor<TC_BN>(Bhi, Blo, P.Bm, P.ldb, bvec, n0, P.N, k0, P.K, tid);        // W[n*ldb + k]
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int p = 0; p < passes; ++p) {
+        const uint8_t* Ap = (p == 2) ? Alo : Ahi;
+        const uint8_t* Bp = (p == 1) ? Blo : Bhi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ad = make_smem_desc(smem_u32(Ap + ks * 32), 16, 1024);
+          const uint64_t bd = make_smem_desc(smem_u32(Bp + ks * 32), 16, 1024);
+          mma_tf32(tmem_d, ad, bd, idesc, (c | p | ks) != 0);
+        }
+      }
+      mma_commit(&empty[st]);
+      if (c == nchunks - 1) mma_commit(done);
+    }
+  }
+  mbar_wait(done, 0);
+  tc_fence_after_sync();
+
+  // ---- epilogue: one TMEM lane (= output row) per thread, 32 columns ------------------------------
+  float r[32];
+  tmem_ld_32x32(tmem_d + (uint32_t(warp * 32) << 16), r);
+  const int gi = m0 + warp * 32 + lane;
+  if (gi < P.M) {
+    float* crow = P.C + size_t(gi) * P.ldc + n0;
+    const float* arow = P.aux ? P.aux + size_t(gi) * P.ldaux + n0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (n0 + j >= P.N) break;
+      float x = r[j];
+      switch (P.epi) {
+        case EPI_BIAS: x += __ldg(P.bias + n0 + j); break;
+        case EPI_BIAS_RELU: x = fmaxf(x + __ldg(P.bias + n0 + j), 0.f); break;
+        case EPI_BIAS_TANH: x = tanhf(x + __ldg(P.bias + n0 + j)); break;
+        case EPI_RELU_MASK: x = (__ldg(arow + j) > 0.f) ? x : 0.f; break;
+        case EPI_TANH_MASK: { const float t = __ldg(arow + j); x *= (1.f - t * t); } break;
+        default: break;
+      }
+      crow[j] = x;
+    }
+  }
+  // ---- dW: bias gradient = column sums of dZ (rows of A), exact fp32, tn == 0 tiles only -------------
+  if (MODE == GEMM_DW && P.bias_grad != nullptr && tn == 0) {
+    const int m = m0 + tid;                                   // 128 threads <-> 128 A rows
+    if (m < P.M) {
+      float s = 0.f;
+      for (int k = 0; k < P.K; ++k) s += __ldg(P.A + size_t(k) * P.lda + m);    // coalesced across threads
+      P.bias_grad[m] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ GemmBatch batch, int passes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bars[TC_STAGES + 1];
+  __shared__ uint32_t tmem_base_s;
+
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
+    if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
+  const GemmProblem P = batch.p[pi];
+  const int tile = blockIdx.x - P.tile_begin;
+  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+
+  if (threadIdx.x < 32) tmem_alloc(&tmem_base_s, 32);
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < TC_STAGES + 1; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (P.mode == GEMM_FWD) tc_tile<GEMM_FWD>(P, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
+  else if (P.mode == GEMM_DX) tc_tile<GEMM_DX>(P, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
+  else tc_tile<GEMM_DW>(P, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_d, 32);
+}
+
+int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {
+  D4PG_REQUIRE(b.n > 0 && b.n <= GEMM_MAX_PROBLEMS, D4PG_EINVAL, "gemm_tc_batch_launch: %d problems", b.n);
+  for (int i = 0; i < b.n; ++i)
+    D4PG_REQUIRE(b.p[i].mode != GEMM_FWD || b.p[i].K1 == b.p[i].K || b.p[i].K1 % TC_KC == 0, D4PG_ENOTSUP,
+                 "gemm_tc_batch_launch: concat split K1=%d must be a multiple of %d", b.p[i].K1, TC_KC);
+  static bool attr_set = false;
+  if (!attr_set) {
+    D4PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM)));
+    attr_set = true;
+  }
+  gemm_tc_kernel<<<b.total_tiles, TC_THREADS, TC_SMEM, st>>>(b, passes);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+}  // namespace d4pg

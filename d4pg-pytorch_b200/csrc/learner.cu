@@ -98,7 +98,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 #define RUN(expr)                                                                          \
   do {                                                                                     \
     if (L->profiling) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);    \
-      std::string nm0(#expr); const bool rep = nm0.rfind("gemm_batch_launch", 0) == 0 || nm0.rfind("launch_heads", 0) == 0; \
+      std::string nm0(#expr); const bool rep = nm0.rfind("gemm_launch", 0) == 0 || nm0.rfind("launch_heads", 0) == 0; \
       cudaEventRecord(e0, st); rc = (expr);                                                \
       for (int _r = 1; rep && _r < PROFILE_REPS && rc == 0; ++_r) rc = (expr);             \
       cudaEventRecord(e1, st);                                                             \
@@ -126,38 +126,38 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   gemm_batch_add(g, gemm_fwd(w.s2, S, nullptr, 0, 0, Wct + dc.w_off[0], S, Wct + dc.b_off[0], w.h1[1], H, B, H, S, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.s, S, nullptr, 0, 0, Wc + dc.w_off[0], S, Wc + dc.b_off[0], w.h1[2], H, B, H, S, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.s, S, nullptr, 0, 0, Wa + da.w_off[0], S, Wa + da.b_off[0], w.h1[3], H, B, H, S, EPI_BIAS_RELU));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level 2: fc2 (actor: no activation, models.py:36; critic: cat(h1, a) + relu, models.py:80)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h1[0], H, nullptr, 0, 0, Wat + da.w_off[1], H, Wat + da.b_off[1], w.h2[0], H, B, H, H, EPI_BIAS));
   gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.a, A, H, Wc + dc.w_off[1], H + A, Wc + dc.b_off[1], w.h2[2], H, B, H, H + A, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h1[3], H, nullptr, 0, 0, Wa + da.w_off[1], H, Wa + da.b_off[1], w.h2[3], H, B, H, H, EPI_BIAS));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level 3: fc2_2 + relu
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h2[0], H, nullptr, 0, 0, Wat + da.w_off[2], H, Wat + da.b_off[2], w.h3[0], H, B, H, H, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h2[2], H, nullptr, 0, 0, Wc + dc.w_off[2], H, Wc + dc.b_off[2], w.h3[2], H, B, H, H, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h2[3], H, nullptr, 0, 0, Wa + da.w_off[2], H, Wa + da.b_off[2], w.h3[3], H, B, H, H, EPI_BIAS_RELU));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level 4: fc3 (actor: tanh; critic: logits)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h3[0], H, nullptr, 0, 0, Wat + da.w_off[3], H, Wat + da.b_off[3], w.out[0], A, B, A, H, EPI_BIAS_TANH));
   gemm_batch_add(g, gemm_fwd(w.h3[2], H, nullptr, 0, 0, Wc + dc.w_off[3], H, Wc + dc.b_off[3], w.out[2], N, B, N, H, EPI_BIAS));
   gemm_batch_add(g, gemm_fwd(w.h3[3], H, nullptr, 0, 0, Wa + da.w_off[3], H, Wa + da.b_off[3], w.out[3], A, B, A, H, EPI_BIAS_TANH));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level 5: critic_target.fc2([h1t, a_t(s')]) and critic.fc2([h1, actor(s)]) (h1 of the critic is reused)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h1[1], H, w.out[0], A, H, Wct + dc.w_off[1], H + A, Wct + dc.b_off[1], w.h2[1], H, B, H, H + A, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.out[3], A, H, Wc + dc.w_off[1], H + A, Wc + dc.b_off[1], w.h2[4], H, B, H, H + A, EPI_BIAS_RELU));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h2[1], H, nullptr, 0, 0, Wct + dc.w_off[2], H, Wct + dc.b_off[2], w.h3[1], H, B, H, H, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h2[4], H, nullptr, 0, 0, Wc + dc.w_off[2], H, Wc + dc.b_off[2], w.h3[4], H, B, H, H, EPI_BIAS_RELU));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h3[1], H, nullptr, 0, 0, Wct + dc.w_off[3], H, Wct + dc.b_off[3], w.out[1], N, B, N, H, EPI_BIAS));
   gemm_batch_add(g, gemm_fwd(w.h3[4], H, nullptr, 0, 0, Wc + dc.w_off[3], H, Wc + dc.b_off[3], w.out[4], N, B, N, H, EPI_BIAS));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
 
   // 3. heads: softmaxes, projection, CE loss, td, priorities, logit gradients (ddpg.py:214-222,236-238)
   HeadsArgs ha{};
@@ -188,40 +188,40 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   gemm_batch_add(g, gemm_dx(w.dlogits_q, N, Wc + dc.w_off[3], H, w.c_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[2], H));
   gemm_batch_add(g, gemm_dx(w.dlogits_pi, N, Wc + dc.w_off[3], H, w.p_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[4], H));
   gemm_batch_add(g, gemm_dw(w.dlogits_q, N, w.h3[2], H, Gc + dc.w_off[3], H, Gc + dc.b_off[3], N, H, B));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level B2: through critic.fc2_2
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dx(w.c_dz22, H, Wc + dc.w_off[2], H, w.c_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[2], H));
   gemm_batch_add(g, gemm_dx(w.p_dz22, H, Wc + dc.w_off[2], H, w.p_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[4], H));
   gemm_batch_add(g, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], H, Gc + dc.b_off[2], H, H, B));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level B3: through critic.fc2: dh1 (critic loss), d action (policy, tanh' folded in), dW2 = [dz2^T h1 | dz2^T a]
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dx(w.c_dz2, H, Wc + dc.w_off[1], H + A, w.c_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[2], H));
   gemm_batch_add(g, gemm_dx(w.p_dz2, H, Wc + dc.w_off[1] + H, H + A, w.a_dz3, A, B, A, H, EPI_TANH_MASK, w.out[3], A));
   gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], H + A, Gc + dc.b_off[1], H, H, B));
   gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.a, A, Gc + dc.w_off[1] + H, H + A, nullptr, H, A, B));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level B4: critic.fc1 weights; actor.fc3
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dw(w.c_dz1, H, w.s, S, Gc + dc.w_off[0], S, Gc + dc.b_off[0], H, S, B));
   gemm_batch_add(g, gemm_dx(w.a_dz3, A, Wa + da.w_off[3], H, w.a_dz22, H, B, H, A, EPI_RELU_MASK, w.h3[3], H));
   gemm_batch_add(g, gemm_dw(w.a_dz3, A, w.h3[3], H, Ga + da.w_off[3], H, Ga + da.b_off[3], A, H, B));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level B5: actor.fc2_2 (its input h2 has no activation -> plain dX)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dx(w.a_dz22, H, Wa + da.w_off[2], H, w.a_dh2, H, B, H, H, EPI_NONE, nullptr, 0));
   gemm_batch_add(g, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], H, Ga + da.b_off[2], H, H, B));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level B6: actor.fc2
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dx(w.a_dh2, H, Wa + da.w_off[1], H, w.a_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[3], H));
   gemm_batch_add(g, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], H, Ga + da.b_off[1], H, H, B));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
   // level B7: actor.fc1
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dw(w.a_dz1, H, w.s, S, Ga + da.w_off[0], S, Ga + da.b_off[0], H, S, B));
-  RUN(gemm_batch_launch(g, st));
+  RUN(gemm_launch(g, c.precision, st));
 
   // 6. data-parallel gradient exchange: ONE all-reduce over the flat [P_a + P_c] buffer
   if (c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
@@ -254,7 +254,8 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   D4PG_REQUIRE(cfg->n_atoms >= 2 && cfg->n_atoms <= D4PG_MAX_ATOMS, D4PG_EINVAL, "d4pg_learner_create: n_atoms must be in [2,%d]", D4PG_MAX_ATOMS);
   D4PG_REQUIRE(cfg->v_max > cfg->v_min, D4PG_EINVAL, "d4pg_learner_create: v_max <= v_min");
   D4PG_REQUIRE(cfg->proj_mode == 0 || cfg->proj_mode == 1, D4PG_EINVAL, "d4pg_learner_create: proj_mode must be 0/1");
-  D4PG_REQUIRE(cfg->precision == 0, D4PG_ENOTSUP, "d4pg_learner_create: precision %d not available in this build", cfg->precision);
+  D4PG_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, D4PG_ENOTSUP,
+               "d4pg_learner_create: precision %d unknown (0 fp32 FFMA, 1 3xTF32 tcgen05, 2 TF32 tcgen05)", cfg->precision);
   D4PG_REQUIRE(cfg->world_size <= 1 || comm, D4PG_EINVAL, "d4pg_learner_create: world_size>1 needs a communicator");
   D4PG_REQUIRE(buf->actor && buf->actor_target && buf->critic && buf->critic_target && buf->grad_actor && buf->grad_critic &&
                buf->adam_m_actor && buf->adam_v_actor && buf->adam_m_critic && buf->adam_v_critic &&
@@ -340,7 +341,7 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
   for (int i = 0; i < n; ++i) {
     float ms = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, L->ev[2 * i], L->ev[2 * i + 1]);
-    if (L->ev_name[i] == "gemm_batch_launch" || L->ev_name[i] == "launch_heads") ms /= float(PROFILE_REPS);
+    if (L->ev_name[i] == "gemm_launch" || L->ev_name[i] == "launch_heads") ms /= float(PROFILE_REPS);
     if (i < max_launches) {
       ms_out[i] = ms;
       if (names_out && name_stride > 1) {

@@ -72,13 +72,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&r)[32]) {
 // K-major   (rows = M/N index, 128-B rows of 32 tf32 / 64 bf16 along K):  LBO unused (=1), SBO = 8-row group stride
 // MN-major  (rows = K index,   128-B rows of 32 tf32 along M/N):          LBO = stride between 128-B M/N chunks,
 //                                                                          SBO = stride between 8-row K groups
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-B swizzle base), 1 = SWIZZLE_128B_BASE32B (32-B base; the only
+// MN-major layout the hardware accepts for 32-bit (tf32) operands: atoms of 4 K-rows x 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= uint64_t((saddr >> 4) & 0x3FFF);
   d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
+  d |= uint64_t(layout_type & 7) << 61;
   return d;
 }
 
@@ -114,9 +117,10 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 __device__ __forceinline__ uint32_t sw128_kmajor_off(int r, int k) {
   return uint32_t((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + ((k & 3) << 2));
 }
-// MN-major block: element (k, mn32) of a [k rows x 32 fp32] block (128 B per k row, 8-row groups 1024 B)
-__device__ __forceinline__ uint32_t sw128_mnmajor_off(int k, int mn) {
-  return uint32_t((k >> 3) * 1024 + (k & 7) * 128 + ((((mn >> 2) ^ (k & 7)) & 7) << 4) + ((mn & 3) << 2));
+// MN-major tf32 block (SWIZZLE_128B_BASE32B): element (k, mn32) of a [k rows x 32 fp32] block, 128 B per
+// k row, swizzle atom = 4 rows (512 B): the 32-B chunk index is XORed with (row & 3)
+__device__ __forceinline__ uint32_t sw128b32_mnmajor_off(int k, int mn) {
+  return uint32_t((k >> 2) * 512 + (k & 3) * 128 + ((((mn >> 3) ^ (k & 3)) & 3) << 5) + ((mn & 7) << 2));
 }
 
 // tf32 split: hi = x with the low 13 mantissa bits cleared (exactly representable in tf32),

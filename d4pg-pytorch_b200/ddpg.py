@@ -65,7 +65,7 @@ class _Learner(object):
             cfg.prio_eps = ddpg.prioritized_replay_eps
         else:
             cfg.per_beta0, cfg.per_beta_final, cfg.per_beta_iters, cfg.prio_eps = 1.0, 1.0, 1, 1e-6
-        cfg.precision = {"fp32": 0, "tf32x3": 1, "bf16": 2}[ddpg.precision]
+        cfg.precision = {"fp32": 0, "tf32x3": 1, "tf32": 2}[ddpg.precision]
         cfg.sample_mode = 0 if ddpg.sampling == "reference" else 1
         cfg.philox_seed = int(ddpg.philox_seed)
         cfg.world_size = ddpg.comm.world_size if ddpg.comm is not None else 1
@@ -154,7 +154,7 @@ class DDPG:
         self.env = env
         self.device = torch.device(device) if device is not None else default_device()
         assert sampling in ("reference", "device") and projection in ("reference", "nstep")
-        assert precision in ("fp32", "tf32x3", "bf16")
+        assert precision in ("fp32", "tf32x3", "tf32")
         self.sampling, self.projection, self.precision = sampling, projection, precision
         self.use_graph, self.philox_seed, self.comm = use_graph, philox_seed, comm
 

@@ -48,6 +48,8 @@ class _LinearView(nn.Module):
 
 
 class _FlatNet(nn.Module):
+    precision = 0        # 0 fp32 FFMA, 1 3xTF32 tcgen05, 2 TF32 tcgen05 (set per instance to switch forward())
+
     def __init__(self, dims, device=None):
         super().__init__()
         self._dims = list(dims)
@@ -159,7 +161,7 @@ class actor(_FlatNet):
         out = torch.empty(B, self.output_size, dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().d4pg_actor_forward(_lib.ptr(self._flat), self.input_size, self.output_size,
                                                  _lib.ptr(x), B, _lib.ptr(out), _lib.ptr(self._workspace(B)),
-                                                 0, _lib.stream_ptr()), "d4pg_actor_forward")
+                                                 int(self.precision), _lib.stream_ptr()), "d4pg_actor_forward")
         return out
 
 
@@ -189,7 +191,7 @@ class critic(_FlatNet):
         logits = torch.empty_like(probs) if return_logits else None
         _lib.check(_lib.lib().d4pg_critic_forward(_lib.ptr(self._flat), self.state_size, self.action_size, self.n_atoms,
                                                   _lib.ptr(x), _lib.ptr(a), B, _lib.ptr(probs), _lib.ptr(logits),
-                                                  _lib.ptr(self._workspace(B)), 0, _lib.stream_ptr()),
+                                                  _lib.ptr(self._workspace(B)), int(self.precision), _lib.stream_ptr()),
                    "d4pg_critic_forward")
         return (probs, logits) if return_logits else probs
 

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) probe_gemm(const float* A, const float* B
     if (A_MN) { k = e / 128; m = e % 128; } else { m = e / K; k = e % K; }
     float x = A_MN ? A[size_t(k) * lda + m] : A[size_t(m) * lda + k];
     int c = k / 32, kk = k % 32;
-    uint32_t off = c * a_chunk_bytes + (A_MN ? uint32_t((m / 32) * 4096) + sw128_mnmajor_off(kk, m % 32) : sw128_kmajor_off(m, kk));
+    uint32_t off = c * a_chunk_bytes + (A_MN ? uint32_t((m / 32) * 4096) + sw128b32_mnmajor_off(kk, m % 32) : sw128_kmajor_off(m, kk));
     float hi = tf32_hi(x);
     *reinterpret_cast<float*>(Ahi + off) = hi;
     *reinterpret_cast<float*>(Alo + off) = tf32_lo(x, hi);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128) probe_gemm(const float* A, const float* B
     if (B_MN) { k = e / N; n = e % N; } else { n = e / K; k = e % K; }
     float x = B_MN ? B[size_t(k) * ldb + n] : B[size_t(n) * ldb + k];
     int c = k / 32, kk = k % 32;
-    uint32_t off = c * b_chunk_bytes + (B_MN ? uint32_t((n / 32) * 4096) + sw128_mnmajor_off(kk, n % 32) : sw128_kmajor_off(n, kk));
+    uint32_t off = c * b_chunk_bytes + (B_MN ? uint32_t((n / 32) * 4096) + sw128b32_mnmajor_off(kk, n % 32) : sw128_kmajor_off(n, kk));
     float hi = tf32_hi(x);
     *reinterpret_cast<float*>(Bhi + off) = hi;
     *reinterpret_cast<float*>(Blo + off) = tf32_lo(x, hi);
@@ -66,9 +66,9 @@ __global__ void __launch_bounds__(128) probe_gemm(const float* A, const float* B
       const uint8_t* Bp = (p == 1) ? Blo : Bhi;
       for (int c = 0; c < nchunk; ++c) {
         for (int ks = 0; ks < 4; ++ks) {
-          uint64_t ad = A_MN ? make_smem_desc(smem_u32(Ap + c * a_chunk_bytes + ks * 1024), 4096, 1024)
+          uint64_t ad = A_MN ? make_smem_desc(smem_u32(Ap + c * a_chunk_bytes + ks * 1024), 4096, 512, 1)
                              : make_smem_desc(smem_u32(Ap + c * a_chunk_bytes + ks * 32), 16, 1024);
-          uint64_t bd = B_MN ? make_smem_desc(smem_u32(Bp + c * b_chunk_bytes + ks * 1024), 4096, 1024)
+          uint64_t bd = B_MN ? make_smem_desc(smem_u32(Bp + c * b_chunk_bytes + ks * 1024), 4096, 512, 1)
                              : make_smem_desc(smem_u32(Bp + c * b_chunk_bytes + ks * 32), 16, 1024);
           mma_tf32(tmem_d, ad, bd, idesc, acc);
           acc = true;
