@@ -103,14 +103,14 @@ struct Operand { const float* p; int ld; bool vec; };
 template <int MODE>
 __device__ __forceinline__ void load_A(const GemmProblem& P, int m0, int k0, int tid, float (&ra)[PER_THREAD], bool& vec) {
   if (MODE == GEMM_DW) {               // A(i,k) = dZ[k*lda + i]
-    vec = (P.flags & 1) != 0;
+    vec = (P.flags & GEMM_A_VEC) != 0;
     if (vec) load_rowcontig<true>(P.A, P.lda, m0, P.M, k0, P.K, tid, ra);
     else load_rowcontig<false>(P.A, P.lda, m0, P.M, k0, P.K, tid, ra);
   } else if (k0 >= P.K1) {             // concatenated tail (critic fc2's action columns): scalar
     vec = false;
     load_kcontig<false>(P.A2, P.lda2, m0, P.M, k0 - P.K1, P.K - P.K1, tid, ra);
   } else {
-    vec = (P.flags & 1) != 0;
+    vec = (P.flags & GEMM_A_VEC) != 0;
     if (vec) load_kcontig<true>(P.A, P.lda, m0, P.M, k0, P.K1, tid, ra);
     else load_kcontig<false>(P.A, P.lda, m0, P.M, k0, P.K1, tid, ra);
   }
@@ -122,7 +122,7 @@ __device__ __forceinline__ void store_A(float* As, int tid, const float (&ra)[PE
 }
 template <int MODE>
 __device__ __forceinline__ void load_B(const GemmProblem& P, int n0, int k0, int tid, float (&rb)[PER_THREAD]) {
-  const bool vec = (P.flags & 2) != 0;
+  const bool vec = (P.flags & GEMM_B_VEC) != 0;
   if (MODE == GEMM_FWD) {              // B(k,j) = W[j*ldb + k]
     if (vec) load_kcontig<true>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
     else load_kcontig<false>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
@@ -133,7 +133,7 @@ __device__ __forceinline__ void load_B(const GemmProblem& P, int n0, int k0, int
 }
 template <int MODE>
 __device__ __forceinline__ void store_B(const GemmProblem& P, float* Bs, int tid, const float (&rb)[PER_THREAD]) {
-  const bool vec = (P.flags & 2) != 0;
+  const bool vec = (P.flags & GEMM_B_VEC) != 0;
   if (MODE == GEMM_FWD) { if (vec) store_kcontig<true>(Bs, LDS_B, tid, rb); else store_kcontig<false>(Bs, LDS_B, tid, rb); }
   else { if (vec) store_rowcontig<true>(Bs, LDS_B, tid, rb); else store_rowcontig<false>(Bs, LDS_B, tid, rb); }
 }
@@ -284,7 +284,7 @@ void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
   else avec = aligned16(p.A) && p.lda % 4 == 0 && p.K1 % 4 == 0;
   if (p.mode == GEMM_FWD) bvec = aligned16(p.Bm) && p.ldb % 4 == 0 && p.K % 4 == 0;
   else bvec = aligned16(p.Bm) && p.ldb % 4 == 0 && p.N % 4 == 0;
-  p.flags = (avec ? 1 : 0) | (bvec ? 2 : 0);
+  p.flags = (avec ? GEMM_A_VEC : 0) | (bvec ? GEMM_B_VEC : 0);
   p.tiles_m = cdiv(p.M, BM); p.tiles_n = cdiv(p.N, BN); p.tile_begin = b.total_tiles;
   b.total_tiles += p.tiles_m * p.tiles_n;
   b.p[b.n++] = p;
@@ -300,6 +300,7 @@ void gemm_batch_retile(GemmBatch& b, int bm, int bn) {
 int gemm_launch(GemmBatch& b, int precision, cudaStream_t st) {
   if (precision == 0) return gemm_batch_launch(b, st);
   gemm_batch_retile(b, 128, 32);
+  gemm_tc_prepare(b);
   return gemm_tc_batch_launch(b, precision == 1 ? 3 : 1, st);
 }
 int gemm_batch_launch(const GemmBatch& b, cudaStream_t st) {

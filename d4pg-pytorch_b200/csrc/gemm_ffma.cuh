@@ -1,6 +1,7 @@
 // Grouped small-GEMM launcher (exact-fp32 FFMA path) used by the MLP forward/backward.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>     // CUtensorMap (type only; the encoder is resolved through the runtime)
 
 namespace d4pg {
 
@@ -25,10 +26,14 @@ struct GemmProblem {
 };
 
 constexpr int GEMM_MAX_PROBLEMS = 8;
+enum GemmFlags { GEMM_A_VEC = 1, GEMM_B_VEC = 2, GEMM_A_TMA = 4, GEMM_B_TMA = 8 };
 struct GemmBatch {
   GemmProblem p[GEMM_MAX_PROBLEMS];
   int n;
   int total_tiles;
+  // tcgen05 path only: TMA descriptors of the operands that qualify (16-B aligned rows, K-major)
+  alignas(64) CUtensorMap tmap_a[GEMM_MAX_PROBLEMS];
+  alignas(64) CUtensorMap tmap_b[GEMM_MAX_PROBLEMS];
 };
 
 // host helpers ---------------------------------------------------------------------------
@@ -42,6 +47,7 @@ void gemm_batch_begin(GemmBatch& b);
 void gemm_batch_add(GemmBatch& b, const GemmProblem& p);
 int gemm_batch_launch(const GemmBatch& b, cudaStream_t st);                    // exact fp32 FFMA (32x32 tiles)
 void gemm_batch_retile(GemmBatch& b, int bm, int bn);
+void gemm_tc_prepare(GemmBatch& b);                                             // TMA eligibility + tensor maps
 int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st);      // tcgen05 (128x32 tiles)
 // precision: 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = 1xTF32 tcgen05
 int gemm_launch(GemmBatch& b, int precision, cudaStream_t st);

@@ -8,12 +8,17 @@
 //   * 3xTF32: every fp32 operand is split into hi = tf32(x) and lo = tf32(x - hi) while it is
 //     staged; D += Ah*Bh + Ah*Bl + Al*Bh gives ~2^-21 relative accuracy, enough for the 1e-5
 //     parity bar of config 2 (a single-pass TF32 or BF16 product is not),
+//   * operands whose rows are 16-B aligned and K-contiguous (activations, 256-wide weights) are
+//     fetched by TMA (cp.async.bulk.tensor, SWIZZLE_128B tensor maps, mbarrier complete_tx) one
+//     chunk ahead of the MMAs and split hi/lo in place; ragged operands (|s|=17, the 262-wide
+//     critic fc2 rows, transposed uses) are staged by the threads,
 //   * a single elected thread issues tcgen05.mma; tcgen05.commit -> mbarrier releases the smem
 //     stage (2-stage ring: staging of chunk c+1 overlaps the MMAs of chunk c),
 //   * epilogue: tcgen05.ld (one TMEM lane = one output row per thread), bias / ReLU / tanh /
 //     activation-derivative masks fused, 128-B row segments stored straight to global.
 #include "gemm_ffma.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace d4pg {
 
@@ -25,6 +30,7 @@ constexpr uint32_t A_BYTES = TC_BM * 128;          // one K-chunk of A (hi or lo
 constexpr uint32_t B_BYTES = TC_BN * 128;          // one K-chunk of B: 32 rows x 128 B
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo for both operands
 constexpr int TC_STAGES = 2;
+constexpr int BAR_EMPTY = 0, BAR_FULL = TC_STAGES, BAR_DONE = 2 * TC_STAGES, TC_NBARS = 2 * TC_STAGES + 1;
 constexpr uint32_t TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*alignment slack*/;
 
 // ---- staging into SWIZZLE_128B layouts with the hi/lo split ---------------------------------------
@@ -91,17 +97,44 @@ __device__ __forceinline__ void stage_transposed(uint8_t* hi, uint8_t* lo, const
   }
 }
 
+// TMA landed raw fp32 in `hi`; rewrite it as hi and emit lo at the same (already swizzled) offsets
+template <int BYTES>
+__device__ __forceinline__ void split_in_place(uint8_t* hi, uint8_t* lo, int tid) {
+#pragma unroll 4
+  for (int e = tid; e < BYTES / 16; e += TC_THREADS) {
+    const float4 v = *reinterpret_cast<const float4*>(hi + e * 16);
+    put_split4(hi, lo, uint32_t(e) * 16u, v);
+  }
+}
+
 template <int MODE>
-__device__ __forceinline__ void tc_tile(const GemmProblem& P, uint8_t* smem, uint64_t* bars, uint32_t tmem_d,
+__device__ __forceinline__ void tc_tile(const GemmProblem& P, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                        uint8_t* smem, uint64_t* bars, uint32_t tmem_d,
                                         int m0, int n0, int tn, int passes) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr bool A_T = (MODE == GEMM_DW);       // source contiguous along the tile dim -> transposing stage
   constexpr bool B_T = (MODE != GEMM_FWD);
   const uint32_t idesc = make_idesc(FMT_TF32, false, false, TC_BM, TC_BN);
-  const bool avec = (P.flags & 1) != 0, bvec = (P.flags & 2) != 0;
+  const bool avec = (P.flags & GEMM_A_VEC) != 0, bvec = (P.flags & GEMM_B_VEC) != 0;
+  const bool a_tma = (P.flags & GEMM_A_TMA) != 0, b_tma = (P.flags & GEMM_B_TMA) != 0;
   const int nchunks = (P.K + TC_KC - 1) / TC_KC;
-  uint64_t* empty = bars;            // [TC_STAGES]  MMAs that read a stage have completed
-  uint64_t* done = bars + TC_STAGES;  // all MMAs of the tile have completed
+  uint64_t* empty = bars + BAR_EMPTY;  // [TC_STAGES]  MMAs that read a stage have completed
+  uint64_t* full = bars + BAR_FULL;    // [TC_STAGES]  TMA bytes of a stage have landed
+  uint64_t* done = bars + BAR_DONE;    // all MMAs of the tile have completed
+
+  // TMA for chunk c (thread 0): A from the main source only (the concat tail is staged by threads)
+  auto issue_tma = [&](int c) {
+    const int st = c % TC_STAGES, k0 = c * TC_KC;
+    uint8_t* Ahi = smem + st * STAGE_BYTES;
+    uint8_t* Bhi = Ahi + 2 * A_BYTES;
+    const bool a_now = a_tma && k0 < P.K1, b_now = b_tma;
+    if (!(a_now || b_now)) return;
+    mbar_expect_tx(&full[st], (a_now ? A_BYTES : 0u) + (b_now ? B_BYTES : 0u));
+    if (a_now) tma_load_2d(Ahi, tmA, &full[st], k0, m0);
+    if (b_now) tma_load_2d(Bhi, tmB, &full[st], k0, n0);
+  };
+  if (tid == 0 && (a_tma || b_tma)) issue_tma(0);
+  uint32_t full_parity[TC_STAGES] = {0u, 0u};      // per-stage phase of the TMA barrier (not every chunk uses it)
 
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % TC_STAGES;
@@ -109,19 +142,33 @@ __device__ __forceinline__ void tc_tile(const GemmProblem& P, uint8_t* smem, uin
     uint8_t* Alo = Ahi + A_BYTES;
     uint8_t* Bhi = Alo + A_BYTES;
     uint8_t* Blo = Bhi + B_BYTES;
-    if (c >= TC_STAGES) mbar_wait(&empty[st], ((c / TC_STAGES) - 1) & 1);     // stage free again
     const int k0 = c * TC_KC;
-    // ---- A -------------------------------------------------------------------------------------
-    if (A_T) {
-      stage_transposed<TC_BM>(Ahi, Alo, P.A, P.lda, avec, m0, P.M, k0, P.K, tid);       // dZ[k*lda + m]
-    } else if (k0 >= P.K1) {
-      stage_kmajor<TC_BM>(Ahi, Alo, P.A2, P.lda2, false, m0, P.M, k0 - P.K1, P.K - P.K1, tid);   // concat tail
-    } else {
-      stage_kmajor<TC_BM>(Ahi, Alo, P.A, P.lda, avec, m0, P.M, k0, P.K1, tid);
+    // the other stage is reused by chunk c+1: wait until the MMAs of chunk c-1 have drained it, then
+    // let the TMA of chunk c+1 fly while this chunk is staged / split / multiplied
+    if (c + 1 < nchunks) {
+      if (c + 1 >= TC_STAGES) mbar_wait(&empty[(c + 1) % TC_STAGES], (((c + 1) / TC_STAGES) - 1) & 1);
+      if (tid == 0 && (a_tma || b_tma)) issue_tma(c + 1);
     }
-    // ---- B -------------------------------------------------------------------------------------
-    if (B_T) stage_transposed<TC_BN>(Bhi, Blo, P.Bm, P.ldb, bvec, n0, P.N, k0, P.K, tid);  // B[k*ldb + n]
-    else stage_kmajor<TC_BN>(Bhi, Blo, P.Bm, P.ldb, bvec, n0, P.N, k0, P.K, tid);        // W[n*ldb + k]
+    const bool a_now = a_tma && k0 < P.K1;
+    // ---- thread-staged operands -----------------------------------------------------------------
+    if (!a_now) {
+      if (A_T) stage_transposed<TC_BM>(Ahi, Alo, P.A, P.lda, avec, m0, P.M, k0, P.K, tid);              // dZ[k*lda + m]
+      else if (k0 >= P.K1) stage_kmajor<TC_BM>(Ahi, Alo, P.A2, P.lda2, false, m0, P.M, k0 - P.K1, P.K - P.K1, tid);
+      else stage_kmajor<TC_BM>(Ahi, Alo, P.A, P.lda, avec, m0, P.M, k0, P.K1, tid);
+    }
+    if (!b_tma) {
+      if (B_T) stage_transposed<TC_BN>(Bhi, Blo, P.Bm, P.ldb, bvec, n0, P.N, k0, P.K, tid);             // B[k*ldb + n]
+      else stage_kmajor<TC_BN>(Bhi, Blo, P.Bm, P.ldb, bvec, n0, P.N, k0, P.K, tid);                     // W[n*ldb + k]
+    }
+    // ---- TMA-fed operands: wait for the bytes, split hi/lo in place --------------------------------
+    if (a_now || b_tma) {
+      mbar_wait(&full[st], full_parity[st]);
+      full_parity[st] ^= 1u;
+      if (passes > 1) {
+        if (a_now) split_in_place<A_BYTES>(Ahi, Alo, tid);
+        if (b_tma) split_in_place<B_BYTES>(Bhi, Blo, tid);
+      }
+    }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -180,7 +227,7 @@ __device__ __forceinline__ void tc_tile(const GemmProblem& P, uint8_t* smem, uin
 __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ GemmBatch batch, int passes) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bars[TC_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_base_s;
 
   int pi = 0;
@@ -193,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
 
   if (threadIdx.x < 32) tmem_alloc(&tmem_base_s, 32);
   if (threadIdx.x == 32) {
-    for (int i = 0; i < TC_STAGES + 1; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < TC_NBARS; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   tc_fence_before_sync();
@@ -201,13 +248,60 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
 
-  if (P.mode == GEMM_FWD) tc_tile<GEMM_FWD>(P, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
-  else if (P.mode == GEMM_DX) tc_tile<GEMM_DX>(P, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
-  else tc_tile<GEMM_DW>(P, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
+  const CUtensorMap* tmA = &batch.tmap_a[pi];
+  const CUtensorMap* tmB = &batch.tmap_b[pi];
+  if (P.mode == GEMM_FWD) tc_tile<GEMM_FWD>(P, tmA, tmB, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
+  else if (P.mode == GEMM_DX) tc_tile<GEMM_DX>(P, tmA, tmB, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
+  else tc_tile<GEMM_DW>(P, tmA, tmB, smem, bars, tmem_d, tm * TC_BM, tn * TC_BN, tn, passes);
 
   tc_fence_before_sync();
   __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc(tmem_d, 32);
+}
+
+// ---- host: TMA descriptors -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// [rows x inner] fp32, row pitch ld floats, box = 32 x box_rows, 128-B swizzle, zero fill out of bounds
+static bool encode_kmajor(CUtensorMap* tm, const float* base, int inner, int rows, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cuuint64_t(inner), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
+  cuuint32_t box[2] = {32, cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool tma_ok(const float* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0; }
+
+// Decide per operand whether TMA may fetch it (K-contiguous source, 16-B aligned rows) and encode the maps.
+void gemm_tc_prepare(GemmBatch& b) {
+  static const bool disabled = getenv("D4PG_NO_TMA") != nullptr;
+  for (int i = 0; i < b.n; ++i) {
+    GemmProblem& p = b.p[i];
+    p.flags &= ~(GEMM_A_TMA | GEMM_B_TMA);
+    if (disabled) continue;
+    if (p.mode != GEMM_DW && tma_ok(p.A, p.lda) && encode_kmajor(&b.tmap_a[i], p.A, p.K1, p.M, p.lda, TC_BM))
+      p.flags |= GEMM_A_TMA;
+    if (p.mode == GEMM_FWD && tma_ok(p.Bm, p.ldb) && encode_kmajor(&b.tmap_b[i], p.Bm, p.K, p.N, p.ldb, TC_BN))
+      p.flags |= GEMM_B_TMA;
+  }
 }
 
 int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {

@@ -64,6 +64,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- TMA ---------------------------------------------------------------------------------------
+// 2-D tiled bulk tensor load global -> shared (SWIZZLE_128B encoded in the tensor map), completion
+// signalled on an mbarrier by byte count.  c0 = inner (contiguous) coordinate, c1 = row coordinate.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64-bit), SWIZZLE_128B layouts only:
 //   [0,14)  start address >> 4      [16,30) leading-dim byte offset >> 4

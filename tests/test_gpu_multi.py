@@ -1,0 +1,21 @@
+"""Multi-GPU data-parallel parity (needs >= 2 GPUs; skipped on single-GPU boxes)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_data_parallel_two_ranks_match_single_big_batch_oracle(precision):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, D4PG_PRECISION=precision)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "dp_worker.py")]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-3000:]
