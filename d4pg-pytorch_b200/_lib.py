@@ -26,7 +26,7 @@ class D4PGError(RuntimeError):
 
 
 class NetLayout(C.Structure):
-    _fields_ = [("offsets", C.c_int64 * 8), ("sizes", C.c_int64 * 8), ("total", C.c_int64)]
+    _fields_ = [("offsets", C.c_int64 * 8), ("sizes", C.c_int64 * 8), ("pitch", C.c_int64 * 4), ("total", C.c_int64)]
 
 
 class LearnerConfig(C.Structure):
@@ -92,7 +92,7 @@ _PROTOS = {
     "d4pg_learner_destroy": (C.c_int32, [_P]),
     "d4pg_learner_step": (C.c_int32, [_P, _P]),
     "d4pg_learner_run": (C.c_int32, [_P, C.c_int32, _P]),
-    "d4pg_learner_tensor": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "d4pg_learner_tensor": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "d4pg_learner_profile_step": (C.c_int32, [_P, _P, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "d4pg_learner_steps_done": (C.c_int64, [_P]),
     "d4pg_learner_kernels_per_step": (C.c_int32, [_P]),
@@ -157,10 +157,10 @@ def stream_ptr():
 def actor_layout(obs_dim, act_dim):
     out = NetLayout()
     check(lib().d4pg_actor_layout(obs_dim, act_dim, C.byref(out)), "d4pg_actor_layout")
-    return list(out.offsets), list(out.sizes), int(out.total)
+    return list(out.offsets), list(out.sizes), int(out.total), list(out.pitch)
 
 
 def critic_layout(obs_dim, act_dim, n_atoms):
     out = NetLayout()
     check(lib().d4pg_critic_layout(obs_dim, act_dim, n_atoms, C.byref(out)), "d4pg_critic_layout")
-    return list(out.offsets), list(out.sizes), int(out.total)
+    return list(out.offsets), list(out.sizes), int(out.total), list(out.pitch)

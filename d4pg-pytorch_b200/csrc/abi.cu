@@ -18,8 +18,8 @@ static NetDims make_dims(const int* in, const int* out) {
   NetDims d{};
   int64_t off = 0;
   for (int l = 0; l < 4; ++l) {
-    d.in[l] = in[l]; d.out[l] = out[l];
-    d.w_off[l] = off; off = align4(off + int64_t(in[l]) * out[l]);
+    d.in[l] = in[l]; d.out[l] = out[l]; d.ld[l] = pitch4(in[l]);
+    d.w_off[l] = off; off = align4(off + int64_t(d.ld[l]) * out[l]);
     d.b_off[l] = off; off = align4(off + out[l]);
   }
   d.total = off;
@@ -40,7 +40,7 @@ NetDims critic_dims(int obs_dim, int act_dim, int n_atoms) {
 
 static void fill_layout(const NetDims& d, d4pg_net_layout_t* out) {
   for (int l = 0; l < 4; ++l) {
-    out->offsets[2 * l] = d.w_off[l]; out->sizes[2 * l] = int64_t(d.in[l]) * d.out[l];
+    out->offsets[2 * l] = d.w_off[l]; out->sizes[2 * l] = int64_t(d.ld[l]) * d.out[l]; out->pitch[l] = d.ld[l];
     out->offsets[2 * l + 1] = d.b_off[l]; out->sizes[2 * l + 1] = d.out[l];
   }
   out->total = d.total;
@@ -101,7 +101,7 @@ extern "C" int32_t d4pg_actor_forward(const float* params, int32_t obs_dim, int3
   const int epi[4] = {EPI_BIAS_RELU, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_TANH};
   for (int l = 0; l < 4; ++l) {
     GemmBatch b; gemm_batch_begin(b);
-    gemm_batch_add(b, gemm_fwd(X[l], d.in[l], nullptr, 0, 0, params + d.w_off[l], d.in[l], params + d.b_off[l],
+    gemm_batch_add(b, gemm_fwd(X[l], d.in[l], nullptr, 0, 0, params + d.w_off[l], d.ld[l], params + d.b_off[l],
                                Y[l], d.out[l], B, d.out[l], d.in[l], epi[l]));
     int rc = gemm_launch(b, precision, st);
     if (rc) return rc;
@@ -125,10 +125,10 @@ extern "C" int32_t d4pg_critic_forward(const float* params, int32_t obs_dim, int
   int rc;
   GemmBatch b;
   gemm_batch_begin(b);
-  gemm_batch_add(b, gemm_fwd(s, obs_dim, nullptr, 0, 0, params + d.w_off[0], d.in[0], params + d.b_off[0], h1, H, B, H, obs_dim, EPI_BIAS_RELU));
+  gemm_batch_add(b, gemm_fwd(s, obs_dim, nullptr, 0, 0, params + d.w_off[0], d.ld[0], params + d.b_off[0], h1, H, B, H, obs_dim, EPI_BIAS_RELU));
   if ((rc = gemm_launch(b, precision, st))) return rc;
   gemm_batch_begin(b);
-  gemm_batch_add(b, gemm_fwd(h1, H, a, act_dim, H, params + d.w_off[1], d.in[1], params + d.b_off[1], h2, H, B, H, H + act_dim, EPI_BIAS_RELU));
+  gemm_batch_add(b, gemm_fwd(h1, H, a, act_dim, H, params + d.w_off[1], d.ld[1], params + d.b_off[1], h2, H, B, H, H + act_dim, EPI_BIAS_RELU));
   if ((rc = gemm_launch(b, precision, st))) return rc;
   gemm_batch_begin(b);
   gemm_batch_add(b, gemm_fwd(h2, H, nullptr, 0, 0, params + d.w_off[2], H, params + d.b_off[2], h3, H, B, H, H, EPI_BIAS_RELU));

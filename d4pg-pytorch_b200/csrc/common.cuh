@@ -77,9 +77,12 @@ struct Philox {
 // ---- network layout ------------------------------------------------------------------
 struct NetDims {
   int in[4], out[4];        // per layer fc1, fc2, fc2_2, fc3
+  int ld[4];                // row pitch of each weight matrix in floats: in[] rounded up to 4 (16-B rows,
+                            // so every operand is TMA- and float4-addressable); pad columns stay zero
   int64_t w_off[4], b_off[4];
   int64_t total;
 };
+__host__ __device__ static inline int pitch4(int x) { return (x + 3) & ~3; }
 NetDims actor_dims(int obs_dim, int act_dim);
 NetDims critic_dims(int obs_dim, int act_dim, int n_atoms);
 

@@ -12,6 +12,7 @@ struct HeadsArgs {
   const float* target_logits; const float* q_logits; const float* pi_logits;
   const double* rewards; const uint8_t* dones;
   int B, N; int flags;
+  int ld;                 // row pitch (floats) of every [B,N] array (>= N)
   double v_min, v_max, delta, discount, prio_eps;
   float grad_scale;
   float* m; int32_t* bins_l; int32_t* bins_u; float* target_probs; float* q_probs;
@@ -23,7 +24,7 @@ int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st);
 int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
                    uint64_t seed, LearnerClock* clock, const ClockParams& cp,
                    int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
-                   cudaStream_t st);
+                   int ld_obs, int ld_act, cudaStream_t st);
 int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st);
 int comm_allreduce(d4pg_comm* c, float* buf, int64_t n, cudaStream_t st);
 

@@ -38,26 +38,28 @@ struct Workspace {
   int64_t total;
 };
 
+// Every 2-D plane has a row pitch that is a multiple of 4 floats (16-B rows): |s|=17 -> 20,
+// |a|=6 -> 8, N=51 -> 52.  That makes every GEMM operand TMA- and float4-addressable.
 static Workspace carve(float* base, int B, int S, int A, int N) {
   Workspace w{};
   int64_t off = 0;
   auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
-  const int H = D4PG_HIDDEN;
-  w.s = take(int64_t(B) * S); w.a = take(int64_t(B) * A); w.s2 = take(int64_t(B) * S);
+  const int H = D4PG_HIDDEN, Sp = pitch4(S), Ap = pitch4(A), Np = pitch4(N);
+  w.s = take(int64_t(B) * Sp); w.a = take(int64_t(B) * Ap); w.s2 = take(int64_t(B) * Sp);
   w.r = reinterpret_cast<double*>(take(int64_t(B) * 2));
   w.done = reinterpret_cast<uint8_t*>(take((B + 3) / 4));
   for (int k = 0; k < 5; ++k) {
     if (k != 4) w.h1[k] = take(int64_t(B) * H);
     w.h2[k] = take(int64_t(B) * H); w.h3[k] = take(int64_t(B) * H);
   }
-  w.out[0] = take(int64_t(B) * A); w.out[3] = take(int64_t(B) * A);
-  w.out[1] = take(int64_t(B) * N); w.out[2] = take(int64_t(B) * N); w.out[4] = take(int64_t(B) * N);
-  w.m = take(int64_t(B) * N); w.q_probs = take(int64_t(B) * N); w.target_probs = take(int64_t(B) * N);
-  w.dlogits_q = take(int64_t(B) * N); w.dlogits_pi = take(int64_t(B) * N);
+  w.out[0] = take(int64_t(B) * Ap); w.out[3] = take(int64_t(B) * Ap);
+  w.out[1] = take(int64_t(B) * Np); w.out[2] = take(int64_t(B) * Np); w.out[4] = take(int64_t(B) * Np);
+  w.m = take(int64_t(B) * Np); w.q_probs = take(int64_t(B) * Np); w.target_probs = take(int64_t(B) * Np);
+  w.dlogits_q = take(int64_t(B) * Np); w.dlogits_pi = take(int64_t(B) * Np);
   w.loss_rows = take(B); w.pi_rows = take(B);
   w.c_dz22 = take(int64_t(B) * H); w.c_dz2 = take(int64_t(B) * H); w.c_dz1 = take(int64_t(B) * H);
   w.p_dz22 = take(int64_t(B) * H); w.p_dz2 = take(int64_t(B) * H);
-  w.a_dz3 = take(int64_t(B) * A); w.a_dz22 = take(int64_t(B) * H); w.a_dh2 = take(int64_t(B) * H);
+  w.a_dz3 = take(int64_t(B) * Ap); w.a_dz22 = take(int64_t(B) * H); w.a_dh2 = take(int64_t(B) * H);
   w.a_dz1 = take(int64_t(B) * H);
   w.clock = reinterpret_cast<LearnerClock*>(take(sizeof(LearnerClock) / 4 + 4));
   w.total = off;
@@ -94,6 +96,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   Workspace& w = L->ws;
   const NetDims& da = L->da; const NetDims& dc = L->dc;
   const int B = c.batch, S = c.obs_dim, A = c.act_dim, N = c.n_atoms, H = D4PG_HIDDEN;
+  const int Sp = pitch4(S), Ap = pitch4(A), Np = pitch4(N);          // activation row pitches
+  const int* la = da.ld; const int* lc = dc.ld;                        // weight row pitches per layer
   int rc; int nk = 0;
 #define RUN(expr)                                                                          \
   do {                                                                                     \
@@ -116,53 +120,53 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   RUN(learner_sample(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
                      (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
                      c.philox_seed, w.clock, cp,
-                     b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, st));
+                     b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, Sp, Ap, st));
 
   const float* Wa = b.actor; const float* Wat = b.actor_target; const float* Wc = b.critic; const float* Wct = b.critic_target;
   GemmBatch g;
   // 2. forward level 1: fc1 of actor_target(s'), critic_target(s'), critic(s), actor(s)
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_fwd(w.s2, S, nullptr, 0, 0, Wat + da.w_off[0], S, Wat + da.b_off[0], w.h1[0], H, B, H, S, EPI_BIAS_RELU));
-  gemm_batch_add(g, gemm_fwd(w.s2, S, nullptr, 0, 0, Wct + dc.w_off[0], S, Wct + dc.b_off[0], w.h1[1], H, B, H, S, EPI_BIAS_RELU));
-  gemm_batch_add(g, gemm_fwd(w.s, S, nullptr, 0, 0, Wc + dc.w_off[0], S, Wc + dc.b_off[0], w.h1[2], H, B, H, S, EPI_BIAS_RELU));
-  gemm_batch_add(g, gemm_fwd(w.s, S, nullptr, 0, 0, Wa + da.w_off[0], S, Wa + da.b_off[0], w.h1[3], H, B, H, S, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.s2, Sp, nullptr, 0, 0, Wat + da.w_off[0], la[0], Wat + da.b_off[0], w.h1[0], H, B, H, S, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.s2, Sp, nullptr, 0, 0, Wct + dc.w_off[0], lc[0], Wct + dc.b_off[0], w.h1[1], H, B, H, S, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.s, Sp, nullptr, 0, 0, Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], w.h1[2], H, B, H, S, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.s, Sp, nullptr, 0, 0, Wa + da.w_off[0], la[0], Wa + da.b_off[0], w.h1[3], H, B, H, S, EPI_BIAS_RELU));
   RUN(gemm_launch(g, c.precision, st));
   // level 2: fc2 (actor: no activation, models.py:36; critic: cat(h1, a) + relu, models.py:80)
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_fwd(w.h1[0], H, nullptr, 0, 0, Wat + da.w_off[1], H, Wat + da.b_off[1], w.h2[0], H, B, H, H, EPI_BIAS));
-  gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.a, A, H, Wc + dc.w_off[1], H + A, Wc + dc.b_off[1], w.h2[2], H, B, H, H + A, EPI_BIAS_RELU));
-  gemm_batch_add(g, gemm_fwd(w.h1[3], H, nullptr, 0, 0, Wa + da.w_off[1], H, Wa + da.b_off[1], w.h2[3], H, B, H, H, EPI_BIAS));
+  gemm_batch_add(g, gemm_fwd(w.h1[0], H, nullptr, 0, 0, Wat + da.w_off[1], la[1], Wat + da.b_off[1], w.h2[0], H, B, H, H, EPI_BIAS));
+  gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.a, Ap, H, Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], w.h2[2], H, B, H, H + A, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h1[3], H, nullptr, 0, 0, Wa + da.w_off[1], la[1], Wa + da.b_off[1], w.h2[3], H, B, H, H, EPI_BIAS));
   RUN(gemm_launch(g, c.precision, st));
   // level 3: fc2_2 + relu
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_fwd(w.h2[0], H, nullptr, 0, 0, Wat + da.w_off[2], H, Wat + da.b_off[2], w.h3[0], H, B, H, H, EPI_BIAS_RELU));
-  gemm_batch_add(g, gemm_fwd(w.h2[2], H, nullptr, 0, 0, Wc + dc.w_off[2], H, Wc + dc.b_off[2], w.h3[2], H, B, H, H, EPI_BIAS_RELU));
-  gemm_batch_add(g, gemm_fwd(w.h2[3], H, nullptr, 0, 0, Wa + da.w_off[2], H, Wa + da.b_off[2], w.h3[3], H, B, H, H, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h2[0], H, nullptr, 0, 0, Wat + da.w_off[2], la[2], Wat + da.b_off[2], w.h3[0], H, B, H, H, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h2[2], H, nullptr, 0, 0, Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], w.h3[2], H, B, H, H, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h2[3], H, nullptr, 0, 0, Wa + da.w_off[2], la[2], Wa + da.b_off[2], w.h3[3], H, B, H, H, EPI_BIAS_RELU));
   RUN(gemm_launch(g, c.precision, st));
   // level 4: fc3 (actor: tanh; critic: logits)
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_fwd(w.h3[0], H, nullptr, 0, 0, Wat + da.w_off[3], H, Wat + da.b_off[3], w.out[0], A, B, A, H, EPI_BIAS_TANH));
-  gemm_batch_add(g, gemm_fwd(w.h3[2], H, nullptr, 0, 0, Wc + dc.w_off[3], H, Wc + dc.b_off[3], w.out[2], N, B, N, H, EPI_BIAS));
-  gemm_batch_add(g, gemm_fwd(w.h3[3], H, nullptr, 0, 0, Wa + da.w_off[3], H, Wa + da.b_off[3], w.out[3], A, B, A, H, EPI_BIAS_TANH));
+  gemm_batch_add(g, gemm_fwd(w.h3[0], H, nullptr, 0, 0, Wat + da.w_off[3], la[3], Wat + da.b_off[3], w.out[0], Ap, B, A, H, EPI_BIAS_TANH));
+  gemm_batch_add(g, gemm_fwd(w.h3[2], H, nullptr, 0, 0, Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], w.out[2], Np, B, N, H, EPI_BIAS));
+  gemm_batch_add(g, gemm_fwd(w.h3[3], H, nullptr, 0, 0, Wa + da.w_off[3], la[3], Wa + da.b_off[3], w.out[3], Ap, B, A, H, EPI_BIAS_TANH));
   RUN(gemm_launch(g, c.precision, st));
   // level 5: critic_target.fc2([h1t, a_t(s')]) and critic.fc2([h1, actor(s)]) (h1 of the critic is reused)
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_fwd(w.h1[1], H, w.out[0], A, H, Wct + dc.w_off[1], H + A, Wct + dc.b_off[1], w.h2[1], H, B, H, H + A, EPI_BIAS_RELU));
-  gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.out[3], A, H, Wc + dc.w_off[1], H + A, Wc + dc.b_off[1], w.h2[4], H, B, H, H + A, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h1[1], H, w.out[0], Ap, H, Wct + dc.w_off[1], lc[1], Wct + dc.b_off[1], w.h2[1], H, B, H, H + A, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.out[3], Ap, H, Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], w.h2[4], H, B, H, H + A, EPI_BIAS_RELU));
   RUN(gemm_launch(g, c.precision, st));
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_fwd(w.h2[1], H, nullptr, 0, 0, Wct + dc.w_off[2], H, Wct + dc.b_off[2], w.h3[1], H, B, H, H, EPI_BIAS_RELU));
-  gemm_batch_add(g, gemm_fwd(w.h2[4], H, nullptr, 0, 0, Wc + dc.w_off[2], H, Wc + dc.b_off[2], w.h3[4], H, B, H, H, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h2[1], H, nullptr, 0, 0, Wct + dc.w_off[2], lc[2], Wct + dc.b_off[2], w.h3[1], H, B, H, H, EPI_BIAS_RELU));
+  gemm_batch_add(g, gemm_fwd(w.h2[4], H, nullptr, 0, 0, Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], w.h3[4], H, B, H, H, EPI_BIAS_RELU));
   RUN(gemm_launch(g, c.precision, st));
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_fwd(w.h3[1], H, nullptr, 0, 0, Wct + dc.w_off[3], H, Wct + dc.b_off[3], w.out[1], N, B, N, H, EPI_BIAS));
-  gemm_batch_add(g, gemm_fwd(w.h3[4], H, nullptr, 0, 0, Wc + dc.w_off[3], H, Wc + dc.b_off[3], w.out[4], N, B, N, H, EPI_BIAS));
+  gemm_batch_add(g, gemm_fwd(w.h3[1], H, nullptr, 0, 0, Wct + dc.w_off[3], lc[3], Wct + dc.b_off[3], w.out[1], Np, B, N, H, EPI_BIAS));
+  gemm_batch_add(g, gemm_fwd(w.h3[4], H, nullptr, 0, 0, Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], w.out[4], Np, B, N, H, EPI_BIAS));
   RUN(gemm_launch(g, c.precision, st));
 
   // 3. heads: softmaxes, projection, CE loss, td, priorities, logit gradients (ddpg.py:214-222,236-238)
   HeadsArgs ha{};
   ha.target_logits = w.out[1]; ha.q_logits = w.out[2]; ha.pi_logits = w.out[4];
-  ha.rewards = w.r; ha.dones = w.done; ha.B = B; ha.N = N; ha.flags = 0;
+  ha.rewards = w.r; ha.dones = w.done; ha.B = B; ha.N = N; ha.flags = 0; ha.ld = Np;
   ha.v_min = c.v_min; ha.v_max = c.v_max; ha.delta = (c.v_max - c.v_min) / double(N - 1);
   // live projection discounts with gamma even for n_steps>1; mode 1 uses gamma**n (ddpg.py:24)
   ha.discount = (c.proj_mode == 1) ? pow(c.gamma, double(c.n_steps)) : c.gamma; ha.prio_eps = c.prio_eps;
@@ -185,42 +189,42 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   // 5. backward.  "c_" = critic-loss pass, "p_" = policy pass through the critic, "a_" = actor.
   // level B1: through critic.fc3
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_dx(w.dlogits_q, N, Wc + dc.w_off[3], H, w.c_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[2], H));
-  gemm_batch_add(g, gemm_dx(w.dlogits_pi, N, Wc + dc.w_off[3], H, w.p_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[4], H));
-  gemm_batch_add(g, gemm_dw(w.dlogits_q, N, w.h3[2], H, Gc + dc.w_off[3], H, Gc + dc.b_off[3], N, H, B));
+  gemm_batch_add(g, gemm_dx(w.dlogits_q, Np, Wc + dc.w_off[3], lc[3], w.c_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[2], H));
+  gemm_batch_add(g, gemm_dx(w.dlogits_pi, Np, Wc + dc.w_off[3], lc[3], w.p_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[4], H));
+  gemm_batch_add(g, gemm_dw(w.dlogits_q, Np, w.h3[2], H, Gc + dc.w_off[3], lc[3], Gc + dc.b_off[3], N, H, B));
   RUN(gemm_launch(g, c.precision, st));
   // level B2: through critic.fc2_2
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_dx(w.c_dz22, H, Wc + dc.w_off[2], H, w.c_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[2], H));
-  gemm_batch_add(g, gemm_dx(w.p_dz22, H, Wc + dc.w_off[2], H, w.p_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[4], H));
-  gemm_batch_add(g, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], H, Gc + dc.b_off[2], H, H, B));
+  gemm_batch_add(g, gemm_dx(w.c_dz22, H, Wc + dc.w_off[2], lc[2], w.c_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[2], H));
+  gemm_batch_add(g, gemm_dx(w.p_dz22, H, Wc + dc.w_off[2], lc[2], w.p_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[4], H));
+  gemm_batch_add(g, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], lc[2], Gc + dc.b_off[2], H, H, B));
   RUN(gemm_launch(g, c.precision, st));
   // level B3: through critic.fc2: dh1 (critic loss), d action (policy, tanh' folded in), dW2 = [dz2^T h1 | dz2^T a]
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_dx(w.c_dz2, H, Wc + dc.w_off[1], H + A, w.c_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[2], H));
-  gemm_batch_add(g, gemm_dx(w.p_dz2, H, Wc + dc.w_off[1] + H, H + A, w.a_dz3, A, B, A, H, EPI_TANH_MASK, w.out[3], A));
-  gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], H + A, Gc + dc.b_off[1], H, H, B));
-  gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.a, A, Gc + dc.w_off[1] + H, H + A, nullptr, H, A, B));
+  gemm_batch_add(g, gemm_dx(w.c_dz2, H, Wc + dc.w_off[1], lc[1], w.c_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[2], H));
+  gemm_batch_add(g, gemm_dx(w.p_dz2, H, Wc + dc.w_off[1] + H, lc[1], w.a_dz3, Ap, B, A, H, EPI_TANH_MASK, w.out[3], Ap));
+  gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], lc[1], Gc + dc.b_off[1], H, H, B));
+  gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.a, Ap, Gc + dc.w_off[1] + H, lc[1], nullptr, H, A, B));
   RUN(gemm_launch(g, c.precision, st));
   // level B4: critic.fc1 weights; actor.fc3
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_dw(w.c_dz1, H, w.s, S, Gc + dc.w_off[0], S, Gc + dc.b_off[0], H, S, B));
-  gemm_batch_add(g, gemm_dx(w.a_dz3, A, Wa + da.w_off[3], H, w.a_dz22, H, B, H, A, EPI_RELU_MASK, w.h3[3], H));
-  gemm_batch_add(g, gemm_dw(w.a_dz3, A, w.h3[3], H, Ga + da.w_off[3], H, Ga + da.b_off[3], A, H, B));
+  gemm_batch_add(g, gemm_dw(w.c_dz1, H, w.s, Sp, Gc + dc.w_off[0], lc[0], Gc + dc.b_off[0], H, S, B));
+  gemm_batch_add(g, gemm_dx(w.a_dz3, Ap, Wa + da.w_off[3], la[3], w.a_dz22, H, B, H, A, EPI_RELU_MASK, w.h3[3], H));
+  gemm_batch_add(g, gemm_dw(w.a_dz3, Ap, w.h3[3], H, Ga + da.w_off[3], la[3], Ga + da.b_off[3], A, H, B));
   RUN(gemm_launch(g, c.precision, st));
   // level B5: actor.fc2_2 (its input h2 has no activation -> plain dX)
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_dx(w.a_dz22, H, Wa + da.w_off[2], H, w.a_dh2, H, B, H, H, EPI_NONE, nullptr, 0));
-  gemm_batch_add(g, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], H, Ga + da.b_off[2], H, H, B));
+  gemm_batch_add(g, gemm_dx(w.a_dz22, H, Wa + da.w_off[2], la[2], w.a_dh2, H, B, H, H, EPI_NONE, nullptr, 0));
+  gemm_batch_add(g, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], la[2], Ga + da.b_off[2], H, H, B));
   RUN(gemm_launch(g, c.precision, st));
   // level B6: actor.fc2
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_dx(w.a_dh2, H, Wa + da.w_off[1], H, w.a_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[3], H));
-  gemm_batch_add(g, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], H, Ga + da.b_off[1], H, H, B));
+  gemm_batch_add(g, gemm_dx(w.a_dh2, H, Wa + da.w_off[1], la[1], w.a_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[3], H));
+  gemm_batch_add(g, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], la[1], Ga + da.b_off[1], H, H, B));
   RUN(gemm_launch(g, c.precision, st));
   // level B7: actor.fc1
   gemm_batch_begin(g);
-  gemm_batch_add(g, gemm_dw(w.a_dz1, H, w.s, S, Ga + da.w_off[0], S, Ga + da.b_off[0], H, S, B));
+  gemm_batch_add(g, gemm_dw(w.a_dz1, H, w.s, Sp, Ga + da.w_off[0], la[0], Ga + da.b_off[0], H, S, B));
   RUN(gemm_launch(g, c.precision, st));
 
   // 6. data-parallel gradient exchange: ONE all-reduce over the flat [P_a + P_c] buffer
@@ -368,20 +372,21 @@ extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_ste
   return D4PG_OK;
 }
 
-extern "C" int32_t d4pg_learner_tensor(d4pg_learner_t* L, const char* name, void** ptr, int64_t* count) {
-  D4PG_REQUIRE(L && name && ptr && count, D4PG_EINVAL, "d4pg_learner_tensor: null argument");
+extern "C" int32_t d4pg_learner_tensor(d4pg_learner_t* L, const char* name, void** ptr, int64_t* count, int32_t* ld) {
+  D4PG_REQUIRE(L && name && ptr && count && ld, D4PG_EINVAL, "d4pg_learner_tensor: null argument");
   const Workspace& w = L->ws;
-  const int64_t B = L->cfg.batch, S = L->cfg.obs_dim, A = L->cfg.act_dim, N = L->cfg.n_atoms;
-  struct E { const char* n; void* p; int64_t c; };
+  const int64_t B = L->cfg.batch;
+  const int Sp = pitch4(L->cfg.obs_dim), Ap = pitch4(L->cfg.act_dim), Np = pitch4(L->cfg.n_atoms);
+  struct E { const char* n; void* p; int64_t c; int ld; };
   const E table[] = {
-      {"s", w.s, B * S}, {"a", w.a, B * A}, {"r", w.r, B}, {"s2", w.s2, B * S}, {"done", w.done, B},
-      {"target_logits", w.out[1], B * N}, {"q_logits", w.out[2], B * N}, {"pi_logits", w.out[4], B * N},
-      {"m", w.m, B * N}, {"q_probs", w.q_probs, B * N}, {"target_probs", w.target_probs, B * N},
-      {"dlogits_q", w.dlogits_q, B * N}, {"dlogits_pi", w.dlogits_pi, B * N},
-      {"actor_out", w.out[3], B * A}, {"actor_target_out", w.out[0], B * A},
-      {"loss_rows", w.loss_rows, B}, {"pi_rows", w.pi_rows, B}};
+      {"s", w.s, B * Sp, Sp}, {"a", w.a, B * Ap, Ap}, {"r", w.r, B, 1}, {"s2", w.s2, B * Sp, Sp}, {"done", w.done, B, 1},
+      {"target_logits", w.out[1], B * Np, Np}, {"q_logits", w.out[2], B * Np, Np}, {"pi_logits", w.out[4], B * Np, Np},
+      {"m", w.m, B * Np, Np}, {"q_probs", w.q_probs, B * Np, Np}, {"target_probs", w.target_probs, B * Np, Np},
+      {"dlogits_q", w.dlogits_q, B * Np, Np}, {"dlogits_pi", w.dlogits_pi, B * Np, Np},
+      {"actor_out", w.out[3], B * Ap, Ap}, {"actor_target_out", w.out[0], B * Ap, Ap},
+      {"loss_rows", w.loss_rows, B, 1}, {"pi_rows", w.pi_rows, B, 1}};
   for (const E& e : table)
-    if (strcmp(e.n, name) == 0) { *ptr = e.p; *count = e.c; return D4PG_OK; }
+    if (strcmp(e.n, name) == 0) { *ptr = e.p; *count = e.c; *ld = e.ld; return D4PG_OK; }
   set_error("d4pg_learner_tensor: unknown tensor '%s'", name);
   return D4PG_EINVAL;
 }

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
   const int row = blockIdx.x * HEAD_WARPS + warp;
   if (row >= a.B) return;
   const int N = a.N;
-  const size_t ro = size_t(row) * N;
+  const size_t ro = size_t(row) * a.ld;
 
   // ---- target distribution ------------------------------------------------------------
   float p[NT];
@@ -253,7 +253,7 @@ extern "C" int32_t d4pg_proj_loss(const float* target_logits, const float* q_log
   D4PG_REQUIRE(v_max > v_min, D4PG_EINVAL, "d4pg_proj_loss: v_max <= v_min");
   HeadsArgs a;
   a.target_logits = target_logits; a.q_logits = q_logits; a.pi_logits = pi_logits;
-  a.rewards = rewards; a.dones = dones; a.B = B; a.N = N; a.flags = flags;
+  a.rewards = rewards; a.dones = dones; a.B = B; a.N = N; a.flags = flags; a.ld = N;
   a.v_min = v_min; a.v_max = v_max;
   a.delta = (v_max - v_min) / double(N - 1);        // ddpg.py:46
   a.discount = discount; a.prio_eps = prio_eps; a.grad_scale = grad_scale;

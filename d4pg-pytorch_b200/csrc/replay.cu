@@ -87,6 +87,7 @@ struct SampleArgs {
   ClockParams clock_params;         //   block 0 also derives this step's Adam scalars into it
   const float* obs; const float* act; const double* rew; const float* obs2; const uint8_t* done;
   int obs_dim, act_dim; int B;
+  int ld_obs, ld_act;               // row pitch of the gathered s/s2 and a batches (0 = dense)
   const int32_t* idx_in;            // gather-only mode when non-null
   int uniform_mode;                 // 1: idx = floor(u*len) (device-side uniform replay, with replacement)
   int32_t* idx; float* weights;
@@ -156,15 +157,16 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const Sam
   __syncthreads();
   // coalesced row gathers: consecutive threads walk consecutive features of one transition
   const int od = a.obs_dim, ad = a.act_dim;
+  const int lo = a.ld_obs ? a.ld_obs : od, la = a.ld_act ? a.ld_act : ad;
   for (int e = t; e < nrows * od; e += SAMPLE_THREADS) {
     const int rr = e / od, c = e - rr * od;
-    const size_t src = size_t(idx_s[rr]) * od + c, dst = size_t(row0 + rr) * od + c;
+    const size_t src = size_t(idx_s[rr]) * od + c, dst = size_t(row0 + rr) * lo + c;
     a.s[dst] = __ldg(a.obs + src);
     a.s2[dst] = __ldg(a.obs2 + src);
   }
   for (int e = t; e < nrows * ad; e += SAMPLE_THREADS) {
     const int rr = e / ad, c = e - rr * ad;
-    a.a[size_t(row0 + rr) * ad + c] = __ldg(a.act + size_t(idx_s[rr]) * ad + c);
+    a.a[size_t(row0 + rr) * la + c] = __ldg(a.act + size_t(idx_s[rr]) * ad + c);
   }
 }
 
@@ -356,8 +358,9 @@ int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
 int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
                    uint64_t seed, LearnerClock* clock, const ClockParams& cp,
                    int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
-                   cudaStream_t st) {
+                   int ld_obs, int ld_act, cudaStream_t st) {
   SampleArgs sa{};
+  sa.ld_obs = ld_obs; sa.ld_act = ld_act;
   sa.uniforms = uniforms; sa.seed = seed; sa.counter = 0; sa.clock = clock; sa.clock_params = cp;
   sa.beta = 1.f; sa.B = B; sa.idx = idx; sa.weights = prioritized ? weights : nullptr;
   sa.s = s; sa.a = a; sa.r = r; sa.s2 = s2; sa.d = d;

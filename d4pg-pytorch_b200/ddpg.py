@@ -113,15 +113,18 @@ class _Learner(object):
                                                    _lib.stream_ptr()), "d4pg_learner_set_counters")
 
     def tensor(self, name, dtype=torch.float32):
-        p, n = C.c_void_p(), C.c_int64()
-        _lib.check(_lib.lib().d4pg_learner_tensor(self.handle, name.encode(), C.byref(p), C.byref(n)), "d4pg_learner_tensor")
+        """Copy of a named intermediate.  2-D planes come back as [rows, pitch] (pitch >= width)."""
+        p, n, ld = C.c_void_p(), C.c_int64(), C.c_int32()
+        _lib.check(_lib.lib().d4pg_learner_tensor(self.handle, name.encode(), C.byref(p), C.byref(n), C.byref(ld)),
+                   "d4pg_learner_tensor")
         esize = {torch.float32: 4, torch.float64: 8, torch.uint8: 1}[dtype]
         typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.uint8: "|u1"}[dtype]
 
         class _Arr(object):
             __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": typestr, "data": (int(p.value), False),
                                         "version": 2, "strides": (esize,)}
-        return torch.as_tensor(_Arr(), device=self.workspace.device).clone()
+        t = torch.as_tensor(_Arr(), device=self.workspace.device).clone()
+        return t.view(-1, ld.value) if ld.value > 1 else t
 
     def close(self):
         if self.handle is not None:
@@ -335,6 +338,8 @@ class DDPG:
         L = self._learner
         L.stream.synchronize()
         t = L.tensor(name, dtype)
+        if shape is not None and t.dim() == 2:
+            return t[:, :shape[1]].contiguous()          # drop the pad columns of the row pitch
         return t.view(*shape) if shape is not None else t
 
     def profile_step(self, global_model=None):

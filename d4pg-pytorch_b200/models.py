@@ -27,14 +27,17 @@ def fanin_init(size, fanin=None):
 
 
 def _layout_py(dims):
-    """Pure-Python mirror of the C layout rule (4-float aligned tensors) for GPU-less hosts."""
-    offs, sizes, off = [], [], 0
+    """Pure-Python mirror of the C layout rule (d4pg_*_layout): weight rows are padded to a pitch
+    of 4 floats (16-B rows, TMA / float4 addressable), every tensor starts 4-float aligned."""
+    offs, sizes, pitches, off = [], [], [], 0
     for fin, fout in dims:
-        for n in (fin * fout, fout):
+        pitch = (fin + 3) & ~3
+        pitches.append(pitch)
+        for n in (pitch * fout, fout):
             offs.append(off)
             sizes.append(n)
             off = (off + n + 3) & ~3
-    return offs, sizes, off
+    return offs, sizes, off, pitches
 
 
 class _LinearView(nn.Module):
@@ -53,7 +56,7 @@ class _FlatNet(nn.Module):
     def __init__(self, dims, device=None):
         super().__init__()
         self._dims = list(dims)
-        self._offsets, self._sizes, self._total = _layout_py(self._dims)
+        self._offsets, self._sizes, self._total, self._pitch = _layout_py(self._dims)
         self._device = torch.device(device) if device is not None else default_device()
         self._flat = torch.zeros(self._total, dtype=torch.float32, device=self._device)
         self._flat_grad = None
@@ -65,8 +68,9 @@ class _FlatNet(nn.Module):
     def _views(self, flat):
         out = []
         for i, (fin, fout) in enumerate(self._dims):
-            ow, ob = self._offsets[2 * i], self._offsets[2 * i + 1]
-            out.append((flat[ow:ow + fin * fout].view(fout, fin), flat[ob:ob + fout]))
+            ow, ob, pitch = self._offsets[2 * i], self._offsets[2 * i + 1], self._pitch[i]
+            # [out, in] view with a padded row pitch; the pad columns are never exposed
+            out.append((flat[ow:ow + pitch * fout].view(fout, pitch)[:, :fin], flat[ob:ob + fout]))
         return out
 
     def _bind(self):
@@ -87,6 +91,13 @@ class _FlatNet(nn.Module):
 
     def flat_params(self):
         return self._flat
+
+    def named_grad_views(self):
+        """{state_dict key: view into the flat gradient buffer} (same shapes as the parameters)."""
+        out = {}
+        for name, (w, b) in zip(_LAYER_NAMES, self._views(self.flat_grads())):
+            out[name + ".weight"], out[name + ".bias"] = w, b
+        return out
 
     def flat_grads(self):
         """Flat gradient buffer (allocated on first use); `.grad` of every parameter views it."""

@@ -46,12 +46,15 @@ int32_t     d4pg_device_sm(void);
 /* ---------------------------------------------------------------------------------------
  * Parameter layout.  One flat fp32 buffer per network role, tensors in nn.Module order
  * fc1.weight, fc1.bias, fc2.weight, fc2.bias, fc2_2.weight, fc2_2.bias, fc3.weight, fc3.bias
- * (models.py:18-23 actor, models.py:56-62 critic), nn.Linear row-major [out,in], every
- * tensor start aligned to 4 floats.  `offsets[8]`/`sizes[8]` are in floats.
+ * (models.py:18-23 actor, models.py:56-62 critic), nn.Linear row-major [out,in] with the row
+ * PITCH rounded up to 4 floats (16-B aligned rows: every operand is TMA- and 128-bit addressable;
+ * the pad columns are zero and stay zero), every tensor start aligned to 4 floats.
+ * `offsets[8]` / `sizes[8]` (allocated floats, = out*pitch for weights) / `pitch[4]` are in floats.
  * ------------------------------------------------------------------------------------- */
 typedef struct {
   int64_t offsets[8];
   int64_t sizes[8];
+  int64_t pitch[4];
   int64_t total;      /* padded float count of the network */
 } d4pg_net_layout_t;
 
@@ -229,8 +232,9 @@ int32_t d4pg_learner_step(d4pg_learner_t* h, d4pg_stream_t stream);
 int32_t d4pg_learner_run(d4pg_learner_t* h, int32_t n_steps, d4pg_stream_t stream);
 /* Named intermediate (for parity tests): returns device pointer + element count.
  * names: "s","a","r","s2","done","target_logits","q_logits","pi_logits","m","q_probs",
- *        "target_probs","dlogits_q","dlogits_pi","actor_out","loss_rows","pi_rows" */
-int32_t d4pg_learner_tensor(d4pg_learner_t* h, const char* name, void** ptr, int64_t* count);
+ *        "target_probs","dlogits_q","dlogits_pi","actor_out","loss_rows","pi_rows"
+ * 2-D tensors are stored with a row pitch of `*ld` floats (>= the logical width). */
+int32_t d4pg_learner_tensor(d4pg_learner_t* h, const char* name, void** ptr, int64_t* count, int32_t* ld);
 /* One EAGER (non-graph) step with a CUDA-event pair around every launch; synchronises.
  * ms_out[i] = device time of launch i, names_out[i*name_stride] = its launcher name. */
 int32_t d4pg_learner_profile_step(d4pg_learner_t* h, d4pg_stream_t stream, int32_t max_launches,

@@ -49,8 +49,9 @@ def test_layouts_match_between_python_mirror_and_c():
     for (s, a, n) in ((17, 6, 51), (376, 17, 51), (3, 1, 51), (17, 6, 101)):
         act = d4pg_b200.actor(s, a, device="cpu")
         cri = d4pg_b200.critic(s, a, {"type": "categorical", "v_min": -1., "v_max": 1., "n_atoms": n}, device="cpu")
-        assert (act._offsets, act._sizes, act._total) == _lib.actor_layout(s, a)
-        assert (cri._offsets, cri._sizes, cri._total) == _lib.critic_layout(s, a, n)
+        assert (act._offsets, act._sizes, act._total, act._pitch) == _lib.actor_layout(s, a)
+        assert (cri._offsets, cri._sizes, cri._total, cri._pitch) == _lib.critic_layout(s, a, n)
+        assert all(p % 4 == 0 for p in cri._pitch) and cri._pitch[1] >= 256 + a
         assert sum(p.numel() for p in act.parameters()) == s * 256 + 256 + 2 * (256 * 256 + 256) + 256 * a + a
 
 

@@ -75,13 +75,12 @@ def test_train_steps_vs_reference_golden(tag, use_graph, precision):
             st = loc.replayBuffer._store
             st.sum_tree.copy_(torch.from_numpy(g["tree_sum_%d" % t].astype(np.float32)))
             st.min_tree.copy_(torch.from_numpy(g["tree_min_%d" % t].astype(np.float32)))
-        ga = loc.actor.flat_grads().cpu().numpy()
-        gc = loc.critic.flat_grads().cpu().numpy()
-        for name, net, flat in (("actor", loc.actor, ga), ("critic", loc.critic, gc)):
-            for i, k in enumerate(H.NAMES):
-                off, n = net._offsets[i], net._sizes[i]
-                H.check_compact(g, "g_%s_%s_%d" % (name, k, t), flat[off:off + n], TOL)
-                ref, mine = H.golden_vec(g, "g_%s_%s_%d" % (name, k, t), flat[off:off + n])
+        for name, net in (("actor", loc.actor), ("critic", loc.critic)):
+            gviews = net.named_grad_views()
+            for k in H.NAMES:
+                gk = gviews[k].cpu().numpy().reshape(-1)
+                H.check_compact(g, "g_%s_%s_%d" % (name, k, t), gk, TOL)
+                ref, mine = H.golden_vec(g, "g_%s_%s_%d" % (name, k, t), gk)
                 assert H.rel_l2(mine, ref) <= 1e-4, (name, k, t, H.rel_l2(mine, ref))
                 H.check_params(g, "%s_%s_%d" % (name, k, t), net.state_dict()[k].cpu().numpy())
         # local == global (ddpg.py:247)
@@ -90,13 +89,10 @@ def test_train_steps_vs_reference_golden(tag, use_graph, precision):
     for k in H.NAMES:
         H.check_params(g, "actor_target_%s_%d" % (k, t), loc.actor_target.state_dict()[k].cpu().numpy())
         H.check_params(g, "critic_target_%s_%d" % (k, t), loc.critic_target.state_dict()[k].cpu().numpy())
-    ma, va = oa.moments(glob.actor)
-    mc, vc = oc.moments(glob.critic)
-    for i, k in enumerate(H.NAMES):
-        off, n = loc.actor._offsets[i], loc.actor._sizes[i]
-        H.check_compact(g, "adam_m_actor_%s_%d" % (k, t), ma.cpu().numpy()[off:off + n], 1e-6)
-        off, n = loc.critic._offsets[i], loc.critic._sizes[i]
-        H.check_compact(g, "adam_v_critic_%s_%d" % (k, t), vc.cpu().numpy()[off:off + n], 1e-6)
+    for prm, k in zip(glob.actor.parameters(), H.NAMES):
+        H.check_compact(g, "adam_m_actor_%s_%d" % (k, t), oa.state[prm]["exp_avg"].cpu().numpy().reshape(-1), 1e-6)
+    for prm, k in zip(glob.critic.parameters(), H.NAMES):
+        H.check_compact(g, "adam_v_critic_%s_%d" % (k, t), oc.state[prm]["exp_avg_sq"].cpu().numpy().reshape(-1), 1e-6)
     assert loc.kernels_per_step() > 0
 
 
@@ -130,18 +126,15 @@ def test_config2_full_size_vs_oracle():
         ob.update_priorities(batch[6], out["prio"])
         lc, la = dd.last_losses()
         assert abs(lc - float(out["loss_critic"])) <= TOL and abs(la - float(out["loss_actor"])) <= TOL * abs(la)
-        assert np.abs(dd.critic.flat_grads().cpu().numpy()[:dd.critic._sizes[0]] -
-                      out["grads_critic"]["fc1.weight"].numpy().reshape(-1)).max() <= TOL
         for k in H.NAMES:
             for mine, ref in ((dd.actor.state_dict()[k], lo.actor[k]), (dd.critic.state_dict()[k], lo.critic[k]),
                               (dd.critic_target.state_dict()[k], lo.critic_target[k])):
                 err = (mine.cpu() - ref).abs()
                 assert err.max().item() <= 2.5e-4 and (err > TOL).float().mean().item() <= 0.1, k
-            i = H.NAMES.index(k)
             for net, grads in ((dd.actor, out["grads_actor"]), (dd.critic, out["grads_critic"])):
-                off, n = net._offsets[i], net._sizes[i]
-                assert (net.flat_grads()[off:off + n].cpu() - grads[k].reshape(-1)).abs().max().item() <= TOL, k
-                assert H.rel_l2(net.flat_grads()[off:off + n].cpu().numpy(), grads[k].numpy()) <= 1e-4, k
+                gk = net.named_grad_views()[k].cpu()
+                assert (gk - grads[k]).abs().max().item() <= TOL, k
+                assert H.rel_l2(gk.numpy(), grads[k].numpy()) <= 1e-4, k
 
 
 def test_device_sampling_mode_runs_and_is_deterministic():
