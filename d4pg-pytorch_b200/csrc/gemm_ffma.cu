@@ -11,12 +11,17 @@
 namespace d4pg {
 
 constexpr int BM = 32, BN = 32, KC = 64;
-constexpr int LDS_A = BM + 4;   // multiple of 4 (float4 reads)
-constexpr int LDS_B = BN + 4;
+constexpr int LDS_A = BM;       // dense rows; bank conflicts of the transposed stores are handled by swz()
+constexpr int LDS_B = BN;
 constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_WARPS = GEMM_THREADS / 32;
 constexpr int KW = KC / GEMM_WARPS;                  // k values per warp per chunk (intra-CTA split-K)
 constexpr int PER_THREAD = BM * KC / GEMM_THREADS;   // 8 staged elements per thread per operand per chunk
+
+// smem tiles are k-major [kk][32]; the 8 float4 columns of a row are XOR-permuted by (kk>>3)&7 so that
+// the transposed stores of a K-contiguous source (a warp writes one column at 16 different kk) spread
+// over the banks (8-way conflict without it) while float4 reads along a row stay aligned.
+__device__ __forceinline__ int swz(int kk, int idx) { return ((((idx >> 2) ^ (kk >> 3)) & 7) << 2) | (idx & 3); }
 
 // ---- operand staging ---------------------------------------------------------------------------
 // Two source shapes, each with a 128-bit fast path (ncu of the first version: 42 % of all issued
@@ -51,13 +56,13 @@ __device__ __forceinline__ void store_kcontig(float* __restrict__ dst, int lds, 
     for (int q = 0; q < 2; ++q) {
       const int e = tid + q * GEMM_THREADS, row = e >> 4, kk = (e & 15) << 2;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) dst[(kk + c) * lds + row] = r[4 * q + c];
+      for (int c = 0; c < 4; ++c) dst[(kk + c) * lds + swz(kk + c, row)] = r[4 * q + c];
     }
   } else {
 #pragma unroll
     for (int q = 0; q < PER_THREAD; ++q) {
       const int e = tid + q * GEMM_THREADS;
-      dst[(e & 63) * lds + (e >> 6)] = r[q];
+      dst[(e & 63) * lds + swz(e & 63, e >> 6)] = r[q];
     }
   }
 }
@@ -86,13 +91,13 @@ __device__ __forceinline__ void store_rowcontig(float* __restrict__ dst, int lds
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int e = tid + q * GEMM_THREADS, kk = e >> 3, col = (e & 7) << 2;
-      *reinterpret_cast<float4*>(&dst[kk * lds + col]) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+      *reinterpret_cast<float4*>(&dst[kk * lds + swz(kk, col)]) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     }
   } else {
 #pragma unroll
     for (int q = 0; q < PER_THREAD; ++q) {
       const int e = tid + q * GEMM_THREADS;
-      dst[(e >> 5) * lds + (e & 31)] = r[q];
+      dst[(e >> 5) * lds + swz(e >> 5, e & 31)] = r[q];
     }
   }
 }
@@ -175,9 +180,9 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int
 #pragma unroll
     for (int k = 0; k < KW; ++k) {                                              // zero-padded past K
       const int kk = warp * KW + k;
-      const float4 a0 = *reinterpret_cast<const float4*>(&as[kk * LDS_A + r0]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&as[kk * LDS_A + r0 + 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&bs[kk * LDS_B + c0]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&as[kk * LDS_A + swz(kk, r0)]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&as[kk * LDS_A + swz(kk, r0 + 4)]);
+      const float4 b = *reinterpret_cast<const float4*>(&bs[kk * LDS_B + swz(kk, c0)]);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -187,7 +192,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int
     }
     if (want_bias_grad && tid < BM) {
 #pragma unroll 8
-      for (int kk = 0; kk < KC; ++kk) colsum += as[kk * LDS_A + tid];
+      for (int kk = 0; kk < KC; ++kk) colsum += as[kk * LDS_A + swz(kk, tid)];
     }
     if (c + 1 < nchunks) {
       store_A<MODE>(As0 + (cur ^ 1) * KC * LDS_A, tid, ra, avec);
@@ -299,8 +304,7 @@ void gemm_batch_retile(GemmBatch& b, int bm, int bn) {
 }
 int gemm_launch(GemmBatch& b, int precision, cudaStream_t st) {
   if (precision == 0) return gemm_batch_launch(b, st);
-  gemm_batch_retile(b, 128, 32);
-  gemm_tc_prepare(b);
+  gemm_tc_prepare(b);                 // picks the kernel variant and tiles the problems accordingly
   return gemm_tc_batch_launch(b, precision == 1 ? 3 : 1, st);
 }
 int gemm_batch_launch(const GemmBatch& b, cudaStream_t st) {

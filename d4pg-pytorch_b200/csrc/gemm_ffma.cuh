@@ -34,6 +34,8 @@ struct GemmBatch {
   // tcgen05 path only: TMA descriptors of the operands that qualify (16-B aligned rows, K-major)
   alignas(64) CUtensorMap tmap_a[GEMM_MAX_PROBLEMS];
   alignas(64) CUtensorMap tmap_b[GEMM_MAX_PROBLEMS];
+  alignas(64) CUtensorMap tmap_a2[GEMM_MAX_PROBLEMS];   // concatenated tail of A (critic fc2's action columns)
+  int all_tma;                                           // every operand of every problem is TMA-fed -> v2 kernel
 };
 
 // host helpers ---------------------------------------------------------------------------

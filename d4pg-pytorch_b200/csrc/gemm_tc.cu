@@ -259,6 +259,174 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   if (threadIdx.x < 32) tmem_dealloc(tmem_d, 32);
 }
 
+// =====================================================================================================
+// v2: warp-specialised, every operand TMA-fed (needs 16-B row pitches -- the learner's own buffers).
+//   warp 0      : TMA producer (one lane): S-deep ring of raw fp32 chunks, one mbarrier per stage
+//   warp 1      : TMEM owner + the single MMA-issuing lane
+//   warps 2..5  : "converters": split each landed chunk into tf32 hi (in place) / lo (2-stage ring),
+//                 then the epilogue (each warp owns the TMEM lane quadrant warp%4)
+// Operands that are contiguous along the tile dim (dX's W, dW's dZ and X) are loaded with the
+// SWIZZLE_128B_ATOM_32B tensor-map mode and fed to the MMA as MN-major (SWIZZLE_128B_BASE32B
+// descriptors, validated by tests/probe/tc_probe.cu); the split is layout-agnostic (flat float4).
+// =====================================================================================================
+constexpr int T2_BM = 128, T2_BN = 64, T2_KC = 32;
+constexpr int T2_THREADS = 192;
+constexpr int T2_STAGES = 6;
+constexpr uint32_t T2_A_BYTES = T2_BM * 128, T2_B_BYTES = T2_BN * 128;          // 16 KB + 8 KB per chunk
+constexpr uint32_t T2_STAGE = T2_A_BYTES + T2_B_BYTES;
+constexpr uint32_t T2_SMEM = T2_STAGES * T2_STAGE + 2 * T2_STAGE + 1024;
+constexpr int T2_FULL = 0, T2_CONV = T2_STAGES, T2_EMPTY = 2 * T2_STAGES, T2_LOEMPTY = 3 * T2_STAGES,
+              T2_DONE = 3 * T2_STAGES + 2, T2_NBARS = 3 * T2_STAGES + 3;
+
+__global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ GemmBatch batch, int passes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* lo_ring = smem + T2_STAGES * T2_STAGE;
+  __shared__ __align__(8) uint64_t bars[T2_NBARS];
+  __shared__ uint32_t tmem_base_s;
+
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
+    if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
+  const GemmProblem P = batch.p[pi];
+  const int tile = blockIdx.x - P.tile_begin;
+  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+  const int m0 = tm * T2_BM, n0 = tn * T2_BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool a_mn = (P.mode == GEMM_DW), b_mn = (P.mode != GEMM_FWD);
+  const int nchunks = (P.K + T2_KC - 1) / T2_KC;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < T2_NBARS; ++i) mbar_init(&bars[i], (i >= T2_CONV && i < T2_CONV + T2_STAGES) ? 4u : 1u);
+    mbar_fence_init();
+    tma_prefetch_desc(&batch.tmap_a[pi]);
+    tma_prefetch_desc(&batch.tmap_b[pi]);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 64);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    // ================================ TMA producer ==================================================
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % T2_STAGES, k0 = c * T2_KC;
+        if (c >= T2_STAGES) mbar_wait(&bars[T2_EMPTY + s], ((c / T2_STAGES) - 1) & 1);
+        uint8_t* Ad = smem + s * T2_STAGE;
+        uint8_t* Bd = Ad + T2_A_BYTES;
+        uint64_t* full = &bars[T2_FULL + s];
+        mbar_expect_tx(full, T2_STAGE);
+        if (a_mn) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(Ad + j * 4096, &batch.tmap_a[pi], full, m0 + 32 * j, k0);
+        } else if (k0 >= P.K1) {
+          tma_load_2d(Ad, &batch.tmap_a2[pi], full, k0 - P.K1, m0);
+        } else {
+          tma_load_2d(Ad, &batch.tmap_a[pi], full, k0, m0);
+        }
+        if (b_mn) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tma_load_2d(Bd + j * 4096, &batch.tmap_b[pi], full, n0 + 32 * j, k0);
+        } else {
+          tma_load_2d(Bd, &batch.tmap_b[pi], full, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =====================================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(FMT_TF32, a_mn, b_mn, T2_BM, T2_BN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % T2_STAGES, l = c & 1;
+        mbar_wait(&bars[(passes > 1 ? T2_CONV : T2_FULL) + s], (c / T2_STAGES) & 1);
+        tc_fence_after_sync();
+        const uint8_t* Ahi = smem + s * T2_STAGE;
+        const uint8_t* Bhi = Ahi + T2_A_BYTES;
+        const uint8_t* Alo = lo_ring + l * T2_STAGE;
+        const uint8_t* Blo = Alo + T2_A_BYTES;
+#pragma unroll 1
+        for (int p = 0; p < passes; ++p) {
+          const uint8_t* Ap = (p == 2) ? Alo : Ahi;
+          const uint8_t* Bp = (p == 1) ? Blo : Bhi;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = a_mn ? make_smem_desc(smem_u32(Ap + ks * 1024), 4096, 512, 1)
+                                     : make_smem_desc(smem_u32(Ap + ks * 32), 16, 1024, 2);
+            const uint64_t bd = b_mn ? make_smem_desc(smem_u32(Bp + ks * 1024), 4096, 512, 1)
+                                     : make_smem_desc(smem_u32(Bp + ks * 32), 16, 1024, 2);
+            mma_tf32(tmem_d, ad, bd, idesc, (c | p | ks) != 0);
+          }
+        }
+        mma_commit(&bars[T2_EMPTY + s]);
+        if (passes > 1) mma_commit(&bars[T2_LOEMPTY + l]);
+      }
+      mma_commit(&bars[T2_DONE]);
+    }
+  } else {
+    // ================================ converters, then epilogue =======================================
+    const int t2 = tid - 64;                       // 0..127
+    if (passes > 1) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % T2_STAGES, l = c & 1;
+        uint8_t* hi = smem + s * T2_STAGE;
+        uint8_t* lo = lo_ring + l * T2_STAGE;
+        mbar_wait(&bars[T2_FULL + s], (c / T2_STAGES) & 1);
+        if (c >= 2) mbar_wait(&bars[T2_LOEMPTY + l], ((c >> 1) - 1) & 1);
+#pragma unroll 4
+        for (int e = t2; e < int(T2_STAGE / 16); e += 128) {
+          const float4 v = *reinterpret_cast<const float4*>(hi + e * 16);
+          put_split4(hi, lo, uint32_t(e) * 16u, v);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[T2_CONV + s]);
+      }
+    }
+    mbar_wait(&bars[T2_DONE], 0);
+    tc_fence_after_sync();
+    const int quad = warp & 3;
+    const int gi = m0 + quad * 32 + lane;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      float r[32];
+      tmem_ld_32x32(tmem_d + (uint32_t(quad * 32) << 16) + uint32_t(half * 32), r);
+      if (gi < P.M) {
+        const int nb = n0 + half * 32;
+        float* crow = P.C + size_t(gi) * P.ldc + nb;
+        const float* arow = P.aux ? P.aux + size_t(gi) * P.ldaux + nb : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (nb + j >= P.N) break;
+          float x = r[j];
+          switch (P.epi) {
+            case EPI_BIAS: x += __ldg(P.bias + nb + j); break;
+            case EPI_BIAS_RELU: x = fmaxf(x + __ldg(P.bias + nb + j), 0.f); break;
+            case EPI_BIAS_TANH: x = tanhf(x + __ldg(P.bias + nb + j)); break;
+            case EPI_RELU_MASK: x = (__ldg(arow + j) > 0.f) ? x : 0.f; break;
+            case EPI_TANH_MASK: { const float t = __ldg(arow + j); x *= (1.f - t * t); } break;
+            default: break;
+          }
+          crow[j] = x;
+        }
+      }
+    }
+    if (P.mode == GEMM_DW && P.bias_grad != nullptr && tn == 0) {       // bias gradient: column sums of dZ
+      const int m = m0 + t2;
+      if (m < P.M) {
+        float sacc = 0.f;
+        for (int k = 0; k < P.K; ++k) sacc += __ldg(P.A + size_t(k) * P.lda + m);
+        P.bias_grad[m] = sacc;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, 64);
+}
+
 // ---- host: TMA descriptors -------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -288,11 +456,46 @@ static bool encode_kmajor(CUtensorMap* tm, const float* base, int inner, int row
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// [k rows x mn cols] fp32 source that is contiguous along the tile dim: box = 32 mn x 32 k rows,
+// SWIZZLE_128B_ATOM_32B (what the MN-major tf32 UMMA descriptor expects)
+static bool encode_mnmajor(CUtensorMap* tm, const float* base, int mn, int krows, int ld) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cuuint64_t(mn), cuuint64_t(krows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 static bool tma_ok(const float* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0; }
+
+// v2 eligibility: every operand of every problem can be described by a tensor map
+static bool prepare_v2(GemmBatch& b) {
+  static const bool disabled = getenv("D4PG_TC_V1") != nullptr;
+  if (disabled) return false;
+  for (int i = 0; i < b.n; ++i) {
+    const GemmProblem& p = b.p[i];
+    if (!tma_ok(p.A, p.lda) || !tma_ok(p.Bm, p.ldb)) return false;
+    bool ok;
+    if (p.mode == GEMM_DW) ok = encode_mnmajor(&b.tmap_a[i], p.A, p.M, p.K, p.lda);
+    else ok = encode_kmajor(&b.tmap_a[i], p.A, p.K1, p.M, p.lda, T2_BM);
+    if (ok && p.mode == GEMM_FWD && p.K1 < p.K)
+      ok = tma_ok(p.A2, p.lda2) && p.K1 % T2_KC == 0 && encode_kmajor(&b.tmap_a2[i], p.A2, p.K - p.K1, p.M, p.lda2, T2_BM);
+    if (ok) ok = (p.mode == GEMM_FWD) ? encode_kmajor(&b.tmap_b[i], p.Bm, p.K, p.N, p.ldb, T2_BN)
+                                      : encode_mnmajor(&b.tmap_b[i], p.Bm, p.N, p.K, p.ldb);
+    if (!ok) return false;
+  }
+  return true;
+}
 
 // Decide per operand whether TMA may fetch it (K-contiguous source, 16-B aligned rows) and encode the maps.
 void gemm_tc_prepare(GemmBatch& b) {
   static const bool disabled = getenv("D4PG_NO_TMA") != nullptr;
+  b.all_tma = prepare_v2(b) ? 1 : 0;
+  if (b.all_tma) { gemm_batch_retile(b, T2_BM, T2_BN); return; }
+  gemm_batch_retile(b, TC_BM, TC_BN);
   for (int i = 0; i < b.n; ++i) {
     GemmProblem& p = b.p[i];
     p.flags &= ~(GEMM_A_TMA | GEMM_B_TMA);
@@ -312,9 +515,11 @@ int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     D4PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM)));
+    D4PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(T2_SMEM)));
     attr_set = true;
   }
-  gemm_tc_kernel<<<b.total_tiles, TC_THREADS, TC_SMEM, st>>>(b, passes);
+  if (b.all_tma) gemm_tc2_kernel<<<b.total_tiles, T2_THREADS, T2_SMEM, st>>>(b, passes);
+  else gemm_tc_kernel<<<b.total_tiles, TC_THREADS, TC_SMEM, st>>>(b, passes);
   D4PG_LAUNCH_OK();
   return D4PG_OK;
 }
