@@ -123,44 +123,44 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
       }
     }
     __syncwarp();
-    // ordered per-bin accumulation (gather form: lane owns output bins, visits atoms in order)
-    if (MODE == 0) {
-      float acc[NT];
+    // ordered per-bin accumulation (gather form: lane owns output bins, visits atoms in order).
+    // b_j is non-decreasing in j, so the atoms that touch bin k (l_j == k or u_j == k) form one
+    // contiguous run [j0, j1): two binary searches over the shared tables bound the loop to the few
+    // atoms that matter (gamma < 1 => ~2-3 per bin; clamped atoms pile up only on the edge bins).
 #pragma unroll
-      for (int t = 0; t < NT; ++t) acc[t] = 0.f;
-      for (int j = 0; j < N; ++j) {
-        const int l = l_s[warp][j], u = u_s[warp][j];
-        const double pj = double(p_s[warp][j]);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const int k = lane + 32 * t;
+    for (int t = 0; t < NT; ++t) {
+      const int k = lane + 32 * t;
+      if (k >= N) continue;
+      int lo = 0, hi = N;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (u_s[warp][mid] >= k) hi = mid; else lo = mid + 1; }
+      const int j0 = lo;
+      hi = N;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (l_s[warp][mid] > k) hi = mid; else lo = mid + 1; }
+      const int j1 = lo;
+      if (MODE == 0) {
+        float acc = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          const int l = l_s[warp][j], u = u_s[warp][j];
+          const double pj = double(p_s[warp][j]);
           if (k == l) {
             // eq: f32+f32 add; ne: f32 + (f64 product) in f64, rounded to f32
-            double term = (l == u) ? pj : __dmul_rn(pj, wl_s[warp][j]);
-            acc[t] = __double2float_rn(__dadd_rn(double(acc[t]), term));
+            const double term = (l == u) ? pj : __dmul_rn(pj, wl_s[warp][j]);
+            acc = __double2float_rn(__dadd_rn(double(acc), term));
           } else if (k == u) {
-            acc[t] = __double2float_rn(__dadd_rn(double(acc[t]), __dmul_rn(pj, wu_s[warp][j])));
+            acc = __double2float_rn(__dadd_rn(double(acc), __dmul_rn(pj, wu_s[warp][j])));
           }
         }
-      }
-#pragma unroll
-      for (int t = 0; t < NT; ++t) mk[t] = acc[t];
-    } else {
-      double acc[NT];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) acc[t] = 0.;
-      for (int j = 0; j < N; ++j) {
-        const int l = l_s[warp][j], u = u_s[warp][j];
-        const double pj = double(p_s[warp][j]);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const int k = lane + 32 * t;
-          if (k == l) acc[t] = __dadd_rn(acc[t], __dmul_rn(pj, wl_s[warp][j]));
-          if (k == u) acc[t] = __dadd_rn(acc[t], __dmul_rn(pj, wu_s[warp][j]));
+        mk[t] = acc;
+      } else {
+        double acc = 0.;
+        for (int j = j0; j < j1; ++j) {
+          const int l = l_s[warp][j], u = u_s[warp][j];
+          const double pj = double(p_s[warp][j]);
+          if (k == l) acc = __dadd_rn(acc, __dmul_rn(pj, wl_s[warp][j]));
+          if (k == u) acc = __dadd_rn(acc, __dmul_rn(pj, wu_s[warp][j]));
         }
+        mk[t] = __double2float_rn(acc);
       }
-#pragma unroll
-      for (int t = 0; t < NT; ++t) mk[t] = __double2float_rn(acc[t]);
     }
   }
 

@@ -96,10 +96,33 @@ struct SampleArgs {
 
 constexpr int SAMPLE_ROWS = 32;      // rows per CTA
 constexpr int SAMPLE_THREADS = 256;
+constexpr int TOP_LEVELS = 11;       // tree levels 0..10 (nodes 1..2047) are staged in shared memory
+
+// sum(0, len-1) by one warp: the prefix [0,x) (x = len-1) is covered by one node per set bit of x;
+// _reduce_helper (:61-96) adds them right-nested, i.e. lowest bit first: acc = t_b + acc going up.
+// Each lane fetches the node of "its" bit (all loads in flight together), lane 0 folds them in order.
+__device__ __forceinline__ float warp_prefix_sum(const float* __restrict__ V, int64_t cap, int64_t x, int lane) {
+  float term = 0.f;
+  const bool has = ((x >> lane) & 1) != 0;
+  if (has) {
+    const int64_t start = x & ~((int64_t(2) << lane) - 1);
+    term = __ldcg(V + (cap >> lane) + (start >> lane));
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, has);
+  float acc = 0.f;
+  bool first = true;
+  for (int b = 0; b < 32; ++b) {
+    const float t = __shfl_sync(0xffffffffu, term, b);
+    if ((mask >> b) & 1) { acc = first ? t : __fadd_rn(t, acc); first = false; }
+  }
+  return acc;
+}
 
 // _sample_proportional (:258-265) + IS weights (:303-311) + _encode_sample (:189-199), fused.
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const SampleArgs a) {
   __shared__ int32_t idx_s[SAMPLE_ROWS];
+  __shared__ float top_s[1 << TOP_LEVELS];
+  __shared__ float total_s;
   const int row0 = blockIdx.x * SAMPLE_ROWS;
   const int nrows = min(SAMPLE_ROWS, a.B - row0);
   const int t = threadIdx.x;
@@ -107,32 +130,44 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const Sam
     clock_derive(a.clock, a.clock_params);
     a.clock->beta = clock_beta(a.clock, a.clock_params);
   }
+  const bool descend = (a.idx_in == nullptr) && !a.uniform_mode;
+  const int64_t len = a.state->len;
+  int top_levels = 0;
+  if (descend) {
+    // stage the top of the sum tree (one L2 round trip for the whole CTA) and the prefix total
+    while ((int64_t(1) << top_levels) < a.cap && top_levels < TOP_LEVELS) ++top_levels;
+    for (int i = t; i < (1 << top_levels); i += SAMPLE_THREADS) top_s[i] = (i >= 1) ? __ldcg(a.sum + i) : 0.f;
+    if (t < 32) {
+      const float tot = warp_prefix_sum(a.sum, a.cap, len - 1, t);       // sum(0, len-1): leaves [0, len-2]
+      if (t == 0) total_s = tot;
+    }
+    __syncthreads();
+  }
   if (t < nrows) {
     const int row = row0 + t;
     int32_t leaf_idx;
     if (a.idx_in) {
       leaf_idx = a.idx_in[row];
     } else {
-      const int64_t len = a.state->len;
-      const float total = a.uniform_mode ? 0.f : prefix_sum_ref(a.sum, a.cap, len - 2);   // sum(0, len-1)
       const uint64_t ctr = a.counter + (a.clock ? uint64_t(a.clock->steps_done) : 0ull);
       const double u = a.uniforms ? a.uniforms[row] : Philox::uniform53(a.seed, ctr, uint32_t(row));
       int64_t i = 1;
+      const int64_t top_end = int64_t(1) << (top_levels - 1);              // nodes < 2*top_end have children in top_s
       if (a.uniform_mode) {
         int64_t pick = int64_t(u * double(len));
         i = a.cap + (pick < len ? pick : len - 1);
       } else if (a.state->pristine) {
         // tree of Python floats: mass and the descent are fp64 (all node values are integers)
-        double mass = __dmul_rn(u, double(total));
+        double mass = __dmul_rn(u, double(total_s));
         while (i < a.cap) {
-          const double left = double(__ldcg(a.sum + 2 * i));
+          const double left = double((2 * i < 2 * top_end) ? top_s[2 * i] : __ldcg(a.sum + 2 * i));
           if (left > mass) i = 2 * i;                                 // strict, :144
           else { mass = __dsub_rn(mass, left); i = 2 * i + 1; }
         }
       } else {
-        float mass = __fmul_rn(__double2float_rn(u), total);          // weak float * np.float32
+        float mass = __fmul_rn(__double2float_rn(u), total_s);         // weak float * np.float32
         while (i < a.cap) {
-          const float left = __ldcg(a.sum + 2 * i);
+          const float left = (2 * i < 2 * top_end) ? top_s[2 * i] : __ldcg(a.sum + 2 * i);
           if (left > mass) i = 2 * i;
           else { mass = __fsub_rn(mass, left); i = 2 * i + 1; }
         }
