@@ -72,6 +72,7 @@ int launch_adam(const AdamArgs& a, cudaStream_t st) {
   int blocks = int((nmax / 4 + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
+  D4PG_MAX_CARVEOUT(adam_polyak_kernel);
   const int tail = (a.clock || a.loss_out) ? 1 : 0;
   adam_polyak_kernel<<<dim3(blocks, a.nseg + tail), 256, 0, st>>>(a);
   D4PG_LAUNCH_OK();

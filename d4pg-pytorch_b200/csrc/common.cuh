@@ -33,6 +33,20 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
+// All kernels of a step ask for the same (maximum) shared-memory carve-out: a step mixes kernels
+// with 0 KB, 14 KB, 32 KB and 197 KB of shared memory, and letting the driver pick a per-kernel
+// L1/shared split makes every kernel boundary an SM reconfiguration (ncu: ~17 us of a 20 us
+// gemm_tc2 launch had no active SM cycles).
+#define D4PG_MAX_CARVEOUT(kernel)                                                                     \
+  do {                                                                                                \
+    static bool _carved = false;                                                                      \
+    if (!_carved) {                                                                                   \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,                    \
+                           int(cudaSharedmemCarveoutMaxShared));                                      \
+      _carved = true;                                                                                 \
+    }                                                                                                 \
+  } while (0)
+
 static inline cudaStream_t as_stream(d4pg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __host__ __device__ static inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }

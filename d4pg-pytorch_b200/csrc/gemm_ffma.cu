@@ -312,6 +312,7 @@ int gemm_batch_launch(const GemmBatch& b, cudaStream_t st) {
   for (int i = 0; i < b.n; ++i)     // a concatenated input must switch source on a K-chunk boundary
     D4PG_REQUIRE(b.p[i].mode != GEMM_FWD || b.p[i].K1 == b.p[i].K || b.p[i].K1 % KC == 0, D4PG_ENOTSUP,
                  "gemm_batch_launch: concat split K1=%d must be a multiple of %d", b.p[i].K1, KC);
+  D4PG_MAX_CARVEOUT(gemm_ffma_kernel);
   gemm_ffma_kernel<<<b.total_tiles, GEMM_THREADS, 0, st>>>(b);
   D4PG_LAUNCH_OK();
   return D4PG_OK;

@@ -516,6 +516,8 @@ int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {
   if (!attr_set) {
     D4PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM)));
     D4PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(T2_SMEM)));
+    D4PG_MAX_CARVEOUT(gemm_tc_kernel);
+    D4PG_MAX_CARVEOUT(gemm_tc2_kernel);
     attr_set = true;
   }
   if (b.all_tma) gemm_tc2_kernel<<<b.total_tiles, T2_THREADS, T2_SMEM, st>>>(b, passes);

@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
 
 int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st) {
   dim3 grid(cdiv(a.B, HEAD_WARPS)), block(HEAD_WARPS * 32);
+  D4PG_MAX_CARVEOUT((heads_kernel<0, 2>)); D4PG_MAX_CARVEOUT((heads_kernel<1, 2>));
+  D4PG_MAX_CARVEOUT((heads_kernel<0, 4>)); D4PG_MAX_CARVEOUT((heads_kernel<1, 4>));
   // NT = atom slots per lane: 2 covers N<=64 (51 atoms), 4 covers N<=128 (101 atoms)
   if (a.N <= 64) {
     if (mode == 0) heads_kernel<0, 2><<<grid, block, 0, st>>>(a);

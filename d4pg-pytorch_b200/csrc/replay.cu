@@ -385,6 +385,7 @@ int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
   a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.state = reinterpret_cast<const ReplayState*>(h->state);
   a.obs = h->obs; a.act = h->act; a.rew = h->rew; a.obs2 = h->obs2; a.done = h->done;
   a.obs_dim = h->obs_dim; a.act_dim = h->act_dim;
+  D4PG_MAX_CARVEOUT(sample_gather_kernel);
   sample_gather_kernel<<<cdiv(a.B, SAMPLE_ROWS), SAMPLE_THREADS, 0, st>>>(a);
   D4PG_LAUNCH_OK();
   return D4PG_OK;
@@ -407,6 +408,7 @@ int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* p
   TreeArgs a{};
   a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.log2cap = h->log2cap; a.size = h->size;
   a.n = B; a.idx = idx; a.v0 = prio; a.alpha_f32 = h->alpha_f32; a.scratch = h->scratch; a.state = reinterpret_cast<ReplayState*>(h->state);
+  D4PG_MAX_CARVEOUT(tree_write_kernel<TREE_UPDATE>);
   tree_write_kernel<TREE_UPDATE><<<1, TREE_THREADS, 0, st>>>(a);
   D4PG_LAUNCH_OK();
   h->pristine = 0;
