@@ -97,6 +97,7 @@ _PROTOS = {
     "d4pg_learner_steps_done": (C.c_int64, [_P]),
     "d4pg_learner_kernels_per_step": (C.c_int32, [_P]),
     "d4pg_learner_set_counters": (C.c_int32, [_P, C.c_int64, C.c_int64, _P]),
+    "d4pg_debug_tc_trace": (C.c_int32, [_P]),
     "d4pg_comm_unique_id": (C.c_int32, [_P]),
     "d4pg_comm_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "d4pg_comm_destroy": (C.c_int32, [_P]),

@@ -279,7 +279,7 @@ GemmProblem gemm_dw(const float* dZ, int lddz, const float* X, int ldx, float* d
   p.mode = GEMM_DW; p.epi = EPI_NONE;
   return p;
 }
-void gemm_batch_begin(GemmBatch& b) { b.n = 0; b.total_tiles = 0; }
+void gemm_batch_begin(GemmBatch& b) { b.n = 0; b.total_tiles = 0; b.all_tma = 0; b.trace = nullptr; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
   GemmProblem p = pin;

@@ -278,8 +278,16 @@ constexpr uint32_t T2_SMEM = T2_STAGES * T2_STAGE + 2 * T2_STAGE + 1024;
 constexpr int T2_FULL = 0, T2_CONV = T2_STAGES, T2_EMPTY = 2 * T2_STAGES, T2_LOEMPTY = 3 * T2_STAGES,
               T2_DONE = 3 * T2_STAGES + 2, T2_NBARS = 3 * T2_STAGES + 3;
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot) do { if (batch.trace && blockIdx.x == 0) batch.trace[slot] = gtime(); } while (0)
+
 __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ GemmBatch batch, int passes) {
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) TRACE(0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* lo_ring = smem + T2_STAGES * T2_STAGE;
   __shared__ __align__(8) uint64_t bars[T2_NBARS];
@@ -308,6 +316,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
+  if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
     // ================================ TMA producer ==================================================
@@ -333,37 +342,44 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
         } else {
           tma_load_2d(Bd, &batch.tmap_b[pi], full, k0, n0);
         }
+        if (c == 0) TRACE(2);
       }
+      TRACE(3);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer =====================================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(FMT_TF32, a_mn, b_mn, T2_BM, T2_BN);
+      // The issuing lane is a single thread: keep its per-MMA work to a couple of integer adds.  A
+      // descriptor is (template with LBO/SBO/layout bits) + (byte address >> 4) in the low 14 bits;
+      // stepping K by one MMA adds 32 B (K-major) or 1024 B (MN-major) to the start address.
+      const uint64_t a_tmpl = a_mn ? make_smem_desc(0, 4096, 512, 1) : make_smem_desc(0, 16, 1024, 2);
+      const uint64_t b_tmpl = b_mn ? make_smem_desc(0, 4096, 512, 1) : make_smem_desc(0, 16, 1024, 2);
+      const uint32_t a_step = (a_mn ? 1024u : 32u) >> 4, b_step = (b_mn ? 1024u : 32u) >> 4;
+      const uint32_t smem_base = smem_u32(smem) >> 4, lo_base = smem_u32(lo_ring) >> 4;
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % T2_STAGES, l = c & 1;
         mbar_wait(&bars[(passes > 1 ? T2_CONV : T2_FULL) + s], (c / T2_STAGES) & 1);
         tc_fence_after_sync();
-        const uint8_t* Ahi = smem + s * T2_STAGE;
-        const uint8_t* Bhi = Ahi + T2_A_BYTES;
-        const uint8_t* Alo = lo_ring + l * T2_STAGE;
-        const uint8_t* Blo = Alo + T2_A_BYTES;
-#pragma unroll 1
-        for (int p = 0; p < passes; ++p) {
-          const uint8_t* Ap = (p == 2) ? Alo : Ahi;
-          const uint8_t* Bp = (p == 1) ? Blo : Bhi;
+        const uint32_t ahi = smem_base + uint32_t(s) * (T2_STAGE >> 4), bhi = ahi + (T2_A_BYTES >> 4);
+        const uint32_t alo = lo_base + uint32_t(l) * (T2_STAGE >> 4), blo = alo + (T2_A_BYTES >> 4);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = a_mn ? make_smem_desc(smem_u32(Ap + ks * 1024), 4096, 512, 1)
-                                     : make_smem_desc(smem_u32(Ap + ks * 32), 16, 1024, 2);
-            const uint64_t bd = b_mn ? make_smem_desc(smem_u32(Bp + ks * 1024), 4096, 512, 1)
-                                     : make_smem_desc(smem_u32(Bp + ks * 32), 16, 1024, 2);
-            mma_tf32(tmem_d, ad, bd, idesc, (c | p | ks) != 0);
-          }
+        for (int ks = 0; ks < 4; ++ks)
+          mma_tf32(tmem_d, a_tmpl + (ahi + ks * a_step), b_tmpl + (bhi + ks * b_step), idesc, (c | ks) != 0);
+        if (passes > 1) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_tf32(tmem_d, a_tmpl + (ahi + ks * a_step), b_tmpl + (blo + ks * b_step), idesc, true);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_tf32(tmem_d, a_tmpl + (alo + ks * a_step), b_tmpl + (bhi + ks * b_step), idesc, true);
         }
         mma_commit(&bars[T2_EMPTY + s]);
         if (passes > 1) mma_commit(&bars[T2_LOEMPTY + l]);
+        if (c == 0) TRACE(6);
       }
       mma_commit(&bars[T2_DONE]);
+      TRACE(7);
     }
   } else {
     // ================================ converters, then epilogue =======================================
@@ -374,42 +390,62 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
         uint8_t* hi = smem + s * T2_STAGE;
         uint8_t* lo = lo_ring + l * T2_STAGE;
         mbar_wait(&bars[T2_FULL + s], (c / T2_STAGES) & 1);
+        if (c == 0 && t2 == 0) TRACE(4);
         if (c >= 2) mbar_wait(&bars[T2_LOEMPTY + l], ((c >> 1) - 1) & 1);
-#pragma unroll 4
-        for (int e = t2; e < int(T2_STAGE / 16); e += 128) {
-          const float4 v = *reinterpret_cast<const float4*>(hi + e * 16);
-          put_split4(hi, lo, uint32_t(e) * 16u, v);
-        }
+        constexpr int PER = int(T2_STAGE / 16) / 128;        // 12 float4 per thread per chunk
+        float4 v[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) v[q] = *reinterpret_cast<const float4*>(hi + (t2 + q * 128) * 16);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) put_split4(hi, lo, uint32_t(t2 + q * 128) * 16u, v[q]);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[T2_CONV + s]);
+        if (c == 0 && t2 == 0) TRACE(5);
       }
     }
+    if (t2 == 0) TRACE(8);
     mbar_wait(&bars[T2_DONE], 0);
     tc_fence_after_sync();
+    if (t2 == 0) TRACE(9);
     const int quad = warp & 3;
     const int gi = m0 + quad * 32 + lane;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       float r[32];
       tmem_ld_32x32(tmem_d + (uint32_t(quad * 32) << 16) + uint32_t(half * 32), r);
-      if (gi < P.M) {
-        const int nb = n0 + half * 32;
+      const int nb = n0 + half * 32;
+      if (gi < P.M && nb < P.N) {
         float* crow = P.C + size_t(gi) * P.ldc + nb;
         const float* arow = P.aux ? P.aux + size_t(gi) * P.ldaux + nb : nullptr;
+        // 16-B row pitches: whole float4 groups inside [0, N) go out as 128-bit accesses
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int j = j4 * 4;
           if (nb + j >= P.N) break;
-          float x = r[j];
-          switch (P.epi) {
-            case EPI_BIAS: x += __ldg(P.bias + nb + j); break;
-            case EPI_BIAS_RELU: x = fmaxf(x + __ldg(P.bias + nb + j), 0.f); break;
-            case EPI_BIAS_TANH: x = tanhf(x + __ldg(P.bias + nb + j)); break;
-            case EPI_RELU_MASK: x = (__ldg(arow + j) > 0.f) ? x : 0.f; break;
-            case EPI_TANH_MASK: { const float t = __ldg(arow + j); x *= (1.f - t * t); } break;
-            default: break;
+          const bool full4 = (nb + j + 3 < P.N);
+          float x[4] = {r[j], r[j + 1], r[j + 2], r[j + 3]};
+          float ex[4] = {0.f, 0.f, 0.f, 0.f};
+          if (P.epi == EPI_BIAS || P.epi == EPI_BIAS_RELU || P.epi == EPI_BIAS_TANH) {
+            if (full4) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + nb + j)); ex[0] = b4.x; ex[1] = b4.y; ex[2] = b4.z; ex[3] = b4.w; }
+            else for (int q = 0; q < 4; ++q) if (nb + j + q < P.N) ex[q] = __ldg(P.bias + nb + j + q);
+          } else if (P.epi == EPI_RELU_MASK || P.epi == EPI_TANH_MASK) {
+            if (full4) { const float4 a4 = __ldg(reinterpret_cast<const float4*>(arow + j)); ex[0] = a4.x; ex[1] = a4.y; ex[2] = a4.z; ex[3] = a4.w; }
+            else for (int q = 0; q < 4; ++q) if (nb + j + q < P.N) ex[q] = __ldg(arow + j + q);
           }
-          crow[j] = x;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            switch (P.epi) {
+              case EPI_BIAS: x[q] += ex[q]; break;
+              case EPI_BIAS_RELU: x[q] = fmaxf(x[q] + ex[q], 0.f); break;
+              case EPI_BIAS_TANH: x[q] = tanhf(x[q] + ex[q]); break;
+              case EPI_RELU_MASK: x[q] = (ex[q] > 0.f) ? x[q] : 0.f; break;
+              case EPI_TANH_MASK: x[q] *= (1.f - ex[q] * ex[q]); break;
+              default: break;
+            }
+          }
+          if (full4) *reinterpret_cast<float4*>(crow + j) = make_float4(x[0], x[1], x[2], x[3]);
+          else for (int q = 0; q < 4; ++q) if (nb + j + q < P.N) crow[j + q] = x[q];
         }
       }
     }
@@ -422,9 +458,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
       }
     }
   }
+  if (tid == 64) TRACE(10);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_d, 64);
+  if (threadIdx.x == 32) TRACE(11);
 }
 
 // ---- host: TMA descriptors -------------------------------------------------------------------------
@@ -478,6 +516,8 @@ static bool prepare_v2(GemmBatch& b) {
   for (int i = 0; i < b.n; ++i) {
     const GemmProblem& p = b.p[i];
     if (!tma_ok(p.A, p.lda) || !tma_ok(p.Bm, p.ldb)) return false;
+    if (!tma_ok(p.C, p.ldc) || (p.aux && !tma_ok(p.aux, p.ldaux))) return false;      // 128-bit epilogue accesses
+    if (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return false;
     bool ok;
     if (p.mode == GEMM_DW) ok = encode_mnmajor(&b.tmap_a[i], p.A, p.M, p.K, p.lda);
     else ok = encode_kmajor(&b.tmap_a[i], p.A, p.K1, p.M, p.lda, T2_BM);
@@ -491,8 +531,12 @@ static bool prepare_v2(GemmBatch& b) {
 }
 
 // Decide per operand whether TMA may fetch it (K-contiguous source, 16-B aligned rows) and encode the maps.
+static unsigned long long* g_trace = nullptr;
 void gemm_tc_prepare(GemmBatch& b) {
   static const bool disabled = getenv("D4PG_NO_TMA") != nullptr;
+  static const bool tracing = getenv("D4PG_TC_TRACE") != nullptr;
+  if (tracing && !g_trace) { cudaMalloc(&g_trace, 64 * sizeof(unsigned long long)); cudaMemset(g_trace, 0, 64 * 8); }
+  b.trace = tracing ? g_trace : nullptr;
   b.all_tma = prepare_v2(b) ? 1 : 0;
   if (b.all_tma) { gemm_batch_retile(b, T2_BM, T2_BN); return; }
   gemm_batch_retile(b, TC_BM, TC_BN);
@@ -527,3 +571,10 @@ int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {
 }
 
 }  // namespace d4pg
+
+// debug: %globaltimer (ns) phase stamps of CTA 0 of the last gemm_tc2 launch (D4PG_TC_TRACE=1)
+extern "C" int32_t d4pg_debug_tc_trace(unsigned long long* out16) {
+  if (!d4pg::g_trace || !out16) return D4PG_ESTATE;
+  D4PG_CUDA_OK(cudaMemcpy(out16, d4pg::g_trace, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return D4PG_OK;
+}
