@@ -2,10 +2,16 @@
 #include "common.cuh"
 #include "gemm_ffma.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace d4pg {
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+  static const bool on = getenv("D4PG_NO_PDL") == nullptr;
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -31,6 +31,8 @@ __device__ void loss_reduce_block(const float* loss_rows, const float* pi_rows, 
 }
 
 __global__ void __launch_bounds__(256) adam_polyak_kernel(const AdamArgs a) {
+  pdl_trigger();
+  pdl_wait();
   if (int(blockIdx.y) == a.nseg) {
     // tail slice: reported losses + advance the base counters for the NEXT step (nobody in this
     // kernel reads them: the derived scalars were written by the step's first kernel)
@@ -74,8 +76,7 @@ int launch_adam(const AdamArgs& a, cudaStream_t st) {
   if (blocks < 1) blocks = 1;
   D4PG_MAX_CARVEOUT(adam_polyak_kernel);
   const int tail = (a.clock || a.loss_out) ? 1 : 0;
-  adam_polyak_kernel<<<dim3(blocks, a.nseg + tail), 256, 0, st>>>(a);
-  D4PG_LAUNCH_OK();
+  D4PG_CUDA_OK(launch_pdl(adam_polyak_kernel, dim3(blocks, a.nseg + tail), dim3(256), 0, st, a));
   return D4PG_OK;
 }
 

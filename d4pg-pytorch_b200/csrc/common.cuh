@@ -47,6 +47,28 @@ void set_error(const char* fmt, ...);
     }                                                                                                 \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// A step is ~18 small dependent kernels; at batch 256 the kernel boundaries (grid drain -> next grid
+// launch) cost as much as the kernels.  Every step kernel is launched with the programmatic-stream-
+// serialization attribute: it signals `launch_dependents` as soon as it starts, so the next kernel's
+// CTAs are scheduled (and run their prologue) while this one is still executing, and blocks in
+// `griddepcontrol.wait` until all of this kernel's memory is visible.  Captured into the CUDA graph
+// as programmatic dependency edges.  D4PG_NO_PDL=1 disables it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline cudaStream_t as_stream(d4pg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __host__ __device__ static inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }

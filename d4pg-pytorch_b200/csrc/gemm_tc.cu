@@ -243,10 +243,12 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     for (int i = 0; i < TC_NBARS; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
+  pdl_trigger();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
+  pdl_wait();                                   // prologue above overlapped the previous kernel's tail
 
   const CUtensorMap* tmA = &batch.tmap_a[pi];
   const CUtensorMap* tmB = &batch.tmap_b[pi];
@@ -287,6 +289,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ GemmBatch batch, int passes) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   if (threadIdx.x == 0) TRACE(0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* lo_ring = smem + T2_STAGES * T2_STAGE;
@@ -316,7 +319,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
-  if (threadIdx.x == 0) TRACE(1);
+  pdl_wait();                                   // barrier init / TMEM alloc / descriptor prefetch overlapped the
+  if (threadIdx.x == 0) TRACE(1);               // previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ================================ TMA producer ==================================================
@@ -564,9 +568,8 @@ int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {
     D4PG_MAX_CARVEOUT(gemm_tc2_kernel);
     attr_set = true;
   }
-  if (b.all_tma) gemm_tc2_kernel<<<b.total_tiles, T2_THREADS, T2_SMEM, st>>>(b, passes);
-  else gemm_tc_kernel<<<b.total_tiles, TC_THREADS, TC_SMEM, st>>>(b, passes);
-  D4PG_LAUNCH_OK();
+  if (b.all_tma) D4PG_CUDA_OK(launch_pdl(gemm_tc2_kernel, dim3(b.total_tiles), dim3(T2_THREADS), T2_SMEM, st, b, passes));
+  else D4PG_CUDA_OK(launch_pdl(gemm_tc_kernel, dim3(b.total_tiles), dim3(TC_THREADS), TC_SMEM, st, b, passes));
   return D4PG_OK;
 }
 

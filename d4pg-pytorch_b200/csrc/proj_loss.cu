@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
   __shared__ double wl_s[HEAD_WARPS][D4PG_MAX_ATOMS];
   __shared__ double wu_s[HEAD_WARPS][D4PG_MAX_ATOMS];
 
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * HEAD_WARPS + warp;
   if (row >= a.B) return;
@@ -227,13 +229,12 @@ int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st) {
   D4PG_MAX_CARVEOUT((heads_kernel<0, 4>)); D4PG_MAX_CARVEOUT((heads_kernel<1, 4>));
   // NT = atom slots per lane: 2 covers N<=64 (51 atoms), 4 covers N<=128 (101 atoms)
   if (a.N <= 64) {
-    if (mode == 0) heads_kernel<0, 2><<<grid, block, 0, st>>>(a);
-    else heads_kernel<1, 2><<<grid, block, 0, st>>>(a);
+    if (mode == 0) D4PG_CUDA_OK(launch_pdl(heads_kernel<0, 2>, grid, block, 0, st, a));
+    else D4PG_CUDA_OK(launch_pdl(heads_kernel<1, 2>, grid, block, 0, st, a));
   } else {
-    if (mode == 0) heads_kernel<0, 4><<<grid, block, 0, st>>>(a);
-    else heads_kernel<1, 4><<<grid, block, 0, st>>>(a);
+    if (mode == 0) D4PG_CUDA_OK(launch_pdl(heads_kernel<0, 4>, grid, block, 0, st, a));
+    else D4PG_CUDA_OK(launch_pdl(heads_kernel<1, 4>, grid, block, 0, st, a));
   }
-  D4PG_LAUNCH_OK();
   return D4PG_OK;
 }
 

@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const Sam
   __shared__ int32_t idx_s[SAMPLE_ROWS];
   __shared__ float top_s[1 << TOP_LEVELS];
   __shared__ float total_s;
+  pdl_trigger();
+  pdl_wait();
   const int row0 = blockIdx.x * SAMPLE_ROWS;
   const int nrows = min(SAMPLE_ROWS, a.B - row0);
   const int t = threadIdx.x;
@@ -386,8 +388,7 @@ int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
   a.obs = h->obs; a.act = h->act; a.rew = h->rew; a.obs2 = h->obs2; a.done = h->done;
   a.obs_dim = h->obs_dim; a.act_dim = h->act_dim;
   D4PG_MAX_CARVEOUT(sample_gather_kernel);
-  sample_gather_kernel<<<cdiv(a.B, SAMPLE_ROWS), SAMPLE_THREADS, 0, st>>>(a);
-  D4PG_LAUNCH_OK();
+  D4PG_CUDA_OK(launch_pdl(sample_gather_kernel, dim3(cdiv(a.B, SAMPLE_ROWS)), dim3(SAMPLE_THREADS), 0, st, a));
   return D4PG_OK;
 }
 
