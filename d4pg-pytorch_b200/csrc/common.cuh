@@ -53,7 +53,7 @@ void set_error(const char* fmt, ...);
 // serialization attribute: it signals `launch_dependents` as soon as it starts, so the next kernel's
 // CTAs are scheduled (and run their prologue) while this one is still executing, and blocks in
 // `griddepcontrol.wait` until all of this kernel's memory is visible.  Captured into the CUDA graph
-// as programmatic dependency edges.  D4PG_NO_PDL=1 disables it.
+// as programmatic dependency edges.  Opt-in with D4PG_PDL=1 (see pdl_enabled()).
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
