@@ -271,6 +271,41 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_write_kernel(const TreeArgs
   }
 }
 
+// add(): the new leaves are one contiguous ring range [start, start+n) (no wrap: the host splits a
+// wrapping add), so level l only has the nodes (cap+start)>>l .. (cap+start+n-1)>>l to recompute:
+// ~2n node updates in total instead of n*log2(cap), and the narrow top of the tree is finished by
+// one warp without block-wide barriers.
+__global__ void __launch_bounds__(TREE_THREADS) tree_add_range_kernel(float* sum, float* mn, int64_t cap, int log2cap,
+                                                                      int64_t start, int64_t n, const ReplayState* state,
+                                                                      float alpha_f32) {
+  const int t = threadIdx.x;
+  const float leaf = pow_alpha(state->max_priority, alpha_f32);      // :255-256
+  for (int64_t i = t; i < n; i += TREE_THREADS) { sum[cap + start + i] = leaf; mn[cap + start + i] = leaf; }
+  int lvl = 1;
+  for (; lvl <= log2cap; ++lvl) {
+    const int64_t lo = (cap + start) >> lvl, hi = (cap + start + n - 1) >> lvl;
+    if (hi - lo + 1 <= 32) break;                                     // narrow: hand over to warp 0
+    __syncthreads();
+    for (int64_t node = lo + t; node <= hi; node += TREE_THREADS) {
+      sum[node] = __fadd_rn(__ldcg(sum + 2 * node), __ldcg(sum + 2 * node + 1));
+      mn[node] = fminf(__ldcg(mn + 2 * node), __ldcg(mn + 2 * node + 1));
+    }
+  }
+  __syncthreads();
+  if (t < 32) {
+    for (; lvl <= log2cap; ++lvl) {
+      const int64_t lo = (cap + start) >> lvl, hi = (cap + start + n - 1) >> lvl;
+      const int64_t node = lo + t;
+      if (node <= hi) {
+        sum[node] = __fadd_rn(__ldcg(sum + 2 * node), __ldcg(sum + 2 * node + 1));
+        mn[node] = fminf(__ldcg(mn + 2 * node), __ldcg(mn + 2 * node + 1));
+      }
+      __threadfence_block();
+      __syncwarp();
+    }
+  }
+}
+
 // bulk path for large adds: grid-wide leaf fill, then one launch per level
 __global__ void leaf_fill_kernel(float* sum, float* mn, int64_t cap, int64_t size, int64_t ring_start,
                                  int64_t n, const ReplayState* state, float alpha_f32) {
@@ -480,12 +515,17 @@ extern "C" int32_t d4pg_replay_add(d4pg_replay_t* h, int64_t n, const float* obs
                                              reinterpret_cast<ReplayState*>(h->state), new_len, new_next);
   D4PG_LAUNCH_OK();
   if (prioritized) {
-    if (n <= 4096) {
-      TreeArgs a{};
-      a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.log2cap = h->log2cap; a.size = h->size;
-      a.n = int(n); a.ring_start = start; a.alpha_f32 = h->alpha_f32; a.scratch = h->scratch; a.state = reinterpret_cast<ReplayState*>(h->state);
-      tree_write_kernel<TREE_ADD><<<1, TREE_THREADS, 0, st>>>(a);
+    if (n <= 65536) {
+      // split a wrapping add into its two contiguous pieces
+      const int64_t n1 = std::min<int64_t>(n, h->size - start);
+      tree_add_range_kernel<<<1, TREE_THREADS, 0, st>>>(h->sum, h->mn, h->cap, h->log2cap, start, n1,
+                                                        reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);
       D4PG_LAUNCH_OK();
+      if (n1 < n) {
+        tree_add_range_kernel<<<1, TREE_THREADS, 0, st>>>(h->sum, h->mn, h->cap, h->log2cap, 0, n - n1,
+                                                          reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);
+        D4PG_LAUNCH_OK();
+      }
     } else {
       leaf_fill_kernel<<<296, 256, 0, st>>>(h->sum, h->mn, h->cap, h->size, start, n,
                                             reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);

@@ -107,6 +107,9 @@ class _Learner(object):
         self.handle = h
         self.global_model = g
         self.stream = torch.cuda.Stream(device=dev)      # graph capture needs a non-default stream
+        self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
+        self.step_fn = L.d4pg_learner_step
+        self.host_u_np = self.host_u.numpy()
         if opt_a.step_count or (ddpg.prioritized_replay and ddpg.beta_schedule.t):
             _lib.check(L.d4pg_learner_set_counters(h, opt_a.step_count,
                                                    ddpg.beta_schedule.t if ddpg.prioritized_replay else 0,
@@ -281,24 +284,29 @@ class DDPG:
         Results (losses, td, priorities, sampled indices) stay on the device; read them with
         `last_losses()` / `last_batch_info()`."""
         g = global_model if global_model is not None else self
-        L = self._get_learner(g)
+        L = self._learner
+        if L is None or L.global_model is not g:
+            L = self._get_learner(g)
         store = self.replayBuffer._store
-        store.flush()
+        if store._n_staged:
+            store.flush()
         B = self.batch_size
-        L.stream.wait_stream(torch.cuda.current_stream())      # adds / weight loads issued by the caller
-        with torch.cuda.stream(L.stream):
-            if self.sampling == "reference":
+        cur = torch.cuda.current_stream()
+        L.stream.wait_stream(cur)                               # adds / weight loads issued by the caller
+        if self.sampling == "reference":
+            with torch.cuda.stream(L.stream):
                 if self.prioritized_replay:
-                    hu = L.host_u.numpy()
-                    for i in range(B):                                   # random.random() x B, as
-                        hu[i] = random.random()                          # prioritized_replay_memory.py:262
+                    rnd = random.random                                   # random.random() x B, in order, as
+                    L.host_u_np[:] = [rnd() for _ in range(B)]            # prioritized_replay_memory.py:262
                     L.uniforms.copy_(L.host_u, non_blocking=True)
                 else:
                     L.host_pos.numpy()[:] = self.replayBuffer.sample_positions(B)
                     L.positions.copy_(L.host_pos, non_blocking=True)
-            _lib.check(_lib.lib().d4pg_learner_step(L.handle, C.c_void_p(L.stream.cuda_stream)), "d4pg_learner_step")
+        rc = L.step_fn(L.handle, L.stream_ptr)
+        if rc:
+            _lib.check(rc, "d4pg_learner_step")
         # ordering with work the caller issues on the current stream (adds, forwards)
-        torch.cuda.current_stream().wait_stream(L.stream)
+        cur.wait_stream(L.stream)
         if self.prioritized_replay:
             self.beta_schedule.t += 1
         for opt in (self.optimizer_global_actor, self.optimizer_global_critic):

@@ -122,6 +122,52 @@ class _DeviceReplay(object):
         if self._n_staged == self.STAGE_ROWS or self._n_staged == self.size:
             self.flush()
 
+    def _pack_layout(self, n):
+        """Byte offsets of (obs, act, rew, obs2, done) for n rows packed into one staging buffer."""
+        S, A = self.obs_dim * 4, self.act_dim * 4
+        o_obs = 0
+        o_obs2 = o_obs + n * S
+        o_act = o_obs2 + n * S
+        o_rew = (o_act + n * A + 15) & ~15
+        o_done = o_rew + n * 8
+        return o_obs, o_act, o_rew, o_obs2, o_done, (o_done + n + 15) & ~15
+
+    def add_batch_host(self, s, a, r, s2, done):
+        """Fast ingest of n <= STAGE_ROWS host transitions: the five arrays are packed into ONE pinned
+        staging buffer, moved with ONE H2D copy and unpacked by the ring-write kernel."""
+        s = np.asarray(s, dtype=np.float32)
+        n = s.shape[0] if s.ndim == 2 else 1
+        if self.handle is None:
+            self._allocate(s.reshape(n, -1).shape[1], np.asarray(a).reshape(n, -1).shape[1])
+        if n > self.STAGE_ROWS or n > self.size:
+            return self.add_batch(s, a, r, s2, done)
+        self.flush()
+        if getattr(self, "_pack_host", None) is None:
+            nbytes = self._pack_layout(self.STAGE_ROWS)[5]
+            self._pack_host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            self._pack_dev = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._pack_np = self._pack_host.numpy()
+            self._pack_evt = torch.cuda.Event()
+            self._pack_busy = False
+        if self._pack_busy:
+            self._pack_evt.synchronize()              # previous copy out of the pinned buffer has finished
+        oo, oa, orw, oo2, od, tot = self._pack_layout(n)
+        hp = self._pack_np
+        hp[oo:oo + n * self.obs_dim * 4].view(np.float32)[:] = s.reshape(-1)
+        hp[oo2:oo2 + n * self.obs_dim * 4].view(np.float32)[:] = np.asarray(s2, dtype=np.float32).reshape(-1)
+        hp[oa:oa + n * self.act_dim * 4].view(np.float32)[:] = np.asarray(a, dtype=np.float32).reshape(-1)
+        hp[orw:orw + n * 8].view(np.float64)[:] = np.asarray(r, dtype=np.float64).reshape(-1)
+        hp[od:od + n] = np.asarray(done).reshape(-1).astype(np.uint8)
+        self._pack_dev[:tot].copy_(self._pack_host[:tot], non_blocking=True)
+        self._pack_evt.record()
+        self._pack_busy = True
+        base = self._pack_dev.data_ptr()
+        _lib.check(_lib.lib().d4pg_replay_add(self.handle, n, C.c_void_p(base + oo), C.c_void_p(base + oa),
+                                              C.c_void_p(base + orw), C.c_void_p(base + oo2), C.c_void_p(base + od),
+                                              1 if self.prioritized else 0, _lib.stream_ptr()), "d4pg_replay_add")
+        self._next_idx = (self._next_idx + n) % self.size
+        self._len = min(self.size, self._len + n)
+
     def add_batch(self, s, a, r, s2, done):
         """Vectorised ingest of n transitions (host numpy / CPU or CUDA tensors)."""
         self.flush()
@@ -337,7 +383,11 @@ class ReplayBuffer(object):
         self._store.add(obs_t, action, reward, obs_tp1, done)
 
     def add_batch(self, obs_t, action, reward, obs_tp1, done):
-        self._store.add_batch(obs_t, action, reward, obs_tp1, done)
+        """n transitions at once.  Host arrays of up to 4096 rows take the packed single-copy path."""
+        if isinstance(obs_t, np.ndarray) or (torch.is_tensor(obs_t) and not obs_t.is_cuda):
+            self._store.add_batch_host(obs_t, action, reward, obs_tp1, done)
+        else:
+            self._store.add_batch(obs_t, action, reward, obs_tp1, done)
 
     def _encode_sample(self, idxes):
         return _to_host_batch(self._store.gather(idxes))

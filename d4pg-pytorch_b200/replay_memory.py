@@ -34,7 +34,10 @@ class Replay(object):
         self._store.add(state, action, reward, next_state, done)
 
     def add_batch(self, state, action, reward, next_state, done):
-        self._store.add_batch(state, action, reward, next_state, done)
+        if isinstance(state, np.ndarray):
+            self._store.add_batch_host(state, action, reward, next_state, done)
+        else:
+            self._store.add_batch(state, action, reward, next_state, done)
 
     def initialize(self, init_length):
         """Random-policy filler with n-step return accumulation at insert time
