@@ -178,7 +178,7 @@ def gpu_main(args):
         torch.manual_seed(0); random.seed(0)            # identical replicas on every rank
         dd = d4pg.DDPG(cfg["obs"], cfg["act"], memory_size=cap, batch_size=B, critic_dist_info=info,
                        n_steps=cfg["n_steps"], projection=cfg["proj"], sampling=sampling, philox_seed=1234 + rank,
-                       comm=comm, precision=args.precision)
+                       comm=comm, precision=args.precision, persistent=bool(args.persistent) and world == 1)
         dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
                                    d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
         dd.replayBuffer.add_batch(*synth(cfg, cap, seed=rank))     # this rank's shard, resident in HBM
@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CFG))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--persistent", type=int, default=0, help="1 = one cooperative kernel per step (fp32, 1 GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)

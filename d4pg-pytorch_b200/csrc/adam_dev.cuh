@@ -1,0 +1,60 @@
+// Device code of the fused Adam + Polyak update (shared by adam.cu and the persistent step kernel).
+#pragma once
+#include "adam.cuh"
+
+namespace d4pg {
+
+// mean over the batch of the per-row loss terms (ddpg.py:217 `.mean()`, ddpg.py:238 `.mean()`),
+// fixed-order single-block reduction so the reported scalars are run-to-run deterministic.
+__device__ __forceinline__ void loss_reduce_block(const float* loss_rows, const float* pi_rows, int B, float inv_count,
+                                                  float* out, float (*red)[8]) {
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) { a += loss_rows[i]; if (pi_rows) b += pi_rows[i]; }
+  a = warp_sum(a); b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sa = 0.f, sb = 0.f;
+    for (int w = 0; w < 8; ++w) { sa += red[0][w]; sb += red[1][w]; }
+    out[0] = sa * inv_count; out[1] = sb * inv_count;
+  }
+}
+
+// tail: reported losses + advance the base counters for the NEXT step (nobody in the same kernel /
+// phase reads them: the derived scalars were written by the step's first kernel).  One 256-thread CTA.
+__device__ __forceinline__ void adam_tail(const AdamArgs& a, float (*red)[8]) {
+  if (a.loss_out) loss_reduce_block(a.loss_rows, a.pi_rows, a.B, a.inv_count, a.loss_out, red);
+  if (threadIdx.x == 0 && a.clock) { a.clock->adam_step += 1; a.clock->beta_t += 1; a.clock->steps_done += 1; }
+}
+
+// segment `seg`, grid-stride over float4 groups: CTA bx of gx (256 threads each)
+__device__ __forceinline__ void adam_segment(const AdamArgs& a, int seg, int bx, int gx) {
+  const AdamSeg& s = a.seg[seg];
+  const float nss = (a.clock && s.clock_slot >= 0) ? a.clock->neg_step_size[s.clock_slot] : s.neg_step_size;
+  const float bc2s = a.clock ? a.clock->bc2_sqrt : a.bc2_sqrt;
+  const int64_t n4 = s.n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(s.p);
+  const float4* g4 = reinterpret_cast<const float4*>(s.g);
+  float4* m4 = reinterpret_cast<float4*>(s.m);
+  float4* v4 = reinterpret_cast<float4*>(s.v);
+  float4* t4 = reinterpret_cast<float4*>(s.target);
+  for (int64_t i = bx * int64_t(256) + threadIdx.x; i < n4; i += int64_t(gx) * 256) {
+    float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+    float4 t = s.target ? t4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x; float* tt = &t.x;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float gr = gg[c] * a.grad_scale;
+      mm[c] = fmaf(a.w1, gr - mm[c], mm[c]);                                   // lerp, weight < 0.5
+      vv[c] = __fadd_rn(__fmul_rn(vv[c], a.beta2), __fmul_rn(__fmul_rn(a.w2, gr), gr));
+      const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[c]), bc2s), a.eps);
+      pp[c] = __fadd_rn(pp[c], __fmul_rn(nss, __fdiv_rn(mm[c], denom)));
+      tt[c] = __fadd_rn(__fmul_rn(a.one_minus_tau, tt[c]), __fmul_rn(a.tau, pp[c]));
+    }
+    p4[i] = p; m4[i] = m; v4[i] = v;
+    if (s.target) t4[i] = t;
+  }
+}
+
+
+}  // namespace d4pg

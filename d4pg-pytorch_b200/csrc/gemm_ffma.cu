@@ -6,237 +6,9 @@
 // tiled 32x32 so a 256x256x256 layer spreads over 64 CTAs: at batch 256 the whole step is
 // latency-bound, so small tiles on many SMs beat big tiles on few.  Accumulation is plain FFMA
 // in k order, i.e. a true fp32 dot product (needed for the 1e-5 parity of config 2).
-#include "gemm_ffma.cuh"
+#include "gemm_ffma_dev.cuh"
 
 namespace d4pg {
-
-constexpr int BM = 32, BN = 32, KC = 64;
-constexpr int LDS_A = BM;       // dense rows; bank conflicts of the transposed stores are handled by swz()
-constexpr int LDS_B = BN;
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_WARPS = GEMM_THREADS / 32;
-constexpr int KW = KC / GEMM_WARPS;                  // k values per warp per chunk (intra-CTA split-K)
-constexpr int PER_THREAD = BM * KC / GEMM_THREADS;   // 8 staged elements per thread per operand per chunk
-
-// smem tiles are k-major [kk][32]; the 8 float4 columns of a row are XOR-permuted by (kk>>3)&7 so that
-// the transposed stores of a K-contiguous source (a warp writes one column at 16 different kk) spread
-// over the banks (8-way conflict without it) while float4 reads along a row stay aligned.
-__device__ __forceinline__ int swz(int kk, int idx) { return ((((idx >> 2) ^ (kk >> 3)) & 7) << 2) | (idx & 3); }
-
-// ---- operand staging ---------------------------------------------------------------------------
-// Two source shapes, each with a 128-bit fast path (ncu of the first version: 42 % of all issued
-// instructions were address arithmetic / predicate / constant-bank loads of the scalar staging):
-//   K-contiguous  src[row*ld + k]  (rows = tile dim): thread reads 2 float4 along k
-//   row-contiguous src[k*ld + col] (cols = tile dim): thread reads 2 float4 along the tile dim
-// Everything is read into registers first (all loads of a chunk in flight together), then
-// written to the k-major smem tiles As[kk][i] / Bs[kk][j].
-template <bool VEC>
-__device__ __forceinline__ void load_kcontig(const float* __restrict__ src, int ld, int row0, int nrows, int k0, int K,
-                                             int tid, float (&r)[PER_THREAD]) {
-  if (VEC) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * GEMM_THREADS, row = e >> 4, k = k0 + ((e & 15) << 2);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + row < nrows && k < K) v = __ldg(reinterpret_cast<const float4*>(src + size_t(row0 + row) * ld + k));
-      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < PER_THREAD; ++q) {
-      const int e = tid + q * GEMM_THREADS, row = e >> 6, k = k0 + (e & 63);
-      r[q] = (row0 + row < nrows && k < K) ? __ldg(src + size_t(row0 + row) * ld + k) : 0.f;
-    }
-  }
-}
-template <bool VEC>
-__device__ __forceinline__ void store_kcontig(float* __restrict__ dst, int lds, int tid, const float (&r)[PER_THREAD]) {
-  if (VEC) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * GEMM_THREADS, row = e >> 4, kk = (e & 15) << 2;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) dst[(kk + c) * lds + swz(kk + c, row)] = r[4 * q + c];
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < PER_THREAD; ++q) {
-      const int e = tid + q * GEMM_THREADS;
-      dst[(e & 63) * lds + swz(e & 63, e >> 6)] = r[q];
-    }
-  }
-}
-template <bool VEC>
-__device__ __forceinline__ void load_rowcontig(const float* __restrict__ src, int ld, int col0, int ncols, int k0, int K,
-                                               int tid, float (&r)[PER_THREAD]) {
-  if (VEC) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * GEMM_THREADS, kk = e >> 3, col = col0 + ((e & 7) << 2);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + kk < K && col < ncols) v = __ldg(reinterpret_cast<const float4*>(src + size_t(k0 + kk) * ld + col));
-      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < PER_THREAD; ++q) {
-      const int e = tid + q * GEMM_THREADS, kk = e >> 5, col = col0 + (e & 31);
-      r[q] = (k0 + kk < K && col < ncols) ? __ldg(src + size_t(k0 + kk) * ld + col) : 0.f;
-    }
-  }
-}
-template <bool VEC>
-__device__ __forceinline__ void store_rowcontig(float* __restrict__ dst, int lds, int tid, const float (&r)[PER_THREAD]) {
-  if (VEC) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * GEMM_THREADS, kk = e >> 3, col = (e & 7) << 2;
-      *reinterpret_cast<float4*>(&dst[kk * lds + swz(kk, col)]) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < PER_THREAD; ++q) {
-      const int e = tid + q * GEMM_THREADS;
-      dst[(e >> 5) * lds + swz(e >> 5, e & 31)] = r[q];
-    }
-  }
-}
-
-struct Operand { const float* p; int ld; bool vec; };
-
-// A-operand source for chunk k0: FWD may switch to the concatenated second source (k >= K1)
-template <int MODE>
-__device__ __forceinline__ void load_A(const GemmProblem& P, int m0, int k0, int tid, float (&ra)[PER_THREAD], bool& vec) {
-  if (MODE == GEMM_DW) {               // A(i,k) = dZ[k*lda + i]
-    vec = (P.flags & GEMM_A_VEC) != 0;
-    if (vec) load_rowcontig<true>(P.A, P.lda, m0, P.M, k0, P.K, tid, ra);
-    else load_rowcontig<false>(P.A, P.lda, m0, P.M, k0, P.K, tid, ra);
-  } else if (k0 >= P.K1) {             // concatenated tail (critic fc2's action columns): scalar
-    vec = false;
-    load_kcontig<false>(P.A2, P.lda2, m0, P.M, k0 - P.K1, P.K - P.K1, tid, ra);
-  } else {
-    vec = (P.flags & GEMM_A_VEC) != 0;
-    if (vec) load_kcontig<true>(P.A, P.lda, m0, P.M, k0, P.K1, tid, ra);
-    else load_kcontig<false>(P.A, P.lda, m0, P.M, k0, P.K1, tid, ra);
-  }
-}
-template <int MODE>
-__device__ __forceinline__ void store_A(float* As, int tid, const float (&ra)[PER_THREAD], bool vec) {
-  if (MODE == GEMM_DW) { if (vec) store_rowcontig<true>(As, LDS_A, tid, ra); else store_rowcontig<false>(As, LDS_A, tid, ra); }
-  else { if (vec) store_kcontig<true>(As, LDS_A, tid, ra); else store_kcontig<false>(As, LDS_A, tid, ra); }
-}
-template <int MODE>
-__device__ __forceinline__ void load_B(const GemmProblem& P, int n0, int k0, int tid, float (&rb)[PER_THREAD]) {
-  const bool vec = (P.flags & GEMM_B_VEC) != 0;
-  if (MODE == GEMM_FWD) {              // B(k,j) = W[j*ldb + k]
-    if (vec) load_kcontig<true>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
-    else load_kcontig<false>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
-  } else {                             // B(k,j) = B[k*ldb + j]
-    if (vec) load_rowcontig<true>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
-    else load_rowcontig<false>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
-  }
-}
-template <int MODE>
-__device__ __forceinline__ void store_B(const GemmProblem& P, float* Bs, int tid, const float (&rb)[PER_THREAD]) {
-  const bool vec = (P.flags & GEMM_B_VEC) != 0;
-  if (MODE == GEMM_FWD) { if (vec) store_kcontig<true>(Bs, LDS_B, tid, rb); else store_kcontig<false>(Bs, LDS_B, tid, rb); }
-  else { if (vec) store_rowcontig<true>(Bs, LDS_B, tid, rb); else store_rowcontig<false>(Bs, LDS_B, tid, rb); }
-}
-
-// One 32x32 output tile.  The 8 warps split K inside the CTA: each warp owns the whole tile for
-// 1/8 of every K-chunk with an 8x4 register tile per lane (32 independent FFMAs per 3 LDS.128);
-// the 8 partial tiles are summed through shared memory in fixed warp order (deterministic).
-template <int MODE>
-__device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int m0, int n0, int tn) {
-  float* As0 = smem;                      // [2][KC*LDS_A]
-  float* Bs0 = smem + 2 * KC * LDS_A;     // [2][KC*LDS_B]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r0 = (lane >> 3) * 8, c0 = (lane & 7) * 4;      // lane's 8x4 sub-tile
-
-  float acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float colsum = 0.f;                       // DW: bias gradient, threads < BM of the tn==0 tiles
-  const bool want_bias_grad = (MODE == GEMM_DW) && (P.bias_grad != nullptr) && (tn == 0);
-
-  float ra[PER_THREAD], rb[PER_THREAD];
-  bool avec;
-  const int nchunks = (P.K + KC - 1) / KC;
-  load_A<MODE>(P, m0, 0, tid, ra, avec);
-  load_B<MODE>(P, n0, 0, tid, rb);
-  store_A<MODE>(As0, tid, ra, avec);
-  store_B<MODE>(P, Bs0, tid, rb);
-  __syncthreads();
-  for (int c = 0; c < nchunks; ++c) {
-    const int cur = c & 1;
-    if (c + 1 < nchunks) {                                                      // in flight during the FMAs
-      load_A<MODE>(P, m0, (c + 1) * KC, tid, ra, avec);
-      load_B<MODE>(P, n0, (c + 1) * KC, tid, rb);
-    }
-    const float* __restrict__ as = As0 + cur * KC * LDS_A;
-    const float* __restrict__ bs = Bs0 + cur * KC * LDS_B;
-#pragma unroll
-    for (int k = 0; k < KW; ++k) {                                              // zero-padded past K
-      const int kk = warp * KW + k;
-      const float4 a0 = *reinterpret_cast<const float4*>(&as[kk * LDS_A + swz(kk, r0)]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&as[kk * LDS_A + swz(kk, r0 + 4)]);
-      const float4 b = *reinterpret_cast<const float4*>(&bs[kk * LDS_B + swz(kk, c0)]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-    if (want_bias_grad && tid < BM) {
-#pragma unroll 8
-      for (int kk = 0; kk < KC; ++kk) colsum += as[kk * LDS_A + swz(kk, tid)];
-    }
-    if (c + 1 < nchunks) {
-      store_A<MODE>(As0 + (cur ^ 1) * KC * LDS_A, tid, ra, avec);
-      store_B<MODE>(P, Bs0 + (cur ^ 1) * KC * LDS_B, tid, rb);
-    }
-    __syncthreads();
-  }
-
-  // ---- cross-warp reduction of the 8 partial tiles (fixed order w = 0..7) ---------------------
-  float* red = smem;                        // [GEMM_WARPS][BM][BN]
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<float4*>(&red[(warp * BM + r0 + i) * BN + c0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  __syncthreads();
-  const int orow = tid >> 3, ocol = (tid & 7) * 4;          // thread's 4 outputs
-  float4 sum = *reinterpret_cast<const float4*>(&red[orow * BN + ocol]);
-#pragma unroll
-  for (int w = 1; w < GEMM_WARPS; ++w) {
-    const float4 t = *reinterpret_cast<const float4*>(&red[(w * BM + orow) * BN + ocol]);
-    sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
-  }
-
-  // ---- epilogue ------------------------------------------------------------------------------
-  const int gi = m0 + orow;
-  if (gi < P.M) {
-    const float v[4] = {sum.x, sum.y, sum.z, sum.w};
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int gj = n0 + ocol + cc;
-      if (gj >= P.N) continue;
-      float x = v[cc];
-      switch (P.epi) {
-        case EPI_BIAS: x += __ldg(P.bias + gj); break;
-        case EPI_BIAS_RELU: x = fmaxf(x + __ldg(P.bias + gj), 0.f); break;
-        case EPI_BIAS_TANH: x = tanhf(x + __ldg(P.bias + gj)); break;
-        case EPI_RELU_MASK: x = (__ldg(P.aux + size_t(gi) * P.ldaux + gj) > 0.f) ? x : 0.f; break;
-        case EPI_TANH_MASK: { const float t = __ldg(P.aux + size_t(gi) * P.ldaux + gj); x *= (1.f - t * t); } break;
-        default: break;
-      }
-      P.C[size_t(gi) * P.ldc + gj] = x;
-    }
-  }
-  if (want_bias_grad && tid < BM && m0 + tid < P.M) P.bias_grad[m0 + tid] = colsum;
-}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid_constant__ GemmBatch batch) {
   __shared__ __align__(16) float smem[2 * KC * LDS_A + 2 * KC * LDS_B];
@@ -248,11 +20,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid
   for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
     if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
   const GemmProblem P = batch.p[pi];        // one copy into registers (no constant-bank reads in the loops)
-  const int tile = blockIdx.x - P.tile_begin;
-  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
-  if (P.mode == GEMM_FWD) gemm_tile<GEMM_FWD>(P, smem, tm * BM, tn * BN, tn);
-  else if (P.mode == GEMM_DX) gemm_tile<GEMM_DX>(P, smem, tm * BM, tn * BN, tn);
-  else gemm_tile<GEMM_DW>(P, smem, tm * BM, tn * BN, tn);
+  gemm_tile_dispatch(P, smem, blockIdx.x - P.tile_begin);
 }
 
 // ---- host side -------------------------------------------------------------------------------

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "internal.cuh"
+#include "step_mega.cuh"
 
 namespace d4pg {
 
@@ -35,6 +36,7 @@ struct Workspace {
   // backward
   float *c_dz22, *c_dz2, *c_dz1, *p_dz22, *p_dz2, *a_dz3, *a_dz22, *a_dh2, *a_dz1;
   LearnerClock* clock;
+  unsigned long long* barrier;     // grid-barrier counter of the persistent step kernel
   int64_t total;
 };
 
@@ -62,6 +64,7 @@ static Workspace carve(float* base, int B, int S, int A, int N) {
   w.a_dz3 = take(int64_t(B) * Ap); w.a_dz22 = take(int64_t(B) * H); w.a_dh2 = take(int64_t(B) * H);
   w.a_dz1 = take(int64_t(B) * H);
   w.clock = reinterpret_cast<LearnerClock*>(take(sizeof(LearnerClock) / 4 + 4));
+  w.barrier = reinterpret_cast<unsigned long long*>(take(4));
   w.total = off;
   return w;
 }
@@ -82,6 +85,7 @@ struct d4pg_learner {
   int kernels_per_step;
   // profiling (d4pg_learner_profile_step): CUDA-event pair around every launch of an eager step
   cudaStream_t side; cudaEvent_t ev_fork, ev_join;
+  MegaParams mega;
   bool profiling;
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> ev_name;
@@ -99,6 +103,20 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   const int Sp = pitch4(S), Ap = pitch4(A), Np = pitch4(N);          // activation row pitches
   const int* la = da.ld; const int* lc = dc.ld;                        // weight row pitches per layer
   int rc; int nk = 0;
+  const bool mega = c.persistent != 0;
+  MegaParams* mp = mega ? &L->mega : nullptr;
+  int n_levels = 0;
+  if (mega) { mp->n_fwd = 0; mp->n_bwd = 0; }
+  // a GEMM level is either launched or (persistent kernel) recorded as a phase
+#define LEVEL(gb)                                                                           \
+  do {                                                                                      \
+    if (mega) {                                                                             \
+      D4PG_REQUIRE(n_levels < MEGA_MAX_LEVELS, D4PG_ENOTSUP, "too many GEMM levels");       \
+      GemmBatchLite& lv = mp->level[n_levels++];                                            \
+      for (int _i = 0; _i < (gb).n; ++_i) lv.p[_i] = (gb).p[_i];                            \
+      lv.n = (gb).n; lv.total_tiles = (gb).total_tiles;                                     \
+    } else RUN(gemm_launch(gb, c.precision, st));                                           \
+  } while (0)
 #define RUN(expr)                                                                          \
   do {                                                                                     \
     if (L->profiling) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);    \
@@ -117,10 +135,15 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   //    scalars (Adam bias corrections, PER beta, Philox counter) from the learner clock.
   ClockParams cp{c.lr_actor, c.lr_critic, c.beta1, c.beta2, c.per_beta0, c.per_beta_final,
                  c.per_beta_iters > 0 ? c.per_beta_iters : 1};
-  RUN(learner_sample(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
-                     (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
-                     c.philox_seed, w.clock, cp,
-                     b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, Sp, Ap, st));
+  if (mega)
+    learner_sample_args(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
+                        (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
+                        c.philox_seed, w.clock, cp, b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, Sp, Ap, mp->sample);
+  else
+    RUN(learner_sample(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
+                       (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
+                       c.philox_seed, w.clock, cp,
+                       b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, Sp, Ap, st));
 
   const float* Wa = b.actor; const float* Wat = b.actor_target; const float* Wc = b.critic; const float* Wct = b.critic_target;
   GemmBatch g;
@@ -130,38 +153,38 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   gemm_batch_add(g, gemm_fwd(w.s2, Sp, nullptr, 0, 0, Wct + dc.w_off[0], lc[0], Wct + dc.b_off[0], w.h1[1], H, B, H, S, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.s, Sp, nullptr, 0, 0, Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], w.h1[2], H, B, H, S, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.s, Sp, nullptr, 0, 0, Wa + da.w_off[0], la[0], Wa + da.b_off[0], w.h1[3], H, B, H, S, EPI_BIAS_RELU));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level 2: fc2 (actor: no activation, models.py:36; critic: cat(h1, a) + relu, models.py:80)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h1[0], H, nullptr, 0, 0, Wat + da.w_off[1], la[1], Wat + da.b_off[1], w.h2[0], H, B, H, H, EPI_BIAS));
   gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.a, Ap, H, Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], w.h2[2], H, B, H, H + A, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h1[3], H, nullptr, 0, 0, Wa + da.w_off[1], la[1], Wa + da.b_off[1], w.h2[3], H, B, H, H, EPI_BIAS));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level 3: fc2_2 + relu
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h2[0], H, nullptr, 0, 0, Wat + da.w_off[2], la[2], Wat + da.b_off[2], w.h3[0], H, B, H, H, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h2[2], H, nullptr, 0, 0, Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], w.h3[2], H, B, H, H, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h2[3], H, nullptr, 0, 0, Wa + da.w_off[2], la[2], Wa + da.b_off[2], w.h3[3], H, B, H, H, EPI_BIAS_RELU));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level 4: fc3 (actor: tanh; critic: logits)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h3[0], H, nullptr, 0, 0, Wat + da.w_off[3], la[3], Wat + da.b_off[3], w.out[0], Ap, B, A, H, EPI_BIAS_TANH));
   gemm_batch_add(g, gemm_fwd(w.h3[2], H, nullptr, 0, 0, Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], w.out[2], Np, B, N, H, EPI_BIAS));
   gemm_batch_add(g, gemm_fwd(w.h3[3], H, nullptr, 0, 0, Wa + da.w_off[3], la[3], Wa + da.b_off[3], w.out[3], Ap, B, A, H, EPI_BIAS_TANH));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level 5: critic_target.fc2([h1t, a_t(s')]) and critic.fc2([h1, actor(s)]) (h1 of the critic is reused)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h1[1], H, w.out[0], Ap, H, Wct + dc.w_off[1], lc[1], Wct + dc.b_off[1], w.h2[1], H, B, H, H + A, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h1[2], H, w.out[3], Ap, H, Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], w.h2[4], H, B, H, H + A, EPI_BIAS_RELU));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h2[1], H, nullptr, 0, 0, Wct + dc.w_off[2], lc[2], Wct + dc.b_off[2], w.h3[1], H, B, H, H, EPI_BIAS_RELU));
   gemm_batch_add(g, gemm_fwd(w.h2[4], H, nullptr, 0, 0, Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], w.h3[4], H, B, H, H, EPI_BIAS_RELU));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.h3[1], H, nullptr, 0, 0, Wct + dc.w_off[3], lc[3], Wct + dc.b_off[3], w.out[1], Np, B, N, H, EPI_BIAS));
   gemm_batch_add(g, gemm_fwd(w.h3[4], H, nullptr, 0, 0, Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], w.out[4], Np, B, N, H, EPI_BIAS));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
 
   // 3. heads: softmaxes, projection, CE loss, td, priorities, logit gradients (ddpg.py:214-222,236-238)
   HeadsArgs ha{};
@@ -174,11 +197,15 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   ha.m = w.m; ha.target_probs = w.target_probs; ha.q_probs = w.q_probs;
   ha.loss_rows = w.loss_rows; ha.td = b.td; ha.prio = b.prio; ha.dlogits_q = w.dlogits_q;
   ha.pi_rows = w.pi_rows; ha.dlogits_pi = w.dlogits_pi;
-  RUN(launch_heads(ha, c.proj_mode, st));
+  if (mega) { mp->heads = ha; mp->heads_mode = c.proj_mode; mp->n_fwd = n_levels; }
+  else RUN(launch_heads(ha, c.proj_mode, st));
 
   // 4. priorities into the trees (ddpg.py:252-255): independent of the backward pass, so it runs
   //    on a forked branch (side stream -> parallel graph branch) and joins before the step ends
-  if (c.prioritized) {
+  if (mega) {
+    mp->do_tree = c.prioritized ? 1 : 0;
+    if (c.prioritized) tree_update_args(L->replay, B, b.idx, b.prio, mp->tree);
+  } else if (c.prioritized) {
     D4PG_CUDA_OK(cudaEventRecord(L->ev_fork, st));
     D4PG_CUDA_OK(cudaStreamWaitEvent(L->side, L->ev_fork, 0));
     RUN(launch_tree_update(L->replay, B, b.idx, b.prio, L->side));
@@ -192,40 +219,40 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   gemm_batch_add(g, gemm_dx(w.dlogits_q, Np, Wc + dc.w_off[3], lc[3], w.c_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[2], H));
   gemm_batch_add(g, gemm_dx(w.dlogits_pi, Np, Wc + dc.w_off[3], lc[3], w.p_dz22, H, B, H, N, EPI_RELU_MASK, w.h3[4], H));
   gemm_batch_add(g, gemm_dw(w.dlogits_q, Np, w.h3[2], H, Gc + dc.w_off[3], lc[3], Gc + dc.b_off[3], N, H, B));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level B2: through critic.fc2_2
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dx(w.c_dz22, H, Wc + dc.w_off[2], lc[2], w.c_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[2], H));
   gemm_batch_add(g, gemm_dx(w.p_dz22, H, Wc + dc.w_off[2], lc[2], w.p_dz2, H, B, H, H, EPI_RELU_MASK, w.h2[4], H));
   gemm_batch_add(g, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], lc[2], Gc + dc.b_off[2], H, H, B));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level B3: through critic.fc2: dh1 (critic loss), d action (policy, tanh' folded in), dW2 = [dz2^T h1 | dz2^T a]
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dx(w.c_dz2, H, Wc + dc.w_off[1], lc[1], w.c_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[2], H));
   gemm_batch_add(g, gemm_dx(w.p_dz2, H, Wc + dc.w_off[1] + H, lc[1], w.a_dz3, Ap, B, A, H, EPI_TANH_MASK, w.out[3], Ap));
   gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], lc[1], Gc + dc.b_off[1], H, H, B));
   gemm_batch_add(g, gemm_dw(w.c_dz2, H, w.a, Ap, Gc + dc.w_off[1] + H, lc[1], nullptr, H, A, B));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level B4: critic.fc1 weights; actor.fc3
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dw(w.c_dz1, H, w.s, Sp, Gc + dc.w_off[0], lc[0], Gc + dc.b_off[0], H, S, B));
   gemm_batch_add(g, gemm_dx(w.a_dz3, Ap, Wa + da.w_off[3], la[3], w.a_dz22, H, B, H, A, EPI_RELU_MASK, w.h3[3], H));
   gemm_batch_add(g, gemm_dw(w.a_dz3, Ap, w.h3[3], H, Ga + da.w_off[3], la[3], Ga + da.b_off[3], A, H, B));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level B5: actor.fc2_2 (its input h2 has no activation -> plain dX)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dx(w.a_dz22, H, Wa + da.w_off[2], la[2], w.a_dh2, H, B, H, H, EPI_NONE, nullptr, 0));
   gemm_batch_add(g, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], la[2], Ga + da.b_off[2], H, H, B));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level B6: actor.fc2
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dx(w.a_dh2, H, Wa + da.w_off[1], la[1], w.a_dz1, H, B, H, H, EPI_RELU_MASK, w.h1[3], H));
   gemm_batch_add(g, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], la[1], Ga + da.b_off[1], H, H, B));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
   // level B7: actor.fc1
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_dw(w.a_dz1, H, w.s, Sp, Ga + da.w_off[0], la[0], Ga + da.b_off[0], H, S, B));
-  RUN(gemm_launch(g, c.precision, st));
+  LEVEL(g);
 
   // 6. data-parallel gradient exchange: ONE all-reduce over the flat [P_a + P_c] buffer
   if (c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
@@ -239,8 +266,15 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   aa.tau = float(c.tau); aa.one_minus_tau = float(1.0 - c.tau); aa.grad_scale = 1.0f; aa.clock = w.clock;
   // tail slice of the same launch: reported batch-mean losses + advance the device clock
   aa.loss_rows = w.loss_rows; aa.pi_rows = w.pi_rows; aa.B = B; aa.inv_count = 1.0f / float(B); aa.loss_out = b.losses;
-  RUN(launch_adam(aa, st));
-  if (c.prioritized) D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join, 0));
+  if (mega) {
+    mp->n_bwd = n_levels - mp->n_fwd;
+    mp->adam = aa; mp->clock = w.clock; mp->barrier = w.barrier;
+    RUN(launch_step_mega(*mp, st));
+  } else {
+    RUN(launch_adam(aa, st));
+    if (c.prioritized) D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join, 0));
+  }
+#undef LEVEL
 #undef RUN
   L->kernels_per_step = nk;
   return D4PG_OK;
@@ -261,6 +295,8 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   D4PG_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, D4PG_ENOTSUP,
                "d4pg_learner_create: precision %d unknown (0 fp32 FFMA, 1 3xTF32 tcgen05, 2 TF32 tcgen05)", cfg->precision);
   D4PG_REQUIRE(cfg->world_size <= 1 || comm, D4PG_EINVAL, "d4pg_learner_create: world_size>1 needs a communicator");
+  D4PG_REQUIRE(!cfg->persistent || (cfg->precision == 0 && cfg->world_size <= 1), D4PG_ENOTSUP,
+               "d4pg_learner_create: the persistent step kernel needs precision 0 and a single GPU");
   D4PG_REQUIRE(buf->actor && buf->actor_target && buf->critic && buf->critic_target && buf->grad_actor && buf->grad_critic &&
                buf->adam_m_actor && buf->adam_v_actor && buf->adam_m_critic && buf->adam_v_critic &&
                buf->idx && buf->prio && buf->td && buf->losses && buf->workspace, D4PG_EINVAL,
@@ -368,6 +404,7 @@ extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_ste
   LearnerClock c{};
   c.adam_step = adam_step; c.beta_t = beta_t; c.steps_done = adam_step;
   D4PG_CUDA_OK(cudaMemcpyAsync(L->ws.clock, &c, sizeof(c), cudaMemcpyHostToDevice, as_stream(stream)));
+  D4PG_CUDA_OK(cudaMemsetAsync(L->ws.barrier, 0, sizeof(unsigned long long), as_stream(stream)));
   D4PG_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
   return D4PG_OK;
 }

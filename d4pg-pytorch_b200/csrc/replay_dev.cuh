@@ -1,0 +1,255 @@
+// Device code of the GPU-resident prioritized replay (shared by replay.cu and the persistent step kernel).
+#pragma once
+#include "internal.cuh"
+#include "adam.cuh"
+
+namespace d4pg {
+
+// Device-resident bookkeeping (lives in the caller's `state` buffer, 32 bytes).  Kernels read
+// len / pristine from here so a captured CUDA graph stays valid while add() keeps filling.
+struct ReplayState {
+  float max_priority;      // PrioritizedReplayBuffer._max_priority, :249,335
+  int32_t pristine;        // 1 until the first update_priorities (tree still "all Python floats")
+  int64_t len;             // len(self._storage)
+  int64_t next_idx;        // self._next_idx
+  int64_t reserved;
+};
+static_assert(sizeof(ReplayState) == 32, "ReplayState must fit the 8-float state buffer");
+
+// leaf = priority ** alpha with np.float32 ** float semantics: powf(p, (float)alpha).  glibc's
+// powf is correctly rounded in all but vanishing cases, so we evaluate in fp64 and round once.
+__device__ __forceinline__ float pow_alpha(float p, float alpha_f32) {
+  if (p == 1.0f) return 1.0f;
+  return __double2float_rn(pow(double(p), double(alpha_f32)));
+}
+
+// SumSegmentTree.sum(0, end+1): reduce over leaves [0, end] with _reduce_helper's association
+// (prioritized_replay_memory.py:61-96): V[left] + (V[left'] + (... + V[last])), fp32.
+static __device__ float prefix_sum_ref(const float* __restrict__ V, int64_t cap, int64_t e) {
+  // the node cover depends only on (cap, e): collect the addresses first so the loads are
+  // independent and overlap (one L2 round trip instead of log2(cap) dependent ones)
+  int64_t nodes[40];
+  int n = 0;
+  int64_t node = 1, lo = 0, hi = cap - 1;
+  while (true) {
+    if (e == hi) { nodes[n++] = node; break; }
+    int64_t mid = (lo + hi) >> 1;
+    if (e <= mid) { node = 2 * node; hi = mid; }
+    else { nodes[n++] = 2 * node; node = 2 * node + 1; lo = mid + 1; }
+  }
+  float terms[40];
+#pragma unroll 8
+  for (int i = 0; i < n; ++i) terms[i] = __ldcg(V + nodes[i]);
+  float acc = terms[n - 1];
+  for (int i = n - 2; i >= 0; --i) acc = __fadd_rn(terms[i], acc);
+  return acc;
+}
+static __device__ float prefix_min_ref(const float* __restrict__ V, int64_t cap, int64_t e) {
+  float acc = INFINITY;
+  int64_t node = 1, lo = 0, hi = cap - 1;
+  while (true) {
+    if (e == hi) { acc = fminf(acc, __ldcg(V + node)); break; }
+    int64_t mid = (lo + hi) >> 1;
+    if (e <= mid) { node = 2 * node; hi = mid; }
+    else { acc = fminf(acc, __ldcg(V + 2 * node)); node = 2 * node + 1; lo = mid + 1; }
+  }
+  return acc;
+}
+
+struct SampleArgs {
+  const float* sum; const float* mn; int64_t cap; const ReplayState* state;
+  const double* uniforms; uint64_t seed, counter; float beta;
+  LearnerClock* clock;              // optional (learner): Philox counter / beta from the device clock;
+  ClockParams clock_params;         //   block 0 also derives this step's Adam scalars into it
+  const float* obs; const float* act; const double* rew; const float* obs2; const uint8_t* done;
+  int obs_dim, act_dim; int B;
+  int ld_obs, ld_act;               // row pitch of the gathered s/s2 and a batches (0 = dense)
+  const int32_t* idx_in;            // gather-only mode when non-null
+  int uniform_mode;                 // 1: idx = floor(u*len) (device-side uniform replay, with replacement)
+  int32_t* idx; float* weights;
+  float* s; float* a; double* r; float* s2; uint8_t* d;
+};
+
+constexpr int SAMPLE_ROWS = 32;      // rows per CTA
+constexpr int SAMPLE_THREADS = 256;
+constexpr int TOP_LEVELS = 11;       // tree levels 0..10 (nodes 1..2047) are staged in shared memory
+
+// sum(0, len-1) by one warp: the prefix [0,x) (x = len-1) is covered by one node per set bit of x;
+// _reduce_helper (:61-96) adds them right-nested, i.e. lowest bit first: acc = t_b + acc going up.
+// Each lane fetches the node of "its" bit (all loads in flight together), lane 0 folds them in order.
+__device__ __forceinline__ float warp_prefix_sum(const float* __restrict__ V, int64_t cap, int64_t x, int lane) {
+  float term = 0.f;
+  const bool has = ((x >> lane) & 1) != 0;
+  if (has) {
+    const int64_t start = x & ~((int64_t(2) << lane) - 1);
+    term = __ldcg(V + (cap >> lane) + (start >> lane));
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, has);
+  float acc = 0.f;
+  bool first = true;
+  for (int b = 0; b < 32; ++b) {
+    const float t = __shfl_sync(0xffffffffu, term, b);
+    if ((mask >> b) & 1) { acc = first ? t : __fadd_rn(t, acc); first = false; }
+  }
+  return acc;
+}
+
+// _sample_proportional (:258-265) + IS weights (:303-311) + _encode_sample (:189-199), fused.
+struct SampleSmem {
+  float top[1 << TOP_LEVELS];
+  int32_t idx[SAMPLE_ROWS];
+  float total;
+};
+// rows [bid*32, bid*32+32) of the batch, executed by one 256-thread CTA
+__device__ __forceinline__ void sample_body(const SampleArgs& a, int bid, SampleSmem& sm) {
+  int32_t* idx_s = sm.idx;
+  float* top_s = sm.top;
+  float& total_s = sm.total;
+  const int row0 = bid * SAMPLE_ROWS;
+  const int nrows = min(SAMPLE_ROWS, a.B - row0);
+  const int t = threadIdx.x;
+  if (a.clock && bid == 0 && t == SAMPLE_THREADS - 1) {
+    clock_derive(a.clock, a.clock_params);
+    a.clock->beta = clock_beta(a.clock, a.clock_params);
+  }
+  const bool descend = (a.idx_in == nullptr) && !a.uniform_mode;
+  const int64_t len = a.state->len;
+  int top_levels = 0;
+  if (descend) {
+    // stage the top of the sum tree (one L2 round trip for the whole CTA) and the prefix total
+    while ((int64_t(1) << top_levels) < a.cap && top_levels < TOP_LEVELS) ++top_levels;
+    for (int i = t; i < (1 << top_levels); i += SAMPLE_THREADS) top_s[i] = (i >= 1) ? __ldcg(a.sum + i) : 0.f;
+    if (t < 32) {
+      const float tot = warp_prefix_sum(a.sum, a.cap, len - 1, t);       // sum(0, len-1): leaves [0, len-2]
+      if (t == 0) total_s = tot;
+    }
+    __syncthreads();
+  }
+  if (t < nrows) {
+    const int row = row0 + t;
+    int32_t leaf_idx;
+    if (a.idx_in) {
+      leaf_idx = a.idx_in[row];
+    } else {
+      const uint64_t ctr = a.counter + (a.clock ? uint64_t(a.clock->steps_done) : 0ull);
+      const double u = a.uniforms ? a.uniforms[row] : Philox::uniform53(a.seed, ctr, uint32_t(row));
+      int64_t i = 1;
+      const int64_t top_end = int64_t(1) << (top_levels - 1);              // nodes < 2*top_end have children in top_s
+      if (a.uniform_mode) {
+        int64_t pick = int64_t(u * double(len));
+        i = a.cap + (pick < len ? pick : len - 1);
+      } else if (a.state->pristine) {
+        // tree of Python floats: mass and the descent are fp64 (all node values are integers)
+        double mass = __dmul_rn(u, double(total_s));
+        while (i < a.cap) {
+          const double left = double((2 * i < 2 * top_end) ? top_s[2 * i] : __ldcg(a.sum + 2 * i));
+          if (left > mass) i = 2 * i;                                 // strict, :144
+          else { mass = __dsub_rn(mass, left); i = 2 * i + 1; }
+        }
+      } else {
+        float mass = __fmul_rn(__double2float_rn(u), total_s);         // weak float * np.float32
+        while (i < a.cap) {
+          const float left = (2 * i < 2 * top_end) ? top_s[2 * i] : __ldcg(a.sum + 2 * i);
+          if (left > mass) i = 2 * i;
+          else { mass = __fsub_rn(mass, left); i = 2 * i + 1; }
+        }
+      }
+      leaf_idx = int32_t(i - a.cap);
+      if (a.weights && !a.uniform_mode) {
+        const float tot = __ldcg(a.sum + 1);
+        const float pmin = __fdiv_rn(__ldcg(a.mn + 1), tot);
+        const float n = float(len);
+        const float beta = a.clock ? clock_beta(a.clock, a.clock_params) : a.beta;
+        const float maxw = __double2float_rn(pow(double(__fmul_rn(pmin, n)), double(-beta)));
+        const float ps = __fdiv_rn(__ldcg(a.sum + a.cap + leaf_idx), tot);
+        const float w = __double2float_rn(pow(double(__fmul_rn(ps, n)), double(-beta)));
+        a.weights[row] = __fdiv_rn(w, maxw);
+      }
+    }
+    idx_s[t] = leaf_idx;
+    if (a.idx) a.idx[row] = leaf_idx;
+    if (a.r) a.r[row] = a.rew[leaf_idx];
+    if (a.d) a.d[row] = a.done[leaf_idx];
+  }
+  __syncthreads();
+  // coalesced row gathers: consecutive threads walk consecutive features of one transition
+  const int od = a.obs_dim, ad = a.act_dim;
+  const int lo = a.ld_obs ? a.ld_obs : od, la = a.ld_act ? a.ld_act : ad;
+  for (int e = t; e < nrows * od; e += SAMPLE_THREADS) {
+    const int rr = e / od, c = e - rr * od;
+    const size_t src = size_t(idx_s[rr]) * od + c, dst = size_t(row0 + rr) * lo + c;
+    a.s[dst] = __ldg(a.obs + src);
+    a.s2[dst] = __ldg(a.obs2 + src);
+  }
+  for (int e = t; e < nrows * ad; e += SAMPLE_THREADS) {
+    const int rr = e / ad, c = e - rr * ad;
+    a.a[size_t(row0 + rr) * la + c] = __ldg(a.act + size_t(idx_s[rr]) * ad + c);
+  }
+}
+
+// ---- leaf writes + level-synchronous parent recompute, one CTA ---------------------------
+// update_priorities (:315-335) is a sequential Python loop; its final state equals "write all
+// leaves (last writer wins on duplicates), then recompute every touched ancestor bottom-up",
+// because each node's last recompute sees its children's final values.
+enum { TREE_UPDATE = 0, TREE_SET = 1, TREE_ADD = 2 };
+struct TreeArgs {
+  float* sum; float* mn; int64_t cap; int log2cap; int64_t size;
+  int n; const int32_t* idx; const float* v0; const float* v1;   // UPDATE: v0=prio; SET: v0=sum vals, v1=min vals
+  int64_t ring_start;                                              // ADD: positions (ring_start+i) % size
+  float alpha_f32; int32_t* scratch; ReplayState* state;
+};
+constexpr int TREE_THREADS = 1024;
+
+// executed by ONE CTA of NT threads (1024 standalone, 256 inside the persistent step kernel)
+template <int MODE, int NT>
+__device__ __forceinline__ void tree_write_body(const TreeArgs& a, float* red) {
+  const int t = threadIdx.x;
+  auto pos = [&](int i) -> int64_t {
+    return MODE == TREE_ADD ? (a.ring_start + i) % a.size : int64_t(a.idx[i]);
+  };
+  if (MODE != TREE_ADD) {
+    for (int i = t; i < a.n; i += NT) atomicMax(a.scratch + pos(i), i);
+    __syncthreads();
+  }
+  float local_max = 0.f;
+  const float add_leaf = (MODE == TREE_ADD) ? pow_alpha(a.state->max_priority, a.alpha_f32) : 0.f;  // :255-256
+  for (int i = t; i < a.n; i += NT) {
+    const int64_t p = pos(i);
+    if (MODE == TREE_ADD || a.scratch[p] == i) {
+      float ls, lm;
+      if (MODE == TREE_UPDATE) { ls = lm = pow_alpha(a.v0[i], a.alpha_f32); }
+      else if (MODE == TREE_SET) { ls = a.v0[i]; lm = a.v1[i]; }
+      else { ls = lm = add_leaf; }
+      a.sum[a.cap + p] = ls;
+      a.mn[a.cap + p] = lm;
+    }
+    if (MODE == TREE_UPDATE) local_max = fmaxf(local_max, a.v0[i]);
+  }
+  if (MODE == TREE_UPDATE) {                                       // _max_priority, :335
+    local_max = warp_max(local_max);
+    if ((t & 31) == 0) red[t >> 5] = local_max;
+    __syncthreads();
+    if (t < 32) {
+      float v = warp_max(t < NT / 32 ? red[t] : 0.f);
+      if (t == 0) {
+        if (v > a.state->max_priority) a.state->max_priority = v;
+        a.state->pristine = 0;
+      }
+    }
+  }
+  __syncthreads();
+  if (MODE != TREE_ADD)
+    for (int i = t; i < a.n; i += NT) a.scratch[pos(i)] = -1;
+  for (int lvl = 1; lvl <= a.log2cap; ++lvl) {
+    __syncthreads();
+    for (int i = t; i < a.n; i += NT) {
+      const int64_t node = (a.cap + pos(i)) >> lvl;
+      const float l = __ldcg(a.sum + 2 * node), r = __ldcg(a.sum + 2 * node + 1);
+      a.sum[node] = __fadd_rn(l, r);
+      a.mn[node] = fminf(__ldcg(a.mn + 2 * node), __ldcg(a.mn + 2 * node + 1));
+    }
+  }
+}
+
+
+}  // namespace d4pg

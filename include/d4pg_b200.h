@@ -201,6 +201,7 @@ typedef struct {
   uint64_t philox_seed;
   int32_t world_size;         /* >1: gradients are averaged over ranks before Adam */
   int32_t use_graph;          /* 1 = capture the step into a CUDA graph */
+  int32_t persistent;         /* 1 = run the step as ONE cooperative kernel with grid barriers (precision 0 only) */
 } d4pg_learner_config_t;
 
 /* Caller-owned device buffers.  P_a / P_c = d4pg_*_layout().total. */

@@ -14,14 +14,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def _build(d4pg, g, use_graph, sampling="reference", precision="fp32"):
+def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", persistent=False):
     obs_dim, act_dim, N, B, mem, n_fill, per, steps = [int(x) for x in g["meta"]]
     v_min, v_max = [float(x) for x in g["dist"]]
     info = {"type": "categorical", "v_min": v_min, "v_max": v_max, "n_atoms": N}
     seed = int(g["seed"])
     torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
     kw = dict(memory_size=mem, batch_size=B, critic_dist_info=info, prioritized_replay=bool(per),
-              use_graph=use_graph, sampling=sampling, precision=precision)
+              use_graph=use_graph, sampling=sampling, precision=precision, persistent=persistent)
     glob = d4pg.DDPG(obs_dim, act_dim, **kw)               # main.py:382-385
     oa = d4pg.SharedAdam(glob.actor.parameters(), lr=1e-3)
     oc = d4pg.SharedAdam(glob.critic.parameters(), lr=1e-3)
@@ -38,13 +38,15 @@ def _build(d4pg, g, use_graph, sampling="reference", precision="fp32"):
 
 
 @pytest.mark.parametrize("tag", ["per_c2", "per_part", "uniform_c1"])
-@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "tf32x3")])
+@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "tf32x3"), (True, "mega"), (False, "mega")])
 def test_train_steps_vs_reference_golden(tag, use_graph, precision):
     """precision fp32 = exact-FFMA kernels; tf32x3 = tcgen05 tensor cores with the 3xTF32 split.
     Both must meet the same 1e-5 bar against the reference's fp32 CPU results."""
     import d4pg_b200 as d4pg
     g = H.load("train_%s.npz" % tag)
-    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision=precision)
+    persistent = precision == "mega"          # fp32 kernels as phases of ONE cooperative kernel per step
+    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision="fp32" if persistent else precision,
+                                     persistent=persistent)
     obs_dim, act_dim, N, B, mem, n_fill, per, steps, v_min, v_max = meta
     for t in range(steps):
         random.seed(9000 + t)                       # same generator state as the reference run
