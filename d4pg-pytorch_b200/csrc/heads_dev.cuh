@@ -157,6 +157,8 @@ __device__ __forceinline__ void heads_row(const HeadsArgs& a, int row, int lane,
   row_softmax(a.q_logits + ro, N, lane, q, (a.flags & D4PG_PROJ_Q_IS_PROBS) != 0);
   float ce = 0.f, mq = 0.f, sq = 0.f;
   float gq[NT];
+  const float isw = a.is_weights ? __ldg(a.is_weights + row) : 1.f;
+  const float gscale = a.grad_scale * isw;
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
     int k = lane + 32 * t;
@@ -165,7 +167,7 @@ __device__ __forceinline__ void heads_row(const HeadsArgs& a, int row, int lane,
       float qe = q[t] + 1e-10f;
       ce += mk[t] * logf(qe);
       mq += mk[t] * q[t];
-      gq[t] = -(mk[t] / qe) * a.grad_scale;          // d mean-loss / d q_k
+      gq[t] = -(mk[t] / qe) * gscale;                // d mean-loss / d q_k
       sq += q[t] * gq[t];
     }
   }
@@ -182,9 +184,9 @@ __device__ __forceinline__ void heads_row(const HeadsArgs& a, int row, int lane,
   }
   if (lane == 0) {
     float tdv = -mq;
-    if (a.loss_rows) a.loss_rows[row] = -ce;
+    if (a.loss_rows) a.loss_rows[row] = -ce * isw;
     if (a.td) a.td[row] = tdv;
-    if (a.prio) a.prio[row] = fabsf(tdv) + float(a.prio_eps);       // np.abs(f32) + 1e-6 (f32)
+    if (a.prio) a.prio[row] = (a.ce_priority ? -ce : fabsf(tdv)) + float(a.prio_eps);   // np.abs(f32) + 1e-6 (f32)
   }
 
   // ---- policy head: -E_q[z] and its logit gradient --------------------------------------

@@ -17,6 +17,9 @@ struct HeadsArgs {
   float grad_scale;
   float* m; int32_t* bins_l; int32_t* bins_u; float* target_probs; float* q_probs;
   float* loss_rows; float* td; float* prio; float* dlogits_q; float* pi_rows; float* dlogits_pi;
+  // corrected-semantics switches (the reference does neither, H3 / H4):
+  const float* is_weights;   // non-null: critic CE row i is scaled by the PER importance weight w_i
+  int ce_priority;           // 1: priority = CE_i + eps instead of |sum_j m_ij q_ij| + eps
 };
 int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st);
 

@@ -197,6 +197,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   ha.m = w.m; ha.target_probs = w.target_probs; ha.q_probs = w.q_probs;
   ha.loss_rows = w.loss_rows; ha.td = b.td; ha.prio = b.prio; ha.dlogits_q = w.dlogits_q;
   ha.pi_rows = w.pi_rows; ha.dlogits_pi = w.dlogits_pi;
+  ha.is_weights = ((c.loss_flags & 1) && c.prioritized) ? b.weights : nullptr;
+  ha.ce_priority = (c.loss_flags & 2) ? 1 : 0;
   if (mega) { mp->heads = ha; mp->heads_mode = c.proj_mode; mp->n_fwd = n_levels; }
   else RUN(launch_heads(ha, c.proj_mode, st));
 

@@ -58,5 +58,6 @@ extern "C" int32_t d4pg_proj_loss(const float* target_logits, const float* q_log
   a.m = m; a.bins_l = bins_l; a.bins_u = bins_u; a.target_probs = target_probs; a.q_probs = q_probs;
   a.loss_rows = loss_rows; a.td = td; a.prio = prio; a.dlogits_q = dlogits_q;
   a.pi_rows = pi_rows; a.dlogits_pi = dlogits_pi;
+  a.is_weights = nullptr; a.ce_priority = 0;
   return launch_heads(a, proj_mode, as_stream(stream));
 }

@@ -70,6 +70,7 @@ class _Learner(object):
         cfg.philox_seed = int(ddpg.philox_seed)
         cfg.world_size = ddpg.comm.world_size if ddpg.comm is not None else 1
         cfg.use_graph = 1 if ddpg.use_graph else 0
+        cfg.loss_flags = (1 if ddpg.importance_weighted else 0) | (2 if ddpg.priority == "ce" else 0)
         cfg.persistent = 1 if (ddpg.persistent and ddpg.precision == "fp32" and cfg.world_size == 1) else 0
         self.cfg = cfg
         nws = L.d4pg_learner_workspace_floats(C.byref(cfg))
@@ -150,7 +151,8 @@ class DDPG:
                  critic_dist_info=None, n_steps=1,
                  # ---- B200 build extensions (keyword-only in spirit; reference callers never pass them)
                  device=None, sampling="reference", projection="reference", precision="fp32",
-                 use_graph=True, philox_seed=0, comm=None, persistent=False):
+                 use_graph=True, philox_seed=0, comm=None, persistent=False,
+                 importance_weighted=False, priority="reference"):
         self.gamma = gamma
         self.n_steps = n_steps
         self.n_step_gamma = self.gamma ** self.n_steps
@@ -165,6 +167,9 @@ class DDPG:
         self.sampling, self.projection, self.precision = sampling, projection, precision
         self.use_graph, self.philox_seed, self.comm = use_graph, philox_seed, comm
         self.persistent = persistent        # one cooperative kernel per step (fp32, single GPU)
+        # corrected-semantics switches (default = the reference's behaviour)
+        assert priority in ("reference", "ce")
+        self.importance_weighted, self.priority = bool(importance_weighted), priority
 
         self.dist_type = critic_dist_info["type"]
         if self.dist_type != "categorical":

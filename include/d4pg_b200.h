@@ -202,6 +202,10 @@ typedef struct {
   int32_t world_size;         /* >1: gradients are averaged over ranks before Adam */
   int32_t use_graph;          /* 1 = capture the step into a CUDA graph */
   int32_t persistent;         /* 1 = run the step as ONE cooperative kernel with grid barriers (precision 0 only) */
+  int32_t loss_flags;         /* corrected-semantics switches, 0 = reference behaviour:
+                                 1 = importance-weighted critic CE (the reference samples the weights but
+                                     ignores them, ddpg.py:217), 2 = priority = CE_i + eps instead of
+                                     |sum_j m_ij q_ij| + eps (ddpg.py:221-222,253) */
 } d4pg_learner_config_t;
 
 /* Caller-owned device buffers.  P_a / P_c = d4pg_*_layout().total. */

@@ -509,9 +509,11 @@ class LearnerOracle:
         return project_nstep(target_probs, r, done, self.v_min, self.v_max,
                              self.n_atoms, self.gamma, self.n_steps).astype(F32)
 
-    def train_step(self, s, a, r, s2, done, grad_hook=None):
+    def train_step(self, s, a, r, s2, done, grad_hook=None, is_weights=None, ce_priority=False):
         """One `DDPG.train` body on a given batch.  `grad_hook(flat_grads)` lets a
-        data-parallel test average gradients across ranks before Adam."""
+        data-parallel test average gradients across ranks before Adam.
+        `is_weights` / `ce_priority` are the corrected-semantics variants of SURVEY.md section 8f.4
+        (DERIVED oracle: the reference implements neither, ddpg.py:217,221-222)."""
         s_t = torch.from_numpy(np.asarray(s, dtype=F32))
         a_t = torch.from_numpy(np.asarray(a, dtype=F32))
         s2_t = torch.from_numpy(np.asarray(s2, dtype=F32))
@@ -524,7 +526,10 @@ class LearnerOracle:
         q = critic_forward(cw, s_t, a_t)                           # ddpg.py:208
         m = self.project(tz.numpy(), np.asarray(r, dtype=F64), np.asarray(done))
         m_t = torch.from_numpy(m)
-        loss_c = -(m_t * torch.log(q + 1e-10)).sum(dim=1).mean()   # ddpg.py:217
+        rows_c = -(m_t * torch.log(q + 1e-10)).sum(dim=1)
+        if is_weights is not None:
+            rows_c = rows_c * torch.from_numpy(np.asarray(is_weights, dtype=F32))
+        loss_c = rows_c.mean()                                     # ddpg.py:217 (unweighted there)
         td = -(m_t * q).sum(dim=1)                                 # ddpg.py:221-222
         loss_c.backward()                                          # ddpg.py:230
         g_c = {k: cw[k].grad.detach().clone() for k in PARAM_ORDER}
@@ -551,6 +556,8 @@ class LearnerOracle:
             polyak(self.actor_target[k], self.actor[k], self.tau)
             polyak(self.critic_target[k], self.critic[k], self.tau)
         prio = (np.abs(td.detach().numpy()) + 1e-6).astype(F32)    # ddpg.py:253
+        if ce_priority:
+            prio = ((-(m_t * torch.log(q + 1e-10)).sum(dim=1)).detach().numpy() + F32(1e-6)).astype(F32)
         out.update(target_probs=tz.numpy(), q=q.detach().numpy(), m=m,
                    loss_critic=loss_c.detach().numpy(), loss_actor=loss_a.detach().numpy(),
                    td=td.detach().numpy(), prio=prio, grads_actor=g_a, grads_critic=g_c)

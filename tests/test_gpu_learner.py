@@ -178,3 +178,47 @@ def test_nstep_projection_learner_mode():
     assert np.abs(m - out["m"]).max() <= TOL
     lc, la = dd.last_losses()
     assert abs(lc - float(out["loss_critic"])) <= TOL
+
+
+def test_corrected_semantics_switches_vs_derived_oracle():
+    """importance-weighted CE (H3) and CE priorities (H4): extensions the reference does not implement;
+    checked against the oracle's derived variants (not reference-pinned)."""
+    import d4pg_b200 as d4pg
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": 51}
+    torch.manual_seed(4); random.seed(4)
+    B, n = 64, 1024
+    dd = d4pg.DDPG(17, 6, memory_size=n, batch_size=B, critic_dist_info=info, importance_weighted=True, priority="ce")
+    dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters()), d4pg.SharedAdam(dd.critic.parameters()))
+    rng = np.random.RandomState(6)
+    S = rng.randn(n, 17).astype(np.float32); A = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+    R = -3 * rng.rand(n); S2 = rng.randn(n, 17).astype(np.float32); D = rng.rand(n) < 0.05
+    dd.replayBuffer.add_batch(S, A, R, S2, D)
+    lo = O.LearnerOracle(17, 6, info, actor_w={k: v.cpu().clone() for k, v in dd.actor.state_dict().items()},
+                         critic_w={k: v.cpu().clone() for k, v in dd.critic.state_dict().items()})
+    ob = O.PrioritizedReplayOracle(n, 0.6, 17, 6)
+    ob.add_batch(S, A, R, S2, D)
+    # make the tree non-uniform first so the weights are not all 1
+    pr0 = (rng.rand(n).astype(np.float32) + np.float32(1e-3))
+    dd.replayBuffer.update_priorities(np.arange(n), pr0)
+    ob.update_priorities(np.arange(n), pr0)
+    H.assert_tree_close_and_sync(dd.replayBuffer, ob.sum.value, ob.min.value)
+    sched = O.LinearScheduleOracle(100000, 1.0, 0.4)
+    for t in range(2):
+        random.seed(70 + t)
+        st = random.getstate(); us = [random.random() for _ in range(B)]; random.setstate(st)
+        dd.train()
+        batch = ob.sample(B, sched.value(), us)
+        assert np.array_equal(dd.last_batch_info()["idx"].cpu().numpy(), batch[6])
+        w = dd.last_batch_info()["weights"].cpu().numpy()
+        np.testing.assert_allclose(w, batch[5], rtol=1e-5)
+        assert w.min() < 0.999
+        out = lo.train_step(*batch[:5], is_weights=batch[5], ce_priority=True)
+        lc, la = dd.last_losses()
+        assert abs(lc - float(out["loss_critic"])) <= TOL
+        assert np.abs(dd.last_batch_info()["prio"].cpu().numpy() - out["prio"]).max() <= TOL
+        for k in H.NAMES:
+            gk = dd.critic.named_grad_views()[k].cpu()
+            assert (gk - out["grads_critic"][k]).abs().max().item() <= TOL and H.rel_l2(gk.numpy(), out["grads_critic"][k].numpy()) <= 1e-4
+        ob.update_priorities(batch[6], out["prio"])
+        st_ = dd.replayBuffer._store          # adopt the oracle tree (priorities agree to 1e-5, not bit-wise)
+        st_.sum_tree.copy_(torch.from_numpy(ob.sum.value)); st_.min_tree.copy_(torch.from_numpy(ob.min.value))
