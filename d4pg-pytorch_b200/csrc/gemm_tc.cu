@@ -536,11 +536,14 @@ static bool prepare_v2(GemmBatch& b) {
 
 // Decide per operand whether TMA may fetch it (K-contiguous source, 16-B aligned rows) and encode the maps.
 static unsigned long long* g_trace = nullptr;
-void gemm_tc_prepare(GemmBatch& b) {
-  static const bool disabled = getenv("D4PG_NO_TMA") != nullptr;
+unsigned long long* debug_trace_buffer() {
   static const bool tracing = getenv("D4PG_TC_TRACE") != nullptr;
   if (tracing && !g_trace) { cudaMalloc(&g_trace, 64 * sizeof(unsigned long long)); cudaMemset(g_trace, 0, 64 * 8); }
-  b.trace = tracing ? g_trace : nullptr;
+  return tracing ? g_trace : nullptr;
+}
+void gemm_tc_prepare(GemmBatch& b) {
+  static const bool disabled = getenv("D4PG_NO_TMA") != nullptr;
+  b.trace = debug_trace_buffer();
   b.all_tma = prepare_v2(b) ? 1 : 0;
   if (b.all_tma) { gemm_batch_retile(b, T2_BM, T2_BN); return; }
   gemm_batch_retile(b, TC_BM, TC_BN);
@@ -578,6 +581,6 @@ int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {
 // debug: %globaltimer (ns) phase stamps of CTA 0 of the last gemm_tc2 launch (D4PG_TC_TRACE=1)
 extern "C" int32_t d4pg_debug_tc_trace(unsigned long long* out16) {
   if (!d4pg::g_trace || !out16) return D4PG_ESTATE;
-  D4PG_CUDA_OK(cudaMemcpy(out16, d4pg::g_trace, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  D4PG_CUDA_OK(cudaMemcpy(out16, d4pg::g_trace, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return D4PG_OK;
 }

@@ -64,7 +64,7 @@ static Workspace carve(float* base, int B, int S, int A, int N) {
   w.a_dz3 = take(int64_t(B) * Ap); w.a_dz22 = take(int64_t(B) * H); w.a_dh2 = take(int64_t(B) * H);
   w.a_dz1 = take(int64_t(B) * H);
   w.clock = reinterpret_cast<LearnerClock*>(take(sizeof(LearnerClock) / 4 + 4));
-  w.barrier = reinterpret_cast<unsigned long long*>(take(4));
+  w.barrier = reinterpret_cast<unsigned long long*>(take(64));   // [0] arrival counter, [16] release flag (own line)
   w.total = off;
   return w;
 }
@@ -270,7 +270,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   aa.loss_rows = w.loss_rows; aa.pi_rows = w.pi_rows; aa.B = B; aa.inv_count = 1.0f / float(B); aa.loss_out = b.losses;
   if (mega) {
     mp->n_bwd = n_levels - mp->n_fwd;
-    mp->adam = aa; mp->clock = w.clock; mp->barrier = w.barrier;
+    mp->adam = aa; mp->clock = w.clock; mp->barrier = w.barrier; mp->trace = debug_trace_buffer();
     RUN(launch_step_mega(*mp, st));
   } else {
     RUN(launch_adam(aa, st));
@@ -406,7 +406,7 @@ extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_ste
   LearnerClock c{};
   c.adam_step = adam_step; c.beta_t = beta_t; c.steps_done = adam_step;
   D4PG_CUDA_OK(cudaMemcpyAsync(L->ws.clock, &c, sizeof(c), cudaMemcpyHostToDevice, as_stream(stream)));
-  D4PG_CUDA_OK(cudaMemsetAsync(L->ws.barrier, 0, sizeof(unsigned long long), as_stream(stream)));
+  D4PG_CUDA_OK(cudaMemsetAsync(L->ws.barrier, 0, 64 * sizeof(float), as_stream(stream)));
   D4PG_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
   return D4PG_OK;
 }

@@ -24,19 +24,35 @@
 
 namespace d4pg {
 
-__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
+// Arrivals are counted with one atomic each on `bar[0]`; the LAST arriver publishes the reached target
+// in `bar[16]` (its own 128-B line) and everybody else polls that read-mostly line with back-off, so
+// the atomics and the polls do not fight over one L2 line.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(counter, 1ull);
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
-    } while (v < target);
-    __threadfence();
+    const unsigned long long old = atomicAdd(bar, 1ull);
+    unsigned long long* flag = bar + 16;
+    if (old + 1 == target) {
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flag), "l"(target) : "memory");
+    } else {
+      unsigned long long v;
+      while (true) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= target) break;
+        __nanosleep(40);
+      }
+    }
   }
   __syncthreads();
 }
+
+__device__ __forceinline__ unsigned long long mega_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define MTRACE(slot) do { if (p.trace && bid == 0 && tid == 0) p.trace[slot] = mega_gtime(); } while (0)
 
 union MegaSmem {
   float gemm[GEMM_SMEM_FLOATS];
@@ -54,9 +70,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) step_mega_kernel(const __grid
   const unsigned long long per_step = (unsigned long long)(2 + p.n_fwd) * G + (unsigned long long)p.n_bwd * (G - 1);
   unsigned long long target = (unsigned long long)(p.clock->mega_epoch) * per_step;
 
+  int slot = 0;
+  MTRACE(slot); ++slot;
   // ---- phase 0: sample + gather ----------------------------------------------------------------------
   if (bid < cdiv(p.sample.B, SAMPLE_ROWS)) sample_body(p.sample, bid, sm.sample);
+  MTRACE(slot); ++slot;
   target += G; grid_barrier(p.barrier, target);
+  MTRACE(slot); ++slot;
 
   // ---- forward levels ---------------------------------------------------------------------------------
   for (int lv = 0; lv < p.n_fwd; ++lv) {
@@ -69,6 +89,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) step_mega_kernel(const __grid
       __syncthreads();                                     // smem reuse by the next tile
     }
     target += G; grid_barrier(p.barrier, target);
+    MTRACE(slot); ++slot;
   }
 
   // ---- heads: one warp per batch row -------------------------------------------------------------------
@@ -85,7 +106,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) step_mega_kernel(const __grid
       __syncwarp();
     }
   }
+  MTRACE(slot); ++slot;
   target += G; grid_barrier(p.barrier, target);
+  MTRACE(slot); ++slot;
 
   // ---- priorities -> trees on the last CTA, which then retires -------------------------------------------
   const int Gw = G - 1;                                        // CTAs that keep working
@@ -105,6 +128,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) step_mega_kernel(const __grid
       __syncthreads();
     }
     target += Gw; grid_barrier(p.barrier, target);
+    MTRACE(slot); ++slot;
   }
 
   // ---- Adam + Polyak (+ losses, clock) -------------------------------------------------------------------
@@ -113,6 +137,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) step_mega_kernel(const __grid
     adam_tail(p.adam, sm.red);
     if (tid == 0) p.clock->mega_epoch += 1;     // every CTA read it before the first barrier of this step
   }
+  MTRACE(slot);
 }
 
 int launch_step_mega(const MegaParams& p, cudaStream_t st) {

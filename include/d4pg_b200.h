@@ -261,7 +261,8 @@ int32_t d4pg_comm_destroy(d4pg_comm_t* c);
 int32_t d4pg_comm_allreduce_sum(d4pg_comm_t* c, float* buf, int64_t n, d4pg_stream_t stream);
 
 /* Debug: %globaltimer (ns) phase stamps written by CTA 0 of the most recent tcgen05 GEMM launch when
- * the environment variable D4PG_TC_TRACE is set (out16 = 16 x uint64, host memory). */
+ * the environment variable D4PG_TC_TRACE is set; the persistent step kernel writes one stamp per
+ * phase boundary instead (out16 = 32 x uint64, host memory). */
 int32_t d4pg_debug_tc_trace(unsigned long long* out16);
 
 #ifdef __cplusplus
