@@ -7,6 +7,7 @@
 // latency-bound, so small tiles on many SMs beat big tiles on few.  Accumulation is plain FFMA
 // in k order, i.e. a true fp32 dot product (needed for the 1e-5 parity of config 2).
 #include "gemm_ffma_dev.cuh"
+#include <algorithm>
 
 namespace d4pg {
 
@@ -60,8 +61,15 @@ void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
   if (p.mode == GEMM_FWD) bvec = aligned16(p.Bm) && p.ldb % 4 == 0 && p.K % 4 == 0;
   else bvec = aligned16(p.Bm) && p.ldb % 4 == 0 && p.N % 4 == 0;
   p.flags = (avec ? GEMM_A_VEC : 0) | (bvec ? GEMM_B_VEC : 0);
+  // dW over a large batch: 8 tiles x (B/32) serial chunks would leave the GPU idle -> split K
+  p.ksplit = 1; p.kslice = p.K;
+  if (p.mode == GEMM_DW && p.K >= 1024) {
+    p.ksplit = std::min(8, cdiv(p.K, 512));
+    p.kslice = cdiv(cdiv(p.K, p.ksplit), 64) * 64;
+    p.ksplit = cdiv(p.K, p.kslice);
+  }
   p.tiles_m = cdiv(p.M, BM); p.tiles_n = cdiv(p.N, BN); p.tile_begin = b.total_tiles;
-  b.total_tiles += p.tiles_m * p.tiles_n;
+  b.total_tiles += p.tiles_m * p.tiles_n * p.ksplit;
   b.p[b.n++] = p;
 }
 void gemm_batch_retile(GemmBatch& b, int bm, int bn) {
@@ -69,8 +77,12 @@ void gemm_batch_retile(GemmBatch& b, int bm, int bn) {
   for (int i = 0; i < b.n; ++i) {
     GemmProblem& p = b.p[i];
     p.tiles_m = cdiv(p.M, bm); p.tiles_n = cdiv(p.N, bn); p.tile_begin = b.total_tiles;
-    b.total_tiles += p.tiles_m * p.tiles_n;
+    b.total_tiles += p.tiles_m * p.tiles_n * p.ksplit;
   }
+}
+bool gemm_batch_has_splitk(const GemmBatch& b) {
+  for (int i = 0; i < b.n; ++i) if (b.p[i].ksplit > 1) return true;
+  return false;
 }
 int gemm_launch(GemmBatch& b, int precision, cudaStream_t st) {
   if (precision == 0) return gemm_batch_launch(b, st);

@@ -23,6 +23,10 @@ struct GemmProblem {
   int lda, lda2, ldb, ldc, ldaux;
   int mode, epi, flags;
   int tiles_m, tiles_n, tile_begin;
+  // split-K (dW only, large batches): the contraction dim is cut into `ksplit` slices of `kslice`
+  // (a multiple of every kernel's K chunk); slice CTAs accumulate into C with fp32 atomics, so C must
+  // be zero beforehand (the learner clears the gradient buffer at the start of such a step).
+  int ksplit, kslice;
 };
 
 constexpr int GEMM_MAX_PROBLEMS = 8;
@@ -50,6 +54,7 @@ void gemm_batch_begin(GemmBatch& b);
 void gemm_batch_add(GemmBatch& b, const GemmProblem& p);
 int gemm_batch_launch(const GemmBatch& b, cudaStream_t st);                    // exact fp32 FFMA (32x32 tiles)
 void gemm_batch_retile(GemmBatch& b, int bm, int bn);
+bool gemm_batch_has_splitk(const GemmBatch& b);
 void gemm_tc_prepare(GemmBatch& b);                                             // TMA eligibility + tensor maps
 int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st);      // tcgen05 (128x32 tiles)
 // precision: 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = 1xTF32 tcgen05

@@ -100,11 +100,11 @@ struct Operand { const float* p; int ld; bool vec; };
 
 // A-operand source for chunk k0: FWD may switch to the concatenated second source (k >= K1)
 template <int MODE>
-__device__ __forceinline__ void load_A(const GemmProblem& P, int m0, int k0, int tid, float (&ra)[PER_THREAD], bool& vec) {
+__device__ __forceinline__ void load_A(const GemmProblem& P, int m0, int k0, int kend, int tid, float (&ra)[PER_THREAD], bool& vec) {
   if (MODE == GEMM_DW) {               // A(i,k) = dZ[k*lda + i]
     vec = (P.flags & GEMM_A_VEC) != 0;
-    if (vec) load_rowcontig<true>(P.A, P.lda, m0, P.M, k0, P.K, tid, ra);
-    else load_rowcontig<false>(P.A, P.lda, m0, P.M, k0, P.K, tid, ra);
+    if (vec) load_rowcontig<true>(P.A, P.lda, m0, P.M, k0, kend, tid, ra);
+    else load_rowcontig<false>(P.A, P.lda, m0, P.M, k0, kend, tid, ra);
   } else if (k0 >= P.K1) {             // concatenated tail (critic fc2's action columns): scalar
     vec = false;
     load_kcontig<false>(P.A2, P.lda2, m0, P.M, k0 - P.K1, P.K - P.K1, tid, ra);
@@ -120,14 +120,14 @@ __device__ __forceinline__ void store_A(float* As, int tid, const float (&ra)[PE
   else { if (vec) store_kcontig<true>(As, LDS_A, tid, ra); else store_kcontig<false>(As, LDS_A, tid, ra); }
 }
 template <int MODE>
-__device__ __forceinline__ void load_B(const GemmProblem& P, int n0, int k0, int tid, float (&rb)[PER_THREAD]) {
+__device__ __forceinline__ void load_B(const GemmProblem& P, int n0, int k0, int kend, int tid, float (&rb)[PER_THREAD]) {
   const bool vec = (P.flags & GEMM_B_VEC) != 0;
   if (MODE == GEMM_FWD) {              // B(k,j) = W[j*ldb + k]
-    if (vec) load_kcontig<true>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
-    else load_kcontig<false>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
+    if (vec) load_kcontig<true>(P.Bm, P.ldb, n0, P.N, k0, kend, tid, rb);
+    else load_kcontig<false>(P.Bm, P.ldb, n0, P.N, k0, kend, tid, rb);
   } else {                             // B(k,j) = B[k*ldb + j]
-    if (vec) load_rowcontig<true>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
-    else load_rowcontig<false>(P.Bm, P.ldb, n0, P.N, k0, P.K, tid, rb);
+    if (vec) load_rowcontig<true>(P.Bm, P.ldb, n0, P.N, k0, kend, tid, rb);
+    else load_rowcontig<false>(P.Bm, P.ldb, n0, P.N, k0, kend, tid, rb);
   }
 }
 template <int MODE>
@@ -141,7 +141,7 @@ __device__ __forceinline__ void store_B(const GemmProblem& P, float* Bs, int tid
 // 1/8 of every K-chunk with an 8x4 register tile per lane (32 independent FFMAs per 3 LDS.128);
 // the 8 partial tiles are summed through shared memory in fixed warp order (deterministic).
 template <int MODE>
-__device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int m0, int n0, int tn) {
+__device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int m0, int n0, int tn, int kbeg, int kend) {
   float* As0 = smem;                      // [2][KC*LDS_A]
   float* Bs0 = smem + 2 * KC * LDS_A;     // [2][KC*LDS_B]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -157,17 +157,17 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int
 
   float ra[PER_THREAD], rb[PER_THREAD];
   bool avec;
-  const int nchunks = (P.K + KC - 1) / KC;
-  load_A<MODE>(P, m0, 0, tid, ra, avec);
-  load_B<MODE>(P, n0, 0, tid, rb);
+  const int nchunks = (kend - kbeg + KC - 1) / KC;
+  load_A<MODE>(P, m0, kbeg, kend, tid, ra, avec);
+  load_B<MODE>(P, n0, kbeg, kend, tid, rb);
   store_A<MODE>(As0, tid, ra, avec);
   store_B<MODE>(P, Bs0, tid, rb);
   __syncthreads();
   for (int c = 0; c < nchunks; ++c) {
     const int cur = c & 1;
     if (c + 1 < nchunks) {                                                      // in flight during the FMAs
-      load_A<MODE>(P, m0, (c + 1) * KC, tid, ra, avec);
-      load_B<MODE>(P, n0, (c + 1) * KC, tid, rb);
+      load_A<MODE>(P, m0, kbeg + (c + 1) * KC, kend, tid, ra, avec);
+      load_B<MODE>(P, n0, kbeg + (c + 1) * KC, kend, tid, rb);
     }
     const float* __restrict__ as = As0 + cur * KC * LDS_A;
     const float* __restrict__ bs = Bs0 + cur * KC * LDS_B;
@@ -226,19 +226,26 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int
         case EPI_TANH_MASK: { const float t = __ldg(P.aux + size_t(gi) * P.ldaux + gj); x *= (1.f - t * t); } break;
         default: break;
       }
-      P.C[size_t(gi) * P.ldc + gj] = x;
+      if (P.ksplit > 1) atomicAdd(&P.C[size_t(gi) * P.ldc + gj], x);      // split-K slice (C pre-zeroed)
+      else P.C[size_t(gi) * P.ldc + gj] = x;
     }
   }
-  if (want_bias_grad && tid < BM && m0 + tid < P.M) P.bias_grad[m0 + tid] = colsum;
+  if (want_bias_grad && tid < BM && m0 + tid < P.M) {
+    if (P.ksplit > 1) atomicAdd(&P.bias_grad[m0 + tid], colsum);
+    else P.bias_grad[m0 + tid] = colsum;
+  }
 }
 
 
 // dispatch one 32x32 tile of problem P (block-uniform mode switch)
 __device__ __forceinline__ void gemm_tile_dispatch(const GemmProblem& P, float* smem, int tile) {
-  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
-  if (P.mode == GEMM_FWD) gemm_tile<GEMM_FWD>(P, smem, tm * BM, tn * BN, tn);
-  else if (P.mode == GEMM_DX) gemm_tile<GEMM_DX>(P, smem, tm * BM, tn * BN, tn);
-  else gemm_tile<GEMM_DW>(P, smem, tm * BM, tn * BN, tn);
+  const int per_slice = P.tiles_m * P.tiles_n;
+  const int ks = tile / per_slice, t2 = tile - ks * per_slice;
+  const int tm = t2 / P.tiles_n, tn = t2 - tm * P.tiles_n;
+  const int kbeg = ks * P.kslice, kend = min(P.K, kbeg + P.kslice);
+  if (P.mode == GEMM_FWD) gemm_tile<GEMM_FWD>(P, smem, tm * BM, tn * BN, tn, 0, P.K);
+  else if (P.mode == GEMM_DX) gemm_tile<GEMM_DX>(P, smem, tm * BM, tn * BN, tn, 0, P.K);
+  else gemm_tile<GEMM_DW>(P, smem, tm * BM, tn * BN, tn, kbeg, kend);
 }
 constexpr int GEMM_SMEM_FLOATS = 2 * KC * LDS_A + 2 * KC * LDS_B;
 

@@ -302,11 +302,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
     if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
   const GemmProblem P = batch.p[pi];
   const int tile = blockIdx.x - P.tile_begin;
-  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+  const int per_slice = P.tiles_m * P.tiles_n;
+  const int kslice_id = tile / per_slice, tile2 = tile - kslice_id * per_slice;
+  const int tm = tile2 / P.tiles_n, tn = tile2 - tm * P.tiles_n;
   const int m0 = tm * T2_BM, n0 = tn * T2_BN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool a_mn = (P.mode == GEMM_DW), b_mn = (P.mode != GEMM_FWD);
-  const int nchunks = (P.K + T2_KC - 1) / T2_KC;
+  // split-K (dW over a large batch): this CTA contracts K chunks [c_beg, c_beg + nchunks)
+  const int kbeg = kslice_id * P.kslice, kend = min(P.K, kbeg + P.kslice);
+  const int c_beg = kbeg / T2_KC;
+  const int nchunks = (kend - kbeg + T2_KC - 1) / T2_KC;
+  const bool split = P.ksplit > 1;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < T2_NBARS; ++i) mbar_init(&bars[i], (i >= T2_CONV && i < T2_CONV + T2_STAGES) ? 4u : 1u);
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
     // ================================ TMA producer ==================================================
     if (lane == 0) {
       for (int c = 0; c < nchunks; ++c) {
-        const int s = c % T2_STAGES, k0 = c * T2_KC;
+        const int s = c % T2_STAGES, k0 = (c_beg + c) * T2_KC;
         if (c >= T2_STAGES) mbar_wait(&bars[T2_EMPTY + s], ((c / T2_STAGES) - 1) & 1);
         uint8_t* Ad = smem + s * T2_STAGE;
         uint8_t* Bd = Ad + T2_A_BYTES;
@@ -448,7 +454,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
               default: break;
             }
           }
-          if (full4) *reinterpret_cast<float4*>(crow + j) = make_float4(x[0], x[1], x[2], x[3]);
+          if (split) { for (int q = 0; q < 4; ++q) if (nb + j + q < P.N) atomicAdd(crow + j + q, x[q]); }   // C pre-zeroed
+          else if (full4) *reinterpret_cast<float4*>(crow + j) = make_float4(x[0], x[1], x[2], x[3]);
           else for (int q = 0; q < 4; ++q) if (nb + j + q < P.N) crow[j + q] = x[q];
         }
       }
@@ -457,8 +464,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
       const int m = m0 + t2;
       if (m < P.M) {
         float sacc = 0.f;
-        for (int k = 0; k < P.K; ++k) sacc += __ldg(P.A + size_t(k) * P.lda + m);
-        P.bias_grad[m] = sacc;
+        for (int k = kbeg; k < kend; ++k) sacc += __ldg(P.A + size_t(k) * P.lda + m);
+        if (split) atomicAdd(P.bias_grad + m, sacc);
+        else P.bias_grad[m] = sacc;
       }
     }
   }
@@ -546,6 +554,7 @@ void gemm_tc_prepare(GemmBatch& b) {
   b.trace = debug_trace_buffer();
   b.all_tma = prepare_v2(b) ? 1 : 0;
   if (b.all_tma) { gemm_batch_retile(b, T2_BM, T2_BN); return; }
+  for (int i = 0; i < b.n; ++i) { b.p[i].ksplit = 1; b.p[i].kslice = b.p[i].K; }    // v1 kernel has no split-K
   gemm_batch_retile(b, TC_BM, TC_BN);
   for (int i = 0; i < b.n; ++i) {
     GemmProblem& p = b.p[i];

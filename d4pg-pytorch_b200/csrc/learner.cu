@@ -112,6 +112,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   do {                                                                                      \
     if (mega) {                                                                             \
       D4PG_REQUIRE(n_levels < MEGA_MAX_LEVELS, D4PG_ENOTSUP, "too many GEMM levels");       \
+      for (int _i = 0; _i < (gb).n; ++_i) { (gb).p[_i].ksplit = 1; (gb).p[_i].kslice = (gb).p[_i].K; } \
+      gemm_batch_retile(gb, 32, 32);            /* no split-K inside the persistent kernel */ \
       GemmBatchLite& lv = mp->level[n_levels++];                                            \
       for (int _i = 0; _i < (gb).n; ++_i) lv.p[_i] = (gb).p[_i];                            \
       lv.n = (gb).n; lv.total_tiles = (gb).total_tiles;                                     \
@@ -215,6 +217,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   }
 
   float* Ga = b.grad_actor; float* Gc = b.grad_critic;
+  if (B >= 1024 && !mega)                // dW levels run split-K with fp32 atomics: the gradient buffer must start at zero
+    D4PG_CUDA_OK(cudaMemsetAsync(Ga, 0, size_t(da.total + dc.total) * sizeof(float), st));
   // 5. backward.  "c_" = critic-loss pass, "p_" = policy pass through the critic, "a_" = actor.
   // level B1: through critic.fc3
   gemm_batch_begin(g);
@@ -315,6 +319,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms);
   L->graph_exec = nullptr; L->graph_ready = false; L->steps_done = 0; L->kernels_per_step = 0;
   L->profiling = false;
+  (void)debug_trace_buffer();          // allocate outside of any stream capture
   if (cudaStreamCreateWithFlags(&L->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming) != cudaSuccess) {

@@ -222,3 +222,32 @@ def test_corrected_semantics_switches_vs_derived_oracle():
         ob.update_priorities(batch[6], out["prio"])
         st_ = dd.replayBuffer._store          # adopt the oracle tree (priorities agree to 1e-5, not bit-wise)
         st_.sum_tree.copy_(torch.from_numpy(ob.sum.value)); st_.min_tree.copy_(torch.from_numpy(ob.min.value))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_config3_shapes_batch1024_split_k(precision):
+    """Config-3 dims (|s|=376, |a|=17, batch 1024): the dW levels run split-K (fp32 atomics into a
+    zeroed gradient buffer); one step vs the oracle."""
+    import d4pg_b200 as d4pg
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": 51}
+    torch.manual_seed(8); random.seed(8)
+    B, n, S, A = 1024, 4096, 376, 17
+    dd = d4pg.DDPG(S, A, memory_size=n, batch_size=B, critic_dist_info=info, precision=precision)
+    dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters()), d4pg.SharedAdam(dd.critic.parameters()))
+    rng = np.random.RandomState(9)
+    Sx = rng.randn(n, S).astype(np.float32); Ax = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+    R = -3 * rng.rand(n); S2 = rng.randn(n, S).astype(np.float32); D = rng.rand(n) < 0.05
+    dd.replayBuffer.add_batch(Sx, Ax, R, S2, D)
+    lo = O.LearnerOracle(S, A, info, actor_w={k: v.cpu().clone() for k, v in dd.actor.state_dict().items()},
+                         critic_w={k: v.cpu().clone() for k, v in dd.critic.state_dict().items()})
+    for t in range(2):
+        dd.train()
+        idx = dd.last_batch_info()["idx"].cpu().numpy()
+        out = lo.train_step(Sx[idx], Ax[idx], R[idx], S2[idx], D[idx])
+        lc, la = dd.last_losses()
+        assert abs(lc - float(out["loss_critic"])) <= TOL and abs(la - float(out["loss_actor"])) <= TOL * abs(la)
+        for net, grads in ((dd.actor, out["grads_actor"]), (dd.critic, out["grads_critic"])):
+            for k in H.NAMES:
+                gk = net.named_grad_views()[k].cpu()
+                assert (gk - grads[k]).abs().max().item() <= TOL, k
+                assert H.rel_l2(gk.numpy(), grads[k].numpy()) <= 1e-4, (k, H.rel_l2(gk.numpy(), grads[k].numpy()))
