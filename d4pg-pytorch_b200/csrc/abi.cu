@@ -8,6 +8,10 @@ namespace d4pg {
 
 static thread_local char g_err[512] = "";
 
+int pdl_mode() {
+  static const int m = getenv("D4PG_PDL") ? atoi(getenv("D4PG_PDL")) : 0;
+  return m;
+}
 bool pdl_enabled() {
   // measured on B200 (profiles/README.md): +17 % step time for the FFMA path, -5 % for the tcgen05 path
   // -> opt-in.  D4PG_PDL=1 enables it.

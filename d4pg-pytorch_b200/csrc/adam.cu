@@ -16,17 +16,20 @@ namespace d4pg {
 
 __global__ void __launch_bounds__(256) adam_polyak_kernel(const AdamArgs a) {
   __shared__ float red[2][8];
-  pdl_trigger();
+  pdl_trigger(a.pdl);
   pdl_wait();
   if (int(blockIdx.y) == a.nseg) {
     if (blockIdx.x == 0) adam_tail(a, red);
     return;
   }
   adam_segment(a, blockIdx.y, blockIdx.x, gridDim.x);
+  pdl_trigger_end(a.pdl);
 }
 
 
-int launch_adam(const AdamArgs& a, cudaStream_t st) {
+int launch_adam(const AdamArgs& a_in, cudaStream_t st) {
+  AdamArgs a = a_in;
+  a.pdl = pdl_mode();
   int64_t nmax = 0;
   for (int i = 0; i < a.nseg; ++i) nmax = a.seg[i].n > nmax ? a.seg[i].n : nmax;
   int blocks = int((nmax / 4 + 255) / 256);

@@ -48,6 +48,7 @@ struct AdamArgs {
   LearnerClock* clock;                        // optional (learner): scalars in, counters advanced
   // fused tail (learner): deterministic batch means of the per-row losses -> out[0], out[1]
   const float* loss_rows; const float* pi_rows; int B; float inv_count; float* loss_out;
+  int pdl;                                    // programmatic-dependent-launch trigger position (0/1/2)
 };
 int launch_adam(const AdamArgs& a, cudaStream_t st);
 

@@ -54,7 +54,12 @@ void set_error(const char* fmt, ...);
 // CTAs are scheduled (and run their prologue) while this one is still executing, and blocks in
 // `griddepcontrol.wait` until all of this kernel's memory is visible.  Captured into the CUDA graph
 // as programmatic dependency edges.  Opt-in with D4PG_PDL=1 (see pdl_enabled()).
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// PDL trigger position, carried in every step kernel's argument struct (`pdl` field):
+//   1 = `launch_dependents` at kernel entry (next grid becomes resident early), 2 = at kernel exit
+__device__ __forceinline__ void pdl_trigger_raw() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger(int mode) { if (mode == 1) pdl_trigger_raw(); }
+__device__ __forceinline__ void pdl_trigger_end(int mode) { if (mode == 2) pdl_trigger_raw(); }
+int pdl_mode();                      // 0 off, 1 early trigger, 2 late trigger (env D4PG_PDL)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     for (int i = 0; i < TC_NBARS; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
-  pdl_trigger();
+  pdl_trigger(batch.pdl);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -289,7 +289,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ GemmBatch batch, int passes) {
   extern __shared__ uint8_t smem_raw[];
-  pdl_trigger();
+  pdl_trigger(batch.pdl);
   if (threadIdx.x == 0) TRACE(0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* lo_ring = smem + T2_STAGES * T2_STAGE;
@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const __grid_co
     }
   }
   if (tid == 64) TRACE(10);
+  pdl_trigger_end(batch.pdl);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_d, 64);
@@ -580,6 +581,7 @@ int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {
     D4PG_MAX_CARVEOUT(gemm_tc2_kernel);
     attr_set = true;
   }
+  const_cast<GemmBatch&>(b).pdl = pdl_mode();
   if (b.all_tma) D4PG_CUDA_OK(launch_pdl(gemm_tc2_kernel, dim3(b.total_tiles), dim3(T2_THREADS), T2_SMEM, st, b, passes));
   else D4PG_CUDA_OK(launch_pdl(gemm_tc_kernel, dim3(b.total_tiles), dim3(TC_THREADS), TC_SMEM, st, b, passes));
   return D4PG_OK;

@@ -215,12 +215,12 @@ __device__ __forceinline__ void heads_row(const HeadsArgs& a, int row, int lane,
 template <int MODE, int NT>
 __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs a) {
   __shared__ HeadsWarpSmem ws[HEAD_WARPS];
-  pdl_trigger();
+  pdl_trigger(a.pdl);
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * HEAD_WARPS + warp;
-  if (row >= a.B) return;
-  heads_row<MODE, NT>(a, row, lane, ws[warp]);
+  if (row < a.B) heads_row<MODE, NT>(a, row, lane, ws[warp]);
+  pdl_trigger_end(a.pdl);
 }
 
 }  // namespace d4pg

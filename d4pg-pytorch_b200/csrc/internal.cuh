@@ -20,6 +20,7 @@ struct HeadsArgs {
   // corrected-semantics switches (the reference does neither, H3 / H4):
   const float* is_weights;   // non-null: critic CE row i is scaled by the PER importance weight w_i
   int ce_priority;           // 1: priority = CE_i + eps instead of |sum_j m_ij q_ij| + eps
+  int pdl;                   // programmatic-dependent-launch trigger position (0/1/2)
 };
 int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st);
 

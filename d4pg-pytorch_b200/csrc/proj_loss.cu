@@ -18,7 +18,9 @@
 
 namespace d4pg {
 
-int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st) {
+int launch_heads(const HeadsArgs& a_in, int mode, cudaStream_t st) {
+  HeadsArgs a = a_in;
+  a.pdl = pdl_mode();
   dim3 grid(cdiv(a.B, HEAD_WARPS)), block(HEAD_WARPS * 32);
   D4PG_MAX_CARVEOUT((heads_kernel<0, 2>)); D4PG_MAX_CARVEOUT((heads_kernel<1, 2>));
   D4PG_MAX_CARVEOUT((heads_kernel<0, 4>)); D4PG_MAX_CARVEOUT((heads_kernel<1, 4>));

@@ -30,9 +30,10 @@ namespace d4pg {
 
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const SampleArgs a) {
   __shared__ SampleSmem sm;
-  pdl_trigger();
+  pdl_trigger(a.pdl);
   pdl_wait();
   sample_body(a, blockIdx.x, sm);
+  pdl_trigger_end(a.pdl);
 }
 
 template <int MODE>
@@ -193,6 +194,7 @@ int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
   a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.state = reinterpret_cast<const ReplayState*>(h->state);
   a.obs = h->obs; a.act = h->act; a.rew = h->rew; a.obs2 = h->obs2; a.done = h->done;
   a.obs_dim = h->obs_dim; a.act_dim = h->act_dim;
+  a.pdl = pdl_mode();
   D4PG_MAX_CARVEOUT(sample_gather_kernel);
   D4PG_CUDA_OK(launch_pdl(sample_gather_kernel, dim3(cdiv(a.B, SAMPLE_ROWS)), dim3(SAMPLE_THREADS), 0, st, a));
   return D4PG_OK;

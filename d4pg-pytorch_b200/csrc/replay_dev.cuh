@@ -68,6 +68,7 @@ struct SampleArgs {
   int uniform_mode;                 // 1: idx = floor(u*len) (device-side uniform replay, with replacement)
   int32_t* idx; float* weights;
   float* s; float* a; double* r; float* s2; uint8_t* d;
+  int pdl;                          // programmatic-dependent-launch trigger position (0/1/2)
 };
 
 constexpr int SAMPLE_ROWS = 32;      // rows per CTA
