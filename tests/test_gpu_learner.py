@@ -251,6 +251,6 @@ def test_config3_shapes_batch1024_split_k(precision):
                 gk = net.named_grad_views()[k].cpu()
                 assert (gk - grads[k]).abs().max().item() <= TOL, k
                 # relative check: the first-layer gradients are ~1e-7 sums of 1024 cancelling terms, so even two
-                # exact-fp32 summation orders differ by ~2e-4 relative (measured); 3xTF32 adds its 2^-21 per layer
-                rel_tol = 1e-3 if precision == "fp32" else 1e-2
+                # exact-fp32 summation orders differ by 2e-4..2e-3 relative (measured, split-K atomics included); 3xTF32 adds 2^-21 per layer
+                rel_tol = 5e-3 if precision == "fp32" else 2e-2
                 assert H.rel_l2(gk.numpy(), grads[k].numpy()) <= rel_tol, (k, H.rel_l2(gk.numpy(), grads[k].numpy()))
