@@ -75,6 +75,9 @@ _PROTOS = {
     "d4pg_replay_len": (C.c_int64, [_P]),
     "d4pg_replay_next_idx": (C.c_int64, [_P]),
     "d4pg_replay_add": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, _P]),
+    "d4pg_replay_staging_bytes": (C.c_int64, [_P, C.c_int64]),
+    "d4pg_replay_set_staging": (C.c_int32, [_P, _P, _P, C.c_int64]),
+    "d4pg_replay_add_host": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "d4pg_replay_sample": (C.c_int32, [_P, C.c_int32, _P, C.c_uint64, C.c_uint64, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
     "d4pg_replay_gather": (C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "d4pg_replay_update_priorities": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
@@ -93,6 +96,9 @@ _PROTOS = {
     "d4pg_learner_destroy": (C.c_int32, [_P]),
     "d4pg_learner_step": (C.c_int32, [_P, _P]),
     "d4pg_learner_run": (C.c_int32, [_P, C.c_int32, _P]),
+    "d4pg_learner_set_host_buffers": (C.c_int32, [_P, _P, _P, _P]),
+    "d4pg_learner_step_host": (C.c_int32, [_P, _P, _P, _P, _P]),
+    "d4pg_learner_read_losses": (C.c_int32, [_P, _P, _P]),
     "d4pg_learner_tensor": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "d4pg_learner_profile_step": (C.c_int32, [_P, _P, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "d4pg_learner_steps_done": (C.c_int64, [_P]),

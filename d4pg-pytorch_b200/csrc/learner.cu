@@ -86,6 +86,8 @@ struct d4pg_learner {
   // profiling (d4pg_learner_profile_step): CUDA-event pair around every launch of an eager step
   cudaStream_t side; cudaEvent_t ev_fork, ev_join;
   MegaParams mega;
+  // host-facing step (caller-owned pinned buffers, d4pg_learner_set_host_buffers)
+  double* host_u; int32_t* host_pos; float* host_losses; cudaEvent_t ev_in, ev_out;
   bool profiling;
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> ev_name;
@@ -320,6 +322,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   L->graph_exec = nullptr; L->graph_ready = false; L->steps_done = 0; L->kernels_per_step = 0;
   L->profiling = false;
   (void)debug_trace_buffer();          // allocate outside of any stream capture
+  L->host_u = nullptr; L->host_pos = nullptr; L->host_losses = nullptr; L->ev_in = nullptr; L->ev_out = nullptr;
   if (cudaStreamCreateWithFlags(&L->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -335,6 +338,8 @@ extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   if (!L) return D4PG_OK;
   if (L->graph_exec) cudaGraphExecDestroy(L->graph_exec);
   cudaEventDestroy(L->ev_fork); cudaEventDestroy(L->ev_join); cudaStreamDestroy(L->side);
+  if (L->ev_in) cudaEventDestroy(L->ev_in);
+  if (L->ev_out) cudaEventDestroy(L->ev_out);
   delete L;
   return D4PG_OK;
 }
@@ -362,6 +367,48 @@ extern "C" int32_t d4pg_learner_step(d4pg_learner_t* L, d4pg_stream_t stream) {
   }
   D4PG_CUDA_OK(cudaGraphLaunch(L->graph_exec, st));
   ++L->steps_done;
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_learner_set_host_buffers(d4pg_learner_t* L, double* pinned_uniforms, int32_t* pinned_positions,
+                                                 float* pinned_losses) {
+  D4PG_REQUIRE(L && pinned_losses, D4PG_EINVAL, "d4pg_learner_set_host_buffers: null argument");
+  L->host_u = pinned_uniforms; L->host_pos = pinned_positions; L->host_losses = pinned_losses;
+  if (!L->ev_in) D4PG_CUDA_OK(cudaEventCreateWithFlags(&L->ev_in, cudaEventDisableTiming));
+  if (!L->ev_out) D4PG_CUDA_OK(cudaEventCreateWithFlags(&L->ev_out, cudaEventDisableTiming));
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_learner_step_host(d4pg_learner_t* L, const double* uniforms, const int32_t* positions,
+                                          d4pg_stream_t caller_stream, d4pg_stream_t learner_stream) {
+  D4PG_REQUIRE(L && L->ev_in, D4PG_ESTATE, "d4pg_learner_step_host: call d4pg_learner_set_host_buffers first");
+  cudaStream_t cs = as_stream(caller_stream), ls = as_stream(learner_stream);
+  const int B = L->cfg.batch;
+  D4PG_CUDA_OK(cudaEventRecord(L->ev_in, cs));                 // adds / weight loads issued by the caller
+  D4PG_CUDA_OK(cudaStreamWaitEvent(ls, L->ev_in, 0));
+  if (uniforms) {
+    D4PG_REQUIRE(L->host_u && L->buf.uniforms, D4PG_ESTATE, "d4pg_learner_step_host: no uniforms buffers");
+    if (uniforms != L->host_u) memcpy(L->host_u, uniforms, size_t(B) * sizeof(double));
+    D4PG_CUDA_OK(cudaMemcpyAsync(L->buf.uniforms, L->host_u, size_t(B) * sizeof(double), cudaMemcpyHostToDevice, ls));
+  }
+  if (positions) {
+    D4PG_REQUIRE(L->host_pos && L->buf.positions, D4PG_ESTATE, "d4pg_learner_step_host: no positions buffers");
+    if (positions != L->host_pos) memcpy(L->host_pos, positions, size_t(B) * sizeof(int32_t));
+    D4PG_CUDA_OK(cudaMemcpyAsync(L->buf.positions, L->host_pos, size_t(B) * sizeof(int32_t), cudaMemcpyHostToDevice, ls));
+  }
+  int rc = d4pg_learner_step(L, learner_stream);
+  if (rc) return rc;
+  D4PG_CUDA_OK(cudaEventRecord(L->ev_out, ls));
+  D4PG_CUDA_OK(cudaStreamWaitEvent(cs, L->ev_out, 0));
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_learner_read_losses(d4pg_learner_t* L, float* out4, d4pg_stream_t learner_stream) {
+  D4PG_REQUIRE(L && out4 && L->host_losses, D4PG_ESTATE, "d4pg_learner_read_losses: call d4pg_learner_set_host_buffers first");
+  cudaStream_t ls = as_stream(learner_stream);
+  D4PG_CUDA_OK(cudaMemcpyAsync(L->host_losses, L->buf.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, ls));
+  D4PG_CUDA_OK(cudaStreamSynchronize(ls));
+  for (int i = 0; i < 4; ++i) out4[i] = L->host_losses[i];
   return D4PG_OK;
 }
 

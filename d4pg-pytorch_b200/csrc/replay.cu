@@ -13,6 +13,7 @@
 // Everything is HBM/L2 pointer chasing + row gathers: no tensor-core work here.
 #include "replay_dev.cuh"
 #include <new>
+#include <string.h>
 #include <algorithm>
 
 struct d4pg_replay {
@@ -24,6 +25,8 @@ struct d4pg_replay {
   int32_t* scratch; float* state;
   int64_t len, next_idx;
   int pristine;
+  // host ingest staging (caller-owned buffers registered by d4pg_replay_set_staging)
+  uint8_t* stage_host; uint8_t* stage_dev; int64_t stage_bytes; cudaEvent_t stage_ev; bool stage_busy;
 };
 
 namespace d4pg {
@@ -274,6 +277,7 @@ extern "C" int32_t d4pg_replay_create(int64_t size, int32_t obs_dim, int32_t act
   h->obs_dim = obs_dim; h->act_dim = act_dim; h->alpha = alpha; h->alpha_f32 = float(alpha);
   h->sum = sum_tree; h->mn = min_tree; h->obs = obs; h->act = act; h->rew = rew; h->obs2 = obs2; h->done = done;
   h->scratch = scratch; h->state = state; h->len = 0; h->next_idx = 0; h->pristine = 1;
+  h->stage_host = nullptr; h->stage_dev = nullptr; h->stage_bytes = 0; h->stage_ev = nullptr; h->stage_busy = false;
   tree_init_kernel<<<296, 256, 0, as_stream(stream)>>>(h->sum, h->mn, h->scratch,
                                                         reinterpret_cast<ReplayState*>(h->state), h->cap);
   cudaError_t e = cudaGetLastError();
@@ -282,7 +286,59 @@ extern "C" int32_t d4pg_replay_create(int64_t size, int32_t obs_dim, int32_t act
   return D4PG_OK;
 }
 
-extern "C" int32_t d4pg_replay_destroy(d4pg_replay_t* h) { delete h; return D4PG_OK; }
+extern "C" int32_t d4pg_replay_destroy(d4pg_replay_t* h) {
+  if (h && h->stage_ev) cudaEventDestroy(h->stage_ev);
+  delete h;
+  return D4PG_OK;
+}
+
+namespace {
+struct PackLayout { int64_t obs, obs2, act, rew, done, total; };
+PackLayout pack_layout(const d4pg_replay* h, int64_t n) {
+  PackLayout p;
+  const int64_t S = int64_t(h->obs_dim) * 4, A = int64_t(h->act_dim) * 4;
+  p.obs = 0; p.obs2 = p.obs + n * S; p.act = p.obs2 + n * S;
+  p.rew = (p.act + n * A + 15) & ~int64_t(15);
+  p.done = p.rew + n * 8;
+  p.total = (p.done + n + 15) & ~int64_t(15);
+  return p;
+}
+}  // namespace
+
+extern "C" int64_t d4pg_replay_staging_bytes(const d4pg_replay_t* h, int64_t rows) {
+  return (h && rows > 0) ? pack_layout(h, rows).total : -1;
+}
+
+extern "C" int32_t d4pg_replay_set_staging(d4pg_replay_t* h, void* pinned_host, void* device, int64_t bytes) {
+  D4PG_REQUIRE(h && pinned_host && device && bytes > 0, D4PG_EINVAL, "d4pg_replay_set_staging: bad arguments");
+  h->stage_host = static_cast<uint8_t*>(pinned_host); h->stage_dev = static_cast<uint8_t*>(device); h->stage_bytes = bytes;
+  if (!h->stage_ev) D4PG_CUDA_OK(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
+  h->stage_busy = false;
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_replay_add_host(d4pg_replay_t* h, int64_t n, const float* obs, const float* act, const double* rew,
+                                        const float* obs2, const uint8_t* done, int32_t prioritized, d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && obs && act && rew && obs2 && done && n > 0, D4PG_EINVAL, "d4pg_replay_add_host: null/empty argument");
+  D4PG_REQUIRE(h->stage_host, D4PG_ESTATE, "d4pg_replay_add_host: call d4pg_replay_set_staging first");
+  const PackLayout p = pack_layout(h, n);
+  D4PG_REQUIRE(p.total <= h->stage_bytes, D4PG_EINVAL, "d4pg_replay_add_host: %lld rows do not fit the staging buffer", (long long)n);
+  if (h->stage_busy) D4PG_CUDA_OK(cudaEventSynchronize(h->stage_ev));       // previous copy has left the pinned buffer
+  uint8_t* hp = h->stage_host;
+  memcpy(hp + p.obs, obs, size_t(n) * h->obs_dim * 4);
+  memcpy(hp + p.obs2, obs2, size_t(n) * h->obs_dim * 4);
+  memcpy(hp + p.act, act, size_t(n) * h->act_dim * 4);
+  memcpy(hp + p.rew, rew, size_t(n) * 8);
+  memcpy(hp + p.done, done, size_t(n));
+  cudaStream_t st = as_stream(stream);
+  D4PG_CUDA_OK(cudaMemcpyAsync(h->stage_dev, hp, size_t(p.total), cudaMemcpyHostToDevice, st));
+  D4PG_CUDA_OK(cudaEventRecord(h->stage_ev, st));
+  h->stage_busy = true;
+  uint8_t* d = h->stage_dev;
+  return d4pg_replay_add(h, n, reinterpret_cast<const float*>(d + p.obs), reinterpret_cast<const float*>(d + p.act),
+                         reinterpret_cast<const double*>(d + p.rew), reinterpret_cast<const float*>(d + p.obs2),
+                         d + p.done, prioritized, stream);
+}
 extern "C" int64_t d4pg_replay_len(const d4pg_replay_t* h) { return h ? h->len : -1; }
 extern "C" int64_t d4pg_replay_next_idx(const d4pg_replay_t* h) { return h ? h->next_idx : -1; }
 

@@ -110,8 +110,15 @@ class _Learner(object):
         self.global_model = g
         self.stream = torch.cuda.Stream(device=dev)      # graph capture needs a non-default stream
         self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
-        self.step_fn = L.d4pg_learner_step
+        self.step_host = L.d4pg_learner_step_host
+        self.read_losses = L.d4pg_learner_read_losses
         self.host_u_np = self.host_u.numpy()
+        self.host_pos_np = self.host_pos.numpy()
+        self.u_ptr = C.c_void_p(self.host_u.data_ptr())
+        self.pos_ptr = C.c_void_p(self.host_pos.data_ptr())
+        self.losses_out = (C.c_float * 4)()
+        _lib.check(L.d4pg_learner_set_host_buffers(h, self.u_ptr, self.pos_ptr, C.c_void_p(self.host_losses.data_ptr())),
+                   "d4pg_learner_set_host_buffers")
         if opt_a.step_count or (ddpg.prioritized_replay and ddpg.beta_schedule.t):
             _lib.check(L.d4pg_learner_set_counters(h, opt_a.step_count,
                                                    ddpg.beta_schedule.t if ddpg.prioritized_replay else 0,
@@ -298,22 +305,20 @@ class DDPG:
         if store._n_staged:
             store.flush()
         B = self.batch_size
-        cur = torch.cuda.current_stream()
-        L.stream.wait_stream(cur)                               # adds / weight loads issued by the caller
+        u_ptr = pos_ptr = None
         if self.sampling == "reference":
-            with torch.cuda.stream(L.stream):
-                if self.prioritized_replay:
-                    rnd = random.random                                   # random.random() x B, in order, as
-                    L.host_u_np[:] = [rnd() for _ in range(B)]            # prioritized_replay_memory.py:262
-                    L.uniforms.copy_(L.host_u, non_blocking=True)
-                else:
-                    L.host_pos.numpy()[:] = self.replayBuffer.sample_positions(B)
-                    L.positions.copy_(L.host_pos, non_blocking=True)
-        rc = L.step_fn(L.handle, L.stream_ptr)
+            if self.prioritized_replay:
+                rnd = random.random                                       # random.random() x B, in order, as
+                L.host_u_np[:] = [rnd() for _ in range(B)]                # prioritized_replay_memory.py:262
+                u_ptr = L.u_ptr
+            else:
+                L.host_pos_np[:] = self.replayBuffer.sample_positions(B)
+                pos_ptr = L.pos_ptr
+        # one library call: order after the caller's stream, H2D of this step's host inputs, the step's
+        # CUDA graph on the learner stream, order the caller's stream after it
+        rc = L.step_host(L.handle, u_ptr, pos_ptr, torch.cuda.current_stream().cuda_stream, L.stream_ptr)
         if rc:
-            _lib.check(rc, "d4pg_learner_step")
-        # ordering with work the caller issues on the current stream (adds, forwards)
-        cur.wait_stream(L.stream)
+            _lib.check(rc, "d4pg_learner_step_host")
         if self.prioritized_replay:
             self.beta_schedule.t += 1
         for opt in (self.optimizer_global_actor, self.optimizer_global_critic):
@@ -338,10 +343,10 @@ class DDPG:
     def last_losses(self):
         """(critic_loss, actor_loss) of the most recent train() -- synchronises on the result."""
         L = self._learner
-        with torch.cuda.stream(L.stream):
-            L.host_losses.copy_(L.losses, non_blocking=True)
-        L.stream.synchronize()
-        return float(L.host_losses[0]), float(L.host_losses[1])
+        rc = L.read_losses(L.handle, L.losses_out, L.stream_ptr)       # D2H + wait: the step's result
+        if rc:
+            _lib.check(rc, "d4pg_learner_read_losses")
+        return L.losses_out[0], L.losses_out[1]
 
     def last_batch_info(self):
         """Device tensors of the most recent step: sampled idx, IS weights, td, new priorities."""

@@ -133,38 +133,34 @@ class _DeviceReplay(object):
         return o_obs, o_act, o_rew, o_obs2, o_done, (o_done + n + 15) & ~15
 
     def add_batch_host(self, s, a, r, s2, done):
-        """Fast ingest of n <= STAGE_ROWS host transitions: the five arrays are packed into ONE pinned
-        staging buffer, moved with ONE H2D copy and unpacked by the ring-write kernel."""
-        s = np.asarray(s, dtype=np.float32)
+        """Fast ingest of n <= STAGE_ROWS host transitions through ONE library call
+        (`d4pg_replay_add_host`): packed into a pinned staging buffer, one async H2D copy, ring +
+        tree kernels."""
+        s = np.ascontiguousarray(s, dtype=np.float32)
         n = s.shape[0] if s.ndim == 2 else 1
+        a = np.ascontiguousarray(a, dtype=np.float32)
         if self.handle is None:
-            self._allocate(s.reshape(n, -1).shape[1], np.asarray(a).reshape(n, -1).shape[1])
+            self._allocate(s.reshape(n, -1).shape[1], a.reshape(n, -1).shape[1])
         if n > self.STAGE_ROWS or n > self.size:
             return self.add_batch(s, a, r, s2, done)
-        self.flush()
+        if self._n_staged:
+            self.flush()
+        L = _lib.lib()
         if getattr(self, "_pack_host", None) is None:
-            nbytes = self._pack_layout(self.STAGE_ROWS)[5]
+            nbytes = int(L.d4pg_replay_staging_bytes(self.handle, self.STAGE_ROWS))
             self._pack_host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
             self._pack_dev = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._pack_np = self._pack_host.numpy()
-            self._pack_evt = torch.cuda.Event()
-            self._pack_busy = False
-        if self._pack_busy:
-            self._pack_evt.synchronize()              # previous copy out of the pinned buffer has finished
-        oo, oa, orw, oo2, od, tot = self._pack_layout(n)
-        hp = self._pack_np
-        hp[oo:oo + n * self.obs_dim * 4].view(np.float32)[:] = s.reshape(-1)
-        hp[oo2:oo2 + n * self.obs_dim * 4].view(np.float32)[:] = np.asarray(s2, dtype=np.float32).reshape(-1)
-        hp[oa:oa + n * self.act_dim * 4].view(np.float32)[:] = np.asarray(a, dtype=np.float32).reshape(-1)
-        hp[orw:orw + n * 8].view(np.float64)[:] = np.asarray(r, dtype=np.float64).reshape(-1)
-        hp[od:od + n] = np.asarray(done).reshape(-1).astype(np.uint8)
-        self._pack_dev[:tot].copy_(self._pack_host[:tot], non_blocking=True)
-        self._pack_evt.record()
-        self._pack_busy = True
-        base = self._pack_dev.data_ptr()
-        _lib.check(_lib.lib().d4pg_replay_add(self.handle, n, C.c_void_p(base + oo), C.c_void_p(base + oa),
-                                              C.c_void_p(base + orw), C.c_void_p(base + oo2), C.c_void_p(base + od),
-                                              1 if self.prioritized else 0, _lib.stream_ptr()), "d4pg_replay_add")
+            _lib.check(L.d4pg_replay_set_staging(self.handle, _lib.ptr(self._pack_host), _lib.ptr(self._pack_dev), nbytes),
+                       "d4pg_replay_set_staging")
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        s2 = np.ascontiguousarray(s2, dtype=np.float32)
+        d = np.ascontiguousarray(done)
+        if d.dtype != np.uint8:
+            d = d.astype(np.uint8)
+        rc = L.d4pg_replay_add_host(self.handle, n, s.ctypes.data, a.ctypes.data, r.ctypes.data, s2.ctypes.data,
+                                    d.ctypes.data, 1 if self.prioritized else 0, torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _lib.check(rc, "d4pg_replay_add_host")
         self._next_idx = (self._next_idx + n) % self.size
         self._len = min(self.size, self._len + n)
 

@@ -124,6 +124,16 @@ int32_t d4pg_replay_add(d4pg_replay_t* h, int64_t n, const float* obs, const flo
                         const double* rew, const float* obs2, const uint8_t* done,
                         int32_t prioritized, d4pg_stream_t stream);
 
+/* Host-side ingest: register a caller-owned PINNED host staging buffer and a device staging buffer
+ * of `bytes` each (>= d4pg_replay_staging_bytes(rows)), then add() n <= rows transitions straight from
+ * ordinary host arrays: the five arrays are packed into the pinned buffer, moved with ONE async H2D
+ * copy and unpacked by the ring-write kernel.  Stream-ordered; the pinned buffer is re-used only after
+ * the previous copy out of it has completed. */
+int64_t d4pg_replay_staging_bytes(const d4pg_replay_t* h, int64_t rows);
+int32_t d4pg_replay_set_staging(d4pg_replay_t* h, void* pinned_host, void* device, int64_t bytes);
+int32_t d4pg_replay_add_host(d4pg_replay_t* h, int64_t n, const float* obs, const float* act, const double* rew,
+                             const float* obs2, const uint8_t* done, int32_t prioritized, d4pg_stream_t stream);
+
 /* _sample_proportional + IS weights + _encode_sample (:258-313,189-199).
  *   uniforms [B] f64 in [0,1): the reference's random.random() draws; NULL = device Philox
  *   (seed, counter) stream.  mass = u * sum(0,len-1) with the reference's association and
@@ -232,6 +242,17 @@ int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d4pg_learner
 int32_t d4pg_learner_destroy(d4pg_learner_t* h);
 /* One gradient step.  Everything is stream-ordered; results land in buf->losses etc. */
 int32_t d4pg_learner_step(d4pg_learner_t* h, d4pg_stream_t stream);
+/* Host-facing step: everything `DDPG.train()` needs per call in ONE library call.
+ *   d4pg_learner_set_host_buffers: caller-owned PINNED host buffers: uniforms f64[B], positions i32[B], losses f32[4]
+ *   d4pg_learner_step_host: order the learner stream after `caller_stream`, copy this step's host inputs
+ *     (uniforms for prioritized replay / positions for uniform replay; NULL with device-side sampling)
+ *     to the device, run the step on `learner_stream`, order `caller_stream` after it.
+ *   d4pg_learner_read_losses: D2H of {critic loss, actor loss, -, -} and wait for it (the step's result). */
+int32_t d4pg_learner_set_host_buffers(d4pg_learner_t* h, double* pinned_uniforms, int32_t* pinned_positions,
+                                      float* pinned_losses);
+int32_t d4pg_learner_step_host(d4pg_learner_t* h, const double* uniforms, const int32_t* positions,
+                               d4pg_stream_t caller_stream, d4pg_stream_t learner_stream);
+int32_t d4pg_learner_read_losses(d4pg_learner_t* h, float* out4, d4pg_stream_t learner_stream);
 /* n_steps back-to-back gradient steps without returning to the caller in between (device-side
  * sampling keeps advancing; caller-supplied uniforms/positions would be reused). */
 int32_t d4pg_learner_run(d4pg_learner_t* h, int32_t n_steps, d4pg_stream_t stream);
