@@ -11,6 +11,7 @@
 
 namespace d4pg {
 
+template <bool ALLOW_SPLIT>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid_constant__ GemmBatch batch) {
   __shared__ __align__(16) float smem[2 * KC * LDS_A + 2 * KC * LDS_B];
   static_assert(2 * KC * LDS_A + 2 * KC * LDS_B >= GEMM_WARPS * BM * BN, "partial-tile buffer must fit");
@@ -21,7 +22,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid
   for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
     if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
   const GemmProblem P = batch.p[pi];        // one copy into registers (no constant-bank reads in the loops)
-  gemm_tile_dispatch(P, smem, blockIdx.x - P.tile_begin);
+  gemm_tile_dispatch<ALLOW_SPLIT>(P, smem, blockIdx.x - P.tile_begin);
   pdl_trigger_end(batch.pdl);
 }
 
@@ -95,9 +96,11 @@ int gemm_batch_launch(const GemmBatch& b, cudaStream_t st) {
   for (int i = 0; i < b.n; ++i)     // a concatenated input must switch source on a K-chunk boundary
     D4PG_REQUIRE(b.p[i].mode != GEMM_FWD || b.p[i].K1 == b.p[i].K || b.p[i].K1 % KC == 0, D4PG_ENOTSUP,
                  "gemm_batch_launch: concat split K1=%d must be a multiple of %d", b.p[i].K1, KC);
-  D4PG_MAX_CARVEOUT(gemm_ffma_kernel);
+  D4PG_MAX_CARVEOUT(gemm_ffma_kernel<false>);
+  D4PG_MAX_CARVEOUT(gemm_ffma_kernel<true>);
   const_cast<GemmBatch&>(b).pdl = pdl_mode();
-  D4PG_CUDA_OK(launch_pdl(gemm_ffma_kernel, dim3(b.total_tiles), dim3(GEMM_THREADS), 0, st, b));
+  if (gemm_batch_has_splitk(b)) D4PG_CUDA_OK(launch_pdl(gemm_ffma_kernel<true>, dim3(b.total_tiles), dim3(GEMM_THREADS), 0, st, b));
+  else D4PG_CUDA_OK(launch_pdl(gemm_ffma_kernel<false>, dim3(b.total_tiles), dim3(GEMM_THREADS), 0, st, b));
   return D4PG_OK;
 }
 

@@ -140,8 +140,10 @@ __device__ __forceinline__ void store_B(const GemmProblem& P, float* Bs, int tid
 // One 32x32 output tile.  The 8 warps split K inside the CTA: each warp owns the whole tile for
 // 1/8 of every K-chunk with an 8x4 register tile per lane (32 independent FFMAs per 3 LDS.128);
 // the 8 partial tiles are summed through shared memory in fixed warp order (deterministic).
-template <int MODE>
-__device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int m0, int n0, int tn, int kbeg, int kend) {
+template <int MODE, bool SPLIT>
+__device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int m0, int n0, int tn, int kbeg_in, int kend_in) {
+  // the common (non-split) instantiation keeps kbeg = 0 / kend = K as it was before split-K existed
+  const int kbeg = SPLIT ? kbeg_in : 0, kend = SPLIT ? kend_in : P.K;
   float* As0 = smem;                      // [2][KC*LDS_A]
   float* Bs0 = smem + 2 * KC * LDS_A;     // [2][KC*LDS_B]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -226,26 +228,32 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int
         case EPI_TANH_MASK: { const float t = __ldg(P.aux + size_t(gi) * P.ldaux + gj); x *= (1.f - t * t); } break;
         default: break;
       }
-      if (P.ksplit > 1) atomicAdd(&P.C[size_t(gi) * P.ldc + gj], x);      // split-K slice (C pre-zeroed)
+      if (SPLIT) atomicAdd(&P.C[size_t(gi) * P.ldc + gj], x);            // split-K slice (C pre-zeroed)
       else P.C[size_t(gi) * P.ldc + gj] = x;
     }
   }
   if (want_bias_grad && tid < BM && m0 + tid < P.M) {
-    if (P.ksplit > 1) atomicAdd(&P.bias_grad[m0 + tid], colsum);
+    if (SPLIT) atomicAdd(&P.bias_grad[m0 + tid], colsum);
     else P.bias_grad[m0 + tid] = colsum;
   }
 }
 
 
 // dispatch one 32x32 tile of problem P (block-uniform mode switch)
+template <bool ALLOW_SPLIT>
 __device__ __forceinline__ void gemm_tile_dispatch(const GemmProblem& P, float* smem, int tile) {
-  const int per_slice = P.tiles_m * P.tiles_n;
-  const int ks = tile / per_slice, t2 = tile - ks * per_slice;
-  const int tm = t2 / P.tiles_n, tn = t2 - tm * P.tiles_n;
-  const int kbeg = ks * P.kslice, kend = min(P.K, kbeg + P.kslice);
-  if (P.mode == GEMM_FWD) gemm_tile<GEMM_FWD>(P, smem, tm * BM, tn * BN, tn, 0, P.K);
-  else if (P.mode == GEMM_DX) gemm_tile<GEMM_DX>(P, smem, tm * BM, tn * BN, tn, 0, P.K);
-  else gemm_tile<GEMM_DW>(P, smem, tm * BM, tn * BN, tn, kbeg, kend);
+  if (ALLOW_SPLIT && P.ksplit > 1) {        // dW over a large batch (only compiled into the split-K kernel)
+    const int per_slice = P.tiles_m * P.tiles_n;
+    const int ks = tile / per_slice, t2 = tile - ks * per_slice;
+    const int tm = t2 / P.tiles_n, tn = t2 - tm * P.tiles_n;
+    const int kbeg = ks * P.kslice;
+    gemm_tile<GEMM_DW, true>(P, smem, tm * BM, tn * BN, tn, kbeg, min(P.K, kbeg + P.kslice));
+    return;
+  }
+  const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+  if (P.mode == GEMM_FWD) gemm_tile<GEMM_FWD, false>(P, smem, tm * BM, tn * BN, tn, 0, 0);
+  else if (P.mode == GEMM_DX) gemm_tile<GEMM_DX, false>(P, smem, tm * BM, tn * BN, tn, 0, 0);
+  else gemm_tile<GEMM_DW, false>(P, smem, tm * BM, tn * BN, tn, 0, 0);
 }
 constexpr int GEMM_SMEM_FLOATS = 2 * KC * LDS_A + 2 * KC * LDS_B;
 

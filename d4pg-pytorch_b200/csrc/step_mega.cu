@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) step_mega_kernel(const __grid
       int pi = 0;
       for (int i = 1; i < b.n; ++i) if (tile >= b.p[i].tile_begin) pi = i;
       const GemmProblem P = b.p[pi];
-      gemm_tile_dispatch(P, sm.gemm, tile - P.tile_begin);
+      gemm_tile_dispatch<false>(P, sm.gemm, tile - P.tile_begin);
       __syncthreads();                                     // smem reuse by the next tile
     }
     target += G; grid_barrier(p.barrier, target);
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) step_mega_kernel(const __grid
       int pi = 0;
       for (int i = 1; i < b.n; ++i) if (tile >= b.p[i].tile_begin) pi = i;
       const GemmProblem P = b.p[pi];
-      gemm_tile_dispatch(P, sm.gemm, tile - P.tile_begin);
+      gemm_tile_dispatch<false>(P, sm.gemm, tile - P.tile_begin);
       __syncthreads();
     }
     target += Gw; grid_barrier(p.barrier, target);
