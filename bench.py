@@ -45,7 +45,7 @@ def algorithmic(cfg):
     gemm_bytes = (3 * Pa + 5 * Pc) * 4
     byts = (B * (2 * S + A + 2) * 4 + B * log2cap * 4 + B * (1 + log2cap) * 2 * 2 * 4 + 3 * B * N * 4
             + 7 * (Pa + Pc) * 4 + 3 * (Pa + Pc) * 4 + gemm_bytes)
-    return dict(P=Pa + Pc, flops=flops, bytes=byts, gemm_bytes=gemm_bytes)
+    return dict(P=Pa + Pc, Pa=Pa, Pc=Pc, flops=flops, bytes=byts, gemm_bytes=gemm_bytes)
 
 
 def peaks():
@@ -178,7 +178,8 @@ def gpu_main(args):
         torch.manual_seed(0); random.seed(0)            # identical replicas on every rank
         dd = d4pg.DDPG(cfg["obs"], cfg["act"], memory_size=cap, batch_size=B, critic_dist_info=info,
                        n_steps=cfg["n_steps"], projection=cfg["proj"], sampling=sampling, philox_seed=1234 + rank,
-                       comm=comm, precision=args.precision, persistent=bool(args.persistent) and world == 1)
+                       comm=comm, precision=args.precision, persistent=bool(args.persistent) and world == 1,
+                       chain=bool(args.chain))
         dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
                                    d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
         dd.replayBuffer.add_batch(*synth(cfg, cap, seed=rank))     # this rank's shard, resident in HBM
@@ -224,28 +225,52 @@ def gpu_main(args):
     # ---- per-launch device times (eager step, CUDA events on the launching stream) -----------
     prof = {}
     for _ in range(5):
+        seen = {}
         for name, t in dd.profile_step():
-            prof.setdefault(name, []).append(t)
+            k = seen.get(name, 0); seen[name] = k + 1
+            prof.setdefault("%s#%d" % (name, k), []).append(t)
     alg = algorithmic(cfg)
     pk = peaks()
-    gemm_ms = [t for t in prof.get("gemm_launch", [])]
-    n_gemm = len(gemm_ms) // 5 if gemm_ms else 0
-    gemm_avg_ms = float(np.mean(gemm_ms)) if gemm_ms else None
+    S_, A_d, N_, Pa, Pc = cfg["obs"], cfg["act"], cfg["atoms"], alg["Pa"], alg["Pc"]
+    # algorithmic bytes of one launch of each MLP kernel class: weights read once,
+    # batch inputs once, gradients written once
+    kinds = {}
+    if any(k.startswith("launch_mlp_chain") for k in prof):
+        kinds["launch_mlp_chain#0"] = ("mlp_chain_kernel (3 forward chains, 20 layers, 1 launch)", 4 * (2 * Pa + 3 * Pc) + 4 * B * (2 * S_ + A_d), "fwd")
+        kinds["launch_mlp_chain#1"] = ("mlp_chain_kernel (2 dX chains, 9 layers, 1 launch)", 4 * (Pa + 2 * Pc) + 8 * B * N_, "bwd")
+        kinds["gemm_wide_launch#0"] = ("gemm_wide_kernel (9 dW problems, 1 launch)", 4 * (Pa + Pc) + 4 * B * 9 * H, "dw")
+    else:
+        n_gemm = len([k for k in prof if k.startswith("gemm_launch")])
+        for k in prof:
+            if k.startswith("gemm_launch"):
+                kinds[k] = ("%s (MLP level, %d launches/step)" % ("gemm_ffma_kernel" if args.precision == "fp32" else "gemm_tc2_kernel", n_gemm),
+                            alg["gemm_bytes"] / max(n_gemm, 1), "level")
     roofline = None
-    if gemm_avg_ms:
-        ach = alg["gemm_bytes"] / n_gemm / (gemm_avg_ms * 1e-3) / 1e9
+    if kinds:
+        mlp_ms = {k: float(np.mean(prof[k])) for k in kinds if k in prof}
+        if "launch_mlp_chain#0" in mlp_ms:
+            top = max(mlp_ms, key=mlp_ms.get)
+            name, nbytes, _ = kinds[top]
+            t_ms = mlp_ms[top]
+            flops = alg["flops"] * {"fwd": 0.5, "bwd": 0.25, "dw": 0.25}[kinds[top][2]]
+        else:                                   # all levels are one kernel class: average launch
+            top = sorted(mlp_ms)[0]
+            name, nbytes, _ = kinds[top]
+            t_ms = float(np.mean(list(mlp_ms.values())))
+            flops = alg["flops"] / len(mlp_ms)
+        ach = nbytes / (t_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("gemm_ffma_kernel_dram_bytes_per_launch")
-        roofline = {"kernel": "%s (MLP fwd/bwd levels, %d launches/step)" % ("gemm_ffma_kernel" if args.precision == "fp32" else "gemm_tc_kernel", n_gemm), "bound": "hbm",
-                    "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
-                    "peak_source": pk["src"], "avg_launch_us": gemm_avg_ms * 1e3,
-                    "flops_frac_of_bf16_peak": alg["flops"] / n_gemm / (gemm_avg_ms * 1e-3) / 1e12 / pk["tf"]}
+            traffic = json.load(open(tpath)).get(name.split(" ")[0] + ":" + kinds[top][2])
+        roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"] + " (burst copy bandwidth)",
+                    "avg_launch_us": t_ms * 1e3, "algorithmic_bytes_per_launch": int(nbytes),
+                    "flops_frac_of_bf16_peak": flops / (t_ms * 1e-3) / 1e12 / pk["tf"]}
     step_roof = {"hbm_frac": alg["bytes"] / (ms_per_step * 1e-3) / 1e9 / pk["hbm"],
                  "tensor_frac": alg["flops"] / (ms_per_step * 1e-3) / 1e12 / pk["tf"],
                  "algorithmic_bytes": alg["bytes"], "algorithmic_flops": alg["flops"]}
-    launch_breakdown = {k: round(float(np.mean(v)) * 1e3 * (len(v) // 5), 2) for k, v in prof.items()}   # us/step
+    launch_breakdown = {k: round(float(np.mean(v)) * 1e3, 2) for k, v in prof.items()}   # us per launch
     del dd
 
     # ---- e2e: public API with host buffers: per step H2D of new transitions + uniforms, D2H loss
@@ -290,6 +315,7 @@ def gpu_main(args):
                 "config": {"workload": args.config, "batch_per_gpu": B, "global_batch": B * world, "obs_dim": cfg["obs"],
                            "act_dim": cfg["act"], "n_atoms": cfg["atoms"], "replay_capacity_per_gpu": cap,
                            "parallelism": "dp%d" % world,
+                           "step_plan": "chains" if (args.chain and args.precision == "fp32" and not args.persistent) else ("persistent" if args.persistent else "levels"),
                            "precision": {"fp32": "fp32 FFMA", "tf32x3": "3xTF32 tcgen05 (fp32-accurate)", "tf32": "TF32 tcgen05"}[args.precision],
                            "l2": "inputs larger than L2: replay store %.0f MB + trees %.0f MB per GPU, rows sampled at "
                                  "random; parameters (%.1f MB) are L2-resident by design" % (
@@ -315,6 +341,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--persistent", type=int, default=0, help="1 = one cooperative kernel per step (fp32, 1 GPU)")
+    ap.add_argument("--chain", type=int, default=1, help="1 = cluster-fused layer chains (fp32), 0 = one launch per level")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)

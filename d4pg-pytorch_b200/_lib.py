@@ -43,7 +43,7 @@ class LearnerConfig(C.Structure):
         ("precision", C.c_int32), ("sample_mode", C.c_int32),
         ("philox_seed", C.c_uint64),
         ("world_size", C.c_int32), ("use_graph", C.c_int32), ("persistent", C.c_int32),
-        ("loss_flags", C.c_int32),
+        ("loss_flags", C.c_int32), ("chain", C.c_int32),
     ]
 
 
@@ -105,6 +105,7 @@ _PROTOS = {
     "d4pg_learner_kernels_per_step": (C.c_int32, [_P]),
     "d4pg_learner_set_counters": (C.c_int32, [_P, C.c_int64, C.c_int64, _P]),
     "d4pg_debug_tc_trace": (C.c_int32, [_P]),
+    "d4pg_debug_trace_read": (C.c_int32, [_P, C.c_int32]),
     "d4pg_comm_unique_id": (C.c_int32, [_P]),
     "d4pg_comm_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "d4pg_comm_destroy": (C.c_int32, [_P]),

@@ -7,6 +7,7 @@
 // latency-bound, so small tiles on many SMs beat big tiles on few.  Accumulation is plain FFMA
 // in k order, i.e. a true fp32 dot product (needed for the 1e-5 parity of config 2).
 #include "gemm_ffma_dev.cuh"
+#include "mlp_chain.cuh"
 #include <algorithm>
 
 namespace d4pg {
@@ -25,6 +26,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid
   gemm_tile_dispatch<ALLOW_SPLIT>(P, smem, blockIdx.x - P.tile_begin);
   pdl_trigger_end(batch.pdl);
 }
+
+// Same tiles, leaner parameters (no TMA descriptors) and room for every dW problem of a step.
+template <bool ALLOW_SPLIT>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_wide_kernel(const __grid_constant__ GemmWideBatch batch) {
+  extern __shared__ __align__(16) float smem[];        // DW_SMEM_FLOATS
+  pdl_trigger(batch.pdl);
+  pdl_wait();
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < GEMM_WIDE_MAX; ++i)
+    if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
+  const GemmProblem P = batch.p[pi];
+  gemm_tile_dispatch<ALLOW_SPLIT, true>(P, smem, blockIdx.x - P.tile_begin);
+  pdl_trigger_end(batch.pdl);
+}
+static_assert(DW_SMEM_FLOATS >= GEMM_SMEM_FLOATS, "the async dW stage must cover the chunked tile's buffers");
 
 // ---- host side -------------------------------------------------------------------------------
 GemmProblem gemm_fwd(const float* X, int ldx, const float* X2, int ldx2, int K1, const float* W, int ldw,
@@ -54,8 +71,7 @@ GemmProblem gemm_dw(const float* dZ, int lddz, const float* X, int ldx, float* d
 }
 void gemm_batch_begin(GemmBatch& b) { b.n = 0; b.total_tiles = 0; b.all_tma = 0; b.trace = nullptr; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
-  GemmProblem p = pin;
+static void prepare_problem(GemmProblem& p) {
   // 128-bit staging is legal when rows start 16-B aligned and the contiguous extent is a multiple of 4
   bool avec, bvec;
   if (p.mode == GEMM_DW) avec = aligned16(p.A) && p.lda % 4 == 0 && p.M % 4 == 0;
@@ -63,6 +79,7 @@ void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
   if (p.mode == GEMM_FWD) bvec = aligned16(p.Bm) && p.ldb % 4 == 0 && p.K % 4 == 0;
   else bvec = aligned16(p.Bm) && p.ldb % 4 == 0 && p.N % 4 == 0;
   p.flags = (avec ? GEMM_A_VEC : 0) | (bvec ? GEMM_B_VEC : 0);
+  if (p.mode == GEMM_DW && aligned16(p.A) && p.lda % 4 == 0 && aligned16(p.Bm) && p.ldb % 4 == 0) p.flags |= GEMM_ASYNC_OK;
   // dW over a large batch: 8 tiles x (B/32) serial chunks would leave the GPU idle -> split K
   p.ksplit = 1; p.kslice = p.K;
   if (p.mode == GEMM_DW && p.K >= 1024) {
@@ -70,7 +87,12 @@ void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
     p.kslice = cdiv(cdiv(p.K, p.ksplit), 64) * 64;
     p.ksplit = cdiv(p.K, p.kslice);
   }
-  p.tiles_m = cdiv(p.M, BM); p.tiles_n = cdiv(p.N, BN); p.tile_begin = b.total_tiles;
+  p.tiles_m = cdiv(p.M, BM); p.tiles_n = cdiv(p.N, BN);
+}
+void gemm_batch_add(GemmBatch& b, const GemmProblem& pin) {
+  GemmProblem p = pin;
+  prepare_problem(p);
+  p.tile_begin = b.total_tiles;
   b.total_tiles += p.tiles_m * p.tiles_n * p.ksplit;
   b.p[b.n++] = p;
 }
@@ -81,6 +103,33 @@ void gemm_batch_retile(GemmBatch& b, int bm, int bn) {
     p.tiles_m = cdiv(p.M, bm); p.tiles_n = cdiv(p.N, bn); p.tile_begin = b.total_tiles;
     b.total_tiles += p.tiles_m * p.tiles_n * p.ksplit;
   }
+}
+void gemm_wide_begin(GemmWideBatch& b) { b.n = 0; b.total_tiles = 0; b.pdl = 0; }
+void gemm_wide_add(GemmWideBatch& b, const GemmProblem& pin) {
+  if (b.n >= GEMM_WIDE_MAX) { b.n = GEMM_WIDE_MAX + 1; return; }      // reported by gemm_wide_launch
+  GemmProblem p = pin;
+  prepare_problem(p);
+  p.tile_begin = b.total_tiles;
+  b.total_tiles += p.tiles_m * p.tiles_n * p.ksplit;
+  b.p[b.n++] = p;
+}
+int gemm_wide_launch(GemmWideBatch& b, cudaStream_t st) {
+  D4PG_REQUIRE(b.n > 0 && b.n <= GEMM_WIDE_MAX, D4PG_EINVAL, "gemm_wide_launch: %d problems (max %d)", b.n, GEMM_WIDE_MAX);
+  bool split = false;
+  for (int i = 0; i < b.n; ++i) split = split || b.p[i].ksplit > 1;
+  D4PG_MAX_CARVEOUT(gemm_wide_kernel<false>);
+  D4PG_MAX_CARVEOUT(gemm_wide_kernel<true>);
+  const size_t smem = DW_SMEM_FLOATS * sizeof(float);
+  static bool smem_set = false;
+  if (!smem_set) {
+    D4PG_CUDA_OK(cudaFuncSetAttribute(gemm_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    D4PG_CUDA_OK(cudaFuncSetAttribute(gemm_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    smem_set = true;
+  }
+  b.pdl = pdl_mode();
+  if (split) D4PG_CUDA_OK(launch_pdl(gemm_wide_kernel<true>, dim3(b.total_tiles), dim3(GEMM_THREADS), smem, st, b));
+  else D4PG_CUDA_OK(launch_pdl(gemm_wide_kernel<false>, dim3(b.total_tiles), dim3(GEMM_THREADS), smem, st, b));
+  return D4PG_OK;
 }
 bool gemm_batch_has_splitk(const GemmBatch& b) {
   for (int i = 0; i < b.n; ++i) if (b.p[i].ksplit > 1) return true;

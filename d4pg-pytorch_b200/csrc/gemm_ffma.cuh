@@ -30,7 +30,7 @@ struct GemmProblem {
 };
 
 constexpr int GEMM_MAX_PROBLEMS = 8;
-enum GemmFlags { GEMM_A_VEC = 1, GEMM_B_VEC = 2, GEMM_A_TMA = 4, GEMM_B_TMA = 8 };
+enum GemmFlags { GEMM_A_VEC = 1, GEMM_B_VEC = 2, GEMM_A_TMA = 4, GEMM_B_TMA = 8, GEMM_ASYNC_OK = 16 };
 struct GemmBatch {
   GemmProblem p[GEMM_MAX_PROBLEMS];
   int n;

@@ -17,6 +17,15 @@ constexpr int PER_THREAD = BM * KC / GEMM_THREADS;   // 8 staged elements per th
 // over the banks (8-way conflict without it) while float4 reads along a row stay aligned.
 __device__ __forceinline__ int swz(int kk, int idx) { return ((((idx >> 2) ^ (kk >> 3)) & 7) << 2) | (idx & 3); }
 
+// ---- asynchronous copies (LDGSTS, L2-only so planes written by other SMs are read coherently) -------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned d = unsigned(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- operand staging ---------------------------------------------------------------------------
 // Two source shapes, each with a 128-bit fast path (ncu of the first version: 42 % of all issued
 // instructions were address arithmetic / predicate / constant-bank loads of the scalar staging):
@@ -239,18 +248,104 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& P, float* smem, int
 }
 
 
+// dW tile with both operands fetched asynchronously, up to 256 batch rows (the whole contraction at
+// batch 256) in flight at once: the chunk-by-chunk register staging of gemm_tile pays one L2 round
+// trip per 64 rows, which is what a 256-row dW costs almost entirely.  Same order of additions as
+// gemm_tile<GEMM_DW>.  Needs 16-B aligned operands with 16-B row pitches (GEMM_ASYNC_OK).
+constexpr int DW_STAGE = 256;
+constexpr int DW_SMEM_FLOATS = 2 * DW_STAGE * BM;
+template <bool SPLIT>
+__device__ __forceinline__ void gemm_dw_tile_async(const GemmProblem& P, float* smem, int m0, int n0, int tn, int kbeg, int kend) {
+  float* As = smem;                       // [DW_STAGE][32]  dZ[k][m0+i]
+  float* Bs = smem + DW_STAGE * BM;       // [DW_STAGE][32]  X[k][n0+j]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = (lane >> 3) * 8, c0 = (lane & 7) * 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float colsum = 0.f;
+  const bool want_bias_grad = (P.bias_grad != nullptr) && (tn == 0);
+  const float* __restrict__ A = P.A; const float* __restrict__ Bm = P.Bm;
+  const int lda = P.lda, ldb = P.ldb;
+
+  for (int s0 = kbeg; s0 < kend; s0 += DW_STAGE) {
+    const int kn = min(DW_STAGE, kend - s0);
+    for (int e = tid; e < kn * 8; e += GEMM_THREADS) {
+      const int k = e >> 3, c4 = (e & 7) << 2;
+      if (m0 + c4 < lda) cp_async16(As + k * BM + c4, A + size_t(s0 + k) * lda + m0 + c4);
+      if (n0 + c4 < ldb) cp_async16(Bs + k * BN + c4, Bm + size_t(s0 + k) * ldb + n0 + c4);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int kb = warp * KW; kb < kn; kb += KC) {
+#pragma unroll
+      for (int k = 0; k < KW; ++k) {
+        const int kk = kb + k;
+        if (kk >= kn) break;
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk * BM + r0]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk * BM + r0 + 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk * BN + c0]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+    if (want_bias_grad && tid < BM && m0 + tid < P.M) {
+#pragma unroll 8
+      for (int kk = 0; kk < kn; ++kk) colsum += As[kk * BM + tid];
+    }
+    __syncthreads();
+  }
+
+  float* red = smem;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(&red[(warp * BM + r0 + i) * BN + c0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  __syncthreads();
+  const int orow = tid >> 3, ocol = (tid & 7) * 4;
+  float4 sum = *reinterpret_cast<const float4*>(&red[orow * BN + ocol]);
+#pragma unroll
+  for (int w = 1; w < GEMM_WARPS; ++w) {
+    const float4 t = *reinterpret_cast<const float4*>(&red[(w * BM + orow) * BN + ocol]);
+    sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+  }
+  const int gi = m0 + orow;
+  if (gi < P.M) {
+    const float v[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int gj = n0 + ocol + cc;
+      if (gj >= P.N) continue;
+      if (SPLIT) atomicAdd(&P.C[size_t(gi) * P.ldc + gj], v[cc]);
+      else P.C[size_t(gi) * P.ldc + gj] = v[cc];
+    }
+  }
+  if (want_bias_grad && tid < BM && m0 + tid < P.M) {
+    if (SPLIT) atomicAdd(&P.bias_grad[m0 + tid], colsum);
+    else P.bias_grad[m0 + tid] = colsum;
+  }
+}
+
 // dispatch one 32x32 tile of problem P (block-uniform mode switch)
-template <bool ALLOW_SPLIT>
+template <bool ALLOW_SPLIT, bool ASYNC_DW = false>
 __device__ __forceinline__ void gemm_tile_dispatch(const GemmProblem& P, float* smem, int tile) {
   if (ALLOW_SPLIT && P.ksplit > 1) {        // dW over a large batch (only compiled into the split-K kernel)
     const int per_slice = P.tiles_m * P.tiles_n;
     const int ks = tile / per_slice, t2 = tile - ks * per_slice;
     const int tm = t2 / P.tiles_n, tn = t2 - tm * P.tiles_n;
     const int kbeg = ks * P.kslice;
-    gemm_tile<GEMM_DW, true>(P, smem, tm * BM, tn * BN, tn, kbeg, min(P.K, kbeg + P.kslice));
+    if (ASYNC_DW && (P.flags & GEMM_ASYNC_OK)) gemm_dw_tile_async<true>(P, smem, tm * BM, tn * BN, tn, kbeg, min(P.K, kbeg + P.kslice));
+    else gemm_tile<GEMM_DW, true>(P, smem, tm * BM, tn * BN, tn, kbeg, min(P.K, kbeg + P.kslice));
     return;
   }
   const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+  if (ASYNC_DW && P.mode == GEMM_DW && (P.flags & GEMM_ASYNC_OK)) { gemm_dw_tile_async<false>(P, smem, tm * BM, tn * BN, tn, 0, P.K); return; }
   if (P.mode == GEMM_FWD) gemm_tile<GEMM_FWD, false>(P, smem, tm * BM, tn * BN, tn, 0, 0);
   else if (P.mode == GEMM_DX) gemm_tile<GEMM_DX, false>(P, smem, tm * BM, tn * BN, tn, 0, 0);
   else gemm_tile<GEMM_DW, false>(P, smem, tm * BM, tn * BN, tn, 0, 0);

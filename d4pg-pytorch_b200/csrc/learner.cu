@@ -23,6 +23,7 @@
 
 #include "internal.cuh"
 #include "step_mega.cuh"
+#include "mlp_chain.cuh"
 
 namespace d4pg {
 
@@ -37,12 +38,13 @@ struct Workspace {
   float *c_dz22, *c_dz2, *c_dz1, *p_dz22, *p_dz2, *a_dz3, *a_dz22, *a_dh2, *a_dz1;
   LearnerClock* clock;
   unsigned long long* barrier;     // grid-barrier counter of the persistent step kernel
+  float* xchg;                     // exchange planes of the cluster-fused chain kernels (chain mode)
   int64_t total;
 };
 
 // Every 2-D plane has a row pitch that is a multiple of 4 floats (16-B rows): |s|=17 -> 20,
 // |a|=6 -> 8, N=51 -> 52.  That makes every GEMM operand TMA- and float4-addressable.
-static Workspace carve(float* base, int B, int S, int A, int N) {
+static Workspace carve(float* base, int B, int S, int A, int N, bool chain) {
   Workspace w{};
   int64_t off = 0;
   auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
@@ -65,6 +67,7 @@ static Workspace carve(float* base, int B, int S, int A, int N) {
   w.a_dz1 = take(int64_t(B) * H);
   w.clock = reinterpret_cast<LearnerClock*>(take(sizeof(LearnerClock) / 4 + 4));
   w.barrier = reinterpret_cast<unsigned long long*>(take(64));   // [0] arrival counter, [16] release flag (own line)
+  w.xchg = chain ? take(chain_xchg_floats(B)) : nullptr;
   w.total = off;
   return w;
 }
@@ -86,6 +89,8 @@ struct d4pg_learner {
   // profiling (d4pg_learner_profile_step): CUDA-event pair around every launch of an eager step
   cudaStream_t side; cudaEvent_t ev_fork, ev_join;
   MegaParams mega;
+  ChainArgs chain_fwd_args, chain_bwd_args;
+  GemmWideBatch dw_batch;
   // host-facing step (caller-owned pinned buffers, d4pg_learner_set_host_buffers)
   double* host_u; int32_t* host_pos; float* host_losses; cudaEvent_t ev_in, ev_out;
   bool profiling;
@@ -124,7 +129,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 #define RUN(expr)                                                                          \
   do {                                                                                     \
     if (L->profiling) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);    \
-      std::string nm0(#expr); const bool rep = nm0.rfind("gemm_launch", 0) == 0 || nm0.rfind("launch_heads", 0) == 0; \
+      std::string nm0(#expr); const bool rep = nm0.rfind("gemm_launch", 0) == 0 || nm0.rfind("launch_heads", 0) == 0 || nm0.rfind("launch_mlp_chain", 0) == 0; \
       cudaEventRecord(e0, st); rc = (expr);                                                \
       for (int _r = 1; rep && _r < PROFILE_REPS && rc == 0; ++_r) rc = (expr);             \
       cudaEventRecord(e1, st);                                                             \
@@ -151,6 +156,39 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 
   const float* Wa = b.actor; const float* Wat = b.actor_target; const float* Wc = b.critic; const float* Wct = b.critic_target;
   GemmBatch g;
+  const bool chain = c.chain != 0;
+  if (chain) {
+    // 2'. the three forward chains of the step as ONE cluster launch (mlp_chain.cu):
+    //   T: actor_target(s') -> critic_target(s', .)      ddpg.py:205-206
+    //   Q: critic(s, a)                                   ddpg.py:208
+    //   P: actor(s) -> critic(s, actor(s))                ddpg.py:236-238 (fc1 of the critic is recomputed: K=|s|)
+    ChainArgs& ca = L->chain_fwd_args;
+    chain_args_begin(ca, B, w.xchg);
+    ChainSlot sl; int at3, ct1, q1, a3, c1;
+    sl = chain_fwd(Wat + da.w_off[0], la[0], Wat + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[0], H, 1); chain_src_global(sl, w.s2, Sp); int t = chain_add(ca, 0, sl);
+    sl = chain_fwd(Wat + da.w_off[1], la[1], Wat + da.b_off[1], H, H, EPI_BIAS, w.h2[0], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 0, sl);
+    sl = chain_fwd(Wat + da.w_off[2], la[2], Wat + da.b_off[2], H, H, EPI_BIAS_RELU, w.h3[0], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 0, sl);
+    sl = chain_fwd(Wat + da.w_off[3], la[3], Wat + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[0], Ap, 1); chain_src_plane(sl, t); at3 = chain_add(ca, 0, sl);
+    sl = chain_fwd(Wct + dc.w_off[0], lc[0], Wct + dc.b_off[0], H, S, EPI_BIAS_RELU, w.h1[1], H, 1); chain_src_global(sl, w.s2, Sp); ct1 = chain_add(ca, 0, sl);
+    sl = chain_fwd(Wct + dc.w_off[1], lc[1], Wct + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[1], H, 1); chain_src_plane(sl, ct1); chain_src2_plane(sl, H, at3); t = chain_add(ca, 0, sl);
+    sl = chain_fwd(Wct + dc.w_off[2], lc[2], Wct + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[1], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 0, sl);
+    sl = chain_fwd(Wct + dc.w_off[3], lc[3], Wct + dc.b_off[3], N, H, EPI_BIAS, w.out[1], Np, 0); chain_src_plane(sl, t); chain_add(ca, 0, sl);
+
+    sl = chain_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, w.h1[2], H, 1); chain_src_global(sl, w.s, Sp); q1 = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[2], H, 1); chain_src_plane(sl, q1); chain_src2_global(sl, H, w.a, Ap); t = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[2], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[2], Np, 0); chain_src_plane(sl, t); chain_add(ca, 1, sl);
+
+    sl = chain_fwd(Wa + da.w_off[0], la[0], Wa + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[3], H, 1); chain_src_global(sl, w.s, Sp); t = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wa + da.w_off[1], la[1], Wa + da.b_off[1], H, H, EPI_BIAS, w.h2[3], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wa + da.w_off[2], la[2], Wa + da.b_off[2], H, H, EPI_BIAS_RELU, w.h3[3], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wa + da.w_off[3], la[3], Wa + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[3], Ap, 1); chain_src_plane(sl, t); a3 = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, 1); chain_src_global(sl, w.s, Sp); c1 = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[4], H, 1); chain_src_plane(sl, c1); chain_src2_plane(sl, H, a3); t = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[4], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[4], Np, 0); chain_src_plane(sl, t); chain_add(ca, 2, sl);
+    RUN(launch_mlp_chain(ca, st));
+  } else {
   // 2. forward level 1: fc1 of actor_target(s'), critic_target(s'), critic(s), actor(s)
   gemm_batch_begin(g);
   gemm_batch_add(g, gemm_fwd(w.s2, Sp, nullptr, 0, 0, Wat + da.w_off[0], la[0], Wat + da.b_off[0], w.h1[0], H, B, H, S, EPI_BIAS_RELU));
@@ -190,6 +228,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   gemm_batch_add(g, gemm_fwd(w.h3[4], H, nullptr, 0, 0, Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], w.out[4], Np, B, N, H, EPI_BIAS));
   LEVEL(g);
 
+  }
+
   // 3. heads: softmaxes, projection, CE loss, td, priorities, logit gradients (ddpg.py:214-222,236-238)
   HeadsArgs ha{};
   ha.target_logits = w.out[1]; ha.q_logits = w.out[2]; ha.pi_logits = w.out[4];
@@ -221,6 +261,39 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   float* Ga = b.grad_actor; float* Gc = b.grad_critic;
   if (B >= 1024 && !mega)                // dW levels run split-K with fp32 atomics: the gradient buffer must start at zero
     D4PG_CUDA_OK(cudaMemsetAsync(Ga, 0, size_t(da.total + dc.total) * sizeof(float), st));
+  if (chain) {
+    // 5'. both dX chains as ONE cluster launch, then every dW of the step as ONE grouped launch
+    //   C: critic loss  dlogits_q  -> fc3 -> fc2_2 -> fc2[:, :H]                         ddpg.py:230
+    //   P: policy loss  dlogits_pi -> fc3 -> fc2_2 -> fc2[:, H:] (d action, tanh') ->
+    //                   actor fc3 -> fc2_2 -> fc2   (PRE-update critic weights)  ddpg.py:242
+    ChainArgs& cb = L->chain_bwd_args;
+    chain_args_begin(cb, B, w.xchg); cb.trace_base = 6 * CHAIN_MAX_SLOTS;
+    ChainSlot sl; int t;
+    sl = chain_dx(Wc + dc.w_off[3], lc[3], H, N, EPI_RELU_MASK, w.h3[2], H, w.c_dz22, H, 1); chain_src_global(sl, w.dlogits_q, Np); t = chain_add(cb, 0, sl);
+    sl = chain_dx(Wc + dc.w_off[2], lc[2], H, H, EPI_RELU_MASK, w.h2[2], H, w.c_dz2, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 0, sl);
+    sl = chain_dx(Wc + dc.w_off[1], lc[1], H, H, EPI_RELU_MASK, w.h1[2], H, w.c_dz1, H, 0); chain_src_plane(sl, t); chain_add(cb, 0, sl);
+
+    sl = chain_dx(Wc + dc.w_off[3], lc[3], H, N, EPI_RELU_MASK, w.h3[4], H, w.p_dz22, H, 1); chain_src_global(sl, w.dlogits_pi, Np); t = chain_add(cb, 1, sl);
+    sl = chain_dx(Wc + dc.w_off[2], lc[2], H, H, EPI_RELU_MASK, w.h2[4], H, w.p_dz2, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
+    sl = chain_dx(Wc + dc.w_off[1] + H, lc[1], A, H, EPI_TANH_MASK, w.out[3], Ap, w.a_dz3, Ap, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
+    sl = chain_dx(Wa + da.w_off[3], la[3], H, A, EPI_RELU_MASK, w.h3[3], H, w.a_dz22, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
+    sl = chain_dx(Wa + da.w_off[2], la[2], H, H, EPI_NONE, nullptr, 0, w.a_dh2, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
+    sl = chain_dx(Wa + da.w_off[1], la[1], H, H, EPI_RELU_MASK, w.h1[3], H, w.a_dz1, H, 0); chain_src_plane(sl, t); chain_add(cb, 1, sl);
+    RUN(launch_mlp_chain(cb, st));
+
+    GemmWideBatch& gw = L->dw_batch;
+    gemm_wide_begin(gw);
+    gemm_wide_add(gw, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], lc[2], Gc + dc.b_off[2], H, H, B));
+    gemm_wide_add(gw, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], lc[1], Gc + dc.b_off[1], H, H, B));
+    gemm_wide_add(gw, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], la[2], Ga + da.b_off[2], H, H, B));
+    gemm_wide_add(gw, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], la[1], Ga + da.b_off[1], H, H, B));
+    gemm_wide_add(gw, gemm_dw(w.dlogits_q, Np, w.h3[2], H, Gc + dc.w_off[3], lc[3], Gc + dc.b_off[3], N, H, B));
+    gemm_wide_add(gw, gemm_dw(w.c_dz2, H, w.a, Ap, Gc + dc.w_off[1] + H, lc[1], nullptr, H, A, B));
+    gemm_wide_add(gw, gemm_dw(w.c_dz1, H, w.s, Sp, Gc + dc.w_off[0], lc[0], Gc + dc.b_off[0], H, S, B));
+    gemm_wide_add(gw, gemm_dw(w.a_dz3, Ap, w.h3[3], H, Ga + da.w_off[3], la[3], Ga + da.b_off[3], A, H, B));
+    gemm_wide_add(gw, gemm_dw(w.a_dz1, H, w.s, Sp, Ga + da.w_off[0], la[0], Ga + da.b_off[0], H, S, B));
+    RUN(gemm_wide_launch(gw, st));
+  } else {
   // 5. backward.  "c_" = critic-loss pass, "p_" = policy pass through the critic, "a_" = actor.
   // level B1: through critic.fc3
   gemm_batch_begin(g);
@@ -262,6 +335,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   gemm_batch_add(g, gemm_dw(w.a_dz1, H, w.s, Sp, Ga + da.w_off[0], la[0], Ga + da.b_off[0], H, S, B));
   LEVEL(g);
 
+  }
+
   // 6. data-parallel gradient exchange: ONE all-reduce over the flat [P_a + P_c] buffer
   if (c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
 
@@ -290,7 +365,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 
 extern "C" int64_t d4pg_learner_workspace_floats(const d4pg_learner_config_t* cfg) {
   if (!cfg) return -1;
-  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms).total;
+  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, cfg->chain != 0).total;
 }
 
 extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d4pg_learner_buffers_t* buf,
@@ -305,6 +380,8 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   D4PG_REQUIRE(cfg->world_size <= 1 || comm, D4PG_EINVAL, "d4pg_learner_create: world_size>1 needs a communicator");
   D4PG_REQUIRE(!cfg->persistent || (cfg->precision == 0 && cfg->world_size <= 1), D4PG_ENOTSUP,
                "d4pg_learner_create: the persistent step kernel needs precision 0 and a single GPU");
+  D4PG_REQUIRE(!cfg->chain || (cfg->precision == 0 && !cfg->persistent), D4PG_ENOTSUP,
+               "d4pg_learner_create: the cluster-fused chain kernels need precision 0 and persistent 0");
   D4PG_REQUIRE(buf->actor && buf->actor_target && buf->critic && buf->critic_target && buf->grad_actor && buf->grad_critic &&
                buf->adam_m_actor && buf->adam_v_actor && buf->adam_m_critic && buf->adam_v_critic &&
                buf->idx && buf->prio && buf->td && buf->losses && buf->workspace, D4PG_EINVAL,
@@ -318,7 +395,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
     set_error("d4pg_learner_create: grad_critic must equal grad_actor + P_a (one flat gradient buffer)");
     delete L; return D4PG_EINVAL;
   }
-  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms);
+  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, cfg->chain != 0);
   L->graph_exec = nullptr; L->graph_ready = false; L->steps_done = 0; L->kernels_per_step = 0;
   L->profiling = false;
   (void)debug_trace_buffer();          // allocate outside of any stream capture
@@ -435,7 +512,7 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
   for (int i = 0; i < n; ++i) {
     float ms = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, L->ev[2 * i], L->ev[2 * i + 1]);
-    if (L->ev_name[i] == "gemm_launch" || L->ev_name[i] == "launch_heads") ms /= float(PROFILE_REPS);
+    if (L->ev_name[i] == "gemm_launch" || L->ev_name[i] == "launch_heads" || L->ev_name[i] == "launch_mlp_chain") ms /= float(PROFILE_REPS);
     if (i < max_launches) {
       ms_out[i] = ms;
       if (names_out && name_stride > 1) {

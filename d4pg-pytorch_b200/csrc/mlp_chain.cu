@@ -1,0 +1,306 @@
+// Cluster-fused MLP chains: every dependent layer of a network chain in ONE launch.
+//
+// At batch 256 the actor/critic passes of DDPG.train (models.py:32-41,76-88 forward, ddpg.py:230,242
+// backward) are 14 dependent layer levels; as separate grouped-GEMM launches each level costs ~7 us of
+// which most is the kernel boundary (profiles/README.md).  Here a thread-block CLUSTER of 8 CTAs owns
+// 32 batch rows for a whole chain (e.g. actor_target fc1..fc3 -> critic_target fc1..fc3): CTA r of the
+// cluster computes the 32-column slice r of each 256-wide layer, publishes it k-major into an
+// L2-resident exchange plane, and a cluster barrier (barrier.cluster arrive.release / wait.acquire,
+// ~0.2 us) replaces the kernel boundary.  The next layer's first weight chunk is prefetched between
+// the arrive and the wait.  Rows never mix, so clusters are independent: no grid-wide barrier, no
+// co-residency requirement beyond the cluster itself.
+//
+// Arithmetic is the SAME as gemm_tile (gemm_ffma_dev.cuh): 64-deep K chunks, the 8 warps split each
+// chunk, 8x4 lane tiles, partial tiles reduced in warp order -> results are bit-identical to the
+// level-by-level path (tests/test_gpu_learner.py::test_chain_equals_levels).
+#include "gemm_ffma_dev.cuh"
+#include "mlp_chain.cuh"
+
+namespace d4pg {
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long chain_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// optional phase stamps of CTA 0 (D4PG_TC_TRACE): 6 per slot
+#define CTRACE(i) do { if (tr) tr[(i)] = chain_gtime(); } while (0)
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+// Shared-memory layouts (no swizzle needed: every access below is conflict-free as is)
+//   A plane   As[k][32 rows]          lane reads 8 rows of one k: 2 LDS.128, broadcast over 8 lanes
+//   W (FWD)   Ws[j][P], P = 4 mod 32  W[j][k] rows as they lie in memory; lane owns columns
+//                                     j = (lane&7) + 8*jj and reads 4 consecutive k of one j per LDS.128
+//   W (DX)    Ws[k][32 cols]          W[k][n0+j]; lane reads 4 consecutive columns of one k
+__host__ __device__ static inline int chain_wpitch(int K) { return ((((K + 3) & ~3) + 31) & ~31) + 4; }
+
+// A rows [kbase, kbase+kn) from a row-major global array (transposing, through registers)
+__device__ __forceinline__ void fill_from_rows(float* As, int kbase, const float* __restrict__ src, int ld, int m0, int B,
+                                               int kn, int tid) {
+  const int nq = (kn + 3) >> 2;
+  for (int e = tid; e < nq * CHAIN_ROWS; e += GEMM_THREADS) {
+    const int row = e & 31, k = (e >> 5) << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + row < B) v = __ldg(reinterpret_cast<const float4*>(src + size_t(m0 + row) * ld + k));
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (k + c < kn) As[(kbase + k + c) * CHAIN_ROWS + row] = x[c];
+  }
+}
+// A rows [kbase, kbase+kn) from a k-major exchange plane written earlier in this launch by the cluster
+__device__ __forceinline__ void fill_from_plane(float* As, int kbase, const float* plane, int kn, int tid) {
+  for (int e = tid; e < kn * 8; e += GEMM_THREADS) cp_async16(As + kbase * CHAIN_ROWS + e * 4, plane + e * 4);
+}
+// the CTA's 32-column weight slice of one slot, all of K at once
+__device__ __forceinline__ void fetch_weights(float* Ws, const ChainSlot& S, int n0, int tid) {
+  const int K = S.K, N = S.N, ldw = S.ldw;
+  const float* __restrict__ W = S.W;
+  if (S.mode == GEMM_FWD) {                      // rows j = n0..n0+31 of W[N][ldw], K floats each
+    const int kq = (K + 3) >> 2, P = chain_wpitch(K);
+    for (int e = tid; e < kq * BN; e += GEMM_THREADS) {
+      const int j = e / kq, q = e - j * kq;
+      if (n0 + j < N) cp_async16(Ws + j * P + q * 4, W + size_t(n0 + j) * ldw + q * 4);
+    }
+  } else {                                       // rows k = 0..K-1 of W[K][ldw], columns n0..n0+31
+    for (int e = tid; e < K * 8; e += GEMM_THREADS) {
+      const int k = e >> 3, c4 = (e & 7) << 2;
+      if (n0 + c4 < N) cp_async16(Ws + k * BN + c4, W + size_t(k) * ldw + n0 + c4);
+    }
+  }
+}
+
+// One 32x32 tile of one slot with A and W resident for the whole K.  The order of the additions is
+// gemm_tile's: within every 64-deep chunk warp w owns k = 8w..8w+7, partial tiles are summed w = 0..7.
+template <int MODE>
+__device__ __forceinline__ void chain_tile(const ChainSlot& S, float* As, const float* Ws, int m0, int n0, int B, float* xout,
+                                           unsigned long long* tr) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = (lane >> 3) * 8, c0 = (lane & 7) * 4, l7 = lane & 7;
+  const int N = S.N, K = S.K;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int P = chain_wpitch(K);
+  for (int kb = warp * KW; kb < K; kb += KC) {
+    if (MODE == GEMM_FWD) {
+#pragma unroll
+      for (int g = 0; g < KW; g += 4) {
+        const int k4 = kb + g;
+        if (k4 >= K) break;
+        float bq[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 t = *reinterpret_cast<const float4*>(&Ws[(l7 + 8 * jj) * P + k4]);
+          bq[jj][0] = t.x; bq[jj][1] = t.y; bq[jj][2] = t.z; bq[jj][3] = t.w;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int kk = k4 + t;
+          if (kk < K) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk * CHAIN_ROWS + r0]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk * CHAIN_ROWS + r0 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bq[j][t], acc[i][j]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KW; ++k) {
+        const int kk = kb + k;
+        if (kk >= K) break;
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk * CHAIN_ROWS + r0]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk * CHAIN_ROWS + r0 + 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Ws[kk * BN + c0]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+  }
+  __syncthreads();                                   // every warp is done with the A plane: reuse it
+  CTRACE(3);
+
+  // cross-warp reduction in fixed order.  Buffer column c' = 4*(lane&7) + jj holds output column
+  // (FWD) (lane&7) + 8*jj / (DX) c' itself.
+  float* red = As;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(&red[(warp * BM + r0 + i) * BN + c0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  __syncthreads();
+  const int orow = tid >> 3, ocol = (tid & 7) * 4;
+  float4 sum = *reinterpret_cast<const float4*>(&red[orow * BN + ocol]);
+#pragma unroll
+  for (int w = 1; w < GEMM_WARPS; ++w) {
+    const float4 t = *reinterpret_cast<const float4*>(&red[(w * BM + orow) * BN + ocol]);
+    sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+  }
+
+  const int gi = m0 + orow;
+  const float v[4] = {sum.x, sum.y, sum.z, sum.w};
+  const int epi = S.epi;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int gj = n0 + (MODE == GEMM_FWD ? (tid & 7) + 8 * cc : ocol + cc);
+    if (gj >= N) continue;
+    float x = v[cc];
+    if (gi < B) {
+      switch (epi) {
+        case EPI_BIAS: x += __ldg(S.bias + gj); break;
+        case EPI_BIAS_RELU: x = fmaxf(x + __ldg(S.bias + gj), 0.f); break;
+        case EPI_BIAS_TANH: x = tanhf(x + __ldg(S.bias + gj)); break;
+        case EPI_RELU_MASK: x = (__ldg(S.aux + size_t(gi) * S.ldaux + gj) > 0.f) ? x : 0.f; break;
+        case EPI_TANH_MASK: { const float t = __ldg(S.aux + size_t(gi) * S.ldaux + gj); x *= (1.f - t * t); } break;
+        default: break;
+      }
+      if (S.C) S.C[size_t(gi) * S.ldc + gj] = x;
+    } else x = 0.f;                                   // rows past the batch stay finite in the planes
+    if (xout) xout[gj * CHAIN_ROWS + orow] = x;
+  }
+}
+
+__global__ void __cluster_dims__(CHAIN_CLUSTER, 1, 1) __launch_bounds__(GEMM_THREADS, 2)
+mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
+  extern __shared__ __align__(16) float chain_smem[];
+  float* As = chain_smem;                              // [ka][32] resident A plane / reduce buffer
+  float* W0 = chain_smem + args.a_floats;              // two weight-slice buffers (slot l uses buffer l & 1)
+  const int wf = args.w_floats;
+  const int tid = threadIdx.x;
+  const int rank = int(cluster_ctarank());
+  const int cid = blockIdx.x / CHAIN_CLUSTER;
+  const int chain = cid / args.row_blocks, rb_i = cid - chain * args.row_blocks;
+  const int m0 = rb_i * CHAIN_ROWS, B = args.B;
+  const int ns = args.nslots[chain];
+  float* planes = args.xchg + (size_t(chain) * args.row_blocks + rb_i) * (size_t(CHAIN_MAX_SLOTS) * CHAIN_PLANE);
+  const int n0 = rank * BN;
+
+  if (n0 < args.slot[chain][0].N) fetch_weights(W0, args.slot[chain][0], n0, tid);
+  cp_async_commit();
+  unsigned long long* tr0 = (args.trace && blockIdx.x == 0 && tid == 0) ? args.trace : nullptr;
+  const long long clk0 = clock64();
+  for (int l = 0; l < ns; ++l) {
+    const ChainSlot& S = args.slot[chain][l];
+    const bool has_tile = n0 < S.N;
+    unsigned long long* tr = tr0 ? tr0 + 6 * l : nullptr;
+    CTRACE(0);
+    if (l > 0) cluster_wait();                        // previous slot's planes are visible; smem is free
+    CTRACE(1);
+    if (has_tile) {
+      const int K = S.K, K1 = S.K1;
+      if (S.src >= 0) fill_from_plane(As, 0, planes + size_t(S.src) * CHAIN_PLANE, K1, tid);
+      else fill_from_rows(As, 0, S.Ag, S.ldag, m0, B, K1, tid);
+      if (K > K1) {
+        if (S.src2 >= 0) fill_from_plane(As, K1, planes + size_t(S.src2) * CHAIN_PLANE, K - K1, tid);
+        else fill_from_rows(As, K1, S.A2g, S.lda2g, m0, B, K - K1, tid);
+      }
+    }
+    cp_async_commit();
+    // the next layer's weights do not depend on this layer: they travel while it computes
+    if (l + 1 < ns && n0 < args.slot[chain][l + 1].N) fetch_weights(W0 + ((l + 1) & 1) * wf, args.slot[chain][l + 1], n0, tid);
+    cp_async_commit();
+    cp_async_wait<1>();                               // everything but the prefetch has landed
+    __syncthreads();
+    CTRACE(2);
+    if (has_tile) {
+      float* xout = S.publish ? planes + size_t(l) * CHAIN_PLANE : nullptr;
+      if (S.mode == GEMM_FWD) chain_tile<GEMM_FWD>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, tr);
+      else chain_tile<GEMM_DX>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, tr);
+    }
+    CTRACE(4);
+    if (l + 1 < ns) cluster_arrive();
+    CTRACE(5);
+  }
+  cp_async_wait<0>();
+  if (tr0) tr0[6 * CHAIN_MAX_SLOTS - 1] = (unsigned long long)(clock64() - clk0);    // SM cycles of the whole kernel
+}
+
+unsigned long long* debug_trace_buffer();
+static unsigned long long* chain_trace_buffer() { return debug_trace_buffer(); }
+
+// ---- host side -------------------------------------------------------------------------------------
+int64_t chain_xchg_floats(int B) {
+  return int64_t(CHAIN_MAX) * cdiv(B, CHAIN_ROWS) * CHAIN_MAX_SLOTS * CHAIN_PLANE;
+}
+void chain_args_begin(ChainArgs& a, int B, float* xchg) {
+  a = ChainArgs{};
+  a.B = B; a.row_blocks = cdiv(B, CHAIN_ROWS); a.xchg = xchg;
+  a.a_floats = GEMM_WARPS * BM * BN;                 // the A plane doubles as the 8-warp reduce buffer
+  a.w_floats = 0;
+}
+int chain_add(ChainArgs& a, int c, const ChainSlot& s) {
+  if (c >= a.nchains) a.nchains = c + 1;
+  const int l = a.nslots[c]++;
+  a.slot[c][l] = s;
+  const int af = int(align4(int64_t(s.K) * CHAIN_ROWS));
+  const int wf = s.mode == GEMM_FWD ? BN * chain_wpitch(s.K) : int(align4(int64_t(s.K) * BN));
+  if (af > a.a_floats) a.a_floats = af;
+  if (wf > a.w_floats) a.w_floats = wf;
+  return l;
+}
+ChainSlot chain_fwd(const float* W, int ldw, const float* bias, int N, int K, int epi, float* C, int ldc, int publish) {
+  ChainSlot s{};
+  s.W = W; s.ldw = ldw; s.bias = bias; s.N = N; s.K = K; s.K1 = K; s.epi = epi; s.C = C; s.ldc = ldc;
+  s.mode = GEMM_FWD; s.publish = publish; s.src = -1; s.src2 = -1;
+  return s;
+}
+ChainSlot chain_dx(const float* W, int ldw, int N_in, int K_out, int epi, const float* aux, int ldaux,
+                   float* C, int ldc, int publish) {
+  ChainSlot s{};
+  s.W = W; s.ldw = ldw; s.N = N_in; s.K = K_out; s.K1 = K_out; s.epi = epi; s.aux = aux; s.ldaux = ldaux;
+  s.C = C; s.ldc = ldc; s.mode = GEMM_DX; s.publish = publish; s.src = -1; s.src2 = -1;
+  return s;
+}
+void chain_src_global(ChainSlot& s, const float* Ag, int ldag) { s.Ag = Ag; s.ldag = ldag; s.src = -1; }
+void chain_src_plane(ChainSlot& s, int slot) { s.src = slot; }
+void chain_src2_global(ChainSlot& s, int K1, const float* A2g, int lda2g) { s.K1 = K1; s.A2g = A2g; s.lda2g = lda2g; s.src2 = -1; }
+void chain_src2_plane(ChainSlot& s, int K1, int slot) { s.K1 = K1; s.src2 = slot; }
+
+int launch_mlp_chain(ChainArgs& a, cudaStream_t st) {
+  D4PG_REQUIRE(a.nchains > 0 && a.nchains <= CHAIN_MAX, D4PG_EINVAL, "launch_mlp_chain: %d chains", a.nchains);
+  for (int c = 0; c < a.nchains; ++c) {
+    D4PG_REQUIRE(a.nslots[c] > 0 && a.nslots[c] <= CHAIN_MAX_SLOTS, D4PG_EINVAL, "launch_mlp_chain: chain %d has %d slots", c, a.nslots[c]);
+    for (int l = 0; l < a.nslots[c]; ++l) {
+      const ChainSlot& s = a.slot[c][l];
+      D4PG_REQUIRE(s.N > 0 && s.N <= CHAIN_CLUSTER * BN, D4PG_ENOTSUP, "launch_mlp_chain: layer width %d > %d", s.N, CHAIN_CLUSTER * BN);
+      D4PG_REQUIRE(s.ldw % 4 == 0 && (reinterpret_cast<uintptr_t>(s.W) & 15) == 0, D4PG_EINVAL, "launch_mlp_chain: weights must be 16-B pitched");
+      D4PG_REQUIRE(s.src < l && s.src2 < l, D4PG_EINVAL, "launch_mlp_chain: slot %d reads a later plane", l);
+      D4PG_REQUIRE(s.src >= 0 || (s.Ag && s.ldag % 4 == 0 && s.ldag >= s.K1), D4PG_EINVAL, "launch_mlp_chain: bad global A source");
+      D4PG_REQUIRE(s.K == s.K1 || s.src2 >= 0 || (s.A2g && s.lda2g % 4 == 0 && s.lda2g >= s.K - s.K1), D4PG_EINVAL, "launch_mlp_chain: bad second A source");
+      D4PG_REQUIRE(s.src < 0 || (a.slot[c][s.src].publish && a.slot[c][s.src].N >= s.K1), D4PG_EINVAL, "launch_mlp_chain: slot %d reads an unpublished plane", l);
+      D4PG_REQUIRE(s.K == s.K1 || s.src2 < 0 || (a.slot[c][s.src2].publish && a.slot[c][s.src2].N >= s.K - s.K1), D4PG_EINVAL, "launch_mlp_chain: slot %d reads an unpublished plane", l);
+    }
+  }
+  const size_t smem = size_t(a.a_floats + 2 * a.w_floats) * sizeof(float);
+  D4PG_REQUIRE(smem <= 220 * 1024, D4PG_ENOTSUP, "launch_mlp_chain: %zu B of shared memory needed", smem);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    D4PG_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    smem_set = smem;
+  }
+  D4PG_MAX_CARVEOUT(mlp_chain_kernel);
+  a.trace = chain_trace_buffer() ? chain_trace_buffer() + a.trace_base : nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.nchains * a.row_blocks * CHAIN_CLUSTER); cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = nullptr; cfg.numAttrs = 0;              // cluster shape is compiled in (__cluster_dims__)
+  D4PG_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_chain_kernel, a));
+  return D4PG_OK;
+}
+
+}  // namespace d4pg

@@ -216,6 +216,9 @@ typedef struct {
                                  1 = importance-weighted critic CE (the reference samples the weights but
                                      ignores them, ddpg.py:217), 2 = priority = CE_i + eps instead of
                                      |sum_j m_ij q_ij| + eps (ddpg.py:221-222,253) */
+  int32_t chain;              /* 1 = cluster-fused layer chains: the forward passes are ONE launch, the dX passes
+                                 ONE launch and all dW ONE launch (precision 0 only; bit-identical to the
+                                 level-by-level launches of chain = 0) */
 } d4pg_learner_config_t;
 
 /* Caller-owned device buffers.  P_a / P_c = d4pg_*_layout().total. */
@@ -285,6 +288,8 @@ int32_t d4pg_comm_allreduce_sum(d4pg_comm_t* c, float* buf, int64_t n, d4pg_stre
  * the environment variable D4PG_TC_TRACE is set; the persistent step kernel writes one stamp per
  * phase boundary instead (out16 = 32 x uint64, host memory). */
 int32_t d4pg_debug_tc_trace(unsigned long long* out16);
+/* first n (<= 128) stamps of the same buffer: the chain kernels write 6 per layer slot of CTA 0 */
+int32_t d4pg_debug_trace_read(unsigned long long* out, int32_t n);
 
 #ifdef __cplusplus
 }

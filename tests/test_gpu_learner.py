@@ -14,14 +14,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", persistent=False):
+def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", persistent=False, chain=True):
     obs_dim, act_dim, N, B, mem, n_fill, per, steps = [int(x) for x in g["meta"]]
     v_min, v_max = [float(x) for x in g["dist"]]
     info = {"type": "categorical", "v_min": v_min, "v_max": v_max, "n_atoms": N}
     seed = int(g["seed"])
     torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
     kw = dict(memory_size=mem, batch_size=B, critic_dist_info=info, prioritized_replay=bool(per),
-              use_graph=use_graph, sampling=sampling, precision=precision, persistent=persistent)
+              use_graph=use_graph, sampling=sampling, precision=precision, persistent=persistent, chain=chain)
     glob = d4pg.DDPG(obs_dim, act_dim, **kw)               # main.py:382-385
     oa = d4pg.SharedAdam(glob.actor.parameters(), lr=1e-3)
     oc = d4pg.SharedAdam(glob.critic.parameters(), lr=1e-3)
@@ -38,15 +38,17 @@ def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", persisten
 
 
 @pytest.mark.parametrize("tag", ["per_c2", "per_part", "uniform_c1"])
-@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "tf32x3"), (True, "mega"), (False, "mega")])
+@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "levels"), (True, "tf32x3"), (True, "mega"), (False, "mega")])
 def test_train_steps_vs_reference_golden(tag, use_graph, precision):
-    """precision fp32 = exact-FFMA kernels; tf32x3 = tcgen05 tensor cores with the 3xTF32 split.
-    Both must meet the same 1e-5 bar against the reference's fp32 CPU results."""
+    """precision fp32 = exact-FFMA kernels as cluster-fused layer chains (the default); levels = the same
+    arithmetic as one grouped launch per dependency level; tf32x3 = tcgen05 tensor cores with the 3xTF32
+    split.  All must meet the same 1e-5 bar against the reference's fp32 CPU results."""
     import d4pg_b200 as d4pg
     g = H.load("train_%s.npz" % tag)
     persistent = precision == "mega"          # fp32 kernels as phases of ONE cooperative kernel per step
-    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision="fp32" if persistent else precision,
-                                     persistent=persistent)
+    chain = precision == "fp32"
+    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision="fp32" if precision in ("mega", "levels") else precision,
+                                     persistent=persistent, chain=chain)
     obs_dim, act_dim, N, B, mem, n_fill, per, steps, v_min, v_max = meta
     for t in range(steps):
         random.seed(9000 + t)                       # same generator state as the reference run
@@ -96,6 +98,37 @@ def test_train_steps_vs_reference_golden(tag, use_graph, precision):
     for prm, k in zip(glob.critic.parameters(), H.NAMES):
         H.check_compact(g, "adam_v_critic_%s_%d" % (k, t), oc.state[prm]["exp_avg_sq"].cpu().numpy().reshape(-1), 1e-6)
     assert loc.kernels_per_step() > 0
+
+
+@pytest.mark.parametrize("B,obs_dim,act_dim,N", [(256, 17, 6, 51), (96, 376, 17, 51), (40, 3, 1, 101)])
+def test_chain_equals_levels(B, obs_dim, act_dim, N):
+    """The cluster-fused chain kernels keep gemm_tile's accumulation order: after several device-sampled
+    steps every parameter, target, moment and priority is BIT-identical to the level-by-level launches."""
+    import d4pg_b200 as d4pg
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": N}
+    n_fill = 2048
+    rng = np.random.RandomState(11)
+    S = rng.randn(n_fill, obs_dim).astype(np.float32); A = rng.uniform(-1, 1, (n_fill, act_dim)).astype(np.float32)
+    R = (-3 * rng.rand(n_fill)).astype(np.float32).astype(np.float64); S2 = rng.randn(n_fill, obs_dim).astype(np.float32)
+    D = rng.rand(n_fill) < 0.05
+    out = []
+    for chain in (True, False):
+        torch.manual_seed(5); np.random.seed(5); random.seed(5)
+        dd = d4pg.DDPG(obs_dim, act_dim, memory_size=n_fill, batch_size=B, critic_dist_info=info, sampling="device",
+                       philox_seed=77, chain=chain)
+        dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
+                                   d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
+        dd.replayBuffer.add_batch(S, A, R, S2, D)
+        for _ in range(4):
+            dd.train()
+        torch.cuda.synchronize()
+        assert dd.kernels_per_step() == (7 if chain else 18)
+        out.append((dd.actor.flat_params().clone(), dd.critic.flat_params().clone(),
+                    dd.actor_target.flat_params().clone(), dd.critic_target.flat_params().clone(),
+                    dd.replayBuffer._store.sum_tree.clone(), dd.last_batch_info()["idx"].clone(),
+                    torch.tensor(dd.last_losses())))
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
 
 
 def test_config2_full_size_vs_oracle():
