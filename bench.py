@@ -179,7 +179,7 @@ def gpu_main(args):
         dd = d4pg.DDPG(cfg["obs"], cfg["act"], memory_size=cap, batch_size=B, critic_dist_info=info,
                        n_steps=cfg["n_steps"], projection=cfg["proj"], sampling=sampling, philox_seed=1234 + rank,
                        comm=comm, precision=args.precision, persistent=bool(args.persistent) and world == 1,
-                       chain=bool(args.chain))
+                       chain={0: "levels", 1: "cluster", 2: "rows"}[args.chain])
         dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
                                    d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
         dd.replayBuffer.add_batch(*synth(cfg, cap, seed=rank))     # this rank's shard, resident in HBM
@@ -235,7 +235,11 @@ def gpu_main(args):
     # algorithmic bytes of one launch of each MLP kernel class: weights read once,
     # batch inputs once, gradients written once
     kinds = {}
-    if any(k.startswith("launch_mlp_chain") for k in prof):
+    if any(k.startswith("launch_mlp_rows") for k in prof):
+        kinds["launch_mlp_rows#0"] = ("mlp_rows_kernel (3 forward chains, 20 layers, 1 launch)", 4 * (2 * Pa + 3 * Pc) + 4 * B * (2 * S_ + A_d), "fwd")
+        kinds["launch_mlp_rows#1"] = ("mlp_rows_kernel (2 dX chains, 9 layers, 1 launch)", 4 * (Pa + 2 * Pc) + 8 * B * N_, "bwd")
+        kinds["gemm_wide_launch#0"] = ("gemm_wide_kernel (9 dW problems, 1 launch)", 4 * (Pa + Pc) + 4 * B * 9 * H, "dw")
+    elif any(k.startswith("launch_mlp_chain") for k in prof):
         kinds["launch_mlp_chain#0"] = ("mlp_chain_kernel (3 forward chains, 20 layers, 1 launch)", 4 * (2 * Pa + 3 * Pc) + 4 * B * (2 * S_ + A_d), "fwd")
         kinds["launch_mlp_chain#1"] = ("mlp_chain_kernel (2 dX chains, 9 layers, 1 launch)", 4 * (Pa + 2 * Pc) + 8 * B * N_, "bwd")
         kinds["gemm_wide_launch#0"] = ("gemm_wide_kernel (9 dW problems, 1 launch)", 4 * (Pa + Pc) + 4 * B * 9 * H, "dw")
@@ -248,7 +252,7 @@ def gpu_main(args):
     roofline = None
     if kinds:
         mlp_ms = {k: float(np.mean(prof[k])) for k in kinds if k in prof}
-        if "launch_mlp_chain#0" in mlp_ms:
+        if "launch_mlp_chain#0" in mlp_ms or "launch_mlp_rows#0" in mlp_ms:
             top = max(mlp_ms, key=mlp_ms.get)
             name, nbytes, _ = kinds[top]
             t_ms = mlp_ms[top]
@@ -315,7 +319,7 @@ def gpu_main(args):
                 "config": {"workload": args.config, "batch_per_gpu": B, "global_batch": B * world, "obs_dim": cfg["obs"],
                            "act_dim": cfg["act"], "n_atoms": cfg["atoms"], "replay_capacity_per_gpu": cap,
                            "parallelism": "dp%d" % world,
-                           "step_plan": "chains" if (args.chain and args.precision == "fp32" and not args.persistent) else ("persistent" if args.persistent else "levels"),
+                           "step_plan": ({2: "row-owner chains", 1: "cluster chains", 0: "levels"}[args.chain] if (args.precision == "fp32" and not args.persistent) else ("persistent" if args.persistent else "levels")),
                            "precision": {"fp32": "fp32 FFMA", "tf32x3": "3xTF32 tcgen05 (fp32-accurate)", "tf32": "TF32 tcgen05"}[args.precision],
                            "l2": "inputs larger than L2: replay store %.0f MB + trees %.0f MB per GPU, rows sampled at "
                                  "random; parameters (%.1f MB) are L2-resident by design" % (
@@ -341,7 +345,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--persistent", type=int, default=0, help="1 = one cooperative kernel per step (fp32, 1 GPU)")
-    ap.add_argument("--chain", type=int, default=1, help="1 = cluster-fused layer chains (fp32), 0 = one launch per level")
+    ap.add_argument("--chain", type=int, default=1, help="MLP step plan (fp32): 2 = row-owner chains, 1 = cluster-fused chains, 0 = one launch per level")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)

@@ -27,9 +27,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_ffma_kernel(const __grid
   pdl_trigger_end(batch.pdl);
 }
 
-// Same tiles, leaner parameters (no TMA descriptors) and room for every dW problem of a step.
+// Every dW of a step in one launch (mlp_chain.cuh: GemmWideBatch).  Only the asynchronous dW tile is
+// compiled in, which needs no staging registers: 3 CTAs per SM (304 tiles at config 2 are ONE wave; at
+// 2 CTAs per SM the last 8 tiles were a second wave that doubled the launch's duration).
 template <bool ALLOW_SPLIT>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_wide_kernel(const __grid_constant__ GemmWideBatch batch) {
+__global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_wide_kernel(const __grid_constant__ GemmWideBatch batch) {
   extern __shared__ __align__(16) float smem[];        // DW_SMEM_FLOATS
   pdl_trigger(batch.pdl);
   pdl_wait();
@@ -37,11 +39,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_wide_kernel(const __grid
 #pragma unroll
   for (int i = 1; i < GEMM_WIDE_MAX; ++i)
     if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
-  const GemmProblem P = batch.p[pi];
-  gemm_tile_dispatch<ALLOW_SPLIT, true>(P, smem, blockIdx.x - P.tile_begin);
+  const GemmProblem& P = batch.p[pi];
+  const int tile = blockIdx.x - P.tile_begin;
+  if (ALLOW_SPLIT && P.ksplit > 1) {
+    const int per_slice = P.tiles_m * P.tiles_n;
+    const int ks = tile / per_slice, t2 = tile - ks * per_slice;
+    const int tm = t2 / P.tiles_n, tn = t2 - tm * P.tiles_n;
+    const int kbeg = ks * P.kslice;
+    gemm_dw_tile_async<true>(P, smem, tm * BM, tn * BN, tn, kbeg, min(P.K, kbeg + P.kslice));
+  } else {
+    const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+    gemm_dw_tile_async<false>(P, smem, tm * BM, tn * BN, tn, 0, P.K);
+  }
   pdl_trigger_end(batch.pdl);
 }
-static_assert(DW_SMEM_FLOATS >= GEMM_SMEM_FLOATS, "the async dW stage must cover the chunked tile's buffers");
 
 // ---- host side -------------------------------------------------------------------------------
 GemmProblem gemm_fwd(const float* X, int ldx, const float* X2, int ldx2, int K1, const float* W, int ldw,
@@ -116,7 +127,11 @@ void gemm_wide_add(GemmWideBatch& b, const GemmProblem& pin) {
 int gemm_wide_launch(GemmWideBatch& b, cudaStream_t st) {
   D4PG_REQUIRE(b.n > 0 && b.n <= GEMM_WIDE_MAX, D4PG_EINVAL, "gemm_wide_launch: %d problems (max %d)", b.n, GEMM_WIDE_MAX);
   bool split = false;
-  for (int i = 0; i < b.n; ++i) split = split || b.p[i].ksplit > 1;
+  for (int i = 0; i < b.n; ++i) {
+    split = split || b.p[i].ksplit > 1;
+    D4PG_REQUIRE(b.p[i].mode == GEMM_DW && (b.p[i].flags & GEMM_ASYNC_OK), D4PG_ENOTSUP,
+                 "gemm_wide_launch: problem %d is not a dW with 16-B aligned, 16-B pitched operands", i);
+  }
   D4PG_MAX_CARVEOUT(gemm_wide_kernel<false>);
   D4PG_MAX_CARVEOUT(gemm_wide_kernel<true>);
   const size_t smem = DW_SMEM_FLOATS * sizeof(float);

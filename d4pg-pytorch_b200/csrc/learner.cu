@@ -24,6 +24,7 @@
 #include "internal.cuh"
 #include "step_mega.cuh"
 #include "mlp_chain.cuh"
+#include "mlp_rows.cuh"
 
 namespace d4pg {
 
@@ -90,6 +91,7 @@ struct d4pg_learner {
   cudaStream_t side; cudaEvent_t ev_fork, ev_join;
   MegaParams mega;
   ChainArgs chain_fwd_args, chain_bwd_args;
+  RowsArgs rows_fwd_args, rows_bwd_args;
   GemmWideBatch dw_batch;
   // host-facing step (caller-owned pinned buffers, d4pg_learner_set_host_buffers)
   double* host_u; int32_t* host_pos; float* host_losses; cudaEvent_t ev_in, ev_out;
@@ -97,6 +99,10 @@ struct d4pg_learner {
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> ev_name;
 };
+
+// step plan: 0 = one grouped launch per dependency level, 1 = cluster-fused chains (mlp_chain.cu),
+// 2 = row-owner chains (mlp_rows.cu; batches up to 512 rows, larger ones use plan 1)
+static int step_plan(const d4pg_learner_config_t& c) { return (c.chain == 2 && c.batch > 512) ? 1 : c.chain; }
 
 // idempotent launches (pure functions of their inputs) are repeated in profile mode
 constexpr int PROFILE_REPS = 16;
@@ -129,7 +135,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 #define RUN(expr)                                                                          \
   do {                                                                                     \
     if (L->profiling) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);    \
-      std::string nm0(#expr); const bool rep = nm0.rfind("gemm_launch", 0) == 0 || nm0.rfind("launch_heads", 0) == 0 || nm0.rfind("launch_mlp_chain", 0) == 0; \
+      std::string nm0(#expr); const bool rep = nm0.rfind("gemm_launch", 0) == 0 || nm0.rfind("launch_heads", 0) == 0 || nm0.rfind("launch_mlp_chain", 0) == 0 || nm0.rfind("launch_mlp_rows", 0) == 0; \
       cudaEventRecord(e0, st); rc = (expr);                                                \
       for (int _r = 1; rep && _r < PROFILE_REPS && rc == 0; ++_r) rc = (expr);             \
       cudaEventRecord(e1, st);                                                             \
@@ -156,8 +162,41 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 
   const float* Wa = b.actor; const float* Wat = b.actor_target; const float* Wc = b.critic; const float* Wct = b.critic_target;
   GemmBatch g;
-  const bool chain = c.chain != 0;
-  if (chain) {
+  const int plan = step_plan(c);
+  const bool chain = plan == 1, rows = plan == 2;
+  if (rows) {
+    // 2''. the same three chains, row-owner form (mlp_rows.cu): a CTA carries 5-8 rows through a whole chain
+    RowsArgs& ra = L->rows_fwd_args;
+    rows_args_begin(ra, B, S, A);
+    rows_chain_input(ra, 0, w.s2, Sp, S);
+    rows_add(ra, 0, rows_fwd(Wat + da.w_off[0], la[0], Wat + da.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, XB_IN, XB_PING, 0));
+    rows_add(ra, 0, rows_fwd(Wat + da.w_off[1], la[1], Wat + da.b_off[1], H, H, EPI_BIAS, nullptr, H, XB_PING, XB_PONG, 0));
+    rows_add(ra, 0, rows_fwd(Wat + da.w_off[2], la[2], Wat + da.b_off[2], H, H, EPI_BIAS_RELU, nullptr, H, XB_PONG, XB_PING, 0));
+    rows_add(ra, 0, rows_fwd(Wat + da.w_off[3], la[3], Wat + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[0], Ap, XB_PING, XB_CAT, H));
+    rows_add(ra, 0, rows_fwd(Wct + dc.w_off[0], lc[0], Wct + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, XB_IN, XB_CAT, 0));
+    rows_add(ra, 0, rows_fwd(Wct + dc.w_off[1], lc[1], Wct + dc.b_off[1], H, H + A, EPI_BIAS_RELU, nullptr, H, XB_CAT, XB_PING, 0));
+    rows_add(ra, 0, rows_fwd(Wct + dc.w_off[2], lc[2], Wct + dc.b_off[2], H, H, EPI_BIAS_RELU, nullptr, H, XB_PING, XB_PONG, 0));
+    rows_add(ra, 0, rows_fwd(Wct + dc.w_off[3], lc[3], Wct + dc.b_off[3], N, H, EPI_BIAS, w.out[1], Np, XB_PONG, -1, 0));
+
+    rows_chain_input(ra, 1, w.s, Sp, S);
+    rows_chain_input2(ra, 1, w.a, Ap, A, H);
+    rows_add(ra, 1, rows_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, w.h1[2], H, XB_IN, XB_CAT, 0));
+    rows_add(ra, 1, rows_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[2], H, XB_CAT, XB_PING, 0));
+    rows_add(ra, 1, rows_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[2], H, XB_PING, XB_PONG, 0));
+    rows_add(ra, 1, rows_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[2], Np, XB_PONG, -1, 0));
+
+    rows_chain_input(ra, 2, w.s, Sp, S);
+    rows_add(ra, 2, rows_fwd(Wa + da.w_off[0], la[0], Wa + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[3], H, XB_IN, XB_PING, 0));
+    rows_add(ra, 2, rows_fwd(Wa + da.w_off[1], la[1], Wa + da.b_off[1], H, H, EPI_BIAS, w.h2[3], H, XB_PING, XB_PONG, 0));
+    rows_add(ra, 2, rows_fwd(Wa + da.w_off[2], la[2], Wa + da.b_off[2], H, H, EPI_BIAS_RELU, w.h3[3], H, XB_PONG, XB_PING, 0));
+    rows_add(ra, 2, rows_fwd(Wa + da.w_off[3], la[3], Wa + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[3], Ap, XB_PING, XB_CAT, H));
+    rows_add(ra, 2, rows_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, XB_IN, XB_CAT, 0));
+    rows_add(ra, 2, rows_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[4], H, XB_CAT, XB_PING, 0));
+    rows_add(ra, 2, rows_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[4], H, XB_PING, XB_PONG, 0));
+    rows_add(ra, 2, rows_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[4], Np, XB_PONG, -1, 0));
+    if ((rc = rows_finalize(ra)) != 0) return rc;
+    RUN(launch_mlp_rows(ra, st));
+  } else if (chain) {
     // 2'. the three forward chains of the step as ONE cluster launch (mlp_chain.cu):
     //   T: actor_target(s') -> critic_target(s', .)      ddpg.py:205-206
     //   Q: critic(s, a)                                   ddpg.py:208
@@ -261,6 +300,24 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   float* Ga = b.grad_actor; float* Gc = b.grad_critic;
   if (B >= 1024 && !mega)                // dW levels run split-K with fp32 atomics: the gradient buffer must start at zero
     D4PG_CUDA_OK(cudaMemsetAsync(Ga, 0, size_t(da.total + dc.total) * sizeof(float), st));
+  if (rows) {
+    // 5''. both dX chains, row-owner form
+    RowsArgs& rb = L->rows_bwd_args;
+    rows_args_begin(rb, B, S, A); rb.trace_base = 2 * ROWS_MAX_LAYERS + 8;
+    rows_chain_input(rb, 0, w.dlogits_q, Np, N);
+    rows_add(rb, 0, rows_dx(Wc + dc.w_off[3], lc[3], H, N, EPI_RELU_MASK, w.h3[2], H, w.c_dz22, H, XB_IN, XB_PING, 0));
+    rows_add(rb, 0, rows_dx(Wc + dc.w_off[2], lc[2], H, H, EPI_RELU_MASK, w.h2[2], H, w.c_dz2, H, XB_PING, XB_PONG, 0));
+    rows_add(rb, 0, rows_dx(Wc + dc.w_off[1], lc[1], H, H, EPI_RELU_MASK, w.h1[2], H, w.c_dz1, H, XB_PONG, -1, 0));
+    rows_chain_input(rb, 1, w.dlogits_pi, Np, N);
+    rows_add(rb, 1, rows_dx(Wc + dc.w_off[3], lc[3], H, N, EPI_RELU_MASK, w.h3[4], H, nullptr, H, XB_IN, XB_PING, 0));
+    rows_add(rb, 1, rows_dx(Wc + dc.w_off[2], lc[2], H, H, EPI_RELU_MASK, w.h2[4], H, nullptr, H, XB_PING, XB_PONG, 0));
+    rows_add(rb, 1, rows_dx(Wc + dc.w_off[1] + H, lc[1], A, H, EPI_TANH_MASK, w.out[3], Ap, w.a_dz3, Ap, XB_PONG, XB_PING, 0));
+    rows_add(rb, 1, rows_dx(Wa + da.w_off[3], la[3], H, A, EPI_RELU_MASK, w.h3[3], H, w.a_dz22, H, XB_PING, XB_PONG, 0));
+    rows_add(rb, 1, rows_dx(Wa + da.w_off[2], la[2], H, H, EPI_NONE, nullptr, 0, w.a_dh2, H, XB_PONG, XB_PING, 0));
+    rows_add(rb, 1, rows_dx(Wa + da.w_off[1], la[1], H, H, EPI_RELU_MASK, w.h1[3], H, w.a_dz1, H, XB_PING, -1, 0));
+    if ((rc = rows_finalize(rb)) != 0) return rc;
+    RUN(launch_mlp_rows(rb, st));
+  }
   if (chain) {
     // 5'. both dX chains as ONE cluster launch, then every dW of the step as ONE grouped launch
     //   C: critic loss  dlogits_q  -> fc3 -> fc2_2 -> fc2[:, :H]                         ddpg.py:230
@@ -280,7 +337,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
     sl = chain_dx(Wa + da.w_off[2], la[2], H, H, EPI_NONE, nullptr, 0, w.a_dh2, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
     sl = chain_dx(Wa + da.w_off[1], la[1], H, H, EPI_RELU_MASK, w.h1[3], H, w.a_dz1, H, 0); chain_src_plane(sl, t); chain_add(cb, 1, sl);
     RUN(launch_mlp_chain(cb, st));
-
+  }
+  if (chain || rows) {                    // every dW of the step as ONE grouped launch
     GemmWideBatch& gw = L->dw_batch;
     gemm_wide_begin(gw);
     gemm_wide_add(gw, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], lc[2], Gc + dc.b_off[2], H, H, B));
@@ -365,7 +423,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 
 extern "C" int64_t d4pg_learner_workspace_floats(const d4pg_learner_config_t* cfg) {
   if (!cfg) return -1;
-  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, cfg->chain != 0).total;
+  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1).total;
 }
 
 extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d4pg_learner_buffers_t* buf,
@@ -380,8 +438,9 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   D4PG_REQUIRE(cfg->world_size <= 1 || comm, D4PG_EINVAL, "d4pg_learner_create: world_size>1 needs a communicator");
   D4PG_REQUIRE(!cfg->persistent || (cfg->precision == 0 && cfg->world_size <= 1), D4PG_ENOTSUP,
                "d4pg_learner_create: the persistent step kernel needs precision 0 and a single GPU");
+  D4PG_REQUIRE(cfg->chain >= 0 && cfg->chain <= 2, D4PG_EINVAL, "d4pg_learner_create: chain must be 0, 1 or 2");
   D4PG_REQUIRE(!cfg->chain || (cfg->precision == 0 && !cfg->persistent), D4PG_ENOTSUP,
-               "d4pg_learner_create: the cluster-fused chain kernels need precision 0 and persistent 0");
+               "d4pg_learner_create: the fused chain kernels need precision 0 and persistent 0");
   D4PG_REQUIRE(buf->actor && buf->actor_target && buf->critic && buf->critic_target && buf->grad_actor && buf->grad_critic &&
                buf->adam_m_actor && buf->adam_v_actor && buf->adam_m_critic && buf->adam_v_critic &&
                buf->idx && buf->prio && buf->td && buf->losses && buf->workspace, D4PG_EINVAL,
@@ -395,7 +454,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
     set_error("d4pg_learner_create: grad_critic must equal grad_actor + P_a (one flat gradient buffer)");
     delete L; return D4PG_EINVAL;
   }
-  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, cfg->chain != 0);
+  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1);
   L->graph_exec = nullptr; L->graph_ready = false; L->steps_done = 0; L->kernels_per_step = 0;
   L->profiling = false;
   (void)debug_trace_buffer();          // allocate outside of any stream capture
@@ -512,7 +571,7 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
   for (int i = 0; i < n; ++i) {
     float ms = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, L->ev[2 * i], L->ev[2 * i + 1]);
-    if (L->ev_name[i] == "gemm_launch" || L->ev_name[i] == "launch_heads" || L->ev_name[i] == "launch_mlp_chain") ms /= float(PROFILE_REPS);
+    if (L->ev_name[i] == "gemm_launch" || L->ev_name[i] == "launch_heads" || L->ev_name[i] == "launch_mlp_chain" || L->ev_name[i] == "launch_mlp_rows") ms /= float(PROFILE_REPS);
     if (i < max_launches) {
       ms_out[i] = ms;
       if (names_out && name_stride > 1) {

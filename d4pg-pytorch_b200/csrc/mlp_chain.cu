@@ -64,9 +64,11 @@ __device__ __forceinline__ void fetch_weights(float* Ws, const ChainSlot& S, int
   const float* __restrict__ W = S.W;
   if (S.mode == GEMM_FWD) {                      // rows j = n0..n0+31 of W[N][ldw], K floats each
     const int kq = (K + 3) >> 2, P = chain_wpitch(K);
-    for (int e = tid; e < kq * BN; e += GEMM_THREADS) {
-      const int j = e / kq, q = e - j * kq;
-      if (n0 + j < N) cp_async16(Ws + j * P + q * 4, W + size_t(n0 + j) * ldw + q * 4);
+    const int j = tid >> 3;                      // 8 threads per weight row
+    if (n0 + j < N) {
+      float* dst = Ws + j * P;
+      const float* __restrict__ src = W + size_t(n0 + j) * ldw;
+      for (int q = tid & 7; q < kq; q += 8) cp_async16(dst + q * 4, src + q * 4);
     }
   } else {                                       // rows k = 0..K-1 of W[K][ldw], columns n0..n0+31
     for (int e = tid; e < K * 8; e += GEMM_THREADS) {
@@ -80,7 +82,7 @@ __device__ __forceinline__ void fetch_weights(float* Ws, const ChainSlot& S, int
 // gemm_tile's: within every 64-deep chunk warp w owns k = 8w..8w+7, partial tiles are summed w = 0..7.
 template <int MODE>
 __device__ __forceinline__ void chain_tile(const ChainSlot& S, float* As, const float* Ws, int m0, int n0, int B, float* xout,
-                                           unsigned long long* tr) {
+                                           const float (&eop)[4], unsigned long long* tr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = (lane >> 3) * 8, c0 = (lane & 7) * 4, l7 = lane & 7;
   const int N = S.N, K = S.K;
@@ -155,21 +157,23 @@ __device__ __forceinline__ void chain_tile(const ChainSlot& S, float* As, const 
   const int gi = m0 + orow;
   const float v[4] = {sum.x, sum.y, sum.z, sum.w};
   const int epi = S.epi;
+  float* __restrict__ C = S.C; const int ldc = S.ldc;
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
     const int gj = n0 + (MODE == GEMM_FWD ? (tid & 7) + 8 * cc : ocol + cc);
     if (gj >= N) continue;
     float x = v[cc];
     if (gi < B) {
+      const float e = eop[cc];                        // bias / forward activation, fetched before the FMA loop
       switch (epi) {
-        case EPI_BIAS: x += __ldg(S.bias + gj); break;
-        case EPI_BIAS_RELU: x = fmaxf(x + __ldg(S.bias + gj), 0.f); break;
-        case EPI_BIAS_TANH: x = tanhf(x + __ldg(S.bias + gj)); break;
-        case EPI_RELU_MASK: x = (__ldg(S.aux + size_t(gi) * S.ldaux + gj) > 0.f) ? x : 0.f; break;
-        case EPI_TANH_MASK: { const float t = __ldg(S.aux + size_t(gi) * S.ldaux + gj); x *= (1.f - t * t); } break;
+        case EPI_BIAS: x += e; break;
+        case EPI_BIAS_RELU: x = fmaxf(x + e, 0.f); break;
+        case EPI_BIAS_TANH: x = tanhf(x + e); break;
+        case EPI_RELU_MASK: x = (e > 0.f) ? x : 0.f; break;
+        case EPI_TANH_MASK: x *= (1.f - e * e); break;
         default: break;
       }
-      if (S.C) S.C[size_t(gi) * S.ldc + gj] = x;
+      if (C) C[size_t(gi) * ldc + gj] = x;
     } else x = 0.f;                                   // rows past the batch stay finite in the planes
     if (xout) xout[gj * CHAIN_ROWS + orow] = x;
   }
@@ -199,6 +203,16 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
     const bool has_tile = n0 < S.N;
     unsigned long long* tr = tr0 ? tr0 + 6 * l : nullptr;
     CTRACE(0);
+    // this thread's epilogue operands (bias / forward activations) do not depend on the chain: fetch now
+    float eop[4] = {0.f, 0.f, 0.f, 0.f};
+    if (has_tile && S.epi != EPI_NONE) {
+      const int gi = m0 + (tid >> 3);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int gj = n0 + (S.mode == GEMM_FWD ? (tid & 7) + 8 * cc : (tid & 7) * 4 + cc);
+        if (gj < S.N && gi < B) eop[cc] = (S.mode == GEMM_FWD) ? __ldg(S.bias + gj) : __ldg(S.aux + size_t(gi) * S.ldaux + gj);
+      }
+    }
     if (l > 0) cluster_wait();                        // previous slot's planes are visible; smem is free
     CTRACE(1);
     if (has_tile) {
@@ -219,8 +233,8 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
     CTRACE(2);
     if (has_tile) {
       float* xout = S.publish ? planes + size_t(l) * CHAIN_PLANE : nullptr;
-      if (S.mode == GEMM_FWD) chain_tile<GEMM_FWD>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, tr);
-      else chain_tile<GEMM_DX>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, tr);
+      if (S.mode == GEMM_FWD) chain_tile<GEMM_FWD>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
+      else chain_tile<GEMM_DX>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
     }
     CTRACE(4);
     if (l + 1 < ns) cluster_arrive();
@@ -286,7 +300,10 @@ int launch_mlp_chain(ChainArgs& a, cudaStream_t st) {
       D4PG_REQUIRE(s.K == s.K1 || s.src2 < 0 || (a.slot[c][s.src2].publish && a.slot[c][s.src2].N >= s.K - s.K1), D4PG_EINVAL, "launch_mlp_chain: slot %d reads an unpublished plane", l);
     }
   }
-  const size_t smem = size_t(a.a_floats + 2 * a.w_floats) * sizeof(float);
+  size_t smem = size_t(a.a_floats + 2 * a.w_floats) * sizeof(float);
+  // a grid that fits one CTA per SM must not be packed two per SM (they would share the FMA and LSU pipes
+  // while other SMs idle): ask for more than half of the shared memory
+  if (a.nchains * a.row_blocks * CHAIN_CLUSTER <= 148 && smem < 116 * 1024) smem = 116 * 1024;
   D4PG_REQUIRE(smem <= 220 * 1024, D4PG_ENOTSUP, "launch_mlp_chain: %zu B of shared memory needed", smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {

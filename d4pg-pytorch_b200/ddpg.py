@@ -72,7 +72,8 @@ class _Learner(object):
         cfg.use_graph = 1 if ddpg.use_graph else 0
         cfg.loss_flags = (1 if ddpg.importance_weighted else 0) | (2 if ddpg.priority == "ce" else 0)
         cfg.persistent = 1 if (ddpg.persistent and ddpg.precision == "fp32" and cfg.world_size == 1) else 0
-        cfg.chain = 1 if (ddpg.chain and ddpg.precision == "fp32" and not cfg.persistent) else 0
+        plan = {"levels": 0, "cluster": 1, "rows": 2, False: 0, True: 1, 0: 0, 1: 1, 2: 2}[ddpg.chain]
+        cfg.chain = plan if (ddpg.precision == "fp32" and not cfg.persistent) else 0
         self.cfg = cfg
         nws = L.d4pg_learner_workspace_floats(C.byref(cfg))
         f32 = torch.float32
@@ -159,7 +160,7 @@ class DDPG:
                  critic_dist_info=None, n_steps=1,
                  # ---- B200 build extensions (keyword-only in spirit; reference callers never pass them)
                  device=None, sampling="reference", projection="reference", precision="fp32",
-                 use_graph=True, philox_seed=0, comm=None, persistent=False, chain=True,
+                 use_graph=True, philox_seed=0, comm=None, persistent=False, chain="cluster",
                  importance_weighted=False, priority="reference"):
         self.gamma = gamma
         self.n_steps = n_steps
@@ -175,7 +176,9 @@ class DDPG:
         self.sampling, self.projection, self.precision = sampling, projection, precision
         self.use_graph, self.philox_seed, self.comm = use_graph, philox_seed, comm
         self.persistent = persistent        # one cooperative kernel per step (fp32, single GPU)
-        self.chain = chain                  # cluster-fused layer chains (fp32): 7 launches per step instead of 18
+        # step plan of the MLP passes (fp32): "cluster" (default) cluster-fused layer chains, "rows" row-owner
+        # chains with TMA-multicast weight streaming (correct, measured slower), "levels" one launch per level
+        self.chain = chain
         # corrected-semantics switches (default = the reference's behaviour)
         assert priority in ("reference", "ce")
         self.importance_weighted, self.priority = bool(importance_weighted), priority

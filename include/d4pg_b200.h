@@ -216,9 +216,11 @@ typedef struct {
                                  1 = importance-weighted critic CE (the reference samples the weights but
                                      ignores them, ddpg.py:217), 2 = priority = CE_i + eps instead of
                                      |sum_j m_ij q_ij| + eps (ddpg.py:221-222,253) */
-  int32_t chain;              /* 1 = cluster-fused layer chains: the forward passes are ONE launch, the dX passes
-                                 ONE launch and all dW ONE launch (precision 0 only; bit-identical to the
-                                 level-by-level launches of chain = 0) */
+  int32_t chain;              /* step plan of the MLP passes (precision 0 only): 0 = one grouped launch per dependency
+                                 level (18 kernels/step); 1 = cluster-fused layer chains: forward passes, dX passes
+                                 and all dW are ONE launch each (7 kernels/step, bit-identical to 0); 2 = row-owner
+                                 chains: a CTA carries a few batch rows through a whole chain, weights streamed
+                                 (7 kernels/step; same fp32 dot products in a different summation order) */
 } d4pg_learner_config_t;
 
 /* Caller-owned device buffers.  P_a / P_c = d4pg_*_layout().total. */

@@ -38,16 +38,16 @@ def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", persisten
 
 
 @pytest.mark.parametrize("tag", ["per_c2", "per_part", "uniform_c1"])
-@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "levels"), (True, "tf32x3"), (True, "mega"), (False, "mega")])
+@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "rows"), (True, "levels"), (True, "tf32x3"), (True, "mega"), (False, "mega")])
 def test_train_steps_vs_reference_golden(tag, use_graph, precision):
-    """precision fp32 = exact-FFMA kernels as cluster-fused layer chains (the default); levels = the same
-    arithmetic as one grouped launch per dependency level; tf32x3 = tcgen05 tensor cores with the 3xTF32
-    split.  All must meet the same 1e-5 bar against the reference's fp32 CPU results."""
+    """precision fp32 = exact-FFMA kernels as cluster-fused layer chains (the default step plan); rows = the
+    row-owner chains (TMA-multicast weight stream); levels = one grouped launch per dependency level; tf32x3 = tcgen05 tensor cores
+    with the 3xTF32 split.  All must meet the same 1e-5 bar against the reference's fp32 CPU results."""
     import d4pg_b200 as d4pg
     g = H.load("train_%s.npz" % tag)
     persistent = precision == "mega"          # fp32 kernels as phases of ONE cooperative kernel per step
-    chain = precision == "fp32"
-    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision="fp32" if precision in ("mega", "levels") else precision,
+    chain = {"fp32": "cluster", "rows": "rows"}.get(precision, "levels")
+    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision="fp32" if precision in ("mega", "levels", "rows") else precision,
                                      persistent=persistent, chain=chain)
     obs_dim, act_dim, N, B, mem, n_fill, per, steps, v_min, v_max = meta
     for t in range(steps):
@@ -112,7 +112,7 @@ def test_chain_equals_levels(B, obs_dim, act_dim, N):
     R = (-3 * rng.rand(n_fill)).astype(np.float32).astype(np.float64); S2 = rng.randn(n_fill, obs_dim).astype(np.float32)
     D = rng.rand(n_fill) < 0.05
     out = []
-    for chain in (True, False):
+    for chain in ("cluster", "levels"):
         torch.manual_seed(5); np.random.seed(5); random.seed(5)
         dd = d4pg.DDPG(obs_dim, act_dim, memory_size=n_fill, batch_size=B, critic_dist_info=info, sampling="device",
                        philox_seed=77, chain=chain)
@@ -122,13 +122,53 @@ def test_chain_equals_levels(B, obs_dim, act_dim, N):
         for _ in range(4):
             dd.train()
         torch.cuda.synchronize()
-        assert dd.kernels_per_step() == (7 if chain else 18)
+        assert dd.kernels_per_step() == (7 if chain == "cluster" else 18)
         out.append((dd.actor.flat_params().clone(), dd.critic.flat_params().clone(),
                     dd.actor_target.flat_params().clone(), dd.critic_target.flat_params().clone(),
                     dd.replayBuffer._store.sum_tree.clone(), dd.last_batch_info()["idx"].clone(),
                     torch.tensor(dd.last_losses())))
     for a, b in zip(*out):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,obs_dim,act_dim,N", [(256, 17, 6, 51), (96, 376, 17, 51), (37, 3, 1, 101), (512, 17, 6, 51)])
+def test_rows_chain_vs_levels(B, obs_dim, act_dim, N):
+    """The row-owner chain kernels compute the same fp32 dot products in a different summation order:
+    after one device-sampled step the sampled batch, losses, logits and priorities agree with the
+    level-by-level launches to rounding, every gradient to 1e-5 relative L2."""
+    import d4pg_b200 as d4pg
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": N}
+    n_fill = 2048
+    rng = np.random.RandomState(12)
+    S = rng.randn(n_fill, obs_dim).astype(np.float32); A = rng.uniform(-1, 1, (n_fill, act_dim)).astype(np.float32)
+    R = (-3 * rng.rand(n_fill)).astype(np.float32).astype(np.float64); S2 = rng.randn(n_fill, obs_dim).astype(np.float32)
+    D = rng.rand(n_fill) < 0.05
+    out = {}
+    for chain in ("rows", "levels"):
+        torch.manual_seed(6); np.random.seed(6); random.seed(6)
+        dd = d4pg.DDPG(obs_dim, act_dim, memory_size=n_fill, batch_size=B, critic_dist_info=info, sampling="device",
+                       philox_seed=78, chain=chain)
+        dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
+                                   d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
+        dd.replayBuffer.add_batch(S, A, R, S2, D)
+        dd.train()
+        torch.cuda.synchronize()
+        assert dd.kernels_per_step() == (7 if chain == "rows" else 18)
+        g = {("a", k): v.clone() for k, v in dd.actor.named_grad_views().items()}
+        g.update({("c", k): v.clone() for k, v in dd.critic.named_grad_views().items()})
+        out[chain] = dict(idx=dd.last_batch_info()["idx"].clone(), prio=dd.last_batch_info()["prio"].clone(),
+                          losses=np.array(dd.last_losses()), grads=g,
+                          q=dd.debug_tensor("q_probs", (B, N)).clone(), m=dd.debug_tensor("m", (B, N)).clone(),
+                          act=dd.debug_tensor("actor_out", (B, act_dim)).clone())
+    a, b = out["rows"], out["levels"]
+    assert torch.equal(a["idx"], b["idx"])
+    assert np.abs(a["losses"] - b["losses"]).max() <= 1e-5 * max(1.0, np.abs(b["losses"]).max())
+    for k in ("q", "m", "act", "prio"):
+        assert (a[k] - b[k]).abs().max().item() <= 2e-6, k
+    for k in a["grads"]:
+        ga, gb = a["grads"][k].double().reshape(-1), b["grads"][k].double().reshape(-1)
+        rel = (ga - gb).norm().item() / max(gb.norm().item(), 1e-30)
+        assert rel <= 1e-5, (k, rel)
 
 
 def test_config2_full_size_vs_oracle():
