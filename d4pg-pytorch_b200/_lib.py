@@ -43,7 +43,7 @@ class LearnerConfig(C.Structure):
         ("precision", C.c_int32), ("sample_mode", C.c_int32),
         ("philox_seed", C.c_uint64),
         ("world_size", C.c_int32), ("use_graph", C.c_int32), ("persistent", C.c_int32),
-        ("loss_flags", C.c_int32), ("chain", C.c_int32),
+        ("loss_flags", C.c_int32), ("chain", C.c_int32), ("prefetch", C.c_int32),
     ]
 
 

@@ -58,7 +58,7 @@ extern "C" int32_t d4pg_adam_polyak(float* p, const float* g, float* m, float* v
   a.nseg = 1;
   a.w1 = float(1.0 - beta1); a.w2 = float(1.0 - beta2); a.beta2 = float(beta2); a.eps = float(eps);
   a.bc2_sqrt = float(sqrt(bc2)); a.tau = float(tau); a.one_minus_tau = float(1.0 - tau);
-  a.grad_scale = grad_scale; a.clock = nullptr; a.loss_out = nullptr;
+  a.grad_scale = grad_scale; a.clock = nullptr; a.loss_out = nullptr; a.pipe_slot = -1;
   return launch_adam(a, as_stream(stream));
 }
 

@@ -16,6 +16,13 @@ struct LearnerClock {
   float neg_step_size[2];   // -(lr/bc1) for actor, critic
   float bc2_sqrt;        // sqrt(1 - beta2^step)
   float pad;
+  // ---- prefetch pipeline (cfg.prefetch): batch k+1 is sampled on a side branch while step k's backward
+  // pass and Adam still run, so the sampler keeps its OWN counters (advanced by step k's loss kernel, which
+  // runs after sample(k) and before sample(k+1)) and writes the derived scalars of step k into the slot of
+  // the batch buffer it fills (a launch argument); Adam of that step reads the same slot.
+  int64_t s_adam_step, s_beta_t, s_steps_done;
+  float d_neg_step_size[2][2];
+  float d_bc2_sqrt[2];
 };
 
 struct ClockParams {
@@ -23,6 +30,15 @@ struct ClockParams {
   double per_beta0, per_beta_final; int64_t per_beta_iters;
 };
 
+// prefetch pipeline: scalars of the step whose batch is being sampled, into its parity slot
+__device__ __forceinline__ void clock_derive_pipelined(LearnerClock* c, const ClockParams& a, int slot) {
+  const double step = double(c->s_adam_step + 1);
+  const double bc1 = 1.0 - pow(a.beta1, step);
+  const double bc2 = 1.0 - pow(a.beta2, step);
+  c->d_neg_step_size[slot][0] = float(-(a.lr_actor / bc1));
+  c->d_neg_step_size[slot][1] = float(-(a.lr_critic / bc1));
+  c->d_bc2_sqrt[slot] = float(sqrt(bc2));
+}
 // executed by ONE thread of the step's first kernel
 __device__ __forceinline__ void clock_derive(LearnerClock* c, const ClockParams& a) {
   const double step = double(c->adam_step + 1);                      // post-increment step count
@@ -33,8 +49,8 @@ __device__ __forceinline__ void clock_derive(LearnerClock* c, const ClockParams&
   c->bc2_sqrt = float(sqrt(bc2));
 }
 // LinearSchedule.value() for clock t (prioritized_replay_memory.py:25-29)
-__device__ __forceinline__ float clock_beta(const LearnerClock* c, const ClockParams& a) {
-  const double frac = fmin(double(c->beta_t) / double(a.per_beta_iters), 1.0);
+__device__ __forceinline__ float clock_beta(const LearnerClock* c, const ClockParams& a, bool pipelined = false) {
+  const double frac = fmin(double(pipelined ? c->s_beta_t : c->beta_t) / double(a.per_beta_iters), 1.0);
   return float(a.per_beta0 + frac * (a.per_beta_final - a.per_beta0));
 }
 
@@ -46,6 +62,7 @@ struct AdamArgs {
   AdamSeg seg[2]; int nseg;
   float w1, w2, beta2, eps, bc2_sqrt, tau, one_minus_tau, grad_scale;
   LearnerClock* clock;                        // optional (learner): scalars in, counters advanced
+  int pipe_slot;                              // >= 0: the step's scalars are in this slot of the clock (prefetch pipeline)
   // fused tail (learner): deterministic batch means of the per-row losses -> out[0], out[1]
   const float* loss_rows; const float* pi_rows; int B; float inv_count; float* loss_out;
   int pdl;                                    // programmatic-dependent-launch trigger position (0/1/2)

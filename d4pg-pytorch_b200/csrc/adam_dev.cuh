@@ -30,8 +30,16 @@ __device__ __forceinline__ void adam_tail(const AdamArgs& a, float (*red)[8]) {
 // segment `seg`, grid-stride over float4 groups: CTA bx of gx (256 threads each)
 __device__ __forceinline__ void adam_segment(const AdamArgs& a, int seg, int bx, int gx) {
   const AdamSeg& s = a.seg[seg];
-  const float nss = (a.clock && s.clock_slot >= 0) ? a.clock->neg_step_size[s.clock_slot] : s.neg_step_size;
-  const float bc2s = a.clock ? a.clock->bc2_sqrt : a.bc2_sqrt;
+  float nss = s.neg_step_size, bc2s = a.bc2_sqrt;
+  if (a.clock) {
+    if (a.pipe_slot >= 0) {
+      nss = s.clock_slot >= 0 ? a.clock->d_neg_step_size[a.pipe_slot][s.clock_slot] : nss;
+      bc2s = a.clock->d_bc2_sqrt[a.pipe_slot];
+    } else {
+      nss = s.clock_slot >= 0 ? a.clock->neg_step_size[s.clock_slot] : nss;
+      bc2s = a.clock->bc2_sqrt;
+    }
+  }
   const int64_t n4 = s.n >> 2;
   float4* p4 = reinterpret_cast<float4*>(s.p);
   const float4* g4 = reinterpret_cast<const float4*>(s.g);

@@ -40,12 +40,15 @@ struct Workspace {
   LearnerClock* clock;
   unsigned long long* barrier;     // grid-barrier counter of the persistent step kernel
   float* xchg;                     // exchange planes of the cluster-fused chain kernels (chain mode)
+  // prefetch pipeline: the second half of the double-buffered batch, and the sampler's own index / weight buffers
+  float *s_b, *a_b, *s2_b; double* r_b; uint8_t* done_b;
+  int32_t* idx2[2]; float* wts2[2];
   int64_t total;
 };
 
 // Every 2-D plane has a row pitch that is a multiple of 4 floats (16-B rows): |s|=17 -> 20,
 // |a|=6 -> 8, N=51 -> 52.  That makes every GEMM operand TMA- and float4-addressable.
-static Workspace carve(float* base, int B, int S, int A, int N, bool chain) {
+static Workspace carve(float* base, int B, int S, int A, int N, bool chain, bool prefetch) {
   Workspace w{};
   int64_t off = 0;
   auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
@@ -69,6 +72,12 @@ static Workspace carve(float* base, int B, int S, int A, int N, bool chain) {
   w.clock = reinterpret_cast<LearnerClock*>(take(sizeof(LearnerClock) / 4 + 4));
   w.barrier = reinterpret_cast<unsigned long long*>(take(64));   // [0] arrival counter, [16] release flag (own line)
   w.xchg = chain ? take(chain_xchg_floats(B)) : nullptr;
+  if (prefetch) {
+    w.s_b = take(int64_t(B) * Sp); w.a_b = take(int64_t(B) * Ap); w.s2_b = take(int64_t(B) * Sp);
+    w.r_b = reinterpret_cast<double*>(take(int64_t(B) * 2));
+    w.done_b = reinterpret_cast<uint8_t*>(take((B + 3) / 4));
+    for (int k = 0; k < 2; ++k) { w.idx2[k] = reinterpret_cast<int32_t*>(take(B)); w.wts2[k] = take(B); }
+  }
   w.total = off;
   return w;
 }
@@ -83,8 +92,12 @@ struct d4pg_learner {
   d4pg_comm* comm;
   Workspace ws;
   NetDims da, dc;
-  cudaGraphExec_t graph_exec;
-  bool graph_ready;
+  cudaGraphExec_t graph_exec[4];   // [batch parity * 2 + cold]; only [0] without the prefetch pipeline
+  bool graph_ready[4];
+  int pipe_par;                    // half of the double-buffered batch the NEXT step trains on
+  int last_par;                    // ... the last step trained on
+  bool prefetch_valid;             // that half already holds the next step's batch
+  int64_t seen_gen;                // replay generation when it was sampled
   int64_t steps_done;
   int kernels_per_step;
   // profiling (d4pg_learner_profile_step): CUDA-event pair around every launch of an eager step
@@ -103,14 +116,23 @@ struct d4pg_learner {
 // step plan: 0 = one grouped launch per dependency level, 1 = cluster-fused chains (mlp_chain.cu),
 // 2 = row-owner chains (mlp_rows.cu; batches up to 512 rows, larger ones use plan 1)
 static int step_plan(const d4pg_learner_config_t& c) { return (c.chain == 2 && c.batch > 512) ? 1 : c.chain; }
+// prefetch pipeline: batch t+1 is sampled on a side branch of step t (device-side sampling only)
+static bool prefetching(const d4pg_learner_config_t& c) { return c.prefetch != 0 && c.sample_mode == 1 && !c.persistent; }
 
 // idempotent launches (pure functions of their inputs) are repeated in profile mode
 constexpr int PROFILE_REPS = 16;
 
-static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
+// par: half of the double-buffered batch this step trains on; cold: sample it first (no valid prefetch)
+static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   const d4pg_learner_config_t& c = L->cfg;
   const d4pg_learner_buffers_t& b = L->buf;
-  Workspace& w = L->ws;
+  Workspace w = L->ws;                               // local copy: the batch pointers follow `par`
+  const bool pf = prefetching(c);
+  int32_t* bidx = b.idx; float* bwts = b.weights;
+  if (pf) {
+    if (par) { w.s = w.s_b; w.a = w.a_b; w.s2 = w.s2_b; w.r = w.r_b; w.done = w.done_b; }
+    bidx = w.idx2[par]; bwts = w.wts2[par];
+  }
   const NetDims& da = L->da; const NetDims& dc = L->dc;
   const int B = c.batch, S = c.obs_dim, A = c.act_dim, N = c.n_atoms, H = D4PG_HIDDEN;
   const int Sp = pitch4(S), Ap = pitch4(A), Np = pitch4(N);          // activation row pitches
@@ -154,11 +176,11 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
     learner_sample_args(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
                         (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
                         c.philox_seed, w.clock, cp, b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, Sp, Ap, mp->sample);
-  else
+  else if (!pf || cold)
     RUN(learner_sample(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
                        (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
                        c.philox_seed, w.clock, cp,
-                       b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, Sp, Ap, st));
+                       bidx, bwts, w.s, w.a, w.r, w.s2, w.done, Sp, Ap, pf ? par : -1, st));
 
   const float* Wa = b.actor; const float* Wat = b.actor_target; const float* Wc = b.critic; const float* Wct = b.critic_target;
   GemmBatch g;
@@ -280,7 +302,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   ha.m = w.m; ha.target_probs = w.target_probs; ha.q_probs = w.q_probs;
   ha.loss_rows = w.loss_rows; ha.td = b.td; ha.prio = b.prio; ha.dlogits_q = w.dlogits_q;
   ha.pi_rows = w.pi_rows; ha.dlogits_pi = w.dlogits_pi;
-  ha.is_weights = ((c.loss_flags & 1) && c.prioritized) ? b.weights : nullptr;
+  ha.is_weights = ((c.loss_flags & 1) && c.prioritized) ? bwts : nullptr;
+  ha.sampler_clock = pf ? w.clock : nullptr;          // sample(t) is done, sample(t+1) not yet launched
   ha.ce_priority = (c.loss_flags & 2) ? 1 : 0;
   if (mega) { mp->heads = ha; mp->heads_mode = c.proj_mode; mp->n_fwd = n_levels; }
   else RUN(launch_heads(ha, c.proj_mode, st));
@@ -290,10 +313,24 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   if (mega) {
     mp->do_tree = c.prioritized ? 1 : 0;
     if (c.prioritized) tree_update_args(L->replay, B, b.idx, b.prio, mp->tree);
-  } else if (c.prioritized) {
+  } else if (c.prioritized || pf) {
     D4PG_CUDA_OK(cudaEventRecord(L->ev_fork, st));
     D4PG_CUDA_OK(cudaStreamWaitEvent(L->side, L->ev_fork, 0));
-    RUN(launch_tree_update(L->replay, B, b.idx, b.prio, L->side));
+    if (pf) {                                          // the caller-visible copies of this step's indices / IS weights
+      D4PG_CUDA_OK(cudaMemcpyAsync(b.idx, bidx, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToDevice, L->side));
+      if (b.weights && c.prioritized)
+        D4PG_CUDA_OK(cudaMemcpyAsync(b.weights, bwts, size_t(B) * sizeof(float), cudaMemcpyDeviceToDevice, L->side));
+    }
+    if (c.prioritized) RUN(launch_tree_update(L->replay, B, bidx, b.prio, L->side));
+    if (pf) {
+      // 4'. the NEXT step's batch, sampled from the just-updated trees into the other half of the batch buffers
+      // while this step's backward pass, dW and Adam run (it needs the trees, not the weights)
+      const int q = par ^ 1;
+      const Workspace& o = L->ws;
+      RUN(learner_sample(L->replay, B, c.prioritized, nullptr, nullptr, c.philox_seed, w.clock, cp, o.idx2[q], o.wts2[q],
+                         q ? o.s_b : o.s, q ? o.a_b : o.a, q ? o.r_b : o.r, q ? o.s2_b : o.s2, q ? o.done_b : o.done,
+                         Sp, Ap, q, L->side));
+    }
     D4PG_CUDA_OK(cudaEventRecord(L->ev_join, L->side));
   }
 
@@ -405,6 +442,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
   aa.nseg = 2;
   aa.w1 = float(1.0 - c.beta1); aa.w2 = float(1.0 - c.beta2); aa.beta2 = float(c.beta2); aa.eps = float(c.adam_eps);
   aa.tau = float(c.tau); aa.one_minus_tau = float(1.0 - c.tau); aa.grad_scale = 1.0f; aa.clock = w.clock;
+  aa.pipe_slot = pf ? par : -1;
   // tail slice of the same launch: reported batch-mean losses + advance the device clock
   aa.loss_rows = w.loss_rows; aa.pi_rows = w.pi_rows; aa.B = B; aa.inv_count = 1.0f / float(B); aa.loss_out = b.losses;
   if (mega) {
@@ -413,7 +451,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
     RUN(launch_step_mega(*mp, st));
   } else {
     RUN(launch_adam(aa, st));
-    if (c.prioritized) D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join, 0));
+    if (c.prioritized || pf) D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join, 0));
   }
 #undef LEVEL
 #undef RUN
@@ -423,7 +461,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st) {
 
 extern "C" int64_t d4pg_learner_workspace_floats(const d4pg_learner_config_t* cfg) {
   if (!cfg) return -1;
-  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1).total;
+  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1, prefetching(*cfg)).total;
 }
 
 extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d4pg_learner_buffers_t* buf,
@@ -454,8 +492,10 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
     set_error("d4pg_learner_create: grad_critic must equal grad_actor + P_a (one flat gradient buffer)");
     delete L; return D4PG_EINVAL;
   }
-  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1);
-  L->graph_exec = nullptr; L->graph_ready = false; L->steps_done = 0; L->kernels_per_step = 0;
+  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1, prefetching(*cfg));
+  for (int i = 0; i < 4; ++i) { L->graph_exec[i] = nullptr; L->graph_ready[i] = false; }
+  L->pipe_par = 0; L->last_par = 0; L->prefetch_valid = false; L->seen_gen = -1;
+  L->steps_done = 0; L->kernels_per_step = 0;
   L->profiling = false;
   (void)debug_trace_buffer();          // allocate outside of any stream capture
   L->host_u = nullptr; L->host_pos = nullptr; L->host_losses = nullptr; L->ev_in = nullptr; L->ev_out = nullptr;
@@ -472,7 +512,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
 
 extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   if (!L) return D4PG_OK;
-  if (L->graph_exec) cudaGraphExecDestroy(L->graph_exec);
+  for (int i = 0; i < 4; ++i) if (L->graph_exec[i]) cudaGraphExecDestroy(L->graph_exec[i]);
   cudaEventDestroy(L->ev_fork); cudaEventDestroy(L->ev_join); cudaStreamDestroy(L->side);
   if (L->ev_in) cudaEventDestroy(L->ev_in);
   if (L->ev_out) cudaEventDestroy(L->ev_out);
@@ -480,29 +520,44 @@ extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   return D4PG_OK;
 }
 
+// which half of the batch buffers the next step uses, and whether it has to sample it first
+static void next_variant(d4pg_learner* L, int* par, bool* cold) {
+  if (!prefetching(L->cfg)) { *par = 0; *cold = true; return; }
+  *par = L->pipe_par;
+  *cold = !L->prefetch_valid || replay_generation(L->replay) != L->seen_gen;
+}
+static void commit_variant(d4pg_learner* L, int par) {
+  ++L->steps_done;
+  if (!prefetching(L->cfg)) return;
+  L->last_par = par; L->pipe_par = par ^ 1; L->prefetch_valid = true; L->seen_gen = replay_generation(L->replay);
+}
+
 extern "C" int32_t d4pg_learner_step(d4pg_learner_t* L, d4pg_stream_t stream) {
   D4PG_REQUIRE(L, D4PG_EINVAL, "d4pg_learner_step: null handle");
   cudaStream_t st = as_stream(stream);
+  int par; bool cold;
+  next_variant(L, &par, &cold);
   if (!L->cfg.use_graph) {
-    int rc = enqueue_step(L, st);
-    if (rc == D4PG_OK) ++L->steps_done;
+    int rc = enqueue_step(L, st, par, cold);
+    if (rc == D4PG_OK) commit_variant(L, par);
     return rc;
   }
-  if (!L->graph_ready) {
+  const int v = prefetching(L->cfg) ? par * 2 + (cold ? 1 : 0) : 0;
+  if (!L->graph_ready[v]) {
     D4PG_REQUIRE(st != nullptr, D4PG_EINVAL, "d4pg_learner_step: graph capture needs a non-default stream");
     cudaGraph_t graph = nullptr;
     D4PG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(L, st);
+    int rc = enqueue_step(L, st, par, cold);
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     if (rc != D4PG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) { set_error("d4pg_learner_step: end capture: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
-    e = cudaGraphInstantiate(&L->graph_exec, graph, 0);
+    e = cudaGraphInstantiate(&L->graph_exec[v], graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { set_error("d4pg_learner_step: instantiate: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
-    L->graph_ready = true;
+    L->graph_ready[v] = true;
   }
-  D4PG_CUDA_OK(cudaGraphLaunch(L->graph_exec, st));
-  ++L->steps_done;
+  D4PG_CUDA_OK(cudaGraphLaunch(L->graph_exec[v], st));
+  commit_variant(L, par);
   return D4PG_OK;
 }
 
@@ -562,9 +617,11 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
   D4PG_REQUIRE(L && ms_out && n_out && max_launches > 0, D4PG_EINVAL, "d4pg_learner_profile_step: bad arguments");
   cudaStream_t st = as_stream(stream);
   L->profiling = true; L->ev.clear(); L->ev_name.clear();
-  int rc = enqueue_step(L, st);
+  int par; bool cold;
+  next_variant(L, &par, &cold);
+  int rc = enqueue_step(L, st, par, cold);
   L->profiling = false;
-  if (rc == D4PG_OK) ++L->steps_done;
+  if (rc == D4PG_OK) commit_variant(L, par);
   cudaError_t e = cudaStreamSynchronize(st);
   const int n = int(L->ev_name.size());
   *n_out = n < max_launches ? n : max_launches;
@@ -593,6 +650,8 @@ extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_ste
   D4PG_REQUIRE(L && adam_step >= 0 && beta_t >= 0, D4PG_EINVAL, "d4pg_learner_set_counters: bad arguments");
   LearnerClock c{};
   c.adam_step = adam_step; c.beta_t = beta_t; c.steps_done = adam_step;
+  c.s_adam_step = adam_step; c.s_beta_t = beta_t; c.s_steps_done = adam_step;
+  L->prefetch_valid = false;                          // a prefetched batch was drawn with the old counters
   D4PG_CUDA_OK(cudaMemcpyAsync(L->ws.clock, &c, sizeof(c), cudaMemcpyHostToDevice, as_stream(stream)));
   D4PG_CUDA_OK(cudaMemsetAsync(L->ws.barrier, 0, 64 * sizeof(float), as_stream(stream)));
   D4PG_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
@@ -601,7 +660,8 @@ extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_ste
 
 extern "C" int32_t d4pg_learner_tensor(d4pg_learner_t* L, const char* name, void** ptr, int64_t* count, int32_t* ld) {
   D4PG_REQUIRE(L && name && ptr && count && ld, D4PG_EINVAL, "d4pg_learner_tensor: null argument");
-  const Workspace& w = L->ws;
+  Workspace w = L->ws;
+  if (prefetching(L->cfg) && L->last_par) { w.s = w.s_b; w.a = w.a_b; w.s2 = w.s2_b; w.r = w.r_b; w.done = w.done_b; }
   const int64_t B = L->cfg.batch;
   const int Sp = pitch4(L->cfg.obs_dim), Ap = pitch4(L->cfg.act_dim), Np = pitch4(L->cfg.n_atoms);
   struct E { const char* n; void* p; int64_t c; int ld; };

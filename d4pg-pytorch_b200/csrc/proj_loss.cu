@@ -51,7 +51,7 @@ extern "C" int32_t d4pg_proj_loss(const float* target_logits, const float* q_log
   D4PG_REQUIRE(proj_mode == 0 || proj_mode == 1, D4PG_EINVAL, "d4pg_proj_loss: proj_mode must be 0 or 1");
   D4PG_REQUIRE((bins_l == nullptr) == (bins_u == nullptr), D4PG_EINVAL, "d4pg_proj_loss: bins_l/bins_u must both be set or both NULL");
   D4PG_REQUIRE(v_max > v_min, D4PG_EINVAL, "d4pg_proj_loss: v_max <= v_min");
-  HeadsArgs a;
+  HeadsArgs a{};
   a.target_logits = target_logits; a.q_logits = q_logits; a.pi_logits = pi_logits;
   a.rewards = rewards; a.dones = dones; a.B = B; a.N = N; a.flags = flags; a.ld = N;
   a.v_min = v_min; a.v_max = v_max;

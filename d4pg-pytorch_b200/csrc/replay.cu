@@ -25,6 +25,7 @@ struct d4pg_replay {
   int32_t* scratch; float* state;
   int64_t len, next_idx;
   int pristine;
+  int64_t gen;            // bumped by every external mutation (add / set / update): a learner's prefetched batch is stale
   // host ingest staging (caller-owned buffers registered by d4pg_replay_set_staging)
   uint8_t* stage_host; uint8_t* stage_dev; int64_t stage_bytes; cudaEvent_t stage_ev; bool stage_busy;
 };
@@ -206,9 +207,9 @@ int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
 int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
                    uint64_t seed, LearnerClock* clock, const ClockParams& cp,
                    int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
-                   int ld_obs, int ld_act, cudaStream_t st) {
+                   int ld_obs, int ld_act, int pipe_slot, cudaStream_t st) {
   SampleArgs sa{};
-  sa.ld_obs = ld_obs; sa.ld_act = ld_act;
+  sa.ld_obs = ld_obs; sa.ld_act = ld_act; sa.pipe_slot = pipe_slot;
   sa.uniforms = uniforms; sa.seed = seed; sa.counter = 0; sa.clock = clock; sa.clock_params = cp;
   sa.beta = 1.f; sa.B = B; sa.idx = idx; sa.weights = prioritized ? weights : nullptr;
   sa.s = s; sa.a = a; sa.r = r; sa.s2 = s2; sa.d = d;
@@ -221,7 +222,7 @@ void learner_sample_args(d4pg_replay* h, int B, int prioritized, const double* u
                          int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
                          int ld_obs, int ld_act, SampleArgs& sa) {
   sa = SampleArgs{};
-  sa.ld_obs = ld_obs; sa.ld_act = ld_act;
+  sa.ld_obs = ld_obs; sa.ld_act = ld_act; sa.pipe_slot = -1;
   sa.uniforms = uniforms; sa.seed = seed; sa.counter = 0; sa.clock = clock; sa.clock_params = cp;
   sa.beta = 1.f; sa.B = B; sa.idx = idx; sa.weights = prioritized ? weights : nullptr;
   sa.s = s; sa.a = a; sa.r = r; sa.s2 = s2; sa.d = d;
@@ -237,6 +238,8 @@ void tree_update_args(d4pg_replay* h, int B, const int32_t* idx, const float* pr
   a.state = reinterpret_cast<ReplayState*>(h->state);
   h->pristine = 0;
 }
+
+int64_t replay_generation(const d4pg_replay* h) { return h->gen; }
 
 int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st) {
   TreeArgs a{};
@@ -319,6 +322,7 @@ extern "C" int32_t d4pg_replay_set_staging(d4pg_replay_t* h, void* pinned_host, 
 
 extern "C" int32_t d4pg_replay_add_host(d4pg_replay_t* h, int64_t n, const float* obs, const float* act, const double* rew,
                                         const float* obs2, const uint8_t* done, int32_t prioritized, d4pg_stream_t stream) {
+  if (h) ++h->gen;
   D4PG_REQUIRE(h && obs && act && rew && obs2 && done && n > 0, D4PG_EINVAL, "d4pg_replay_add_host: null/empty argument");
   D4PG_REQUIRE(h->stage_host, D4PG_ESTATE, "d4pg_replay_add_host: call d4pg_replay_set_staging first");
   const PackLayout p = pack_layout(h, n);
@@ -343,6 +347,7 @@ extern "C" int64_t d4pg_replay_len(const d4pg_replay_t* h) { return h ? h->len :
 extern "C" int64_t d4pg_replay_next_idx(const d4pg_replay_t* h) { return h ? h->next_idx : -1; }
 
 extern "C" int32_t d4pg_replay_set_len(d4pg_replay_t* h, int64_t len, int64_t next_idx, int32_t pristine) {
+  if (h) ++h->gen;
   D4PG_REQUIRE(h && len >= 0 && len <= h->size && next_idx >= 0 && next_idx < h->size, D4PG_EINVAL,
                "d4pg_replay_set_len: out of range");
   h->len = len; h->next_idx = next_idx; h->pristine = pristine ? 1 : 0;
@@ -354,6 +359,7 @@ extern "C" int32_t d4pg_replay_set_len(d4pg_replay_t* h, int64_t len, int64_t ne
 extern "C" int32_t d4pg_replay_add(d4pg_replay_t* h, int64_t n, const float* obs, const float* act,
                                    const double* rew, const float* obs2, const uint8_t* done,
                                    int32_t prioritized, d4pg_stream_t stream) {
+  if (h) ++h->gen;
   D4PG_REQUIRE(h && obs && act && rew && obs2 && done, D4PG_EINVAL, "d4pg_replay_add: null argument");
   D4PG_REQUIRE(n > 0 && n <= h->size, D4PG_EINVAL, "d4pg_replay_add: need 0 < n <= size (n=%lld)", (long long)n);
   cudaStream_t st = as_stream(stream);
@@ -417,12 +423,14 @@ extern "C" int32_t d4pg_replay_gather(d4pg_replay_t* h, int32_t B, const int32_t
 
 extern "C" int32_t d4pg_replay_update_priorities(d4pg_replay_t* h, int32_t B, const int32_t* idx,
                                                  const float* prio, d4pg_stream_t stream) {
+  if (h) ++h->gen;
   D4PG_REQUIRE(h && B > 0 && idx && prio, D4PG_EINVAL, "d4pg_replay_update_priorities: null/empty argument");
   return launch_tree_update(h, B, idx, prio, as_stream(stream));
 }
 
 extern "C" int32_t d4pg_replay_set_leaves(d4pg_replay_t* h, int32_t n, const int32_t* idx, const float* sum_vals,
                                           const float* min_vals, d4pg_stream_t stream) {
+  if (h) ++h->gen;
   D4PG_REQUIRE(h && n > 0 && idx && sum_vals && min_vals, D4PG_EINVAL, "d4pg_replay_set_leaves: null/empty argument");
   TreeArgs a{};
   a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.log2cap = h->log2cap; a.size = h->size;

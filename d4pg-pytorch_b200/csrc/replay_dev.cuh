@@ -69,6 +69,7 @@ struct SampleArgs {
   int32_t* idx; float* weights;
   float* s; float* a; double* r; float* s2; uint8_t* d;
   int pdl;                          // programmatic-dependent-launch trigger position (0/1/2)
+  int pipe_slot;                    // >= 0 (prefetch pipeline): use the sampler's own counters, derive into this slot
 };
 
 constexpr int SAMPLE_ROWS = 32;      // rows per CTA
@@ -109,9 +110,10 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int bid, Sample
   const int row0 = bid * SAMPLE_ROWS;
   const int nrows = min(SAMPLE_ROWS, a.B - row0);
   const int t = threadIdx.x;
+  const bool piped = a.clock && a.pipe_slot >= 0;
   if (a.clock && bid == 0 && t == SAMPLE_THREADS - 1) {
-    clock_derive(a.clock, a.clock_params);
-    a.clock->beta = clock_beta(a.clock, a.clock_params);
+    if (piped) clock_derive_pipelined(a.clock, a.clock_params, a.pipe_slot);
+    else { clock_derive(a.clock, a.clock_params); a.clock->beta = clock_beta(a.clock, a.clock_params); }
   }
   const bool descend = (a.idx_in == nullptr) && !a.uniform_mode;
   const int64_t len = a.state->len;
@@ -132,7 +134,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int bid, Sample
     if (a.idx_in) {
       leaf_idx = a.idx_in[row];
     } else {
-      const uint64_t ctr = a.counter + (a.clock ? uint64_t(a.clock->steps_done) : 0ull);
+      const uint64_t ctr = a.counter + (a.clock ? uint64_t(piped ? a.clock->s_steps_done : a.clock->steps_done) : 0ull);
       const double u = a.uniforms ? a.uniforms[row] : Philox::uniform53(a.seed, ctr, uint32_t(row));
       int64_t i = 1;
       const int64_t top_end = int64_t(1) << (top_levels - 1);              // nodes < 2*top_end have children in top_s
@@ -160,7 +162,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int bid, Sample
         const float tot = __ldcg(a.sum + 1);
         const float pmin = __fdiv_rn(__ldcg(a.mn + 1), tot);
         const float n = float(len);
-        const float beta = a.clock ? clock_beta(a.clock, a.clock_params) : a.beta;
+        const float beta = a.clock ? clock_beta(a.clock, a.clock_params, piped) : a.beta;
         const float maxw = __double2float_rn(pow(double(__fmul_rn(pmin, n)), double(-beta)));
         const float ps = __fdiv_rn(__ldcg(a.sum + a.cap + leaf_idx), tot);
         const float w = __double2float_rn(pow(double(__fmul_rn(ps, n)), double(-beta)));

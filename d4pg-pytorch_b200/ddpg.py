@@ -74,6 +74,7 @@ class _Learner(object):
         cfg.persistent = 1 if (ddpg.persistent and ddpg.precision == "fp32" and cfg.world_size == 1) else 0
         plan = {"levels": 0, "cluster": 1, "rows": 2, False: 0, True: 1, 0: 0, 1: 1, 2: 2}[ddpg.chain]
         cfg.chain = plan if (ddpg.precision == "fp32" and not cfg.persistent) else 0
+        cfg.prefetch = 1 if (ddpg.prefetch and cfg.sample_mode == 1 and not cfg.persistent) else 0
         self.cfg = cfg
         nws = L.d4pg_learner_workspace_floats(C.byref(cfg))
         f32 = torch.float32
@@ -160,7 +161,7 @@ class DDPG:
                  critic_dist_info=None, n_steps=1,
                  # ---- B200 build extensions (keyword-only in spirit; reference callers never pass them)
                  device=None, sampling="reference", projection="reference", precision="fp32",
-                 use_graph=True, philox_seed=0, comm=None, persistent=False, chain="cluster",
+                 use_graph=True, philox_seed=0, comm=None, persistent=False, chain="cluster", prefetch=True,
                  importance_weighted=False, priority="reference"):
         self.gamma = gamma
         self.n_steps = n_steps
@@ -179,6 +180,8 @@ class DDPG:
         # step plan of the MLP passes (fp32): "cluster" (default) cluster-fused layer chains, "rows" row-owner
         # chains with TMA-multicast weight streaming (correct, measured slower), "levels" one launch per level
         self.chain = chain
+        # device-side sampling only: step t already samples batch t+1 behind its own backward pass (identical results)
+        self.prefetch = prefetch
         # corrected-semantics switches (default = the reference's behaviour)
         assert priority in ("reference", "ce")
         self.importance_weighted, self.priority = bool(importance_weighted), priority

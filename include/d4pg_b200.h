@@ -221,6 +221,11 @@ typedef struct {
                                  and all dW are ONE launch each (7 kernels/step, bit-identical to 0); 2 = row-owner
                                  chains: a CTA carries a few batch rows through a whole chain, weights streamed
                                  (7 kernels/step; same fp32 dot products in a different summation order) */
+  int32_t prefetch;           /* 1 (sample_mode 1 only): step t samples batch t+1 on a side branch, right after its own
+                                 priorities are in the trees, while its backward pass and Adam still run.  Same
+                                 Philox counters and the same trees as sampling at the start of step t+1, so results
+                                 are identical; any replay mutation by the caller (add / set / update) between two
+                                 steps discards the prefetched batch and step t+1 samples again at its start */
 } d4pg_learner_config_t;
 
 /* Caller-owned device buffers.  P_a / P_c = d4pg_*_layout().total. */

@@ -153,7 +153,7 @@ def test_rows_chain_vs_levels(B, obs_dim, act_dim, N):
         dd.replayBuffer.add_batch(S, A, R, S2, D)
         dd.train()
         torch.cuda.synchronize()
-        assert dd.kernels_per_step() == (7 if chain == "rows" else 18)
+        assert dd.kernels_per_step() == (8 if chain == "rows" else 19)      # + the first step's own sample launch
         g = {("a", k): v.clone() for k, v in dd.actor.named_grad_views().items()}
         g.update({("c", k): v.clone() for k, v in dd.critic.named_grad_views().items()})
         out[chain] = dict(idx=dd.last_batch_info()["idx"].clone(), prio=dd.last_batch_info()["prio"].clone(),
@@ -169,6 +169,49 @@ def test_rows_chain_vs_levels(B, obs_dim, act_dim, N):
         ga, gb = a["grads"][k].double().reshape(-1), b["grads"][k].double().reshape(-1)
         rel = (ga - gb).norm().item() / max(gb.norm().item(), 1e-30)
         assert rel <= 1e-5, (k, rel)
+
+
+@pytest.mark.parametrize("prioritized", [True, False])
+def test_prefetch_pipeline_is_exact(prioritized):
+    """Sampling batch t+1 on a side branch of step t (cfg.prefetch) must not change anything: same Philox counters,
+    same trees.  Transitions added between steps invalidate the prefetched batch (the next step re-samples at its
+    start, now seeing the new data), exactly like sampling at the start of every step."""
+    import d4pg_b200 as d4pg
+    B, obs_dim, act_dim, N = 64, 17, 6, 51
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": N}
+    cap, n_fill = 4096, 1024
+    rng = np.random.RandomState(21)
+    def chunk(n):
+        return (rng.randn(n, obs_dim).astype(np.float32), rng.uniform(-1, 1, (n, act_dim)).astype(np.float32),
+                (-3 * rng.rand(n)).astype(np.float32).astype(np.float64), rng.randn(n, obs_dim).astype(np.float32),
+                rng.rand(n) < 0.05)
+    data = [chunk(n_fill), chunk(300), chunk(77)]
+    out = []
+    for prefetch in (True, False):
+        torch.manual_seed(8); np.random.seed(8); random.seed(8)
+        dd = d4pg.DDPG(obs_dim, act_dim, memory_size=cap, batch_size=B, critic_dist_info=info, sampling="device",
+                       philox_seed=5, prefetch=prefetch, prioritized_replay=prioritized)
+        dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
+                                   d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
+        dd.replayBuffer.add_batch(*data[0])
+        trace = []
+        for _ in range(3):
+            dd.train(); trace.append(dd.last_batch_info()["idx"].clone())
+        dd.replayBuffer.add_batch(*data[1])              # invalidates the prefetched batch
+        for _ in range(2):
+            dd.train(); trace.append(dd.last_batch_info()["idx"].clone())
+        dd.replayBuffer.add_batch(*data[2])
+        dd.train(); trace.append(dd.last_batch_info()["idx"].clone())
+        dd.train_n(5)
+        trace.append(dd.last_batch_info()["idx"].clone())
+        torch.cuda.synchronize()
+        out.append((dd.actor.flat_params().clone(), dd.critic.flat_params().clone(), dd.actor_target.flat_params().clone(),
+                    dd.critic_target.flat_params().clone(), torch.stack(trace), torch.tensor(dd.last_losses()),
+                    dd.debug_tensor("s", (B, obs_dim)).clone(), dd.debug_tensor("r", None, torch.float64).clone())
+                   + ((dd.replayBuffer._store.sum_tree.clone(), dd.replayBuffer._store.min_tree.clone()) if prioritized else ()))
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+    assert int(out[0][4][3].max()) >= n_fill                 # a step after the first add did sample new transitions
 
 
 def test_config2_full_size_vs_oracle():
