@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const AdamArgs a) {
     if (blockIdx.x == 0) adam_tail(a, red);
     return;
   }
+  step_stamp(a.trace, 7);
   adam_segment(a, blockIdx.y, blockIdx.x, gridDim.x);
+  step_stamp(a.trace, 7 + 16);
   pdl_trigger_end(a.pdl);
 }
 
@@ -30,6 +32,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const AdamArgs a) {
 int launch_adam(const AdamArgs& a_in, cudaStream_t st) {
   AdamArgs a = a_in;
   a.pdl = pdl_mode();
+  a.trace = (a.clock && debug_trace_buffer()) ? debug_trace_buffer() + STEP_TRACE_BASE : nullptr;
   int64_t nmax = 0;
   for (int i = 0; i < a.nseg; ++i) nmax = a.seg[i].n > nmax ? a.seg[i].n : nmax;
   int blocks = int((nmax / 4 + 255) / 256);
@@ -58,7 +61,7 @@ extern "C" int32_t d4pg_adam_polyak(float* p, const float* g, float* m, float* v
   a.nseg = 1;
   a.w1 = float(1.0 - beta1); a.w2 = float(1.0 - beta2); a.beta2 = float(beta2); a.eps = float(eps);
   a.bc2_sqrt = float(sqrt(bc2)); a.tau = float(tau); a.one_minus_tau = float(1.0 - tau);
-  a.grad_scale = grad_scale; a.clock = nullptr; a.loss_out = nullptr; a.pipe_slot = -1;
+  a.grad_scale = grad_scale; a.clock = nullptr; a.loss_out = nullptr; a.pipe_slot = -1; a.trace = nullptr;
   return launch_adam(a, as_stream(stream));
 }
 

@@ -62,6 +62,7 @@ struct AdamArgs {
   AdamSeg seg[2]; int nseg;
   float w1, w2, beta2, eps, bc2_sqrt, tau, one_minus_tau, grad_scale;
   LearnerClock* clock;                        // optional (learner): scalars in, counters advanced
+  unsigned long long* trace;
   int pipe_slot;                              // >= 0: the step's scalars are in this slot of the clock (prefetch pipeline)
   // fused tail (learner): deterministic batch means of the per-row losses -> out[0], out[1]
   const float* loss_rows; const float* pi_rows; int B; float inv_count; float* loss_out;

@@ -74,6 +74,17 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// step timeline (D4PG_TC_TRACE): thread 0 of CTA 0 of every step kernel stamps %globaltimer at entry / exit
+__device__ __forceinline__ void step_stamp(unsigned long long* tr, int slot) {
+  if (tr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tr[slot] = t;
+  }
+}
+unsigned long long* debug_trace_buffer();
+constexpr int STEP_TRACE_BASE = 96;      // stamps [96, 128) of the debug buffer: entry of kernel k at 96+k, exit at 112+k
+
 static inline cudaStream_t as_stream(d4pg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __host__ __device__ static inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_wide_kernel(const __grid
     if (i < batch.n && int(blockIdx.x) >= batch.p[i].tile_begin) pi = i;
   const GemmProblem& P = batch.p[pi];
   const int tile = blockIdx.x - P.tile_begin;
+  step_stamp(batch.trace, 6);
   if (ALLOW_SPLIT && P.ksplit > 1) {
     const int per_slice = P.tiles_m * P.tiles_n;
     const int ks = tile / per_slice, t2 = tile - ks * per_slice;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_wide_kernel(const __grid
     const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
     gemm_dw_tile_async<false>(P, smem, tm * BM, tn * BN, tn, 0, P.K);
   }
+  step_stamp(batch.trace, 6 + 16);
   pdl_trigger_end(batch.pdl);
 }
 
@@ -142,6 +144,7 @@ int gemm_wide_launch(GemmWideBatch& b, cudaStream_t st) {
     smem_set = true;
   }
   b.pdl = pdl_mode();
+  b.trace = debug_trace_buffer() ? debug_trace_buffer() + STEP_TRACE_BASE : nullptr;
   if (split) D4PG_CUDA_OK(launch_pdl(gemm_wide_kernel<true>, dim3(b.total_tiles), dim3(GEMM_THREADS), smem, st, b));
   else D4PG_CUDA_OK(launch_pdl(gemm_wide_kernel<false>, dim3(b.total_tiles), dim3(GEMM_THREADS), smem, st, b));
   return D4PG_OK;

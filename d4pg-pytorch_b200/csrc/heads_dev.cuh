@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * HEAD_WARPS + warp;
+  step_stamp(a.trace, 2);
   if (row < a.B) heads_row<MODE, NT>(a, row, lane, ws[warp]);
+  step_stamp(a.trace, 2 + 16);
   if (a.sampler_clock && blockIdx.x == 0 && threadIdx.x == 0) {
     a.sampler_clock->s_adam_step += 1; a.sampler_clock->s_beta_t += 1; a.sampler_clock->s_steps_done += 1;
   }

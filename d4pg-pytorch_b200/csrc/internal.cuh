@@ -21,6 +21,7 @@ struct HeadsArgs {
   const float* is_weights;   // non-null: critic CE row i is scaled by the PER importance weight w_i
   int ce_priority;           // 1: priority = CE_i + eps instead of |sum_j m_ij q_ij| + eps
   int pdl;                   // programmatic-dependent-launch trigger position (0/1/2)
+  unsigned long long* trace;
   LearnerClock* sampler_clock;   // prefetch pipeline: thread 0 advances the sampler's counters (after sample(k), before sample(k+1))
 };
 int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st);
@@ -31,7 +32,8 @@ int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniform
                    int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
                    int ld_obs, int ld_act, int pipe_slot, cudaStream_t st);
 int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st);
-int64_t replay_generation(const d4pg_replay* h);     // changes whenever the caller mutates the buffer
+int64_t replay_generation(const d4pg_replay* h);
+void trace_set_side_stream(cudaStream_t s);     // changes whenever the caller mutates the buffer
 int comm_allreduce(d4pg_comm* c, float* buf, int64_t n, cudaStream_t st);
 
 }  // namespace d4pg

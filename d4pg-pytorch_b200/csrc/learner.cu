@@ -504,6 +504,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
       cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     set_error("d4pg_learner_create: stream/event creation failed"); delete L; return D4PG_ECUDA;
   }
+  trace_set_side_stream(L->side);
   cudaError_t e = cudaMemset(L->ws.clock, 0, sizeof(LearnerClock));
   if (e != cudaSuccess) { set_error("d4pg_learner_create: %s", cudaGetErrorString(e)); delete L; return D4PG_ECUDA; }
   *out = L;

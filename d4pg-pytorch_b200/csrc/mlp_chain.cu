@@ -15,6 +15,7 @@
 // level-by-level path (tests/test_gpu_learner.py::test_chain_equals_levels).
 #include "gemm_ffma_dev.cuh"
 #include "mlp_chain.cuh"
+#include <stdlib.h>
 
 namespace d4pg {
 
@@ -196,8 +197,9 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
 
   if (n0 < args.slot[chain][0].N) fetch_weights(W0, args.slot[chain][0], n0, tid);
   cp_async_commit();
-  unsigned long long* tr0 = (args.trace && blockIdx.x == 0 && tid == 0) ? args.trace : nullptr;
+  unsigned long long* tr0 = (args.trace && int(blockIdx.x) == args.trace_cta && tid == 0) ? args.trace : nullptr;
   const long long clk0 = clock64();
+  step_stamp(args.step_trace, args.step_slot);
   for (int l = 0; l < ns; ++l) {
     const ChainSlot& S = args.slot[chain][l];
     const bool has_tile = n0 < S.N;
@@ -241,10 +243,10 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
     CTRACE(5);
   }
   cp_async_wait<0>();
+  step_stamp(args.step_trace, args.step_slot + 16);
   if (tr0) tr0[6 * CHAIN_MAX_SLOTS - 1] = (unsigned long long)(clock64() - clk0);    // SM cycles of the whole kernel
 }
 
-unsigned long long* debug_trace_buffer();
 static unsigned long long* chain_trace_buffer() { return debug_trace_buffer(); }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -300,10 +302,10 @@ int launch_mlp_chain(ChainArgs& a, cudaStream_t st) {
       D4PG_REQUIRE(s.K == s.K1 || s.src2 < 0 || (a.slot[c][s.src2].publish && a.slot[c][s.src2].N >= s.K - s.K1), D4PG_EINVAL, "launch_mlp_chain: slot %d reads an unpublished plane", l);
     }
   }
-  size_t smem = size_t(a.a_floats + 2 * a.w_floats) * sizeof(float);
-  // a grid that fits one CTA per SM must not be packed two per SM (they would share the FMA and LSU pipes
-  // while other SMs idle): ask for more than half of the shared memory
-  if (a.nchains * a.row_blocks * CHAIN_CLUSTER <= 148 && smem < 116 * 1024) smem = 116 * 1024;
+  const size_t smem = size_t(a.a_floats + 2 * a.w_floats) * sizeof(float);
+  // NOT padded to force one CTA per SM: 16 clusters of 8 at one CTA per SM need two free 8-SM groups in every
+  // GPC; a single foreign CTA (the concurrent tree update) pushes clusters into a second wave (measured: the dX
+  // launch took 38 us while every chain in it finished within 25 us).
   D4PG_REQUIRE(smem <= 220 * 1024, D4PG_ENOTSUP, "launch_mlp_chain: %zu B of shared memory needed", smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -312,6 +314,9 @@ int launch_mlp_chain(ChainArgs& a, cudaStream_t st) {
   }
   D4PG_MAX_CARVEOUT(mlp_chain_kernel);
   a.trace = chain_trace_buffer() ? chain_trace_buffer() + a.trace_base : nullptr;
+  a.step_trace = chain_trace_buffer() ? chain_trace_buffer() + STEP_TRACE_BASE : nullptr;
+  a.step_slot = a.trace_base ? 5 : 1;
+  { const char* e = getenv("D4PG_TRACE_CTA"); a.trace_cta = e ? atoi(e) : 0; if (a.trace_cta >= a.nchains * a.row_blocks * CHAIN_CLUSTER) a.trace_cta = 0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.nchains * a.row_blocks * CHAIN_CLUSTER); cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem; cfg.stream = st;

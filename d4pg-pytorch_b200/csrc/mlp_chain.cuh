@@ -34,6 +34,8 @@ struct ChainArgs {
   float* xchg;                    // [nchains][row_blocks][CHAIN_MAX_SLOTS][CHAIN_PLANE]
   unsigned long long* trace;      // optional phase stamps of CTA 0 (D4PG_TC_TRACE), 6 per slot
   int trace_base;                 // first stamp index of this launch in the debug buffer
+  unsigned long long* step_trace; int step_slot;
+  int trace_cta;                  // which CTA writes the per-slot stamps (env D4PG_TRACE_CTA, default 0)   // step timeline stamp (entry / exit of CTA 0)
 };
 
 int64_t chain_xchg_floats(int B);
@@ -54,6 +56,7 @@ constexpr int GEMM_WIDE_MAX = 12;
 struct GemmWideBatch {
   GemmProblem p[GEMM_WIDE_MAX];
   int n, total_tiles, pdl;
+  unsigned long long* trace;
 };
 void gemm_wide_begin(GemmWideBatch& b);
 void gemm_wide_add(GemmWideBatch& b, const GemmProblem& p);

@@ -287,7 +287,6 @@ __global__ void __launch_bounds__(ROWS_BLOCK, 1) mlp_rows_kernel(const __grid_co
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-unsigned long long* debug_trace_buffer();
 
 void rows_args_begin(RowsArgs& a, int B, int obs_dim, int act_dim) {
   a = RowsArgs{};

@@ -12,6 +12,7 @@
 // Node dtype is fp32 -- what the reference's Python evaluates to under NumPy 2.
 // Everything is HBM/L2 pointer chasing + row gathers: no tensor-core work here.
 #include "replay_dev.cuh"
+#include <stdlib.h>
 #include <new>
 #include <string.h>
 #include <algorithm>
@@ -36,16 +37,28 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const Sam
   __shared__ SampleSmem sm;
   pdl_trigger(a.pdl);
   pdl_wait();
+  step_stamp(a.trace, a.trace_slot);
   sample_body(a, blockIdx.x, sm);
+  step_stamp(a.trace, a.trace_slot + 16);
   pdl_trigger_end(a.pdl);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(TREE_THREADS) tree_write_kernel(const TreeArgs a) {
   __shared__ float red[32];
+  step_stamp(a.trace, 3);
   tree_write_body<MODE, TREE_THREADS>(a, red);
+  step_stamp(a.trace, 3 + 16);
 }
 
+
+__global__ void __launch_bounds__(TREE_FAST_MAX) tree_update_fast_kernel(const TreeArgs a, int hs, int D) {
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  __shared__ float red[32];
+  step_stamp(a.trace, 3);
+  tree_update_fast_body(a, tree_smem, hs, red, blockIdx.x, D);
+  step_stamp(a.trace, 3 + 16);
+}
 
 // add(): the new leaves are one contiguous ring range [start, start+n) (no wrap: the host splits a
 // wrapping add), so level l only has the nodes (cap+start)>>l .. (cap+start+n-1)>>l to recompute:
@@ -194,11 +207,16 @@ __global__ void find_prefix_kernel(const float* sum, int64_t cap, int n, const d
   idx[t] = int32_t(i - cap);
 }
 
+static cudaStream_t g_side_stream = nullptr;          // trace only: which launches are the prefetching sampler's
+void trace_set_side_stream(cudaStream_t s) { g_side_stream = s; }
+static bool st_is_side(cudaStream_t st) { return g_side_stream != nullptr && st == g_side_stream; }
 int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
   a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.state = reinterpret_cast<const ReplayState*>(h->state);
   a.obs = h->obs; a.act = h->act; a.rew = h->rew; a.obs2 = h->obs2; a.done = h->done;
   a.obs_dim = h->obs_dim; a.act_dim = h->act_dim;
   a.pdl = pdl_mode();
+  a.trace = (a.clock && debug_trace_buffer()) ? debug_trace_buffer() + STEP_TRACE_BASE : nullptr;
+  a.trace_slot = a.pipe_slot >= 0 && a.uniforms == nullptr && st_is_side(st) ? 4 : 0;
   D4PG_MAX_CARVEOUT(sample_gather_kernel);
   D4PG_CUDA_OK(launch_pdl(sample_gather_kernel, dim3(cdiv(a.B, SAMPLE_ROWS)), dim3(SAMPLE_THREADS), 0, st, a));
   return D4PG_OK;
@@ -245,8 +263,20 @@ int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* p
   TreeArgs a{};
   a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.log2cap = h->log2cap; a.size = h->size;
   a.n = B; a.idx = idx; a.v0 = prio; a.alpha_f32 = h->alpha_f32; a.scratch = h->scratch; a.state = reinterpret_cast<ReplayState*>(h->state);
-  D4PG_MAX_CARVEOUT(tree_write_kernel<TREE_UPDATE>);
-  tree_write_kernel<TREE_UPDATE><<<1, TREE_THREADS, 0, st>>>(a);
+  a.trace = (st_is_side(st) && debug_trace_buffer()) ? debug_trace_buffer() + STEP_TRACE_BASE : nullptr;
+  static const bool slow_tree = getenv("D4PG_TREE_SLOW") != nullptr;      // A/B switch for profiling
+  if (!slow_tree && B <= TREE_FAST_MAX && h->log2cap < TREE_FAST_LEVELS) {
+    int hs = 64;
+    while (hs < 2 * B) hs *= 2;
+    const int threads = ((B + 31) / 32) * 32;
+    const size_t smem = size_t(hs) * 2 * (sizeof(int) + sizeof(float2));     // 12 KB at B = 512
+    D4PG_MAX_CARVEOUT(tree_update_fast_kernel);
+    const int D = std::min(4, h->log2cap);                     // 2^D CTAs, one per top-level subtree
+    tree_update_fast_kernel<<<1 << D, threads, smem, st>>>(a, hs, D);
+  } else {
+    D4PG_MAX_CARVEOUT(tree_write_kernel<TREE_UPDATE>);
+    tree_write_kernel<TREE_UPDATE><<<1, TREE_THREADS, 0, st>>>(a);
+  }
   D4PG_LAUNCH_OK();
   h->pristine = 0;
   return D4PG_OK;

@@ -70,6 +70,7 @@ struct SampleArgs {
   float* s; float* a; double* r; float* s2; uint8_t* d;
   int pdl;                          // programmatic-dependent-launch trigger position (0/1/2)
   int pipe_slot;                    // >= 0 (prefetch pipeline): use the sampler's own counters, derive into this slot
+  unsigned long long* trace; int trace_slot;
 };
 
 constexpr int SAMPLE_ROWS = 32;      // rows per CTA
@@ -200,6 +201,7 @@ struct TreeArgs {
   int n; const int32_t* idx; const float* v0; const float* v1;   // UPDATE: v0=prio; SET: v0=sum vals, v1=min vals
   int64_t ring_start;                                              // ADD: positions (ring_start+i) % size
   float alpha_f32; int32_t* scratch; ReplayState* state;
+  unsigned long long* trace;
 };
 constexpr int TREE_THREADS = 1024;
 
@@ -254,5 +256,134 @@ __device__ __forceinline__ void tree_write_body(const TreeArgs& a, float* red) {
   }
 }
 
+// ---- update_priorities for up to 512 leaves with ONE round trip to L2 -------------------------------------
+// tree_write_body pays an L2 round trip per level (20 at capacity 2^20: 30-50 us, and the next step's sampler
+// waits for it).  Here every thread owns one updated leaf and first fetches the OLD value of the sibling of every
+// node on its leaf-to-root path (2 x log2(cap) independent loads, in flight together, kept in registers).  The
+// walk up is then done entirely in shared memory: at each level the new values of the touched nodes go into a
+// small hash table (key = node id), a thread finds its sibling there if another updated leaf shares it and falls
+// back to the prefetched old value if not, and the parent's value moves up in registers.  fp32 `left + right` is
+// commutative and every thread that shares a node computes the same value from the same inputs, so the final
+// tree is exactly "write all leaves (last writer wins), recompute every touched ancestor" like tree_write_body.
+constexpr int TREE_FAST_MAX = 512;        // leaves per call (one thread each; 2 x 24 prefetched siblings live in registers)
+constexpr int TREE_FAST_LEVELS = 24;      // capacity up to 2^23
+struct TreeHashSmem { int* keys[2]; float2* vals[2]; int mask; };
+
+__device__ __forceinline__ void tree_hash_put(int* keys, float2* vals, int mask, int node, float s, float m) {
+  unsigned h = (unsigned(node) * 2654435761u) >> 7;
+  while (true) {
+    h &= unsigned(mask);
+    const int old = atomicCAS(&keys[h], 0, node);
+    if (old == 0 || old == node) { vals[h] = make_float2(s, m); return; }     // same node -> same value from every writer
+    ++h;
+  }
+}
+__device__ __forceinline__ bool tree_hash_get(const int* keys, const float2* vals, int mask, int node, float& s, float& m) {
+  unsigned h = (unsigned(node) * 2654435761u) >> 7;
+  while (true) {
+    h &= unsigned(mask);
+    const int k = keys[h];
+    if (k == node) { const float2 v = vals[h]; s = v.x; m = v.y; return true; }
+    if (k == 0) return false;
+    ++h;
+  }
+}
+
+// CTA `c` of 2^D owns the leaves (and all their ancestors below depth D) of top-level subtree c: subtrees never
+// share a node, so the CTAs are independent; the last one to finish recomputes the 2^D - 1 nodes above.
+// `hash` = 2 tables of `hs` entries (int key + float2 value), hs = pow2 >= 2 n.
+__device__ __forceinline__ void tree_update_fast_body(const TreeArgs& a, unsigned char* smem_raw, int hs, float* red, int c, int D) {
+  const int t = threadIdx.x, n = a.n;
+  int* keys0 = reinterpret_cast<int*>(smem_raw);
+  int* keys1 = keys0 + hs;
+  float2* vals0 = reinterpret_cast<float2*>(keys1 + hs);
+  float2* vals1 = vals0 + hs;
+  const int mask = hs - 1;
+  const int L = a.log2cap - D;                               // levels walked inside the subtree (its root is level L)
+  for (int i = t; i < 2 * hs; i += blockDim.x) keys0[i] = 0;
+  const int64_t p = t < n ? int64_t(a.idx[t]) : 0;
+  const bool act = t < n && int(p >> L) == c;
+  if (act) atomicMax(a.scratch + p, t);                      // duplicates: the last writer (largest i) wins, :329-333
+  // old sibling values along the path (the loads overlap each other and the barrier)
+  float so[TREE_FAST_LEVELS], mo[TREE_FAST_LEVELS];
+#pragma unroll
+  for (int lvl = 0; lvl < TREE_FAST_LEVELS; ++lvl) {
+    so[lvl] = 0.f; mo[lvl] = 0.f;
+    if (act && lvl < L) {
+      const int64_t sib = ((a.cap + p) >> lvl) ^ 1;
+      so[lvl] = __ldcg(a.sum + sib); mo[lvl] = __ldcg(a.mn + sib);
+    }
+  }
+  __syncthreads();
+  float vs = 0.f, vm = 0.f;
+  if (act) {
+    const int w = a.scratch[p];                               // winning writer of this leaf
+    vs = vm = pow_alpha(a.v0[w], a.alpha_f32);
+  }
+  if (c == 0) {                                               // _max_priority (:335) over the whole call
+    float local_max = warp_max(t < n ? a.v0[t] : 0.f);
+    if ((t & 31) == 0) red[t >> 5] = local_max;
+    __syncthreads();
+    if (t < 32) {
+      const float v = warp_max(t < int(blockDim.x) / 32 ? red[t] : 0.f);
+      if (t == 0) {
+        if (v > a.state->max_priority) a.state->max_priority = v;
+        a.state->pristine = 0;
+      }
+    }
+  }
+  if (act) a.scratch[p] = -1;
+#pragma unroll 1
+  for (int lvl = 0; lvl <= L; ++lvl) {
+    int* keys = (lvl & 1) ? keys1 : keys0;
+    float2* vals = (lvl & 1) ? vals1 : vals0;
+    const int node = int((a.cap + p) >> lvl);
+    // threads of a warp that share the node elect one writer
+    const unsigned peers = __match_any_sync(0xffffffffu, act ? node : -1 - (t & 31));
+    const bool leader = act && (__ffs(peers) - 1) == (t & 31);
+    if (leader) {
+      a.sum[node] = vs; a.mn[node] = vm;                      // every sharer holds the same value
+      if (lvl < L) tree_hash_put(keys, vals, mask, node, vs, vm);
+    }
+    if (lvl == L) break;
+    __syncthreads();                                          // this level's table is complete
+    if (act) {
+      float ss, sm;
+      if (!tree_hash_get(keys, vals, mask, node ^ 1, ss, sm)) {
+        ss = 0.f; sm = 0.f;                                   // static register indexing: the prefetched sibling of this level
+#pragma unroll
+        for (int q = 0; q < TREE_FAST_LEVELS; ++q) if (q == lvl) { ss = so[q]; sm = mo[q]; }
+      }
+      vs = __fadd_rn(vs, ss);
+      vm = fminf(vm, sm);
+    }
+    int* nk = (lvl & 1) ? keys0 : keys1;                      // clear the other table for the next level
+    for (int i = t; i < hs; i += blockDim.x) nk[i] = 0;
+    __syncthreads();
+  }
+  if (D == 0) return;
+  // ---- the 2^D - 1 nodes above the subtree roots: by the last CTA to get here -------------------------------
+  __shared__ int is_last;
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(&a.state->reserved);
+    const unsigned long long k = atomicAdd(ticket, 1ull);
+    is_last = (k == (1ull << D) - 1ull);
+    if (is_last) { *ticket = 0ull; __threadfence(); }
+  }
+  __syncthreads();
+  if (is_last && t < 32) {
+    for (int d = D - 1; d >= 0; --d) {
+      if (t < (1 << d)) {
+        const int node = (1 << d) + t;
+        a.sum[node] = __fadd_rn(__ldcg(a.sum + 2 * node), __ldcg(a.sum + 2 * node + 1));
+        a.mn[node] = fminf(__ldcg(a.mn + 2 * node), __ldcg(a.mn + 2 * node + 1));
+      }
+      __threadfence_block();
+      __syncwarp();
+    }
+  }
+}
 
 }  // namespace d4pg

@@ -24,7 +24,6 @@ struct MegaParams {
   unsigned long long* barrier;
   unsigned long long* trace;       // optional phase stamps (D4PG_TC_TRACE)
 };
-unsigned long long* debug_trace_buffer();
 
 int launch_step_mega(const MegaParams& p, cudaStream_t st);
 void learner_sample_args(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
