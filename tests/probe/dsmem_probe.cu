@@ -137,10 +137,60 @@ __global__ void __launch_bounds__(256, 1) mma_rate(int n, long long* cycles_out,
   if (tid == 0) cycles_out[blockIdx.x] = t1 - t0;
 }
 
+// the same stream with the operand traffic of a 3xTF32 tile step: per 8-deep k-step a warp loads 8 A + 8 B
+// fragment registers from shared memory, splits them into hi/lo (cvt.rna.tf32 + sub) and issues 24 mma
+__global__ void __launch_bounds__(256, 1) mma_tile_rate(int n, long long* cycles_out, float* sink) {
+  __shared__ float As[64 * 40], Bs[64 * 40];
+  const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  for (int i = tid; i < 64 * 40; i += 256) { As[i] = 1.f + i * 1e-3f; Bs[i] = 0.5f + i * 1e-3f; }
+  __syncthreads();
+  float acc[8][4];
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  long long t0 = clock64();
+  for (int it = 0; it < n; ++it) {
+    const int k0 = (it & 7) * 8;
+    uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float x = As[(k0 + t4 + (r >> 1) * 4) * 40 + m * 16 + g + (r & 1) * 8];
+        uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+        const float lo = x - __uint_as_float(h);
+        uint32_t l; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(lo));
+        ah[m][r] = h; al[m][r] = l;
+      }
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float x = Bs[(k0 + t4 + r * 4) * 40 + nn * 8 + g];
+        uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+        const float lo = x - __uint_as_float(h);
+        uint32_t l; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(lo));
+        bh[nn][r] = h; bl[nn][r] = l;
+      }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) {
+        float* c = acc[m * 4 + nn];
+#define MMA(A, B) asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(B[0]), "r"(B[1]))
+        MMA(al[m], bh[nn]); MMA(ah[m], bl[nn]); MMA(ah[m], bh[nn]);
+      }
+  }
+  long long t1 = clock64();
+  float s = 0.f;
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) s += acc[i][j];
+  sink[blockIdx.x * 256 + tid] = s;
+  if (tid == 0) cycles_out[blockIdx.x] = t1 - t0;
+}
+
 int main() {
   const int nclusters = 16, grid = nclusters * CL;
   long long* cyc; float* chk; float* gplanes; float* sink;
-  CK(cudaMalloc(&cyc, grid * sizeof(long long))); CK(cudaMalloc(&chk, grid * sizeof(float)));
+  CK(cudaMalloc(&cyc, 256 * sizeof(long long))); CK(cudaMalloc(&chk, 256 * sizeof(float)));
   CK(cudaMalloc(&gplanes, size_t(nclusters) * 2 * 8192 * sizeof(float)));
   CK(cudaMalloc(&sink, 148 * 256 * sizeof(float)));
   const size_t smem = (2 * 8192 + 1024) * sizeof(float);
@@ -160,12 +210,22 @@ int main() {
   }
   for (int n : {64, 256}) {
     mma_rate<<<148, 256>>>(n, cyc, sink);
+    CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     long long h[148];
     CK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
     // 8 warps x n x 8 mma per CTA on one SM
     printf("mma.sync m16n8k8 tf32: n=%d  %lld cycles for %d mma/SM -> %.2f cycles per mma per SM sub-partition, %.0f MAC/clk/SM\n", n,
            h[0], 8 * n * 8, double(h[0]) / (2.0 * n * 8), double(8 * n * 8) * 1024.0 / double(h[0]));
+  }
+  for (int n : {32, 128}) {
+    mma_tile_rate<<<148, 256>>>(n, cyc, sink);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    long long h[148];
+    CK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("3xTF32 tile step (8 warps x n=%d k-steps: 16 LDS + 48 cvt/sub + 24 mma each): %lld cycles -> %.0f cycles per k-step per CTA; a 32x32x256 tile = 32 k-steps over 8 warps = 4 per warp -> %.0f cycles\n",
+           n, h[0], double(h[0]) / n, double(h[0]) / n * 4);
   }
   return 0;
 }
