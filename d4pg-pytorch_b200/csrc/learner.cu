@@ -94,6 +94,8 @@ struct d4pg_learner {
   NetDims da, dc;
   cudaGraphExec_t graph_exec[4];   // [batch parity * 2 + cold]; only [0] without the prefetch pipeline
   bool graph_ready[4];
+  cudaGraphExec_t multi_exec[2];   // RUN_UNROLL warm steps in one graph, by starting batch parity (d4pg_learner_run)
+  bool multi_ready[2];
   int pipe_par;                    // half of the double-buffered batch the NEXT step trains on
   int last_par;                    // ... the last step trained on
   bool prefetch_valid;             // that half already holds the next step's batch
@@ -494,6 +496,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   }
   L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1, prefetching(*cfg));
   for (int i = 0; i < 4; ++i) { L->graph_exec[i] = nullptr; L->graph_ready[i] = false; }
+  for (int i = 0; i < 2; ++i) { L->multi_exec[i] = nullptr; L->multi_ready[i] = false; }
   L->pipe_par = 0; L->last_par = 0; L->prefetch_valid = false; L->seen_gen = -1;
   L->steps_done = 0; L->kernels_per_step = 0;
   L->profiling = false;
@@ -514,6 +517,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
 extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   if (!L) return D4PG_OK;
   for (int i = 0; i < 4; ++i) if (L->graph_exec[i]) cudaGraphExecDestroy(L->graph_exec[i]);
+  for (int i = 0; i < 2; ++i) if (L->multi_exec[i]) cudaGraphExecDestroy(L->multi_exec[i]);
   cudaEventDestroy(L->ev_fork); cudaEventDestroy(L->ev_join); cudaStreamDestroy(L->side);
   if (L->ev_in) cudaEventDestroy(L->ev_in);
   if (L->ev_out) cudaEventDestroy(L->ev_out);
@@ -604,11 +608,38 @@ extern "C" int32_t d4pg_learner_read_losses(d4pg_learner_t* L, float* out4, d4pg
   return D4PG_OK;
 }
 
+// Back-to-back steps with nothing in between: warm prefetch steps are replayed RUN_UNROLL at a time from one graph
+// (a graph launch boundary costs ~5 us of idle GPU; inside a graph consecutive steps are ordinary dependent nodes).
+constexpr int RUN_UNROLL = 4;
 extern "C" int32_t d4pg_learner_run(d4pg_learner_t* L, int32_t n_steps, d4pg_stream_t stream) {
   D4PG_REQUIRE(L && n_steps > 0, D4PG_EINVAL, "d4pg_learner_run: bad arguments");
-  for (int i = 0; i < n_steps; ++i) {
+  cudaStream_t st = as_stream(stream);
+  int n = n_steps;
+  while (n > 0) {
+    int par; bool cold;
+    next_variant(L, &par, &cold);
+    if (L->cfg.use_graph && prefetching(L->cfg) && !cold && n >= RUN_UNROLL && st != nullptr) {
+      if (!L->multi_ready[par]) {
+        cudaGraph_t graph = nullptr;
+        D4PG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = D4PG_OK;
+        for (int i = 0; i < RUN_UNROLL && rc == D4PG_OK; ++i) rc = enqueue_step(L, st, par ^ (i & 1), false);
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc != D4PG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { set_error("d4pg_learner_run: end capture: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
+        e = cudaGraphInstantiate(&L->multi_exec[par], graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { set_error("d4pg_learner_run: instantiate: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
+        L->multi_ready[par] = true;
+      }
+      D4PG_CUDA_OK(cudaGraphLaunch(L->multi_exec[par], st));
+      for (int i = 0; i < RUN_UNROLL; ++i) commit_variant(L, par ^ (i & 1));
+      n -= RUN_UNROLL;
+      continue;
+    }
     int rc = d4pg_learner_step(L, stream);
     if (rc) return rc;
+    --n;
   }
   return D4PG_OK;
 }
