@@ -158,9 +158,17 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def raw_stream(device_index=None):
+    """cudaStream_t of torch's current stream as an int.  torch.cuda.current_stream() builds a Stream object through
+    several Python layers (~7 us per call, twice per training step); the raw getter is ~0.3 us."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(device_index)
+
+
+def stream_ptr():
+    return C.c_void_p(raw_stream())
 
 
 def actor_layout(obs_dim, act_dim):

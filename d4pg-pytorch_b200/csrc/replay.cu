@@ -95,6 +95,47 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_add_range_kernel(float* sum
   }
 }
 
+// The same update with ONE round trip to L2 (n <= TREE_ADD_FAST_MAX): a parent inside the recomputed range has both
+// children inside the range of the level below, except at the two edges, where the outside child is an OLD node.
+// Those <= 2 old nodes per level (and tree) are fetched up front, in flight together; the levels are then computed
+// from shared memory.  Identical arithmetic (fp32 left + right, fminf), so the resulting tree is bit-identical.
+constexpr int TREE_ADD_FAST_MAX = 2048;
+__global__ void __launch_bounds__(TREE_THREADS) tree_add_range_fast_kernel(float* sum, float* mn, int64_t cap, int log2cap,
+                                                                           int64_t start, int64_t n, const ReplayState* state,
+                                                                           float alpha_f32) {
+  __shared__ float vs[2][TREE_ADD_FAST_MAX], vm[2][TREE_ADD_FAST_MAX];
+  __shared__ float old_s[2][32], old_m[2][32];                         // [left / right edge][level]
+  const int t = threadIdx.x;
+  const float leaf = pow_alpha(state->max_priority, alpha_f32);       // :255-256
+  if (t < 2 * log2cap) {
+    const int lvl = (t >> 1) + 1, side = t & 1;                        // the outside child needed by level `lvl`
+    const int64_t plo = (cap + start) >> (lvl - 1), phi = (cap + start + n - 1) >> (lvl - 1);
+    float a = 0.f, b = INFINITY;
+    if (side == 0 && (plo & 1)) { a = __ldcg(sum + plo - 1); b = __ldcg(mn + plo - 1); }
+    if (side == 1 && !(phi & 1)) { a = __ldcg(sum + phi + 1); b = __ldcg(mn + phi + 1); }
+    old_s[side][lvl] = a; old_m[side][lvl] = b;
+  }
+  for (int64_t i = t; i < n; i += TREE_THREADS) {
+    sum[cap + start + i] = leaf; mn[cap + start + i] = leaf;
+    vs[0][i] = leaf; vm[0][i] = leaf;
+  }
+  __syncthreads();
+  for (int lvl = 1; lvl <= log2cap; ++lvl) {
+    const int cur = lvl & 1, prev = cur ^ 1;
+    const int64_t lo = (cap + start) >> lvl, hi = (cap + start + n - 1) >> lvl;
+    const int64_t plo = (cap + start) >> (lvl - 1), phi = (cap + start + n - 1) >> (lvl - 1);
+    for (int64_t j = t; j <= hi - lo; j += TREE_THREADS) {
+      const int64_t node = lo + j, l = 2 * node, r = 2 * node + 1;
+      const float ls = l >= plo ? vs[prev][l - plo] : old_s[0][lvl], lm = l >= plo ? vm[prev][l - plo] : old_m[0][lvl];
+      const float rs = r <= phi ? vs[prev][r - plo] : old_s[1][lvl], rm = r <= phi ? vm[prev][r - plo] : old_m[1][lvl];
+      const float s2 = __fadd_rn(ls, rs), m2 = fminf(lm, rm);
+      vs[cur][j] = s2; vm[cur][j] = m2;
+      sum[node] = s2; mn[node] = m2;
+    }
+    __syncthreads();
+  }
+}
+
 // bulk path for large adds: grid-wide leaf fill, then one launch per level
 __global__ void leaf_fill_kernel(float* sum, float* mn, int64_t cap, int64_t size, int64_t ring_start,
                                  int64_t n, const ReplayState* state, float alpha_f32) {
@@ -405,12 +446,18 @@ extern "C" int32_t d4pg_replay_add(d4pg_replay_t* h, int64_t n, const float* obs
     if (n <= 65536) {
       // split a wrapping add into its two contiguous pieces
       const int64_t n1 = std::min<int64_t>(n, h->size - start);
-      tree_add_range_kernel<<<1, TREE_THREADS, 0, st>>>(h->sum, h->mn, h->cap, h->log2cap, start, n1,
-                                                        reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);
+      auto add_range = [&](int64_t s0, int64_t cnt) {
+        if (cnt <= TREE_ADD_FAST_MAX && h->log2cap < 32)
+          tree_add_range_fast_kernel<<<1, TREE_THREADS, 0, st>>>(h->sum, h->mn, h->cap, h->log2cap, s0, cnt,
+                                                                 reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);
+        else
+          tree_add_range_kernel<<<1, TREE_THREADS, 0, st>>>(h->sum, h->mn, h->cap, h->log2cap, s0, cnt,
+                                                            reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);
+      };
+      add_range(start, n1);
       D4PG_LAUNCH_OK();
       if (n1 < n) {
-        tree_add_range_kernel<<<1, TREE_THREADS, 0, st>>>(h->sum, h->mn, h->cap, h->log2cap, 0, n - n1,
-                                                          reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);
+        add_range(0, n - n1);
         D4PG_LAUNCH_OK();
       }
     } else {

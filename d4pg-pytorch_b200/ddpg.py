@@ -112,6 +112,7 @@ class _Learner(object):
         self.handle = h
         self.global_model = g
         self.stream = torch.cuda.Stream(device=dev)      # graph capture needs a non-default stream
+        self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
         self.step_host = L.d4pg_learner_step_host
         self.read_losses = L.d4pg_learner_read_losses
@@ -324,7 +325,7 @@ class DDPG:
                 pos_ptr = L.pos_ptr
         # one library call: order after the caller's stream, H2D of this step's host inputs, the step's
         # CUDA graph on the learner stream, order the caller's stream after it
-        rc = L.step_host(L.handle, u_ptr, pos_ptr, torch.cuda.current_stream().cuda_stream, L.stream_ptr)
+        rc = L.step_host(L.handle, u_ptr, pos_ptr, _lib.raw_stream(L.dev_index), L.stream_ptr)
         if rc:
             _lib.check(rc, "d4pg_learner_step_host")
         if self.prioritized_replay:

@@ -136,6 +136,22 @@ class _DeviceReplay(object):
         """Fast ingest of n <= STAGE_ROWS host transitions through ONE library call
         (`d4pg_replay_add_host`): packed into a pinned staging buffer, one async H2D copy, ring +
         tree kernels."""
+        if (torch.is_tensor(s) and self.handle is not None and getattr(self, "_pack_host", None) is not None
+                and s.dtype == torch.float32 and s.dim() == 2 and 0 < s.shape[0] <= min(self.STAGE_ROWS, self.size)
+                and not self._n_staged and torch.is_tensor(a) and torch.is_tensor(r) and torch.is_tensor(s2)
+                and torch.is_tensor(done) and a.dtype == torch.float32 and r.dtype == torch.float64
+                and s2.dtype == torch.float32 and done.dtype in (torch.bool, torch.uint8)
+                and s.is_contiguous() and a.is_contiguous() and r.is_contiguous() and s2.is_contiguous()
+                and done.is_contiguous()):
+            # host tensors of the right types (e.g. slices of a pinned rollout buffer): no numpy round trip
+            n = s.shape[0]
+            rc = _lib.lib().d4pg_replay_add_host(self.handle, n, s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr(),
+                                                 done.data_ptr(), 1 if self.prioritized else 0, _lib.raw_stream())
+            if rc:
+                _lib.check(rc, "d4pg_replay_add_host")
+            self._next_idx = (self._next_idx + n) % self.size
+            self._len = min(self.size, self._len + n)
+            return
         s = np.ascontiguousarray(s, dtype=np.float32)
         n = s.shape[0] if s.ndim == 2 else 1
         a = np.ascontiguousarray(a, dtype=np.float32)
@@ -158,7 +174,7 @@ class _DeviceReplay(object):
         if d.dtype != np.uint8:
             d = d.astype(np.uint8)
         rc = L.d4pg_replay_add_host(self.handle, n, s.ctypes.data, a.ctypes.data, r.ctypes.data, s2.ctypes.data,
-                                    d.ctypes.data, 1 if self.prioritized else 0, torch.cuda.current_stream().cuda_stream)
+                                    d.ctypes.data, 1 if self.prioritized else 0, _lib.raw_stream())
         if rc:
             _lib.check(rc, "d4pg_replay_add_host")
         self._next_idx = (self._next_idx + n) % self.size
