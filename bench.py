@@ -319,8 +319,8 @@ def gpu_main(args):
                 "config": {"workload": args.config, "batch_per_gpu": B, "global_batch": B * world, "obs_dim": cfg["obs"],
                            "act_dim": cfg["act"], "n_atoms": cfg["atoms"], "replay_capacity_per_gpu": cap,
                            "parallelism": "dp%d" % world,
-                           "step_plan": ({2: "row-owner chains", 1: "cluster chains", 0: "levels"}[args.chain] if (args.precision == "fp32" and not args.persistent) else ("persistent" if args.persistent else "levels")),
-                           "precision": {"fp32": "fp32 FFMA", "tf32x3": "3xTF32 tcgen05 (fp32-accurate)", "tf32": "TF32 tcgen05"}[args.precision],
+                           "step_plan": ("persistent" if args.persistent else {2: "row-owner chains" if args.precision == "fp32" else "levels", 1: "cluster chains", 0: "levels"}[args.chain]),
+                           "precision": {"fp32": "fp32 FFMA", "tf32x3": "3xTF32 tensor cores (fp32-accurate; mma.sync chain tiles with --chain 1, tcgen05 per level with --chain 0)", "tf32": "TF32 tensor cores"}[args.precision],
                            "l2": "inputs larger than L2: replay store %.0f MB + trees %.0f MB per GPU, rows sampled at "
                                  "random; parameters (%.1f MB) are L2-resident by design" % (
                                      cap * ((2 * cfg["obs"] + cfg["act"]) * 4 + 9) / 1e6, 16 * cap / 1e6 * 1.05, alg["P"] * 16 / 1e6)},

@@ -226,7 +226,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     //   Q: critic(s, a)                                   ddpg.py:208
     //   P: actor(s) -> critic(s, actor(s))                ddpg.py:236-238 (fc1 of the critic is recomputed: K=|s|)
     ChainArgs& ca = L->chain_fwd_args;
-    chain_args_begin(ca, B, w.xchg);
+    chain_args_begin(ca, B, w.xchg, c.precision);
     ChainSlot sl; int at3, ct1, q1, a3, c1;
     sl = chain_fwd(Wat + da.w_off[0], la[0], Wat + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[0], H, 1); chain_src_global(sl, w.s2, Sp); int t = chain_add(ca, 0, sl);
     sl = chain_fwd(Wat + da.w_off[1], la[1], Wat + da.b_off[1], H, H, EPI_BIAS, w.h2[0], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 0, sl);
@@ -363,7 +363,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     //   P: policy loss  dlogits_pi -> fc3 -> fc2_2 -> fc2[:, H:] (d action, tanh') ->
     //                   actor fc3 -> fc2_2 -> fc2   (PRE-update critic weights)  ddpg.py:242
     ChainArgs& cb = L->chain_bwd_args;
-    chain_args_begin(cb, B, w.xchg); cb.trace_base = 6 * CHAIN_MAX_SLOTS;
+    chain_args_begin(cb, B, w.xchg, c.precision); cb.trace_base = 6 * CHAIN_MAX_SLOTS;
     ChainSlot sl; int t;
     sl = chain_dx(Wc + dc.w_off[3], lc[3], H, N, EPI_RELU_MASK, w.h3[2], H, w.c_dz22, H, 1); chain_src_global(sl, w.dlogits_q, Np); t = chain_add(cb, 0, sl);
     sl = chain_dx(Wc + dc.w_off[2], lc[2], H, H, EPI_RELU_MASK, w.h2[2], H, w.c_dz2, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 0, sl);
@@ -479,8 +479,8 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   D4PG_REQUIRE(!cfg->persistent || (cfg->precision == 0 && cfg->world_size <= 1), D4PG_ENOTSUP,
                "d4pg_learner_create: the persistent step kernel needs precision 0 and a single GPU");
   D4PG_REQUIRE(cfg->chain >= 0 && cfg->chain <= 2, D4PG_EINVAL, "d4pg_learner_create: chain must be 0, 1 or 2");
-  D4PG_REQUIRE(!cfg->chain || (cfg->precision == 0 && !cfg->persistent), D4PG_ENOTSUP,
-               "d4pg_learner_create: the fused chain kernels need precision 0 and persistent 0");
+  D4PG_REQUIRE(!cfg->chain || !cfg->persistent, D4PG_ENOTSUP, "d4pg_learner_create: the fused chain kernels exclude persistent");
+  D4PG_REQUIRE(cfg->chain != 2 || cfg->precision == 0, D4PG_ENOTSUP, "d4pg_learner_create: the row-owner chains are fp32 only");
   D4PG_REQUIRE(buf->actor && buf->actor_target && buf->critic && buf->critic_target && buf->grad_actor && buf->grad_critic &&
                buf->adam_m_actor && buf->adam_v_actor && buf->adam_m_critic && buf->adam_v_critic &&
                buf->idx && buf->prio && buf->td && buf->losses && buf->workspace, D4PG_EINVAL,

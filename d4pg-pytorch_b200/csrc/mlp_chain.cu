@@ -42,6 +42,10 @@ __device__ __forceinline__ unsigned cluster_ctarank() {
 __host__ __device__ static inline int chain_wpitch(int K) { return ((((K + 3) & ~3) + 31) & ~31) + 4; }
 
 // A rows [kbase, kbase+kn) from a row-major global array (transposing, through registers)
+// Tensor-core path: the 32 rows (columns) of k-row k are XOR-permuted in groups of 8 by (k & 3) so that the MMA
+// fragment loads -- 4 consecutive k for 8 rows -- hit 32 different banks with the dense 32-float pitch.
+__device__ __forceinline__ int mma_swz(int k) { return (k & 3) << 3; }
+template <bool SWZ>
 __device__ __forceinline__ void fill_from_rows(float* As, int kbase, const float* __restrict__ src, int ld, int m0, int B,
                                                int kn, int tid) {
   const int nq = (kn + 3) >> 2;
@@ -52,14 +56,19 @@ __device__ __forceinline__ void fill_from_rows(float* As, int kbase, const float
     const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      if (k + c < kn) As[(kbase + k + c) * CHAIN_ROWS + row] = x[c];
+      if (k + c < kn) { const int kk = kbase + k + c; As[kk * CHAIN_ROWS + (SWZ ? (row ^ mma_swz(kk)) : row)] = x[c]; }
   }
 }
 // A rows [kbase, kbase+kn) from a k-major exchange plane written earlier in this launch by the cluster
+template <bool SWZ>
 __device__ __forceinline__ void fill_from_plane(float* As, int kbase, const float* plane, int kn, int tid) {
-  for (int e = tid; e < kn * 8; e += GEMM_THREADS) cp_async16(As + kbase * CHAIN_ROWS + e * 4, plane + e * 4);
+  for (int e = tid; e < kn * 8; e += GEMM_THREADS) {
+    const int kk = kbase + (e >> 3), c4 = (e & 7) * 4;
+    cp_async16(As + kk * CHAIN_ROWS + (SWZ ? (c4 ^ mma_swz(kk)) : c4), plane + e * 4);
+  }
 }
 // the CTA's 32-column weight slice of one slot, all of K at once
+template <bool SWZ>
 __device__ __forceinline__ void fetch_weights(float* Ws, const ChainSlot& S, int n0, int tid) {
   const int K = S.K, N = S.N, ldw = S.ldw;
   const float* __restrict__ W = S.W;
@@ -74,13 +83,117 @@ __device__ __forceinline__ void fetch_weights(float* Ws, const ChainSlot& S, int
   } else {                                       // rows k = 0..K-1 of W[K][ldw], columns n0..n0+31
     for (int e = tid; e < K * 8; e += GEMM_THREADS) {
       const int k = e >> 3, c4 = (e & 7) << 2;
-      if (n0 + c4 < N) cp_async16(Ws + k * BN + c4, W + size_t(k) * ldw + n0 + c4);
+      if (n0 + c4 < N) cp_async16(Ws + k * BN + (SWZ ? (c4 ^ mma_swz(k)) : c4), W + size_t(k) * ldw + n0 + c4);
     }
   }
 }
 
 // One 32x32 tile of one slot with A and W resident for the whole K.  The order of the additions is
 // gemm_tile's: within every 64-deep chunk warp w owns k = 8w..8w+7, partial tiles are summed w = 0..7.
+// ---- tensor-core variant of the tile (PREC 1 = 3xTF32, fp32-accurate; PREC 2 = one TF32 pass) --------------------
+// mma.sync.m16n8k8 (the warp-level MMA that exists for a 32-row tile; tcgen05 tiles start at 64-128 rows).  On sm_100a
+// it issues every 8.1 cycles per sub-partition (tests/probe/dsmem_probe.cu): 4x the FFMA rate, and the operand
+// fragments cost 16 LDS.32 per 8-deep k-step instead of 96 LDS wavefronts for the FFMA lane tiles.
+// 3xTF32: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  D += Al*Bh + Ah*Bl + Ah*Bh  (~2^-21 relative).
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+constexpr int CHAIN_RED_PITCH = 36;   // partial-tile pitch of the tensor-core path
+
+template <int MODE, int PREC>
+__device__ __forceinline__ void chain_tile_mma(const ChainSlot& S, float* As, const float* Ws, int m0, int n0, int B, float* xout,
+                                               const float (&eop)[4], unsigned long long* tr) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int N = S.N, K = S.K;
+  const int P = chain_wpitch(K);
+  float acc[2][4][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][nn][i] = 0.f;
+  const int nks = (K + 7) >> 3;
+  for (int ks = warp; ks < nks; ks += GEMM_WARPS) {           // the 8 warps interleave the 8-deep k-steps
+    const int ka = ks * 8 + t4, kb = ka + 4;
+    const bool va = ka < K, vb = kb < K;                     // operands past K are zero (rows of As / Ws there are stale)
+    const int sw = t4 << 3;
+    uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int r0 = (m * 16 + g) ^ sw, r1 = (m * 16 + g + 8) ^ sw;      // ka & 3 == kb & 3 == t4
+      const float x0 = va ? As[ka * CHAIN_ROWS + r0] : 0.f, x1 = va ? As[ka * CHAIN_ROWS + r1] : 0.f;
+      const float x2 = vb ? As[kb * CHAIN_ROWS + r0] : 0.f, x3 = vb ? As[kb * CHAIN_ROWS + r1] : 0.f;
+      tf32_split(x0, ah[m][0], al[m][0]); tf32_split(x1, ah[m][1], al[m][1]);
+      tf32_split(x2, ah[m][2], al[m][2]); tf32_split(x3, ah[m][3], al[m][3]);
+    }
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      float y0, y1;
+      if (MODE == GEMM_FWD) { y0 = va ? Ws[(nn * 8 + g) * P + ka] : 0.f; y1 = vb ? Ws[(nn * 8 + g) * P + kb] : 0.f; }
+      else { y0 = va ? Ws[ka * BN + ((nn * 8 + g) ^ sw)] : 0.f; y1 = vb ? Ws[kb * BN + ((nn * 8 + g) ^ sw)] : 0.f; }
+      tf32_split(y0, bh[nn][0], bl[nn][0]); tf32_split(y1, bh[nn][1], bl[nn][1]);
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) {
+        if (PREC == 1) { mma_tf32(acc[m][nn], al[m], bh[nn]); mma_tf32(acc[m][nn], ah[m], bl[nn]); }
+        mma_tf32(acc[m][nn], ah[m], bh[nn]);
+      }
+  }
+  __syncthreads();                                            // every warp is done with the A plane: reuse it
+  if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[3] = t; }
+  float* red = As;                                            // [8 warps][32 rows][CHAIN_RED_PITCH]
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      float* q = red + (warp * BM + m * 16 + g) * CHAIN_RED_PITCH + nn * 8 + 2 * t4;
+      *reinterpret_cast<float2*>(q) = make_float2(acc[m][nn][0], acc[m][nn][1]);
+      *reinterpret_cast<float2*>(q + 8 * CHAIN_RED_PITCH) = make_float2(acc[m][nn][2], acc[m][nn][3]);
+    }
+  __syncthreads();
+  const int orow = tid >> 3, ocol = (tid & 7) * 4;
+  float4 sum = *reinterpret_cast<const float4*>(&red[orow * CHAIN_RED_PITCH + ocol]);
+#pragma unroll
+  for (int w = 1; w < GEMM_WARPS; ++w) {
+    const float4 t = *reinterpret_cast<const float4*>(&red[(w * BM + orow) * CHAIN_RED_PITCH + ocol]);
+    sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+  }
+  const int gi = m0 + orow;
+  const float v[4] = {sum.x, sum.y, sum.z, sum.w};
+  const int epi = S.epi;
+  float* __restrict__ C = S.C; const int ldc = S.ldc;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int gj = n0 + ocol + cc;
+    if (gj >= N) continue;
+    float x = v[cc];
+    if (gi < B) {
+      const float e = eop[cc];
+      switch (epi) {
+        case EPI_BIAS: x += e; break;
+        case EPI_BIAS_RELU: x = fmaxf(x + e, 0.f); break;
+        case EPI_BIAS_TANH: x = tanhf(x + e); break;
+        case EPI_RELU_MASK: x = (e > 0.f) ? x : 0.f; break;
+        case EPI_TANH_MASK: x *= (1.f - e * e); break;
+        default: break;
+      }
+      if (C) C[size_t(gi) * ldc + gj] = x;
+    } else x = 0.f;
+    if (xout) xout[gj * CHAIN_ROWS + orow] = x;
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void chain_tile(const ChainSlot& S, float* As, const float* Ws, int m0, int n0, int B, float* xout,
                                            const float (&eop)[4], unsigned long long* tr) {
@@ -180,8 +293,10 @@ __device__ __forceinline__ void chain_tile(const ChainSlot& S, float* As, const 
   }
 }
 
+template <int PREC>
 __global__ void __cluster_dims__(CHAIN_CLUSTER, 1, 1) __launch_bounds__(GEMM_THREADS, 2)
 mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
+  constexpr bool SWZ = PREC != 0;                            // tensor-core path: XOR-permuted A plane / dX weight rows
   extern __shared__ __align__(16) float chain_smem[];
   float* As = chain_smem;                              // [ka][32] resident A plane / reduce buffer
   float* W0 = chain_smem + args.a_floats;              // two weight-slice buffers (slot l uses buffer l & 1)
@@ -195,7 +310,7 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
   float* planes = args.xchg + (size_t(chain) * args.row_blocks + rb_i) * (size_t(CHAIN_MAX_SLOTS) * CHAIN_PLANE);
   const int n0 = rank * BN;
 
-  if (n0 < args.slot[chain][0].N) fetch_weights(W0, args.slot[chain][0], n0, tid);
+  if (n0 < args.slot[chain][0].N) fetch_weights<SWZ>(W0, args.slot[chain][0], n0, tid);
   cp_async_commit();
   unsigned long long* tr0 = (args.trace && int(blockIdx.x) == args.trace_cta && tid == 0) ? args.trace : nullptr;
   const long long clk0 = clock64();
@@ -211,7 +326,7 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
       const int gi = m0 + (tid >> 3);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        const int gj = n0 + (S.mode == GEMM_FWD ? (tid & 7) + 8 * cc : (tid & 7) * 4 + cc);
+        const int gj = n0 + ((S.mode == GEMM_FWD && PREC == 0) ? (tid & 7) + 8 * cc : (tid & 7) * 4 + cc);
         if (gj < S.N && gi < B) eop[cc] = (S.mode == GEMM_FWD) ? __ldg(S.bias + gj) : __ldg(S.aux + size_t(gi) * S.ldaux + gj);
       }
     }
@@ -219,24 +334,29 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
     CTRACE(1);
     if (has_tile) {
       const int K = S.K, K1 = S.K1;
-      if (S.src >= 0) fill_from_plane(As, 0, planes + size_t(S.src) * CHAIN_PLANE, K1, tid);
-      else fill_from_rows(As, 0, S.Ag, S.ldag, m0, B, K1, tid);
+      if (S.src >= 0) fill_from_plane<SWZ>(As, 0, planes + size_t(S.src) * CHAIN_PLANE, K1, tid);
+      else fill_from_rows<SWZ>(As, 0, S.Ag, S.ldag, m0, B, K1, tid);
       if (K > K1) {
-        if (S.src2 >= 0) fill_from_plane(As, K1, planes + size_t(S.src2) * CHAIN_PLANE, K - K1, tid);
-        else fill_from_rows(As, K1, S.A2g, S.lda2g, m0, B, K - K1, tid);
+        if (S.src2 >= 0) fill_from_plane<SWZ>(As, K1, planes + size_t(S.src2) * CHAIN_PLANE, K - K1, tid);
+        else fill_from_rows<SWZ>(As, K1, S.A2g, S.lda2g, m0, B, K - K1, tid);
       }
     }
     cp_async_commit();
     // the next layer's weights do not depend on this layer: they travel while it computes
-    if (l + 1 < ns && n0 < args.slot[chain][l + 1].N) fetch_weights(W0 + ((l + 1) & 1) * wf, args.slot[chain][l + 1], n0, tid);
+    if (l + 1 < ns && n0 < args.slot[chain][l + 1].N) fetch_weights<SWZ>(W0 + ((l + 1) & 1) * wf, args.slot[chain][l + 1], n0, tid);
     cp_async_commit();
     cp_async_wait<1>();                               // everything but the prefetch has landed
     __syncthreads();
     CTRACE(2);
     if (has_tile) {
       float* xout = S.publish ? planes + size_t(l) * CHAIN_PLANE : nullptr;
-      if (S.mode == GEMM_FWD) chain_tile<GEMM_FWD>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
-      else chain_tile<GEMM_DX>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
+      if (PREC == 0) {
+        if (S.mode == GEMM_FWD) chain_tile<GEMM_FWD>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
+        else chain_tile<GEMM_DX>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
+      } else {
+        if (S.mode == GEMM_FWD) chain_tile_mma<GEMM_FWD, PREC>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
+        else chain_tile_mma<GEMM_DX, PREC>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
+      }
     }
     CTRACE(4);
     if (l + 1 < ns) cluster_arrive();
@@ -253,10 +373,11 @@ static unsigned long long* chain_trace_buffer() { return debug_trace_buffer(); }
 int64_t chain_xchg_floats(int B) {
   return int64_t(CHAIN_MAX) * cdiv(B, CHAIN_ROWS) * CHAIN_MAX_SLOTS * CHAIN_PLANE;
 }
-void chain_args_begin(ChainArgs& a, int B, float* xchg) {
+void chain_args_begin(ChainArgs& a, int B, float* xchg, int precision) {
   a = ChainArgs{};
-  a.B = B; a.row_blocks = cdiv(B, CHAIN_ROWS); a.xchg = xchg;
-  a.a_floats = GEMM_WARPS * BM * BN;                 // the A plane doubles as the 8-warp reduce buffer
+  a.B = B; a.row_blocks = cdiv(B, CHAIN_ROWS); a.xchg = xchg; a.precision = precision;
+  // the A plane doubles as the 8-warp reduce buffer
+  a.a_floats = precision ? GEMM_WARPS * BM * CHAIN_RED_PITCH : GEMM_WARPS * BM * BN;
   a.w_floats = 0;
 }
 int chain_add(ChainArgs& a, int c, const ChainSlot& s) {
@@ -307,12 +428,14 @@ int launch_mlp_chain(ChainArgs& a, cudaStream_t st) {
   // GPC; a single foreign CTA (the concurrent tree update) pushes clusters into a second wave (measured: the dX
   // launch took 38 us while every chain in it finished within 25 us).
   D4PG_REQUIRE(smem <= 220 * 1024, D4PG_ENOTSUP, "launch_mlp_chain: %zu B of shared memory needed", smem);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    D4PG_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    smem_set = smem;
+  D4PG_REQUIRE(a.precision >= 0 && a.precision <= 2, D4PG_EINVAL, "launch_mlp_chain: precision %d", a.precision);
+  static size_t smem_set[3] = {0, 0, 0};
+  void (*kern)(ChainArgs) = a.precision == 0 ? mlp_chain_kernel<0> : a.precision == 1 ? mlp_chain_kernel<1> : mlp_chain_kernel<2>;
+  if (smem > smem_set[a.precision]) {
+    D4PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    D4PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared)));
+    smem_set[a.precision] = smem;
   }
-  D4PG_MAX_CARVEOUT(mlp_chain_kernel);
   a.trace = chain_trace_buffer() ? chain_trace_buffer() + a.trace_base : nullptr;
   a.step_trace = chain_trace_buffer() ? chain_trace_buffer() + STEP_TRACE_BASE : nullptr;
   a.step_slot = a.trace_base ? 5 : 1;
@@ -321,7 +444,7 @@ int launch_mlp_chain(ChainArgs& a, cudaStream_t st) {
   cfg.gridDim = dim3(a.nchains * a.row_blocks * CHAIN_CLUSTER); cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cfg.attrs = nullptr; cfg.numAttrs = 0;              // cluster shape is compiled in (__cluster_dims__)
-  D4PG_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_chain_kernel, a));
+  D4PG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
   return D4PG_OK;
 }
 

@@ -30,6 +30,7 @@ struct ChainArgs {
   ChainSlot slot[CHAIN_MAX][CHAIN_MAX_SLOTS];
   int nslots[CHAIN_MAX];
   int nchains, B, row_blocks;
+  int precision;                  // 0 exact fp32 FFMA tile, 1 3xTF32 / 2 TF32 mma.sync tile
   int a_floats, w_floats;         // shared memory: resident A plane, one weight-slice buffer (two are kept)
   float* xchg;                    // [nchains][row_blocks][CHAIN_MAX_SLOTS][CHAIN_PLANE]
   unsigned long long* trace;      // optional phase stamps of CTA 0 (D4PG_TC_TRACE), 6 per slot
@@ -39,7 +40,7 @@ struct ChainArgs {
 };
 
 int64_t chain_xchg_floats(int B);
-void chain_args_begin(ChainArgs& a, int B, float* xchg);
+void chain_args_begin(ChainArgs& a, int B, float* xchg, int precision = 0);   // 0 fp32 FFMA, 1 3xTF32 mma.sync, 2 TF32 mma.sync
 // add a slot to chain `c`; returns its slot index
 int chain_add(ChainArgs& a, int c, const ChainSlot& s);
 ChainSlot chain_fwd(const float* W, int ldw, const float* bias, int N, int K, int epi, float* C, int ldc, int publish);

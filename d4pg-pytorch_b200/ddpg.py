@@ -73,7 +73,9 @@ class _Learner(object):
         cfg.loss_flags = (1 if ddpg.importance_weighted else 0) | (2 if ddpg.priority == "ce" else 0)
         cfg.persistent = 1 if (ddpg.persistent and ddpg.precision == "fp32" and cfg.world_size == 1) else 0
         plan = {"levels": 0, "cluster": 1, "rows": 2, False: 0, True: 1, 0: 0, 1: 1, 2: 2}[ddpg.chain]
-        cfg.chain = plan if (ddpg.precision == "fp32" and not cfg.persistent) else 0
+        if cfg.persistent or (plan == 2 and ddpg.precision != "fp32"):
+            plan = 0
+        cfg.chain = plan                    # tf32x3 / tf32: plan 1 = mma.sync chain tiles, plan 0 = tcgen05 per level
         cfg.prefetch = 1 if (ddpg.prefetch and cfg.sample_mode == 1 and not cfg.persistent) else 0
         self.cfg = cfg
         nws = L.d4pg_learner_workspace_floats(C.byref(cfg))

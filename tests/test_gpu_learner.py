@@ -38,16 +38,18 @@ def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", persisten
 
 
 @pytest.mark.parametrize("tag", ["per_c2", "per_part", "uniform_c1"])
-@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "rows"), (True, "levels"), (True, "tf32x3"), (True, "mega"), (False, "mega")])
+@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "rows"), (True, "levels"), (True, "mma_tf32x3"), (False, "mma_tf32x3"), (True, "tf32x3"),
+                          (True, "mega"), (False, "mega")])
 def test_train_steps_vs_reference_golden(tag, use_graph, precision):
     """precision fp32 = exact-FFMA kernels as cluster-fused layer chains (the default step plan); rows = the
-    row-owner chains (TMA-multicast weight stream); levels = one grouped launch per dependency level; tf32x3 = tcgen05 tensor cores
+    row-owner chains (TMA-multicast weight stream); levels = one grouped launch per dependency level; mma_tf32x3 =
+    the cluster chains with the mma.sync 3xTF32 tile (tensor cores, fp32-accurate); tf32x3 = tcgen05 tensor cores
     with the 3xTF32 split.  All must meet the same 1e-5 bar against the reference's fp32 CPU results."""
     import d4pg_b200 as d4pg
     g = H.load("train_%s.npz" % tag)
     persistent = precision == "mega"          # fp32 kernels as phases of ONE cooperative kernel per step
-    chain = {"fp32": "cluster", "rows": "rows"}.get(precision, "levels")
-    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision="fp32" if precision in ("mega", "levels", "rows") else precision,
+    chain = {"fp32": "cluster", "rows": "rows", "mma_tf32x3": "cluster"}.get(precision, "levels")
+    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision="fp32" if precision in ("mega", "levels", "rows") else ("tf32x3" if precision == "mma_tf32x3" else precision),
                                      persistent=persistent, chain=chain)
     obs_dim, act_dim, N, B, mem, n_fill, per, steps, v_min, v_max = meta
     for t in range(steps):
