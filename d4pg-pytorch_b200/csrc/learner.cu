@@ -116,8 +116,10 @@ struct d4pg_learner {
 };
 
 // step plan: 0 = one grouped launch per dependency level, 1 = cluster-fused chains (mlp_chain.cu),
-// 2 = row-owner chains (mlp_rows.cu; batches up to 512 rows, larger ones use plan 1)
-static int step_plan(const d4pg_learner_config_t& c) { return (c.chain == 2 && c.batch > 512) ? 1 : c.chain; }
+// 2 = row-owner chains (mlp_rows.cu).  The chain plans pay off while the batch fits one wave of clusters: measured
+// on B200, batch 1024 (config 3) 409 us with chains vs 320 us per level, batch 4096 (config 5) 906 vs 733 us
+// (tcgen05 levels), so batches above 512 rows always run plan 0.
+static int step_plan(const d4pg_learner_config_t& c) { return c.batch > 512 ? 0 : c.chain; }
 // prefetch pipeline: batch t+1 is sampled on a side branch of step t (device-side sampling only)
 static bool prefetching(const d4pg_learner_config_t& c) { return c.prefetch != 0 && c.sample_mode == 1 && !c.persistent; }
 

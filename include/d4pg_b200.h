@@ -216,7 +216,7 @@ typedef struct {
                                  1 = importance-weighted critic CE (the reference samples the weights but
                                      ignores them, ddpg.py:217), 2 = priority = CE_i + eps instead of
                                      |sum_j m_ij q_ij| + eps (ddpg.py:221-222,253) */
-  int32_t chain;              /* step plan of the MLP passes (precision 0 only): 0 = one grouped launch per dependency
+  int32_t chain;              /* step plan of the MLP passes (batches above 512 rows always use plan 0): 0 = one grouped launch per dependency
                                  level (18 kernels/step); 1 = cluster-fused layer chains: forward passes, dX passes
                                  and all dW are ONE launch each (7 kernels/step, bit-identical to 0); 2 = row-owner
                                  chains: a CTA carries a few batch rows through a whole chain, weights streamed
