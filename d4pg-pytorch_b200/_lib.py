@@ -109,6 +109,9 @@ _PROTOS = {
     "d4pg_comm_unique_id": (C.c_int32, [_P]),
     "d4pg_comm_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "d4pg_comm_destroy": (C.c_int32, [_P]),
+    "d4pg_comm_peer_alloc": (C.c_int32, [_P, C.c_int64, _P]),
+    "d4pg_comm_peer_open": (C.c_int32, [_P, _P]),
+    "d4pg_comm_peer_ready": (C.c_int32, [_P]),
     "d4pg_comm_allreduce_sum": (C.c_int32, [_P, _P, C.c_int64, _P]),
 }
 EXPORTED_SYMBOLS = sorted(_PROTOS)

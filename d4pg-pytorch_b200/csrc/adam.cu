@@ -57,11 +57,11 @@ extern "C" int32_t d4pg_adam_polyak(float* p, const float* g, float* m, float* v
   AdamArgs a{};
   const double bc1 = 1.0 - pow(beta1, double(step));
   const double bc2 = 1.0 - pow(beta2, double(step));
-  a.seg[0] = AdamSeg{p, g, m, v, target, n, float(-(lr / bc1)), -1};
+  a.seg[0] = AdamSeg{p, g, m, v, target, n, nullptr, 0, float(-(lr / bc1)), -1};
   a.nseg = 1;
   a.w1 = float(1.0 - beta1); a.w2 = float(1.0 - beta2); a.beta2 = float(beta2); a.eps = float(eps);
   a.bc2_sqrt = float(sqrt(bc2)); a.tau = float(tau); a.one_minus_tau = float(1.0 - tau);
-  a.grad_scale = grad_scale; a.clock = nullptr; a.loss_out = nullptr; a.pipe_slot = -1; a.trace = nullptr;
+  a.grad_scale = grad_scale; a.clock = nullptr; a.loss_out = nullptr; a.pipe_slot = -1; a.trace = nullptr; a.npeers = 0; a.my_flags = nullptr;
   return launch_adam(a, as_stream(stream));
 }
 

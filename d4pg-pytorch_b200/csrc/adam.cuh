@@ -54,8 +54,12 @@ __device__ __forceinline__ float clock_beta(const LearnerClock* c, const ClockPa
   return float(a.per_beta0 + frac * (a.per_beta_final - a.per_beta0));
 }
 
+constexpr int D4PG_MAX_PEERS = 8;
+struct PeerInfo { int world, rank; int64_t n; float* x[D4PG_MAX_PEERS]; unsigned long long* flag[D4PG_MAX_PEERS]; };
+
 struct AdamSeg {
   float* p; const float* g; float* m; float* v; float* target; int64_t n;
+  float* g_out; int64_t g_off;                 // peer mode: the summed gradient is also stored here; offset in the exchange half
   float neg_step_size; int clock_slot;        // clock_slot >= 0: read -step_size from the device clock
 };
 struct AdamArgs {
@@ -63,6 +67,12 @@ struct AdamArgs {
   float w1, w2, beta2, eps, bc2_sqrt, tau, one_minus_tau, grad_scale;
   LearnerClock* clock;                        // optional (learner): scalars in, counters advanced
   unsigned long long* trace;
+  // fused all-reduce: g = sum over ranks r = 0..npeers-1 (fixed order: identical on every rank) of peer_g[r][g_off + i],
+  // read over NVLink from IPC-mapped peer memory; the ranks were synchronised by comm_peer_barrier
+  const float* peer_g[D4PG_MAX_PEERS]; int npeers;
+  // non-null: wait inside the kernel until every rank published step count >= this rank's local one
+  // (the signal came from the dW kernel's last CTA); null: a barrier launch already ordered the ranks
+  const unsigned long long* peer_wait[D4PG_MAX_PEERS]; const unsigned long long* my_flags; int rank;
   int pipe_slot;                              // >= 0: the step's scalars are in this slot of the clock (prefetch pipeline)
   // fused tail (learner): deterministic batch means of the per-row losses -> out[0], out[1]
   const float* loss_rows; const float* pi_rows; int B; float inv_count; float* loss_out;

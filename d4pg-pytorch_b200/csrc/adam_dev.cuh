@@ -46,8 +46,32 @@ __device__ __forceinline__ void adam_segment(const AdamArgs& a, int seg, int bx,
   float4* m4 = reinterpret_cast<float4*>(s.m);
   float4* v4 = reinterpret_cast<float4*>(s.v);
   float4* t4 = reinterpret_cast<float4*>(s.target);
+  float4* go4 = reinterpret_cast<float4*>(s.g_out);
+  if (a.npeers > 0 && a.my_flags) {                       // every peer's gradient half of this step is complete
+    const int r = threadIdx.x;
+    if (r < a.npeers && r != a.rank) {
+      const unsigned long long target = __ldcg(a.my_flags + 1);
+      unsigned long long v;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.peer_wait[r]) : "memory");
+        if (v < target) __nanosleep(32);
+      } while (v < target);
+    }
+    __syncthreads();
+  }
   for (int64_t i = bx * int64_t(256) + threadIdx.x; i < n4; i += int64_t(gx) * 256) {
-    float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+    float4 g;
+    if (a.npeers > 0) {
+      g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < D4PG_MAX_PEERS; ++r)
+        if (r < a.npeers) {
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(a.peer_g[r] + s.g_off) + i);
+          g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+      if (go4) go4[i] = g;
+    } else g = g4[i];
+    float4 p = p4[i], m = m4[i], v = v4[i];
     float4 t = s.target ? t4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x; float* tt = &t.x;
 #pragma unroll

@@ -9,6 +9,9 @@
 #include <string.h>
 #include <new>
 
+using d4pg::D4PG_MAX_PEERS;
+using d4pg::PeerInfo;
+
 namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -59,9 +62,57 @@ int load_nccl() {
   } while (0)
 }  // namespace
 
-struct d4pg_comm { ncclComm_t comm; int rank, world; };
+struct d4pg_comm {
+  ncclComm_t comm; int rank, world;
+  // ---- fused all-reduce over peer memory (d4pg_comm_peer_*) ----------------------------------------------------
+  // One cudaMalloc block per rank, exported with CUDA IPC: [2][n] gradient halves (double buffer) + a flag line.
+  float* xbuf; int64_t xn; unsigned long long* flags;       // local block
+  void* peer_base[D4PG_MAX_PEERS];                          // opened IPC mappings (nullptr for self)
+  float* peer_x[D4PG_MAX_PEERS]; unsigned long long* peer_flag[D4PG_MAX_PEERS];
+  bool peer_ready;
+};
 
 namespace d4pg {
+// "my gradient half of this step is complete" + "wait until every peer's is": thread 0 bumps this rank's step
+// counter and publishes it (release, system scope); lane r polls rank r's counter over NVLink (acquire).
+// The counters only ever grow and every rank runs the same number of steps, so no reset is ever needed.
+__global__ void peer_barrier_kernel(unsigned long long* my_flags, PeerInfo info) {
+  __shared__ unsigned long long target;
+  if (threadIdx.x == 0) {
+    const unsigned long long t = my_flags[1] + 1ull;
+    my_flags[1] = t;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(my_flags), "l"(t) : "memory");
+    target = t;
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r < info.world && r != info.rank) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(info.flag[r]) : "memory");
+      if (v < target) __nanosleep(64);
+    } while (v < target);
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+bool comm_peer_info(d4pg_comm* c, PeerInfo* out) {
+  if (!c || !c->peer_ready) return false;
+  if (!out) return true;
+  out->world = c->world; out->rank = c->rank; out->n = c->xn;
+  for (int r = 0; r < c->world; ++r) { out->x[r] = c->peer_x[r]; out->flag[r] = c->peer_flag[r]; }
+  return true;
+}
+int comm_peer_barrier(d4pg_comm* c, cudaStream_t st) {
+  PeerInfo info{};
+  D4PG_REQUIRE(comm_peer_info(c, &info), D4PG_ESTATE, "comm_peer_barrier: peers are not open");
+  peer_barrier_kernel<<<1, 32, 0, st>>>(c->flags, info);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
 int comm_allreduce(d4pg_comm* c, float* buf, int64_t n, cudaStream_t st) {
   D4PG_REQUIRE(c && buf && n > 0, D4PG_EINVAL, "comm_allreduce: bad arguments");
   NCCL_OK(g_nccl.AllReduce(buf, buf, size_t(n), ncclFloat32, ncclSum, c->comm, st));
@@ -88,6 +139,8 @@ extern "C" int32_t d4pg_comm_create(const uint8_t* id128, int32_t rank, int32_t 
   d4pg_comm* c = new (std::nothrow) d4pg_comm();
   D4PG_REQUIRE(c, D4PG_EINVAL, "d4pg_comm_create: out of host memory");
   c->rank = rank; c->world = world;
+  c->xbuf = nullptr; c->xn = 0; c->flags = nullptr; c->peer_ready = false;
+  for (int i = 0; i < D4PG_MAX_PEERS; ++i) { c->peer_base[i] = nullptr; c->peer_x[i] = nullptr; c->peer_flag[i] = nullptr; }
   ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
   if (r != 0) {
     d4pg::set_error("ncclCommInitRank failed: %d (%s)", r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
@@ -100,6 +153,8 @@ extern "C" int32_t d4pg_comm_create(const uint8_t* id128, int32_t rank, int32_t 
 extern "C" int32_t d4pg_comm_destroy(d4pg_comm_t* c) {
   if (!c) return D4PG_OK;
   if (g_nccl.ok && c->comm) g_nccl.CommDestroy(c->comm);
+  for (int i = 0; i < D4PG_MAX_PEERS; ++i) if (c->peer_base[i]) cudaIpcCloseMemHandle(c->peer_base[i]);
+  if (c->xbuf) cudaFree(c->xbuf);
   delete c;
   return D4PG_OK;
 }
@@ -107,3 +162,38 @@ extern "C" int32_t d4pg_comm_destroy(d4pg_comm_t* c) {
 extern "C" int32_t d4pg_comm_allreduce_sum(d4pg_comm_t* c, float* buf, int64_t n, d4pg_stream_t stream) {
   return d4pg::comm_allreduce(c, buf, n, d4pg::as_stream(stream));
 }
+
+// ---- fused all-reduce over peer memory -------------------------------------------------------------------------
+extern "C" int32_t d4pg_comm_peer_alloc(d4pg_comm_t* c, int64_t n_floats, uint8_t* handle64) {
+  D4PG_REQUIRE(c && handle64 && n_floats > 0, D4PG_EINVAL, "d4pg_comm_peer_alloc: bad arguments");
+  D4PG_REQUIRE(c->world <= D4PG_MAX_PEERS, D4PG_ENOTSUP, "d4pg_comm_peer_alloc: at most %d ranks (one node)", D4PG_MAX_PEERS);
+  D4PG_REQUIRE(!c->xbuf, D4PG_ESTATE, "d4pg_comm_peer_alloc: already allocated");
+  const int64_t n = (n_floats + 31) & ~int64_t(31);
+  const size_t bytes = size_t(2 * n) * sizeof(float) + 256;
+  D4PG_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&c->xbuf), bytes));
+  D4PG_CUDA_OK(cudaMemset(c->xbuf, 0, bytes));
+  D4PG_CUDA_OK(cudaDeviceSynchronize());
+  c->xn = n; c->flags = reinterpret_cast<unsigned long long*>(c->xbuf + 2 * n);
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+  D4PG_CUDA_OK(cudaIpcGetMemHandle(&h, c->xbuf));
+  memcpy(handle64, &h, 64);
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_comm_peer_open(d4pg_comm_t* c, const uint8_t* all_handles) {
+  D4PG_REQUIRE(c && all_handles && c->xbuf, D4PG_ESTATE, "d4pg_comm_peer_open: call d4pg_comm_peer_alloc first");
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) { c->peer_x[r] = c->xbuf; c->peer_flag[r] = c->flags; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all_handles + size_t(r) * 64, 64);
+    void* base = nullptr;
+    D4PG_CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_base[r] = base;
+    c->peer_x[r] = static_cast<float*>(base);
+    c->peer_flag[r] = reinterpret_cast<unsigned long long*>(static_cast<float*>(base) + 2 * c->xn);
+  }
+  c->peer_ready = true;
+  return D4PG_OK;
+}
+extern "C" int32_t d4pg_comm_peer_ready(const d4pg_comm_t* c) { return (c && c->peer_ready) ? 1 : 0; }

@@ -35,5 +35,8 @@ int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* p
 int64_t replay_generation(const d4pg_replay* h);
 void trace_set_side_stream(cudaStream_t s);     // changes whenever the caller mutates the buffer
 int comm_allreduce(d4pg_comm* c, float* buf, int64_t n, cudaStream_t st);
+// fused all-reduce over IPC-mapped peer memory (comm.cu): x[r] = rank r's [2][n] gradient halves
+bool comm_peer_info(d4pg_comm* c, PeerInfo* out);
+int comm_peer_barrier(d4pg_comm* c, cudaStream_t st);
 
 }  // namespace d4pg

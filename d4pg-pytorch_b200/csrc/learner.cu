@@ -339,6 +339,12 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   }
 
   float* Ga = b.grad_actor; float* Gc = b.grad_critic;
+  // data parallel with IPC-mapped peers: this step's gradients go straight into this rank's half of the exchange
+  // buffer (double-buffered by step parity), the Adam kernel sums all ranks' halves over NVLink
+  PeerInfo peers{};
+  const bool peer_mode = c.world_size > 1 && comm_peer_info(L->comm, &peers);
+  const int gpar = pf ? par : int(L->steps_done & 1);
+  if (peer_mode) { Ga = peers.x[peers.rank] + int64_t(gpar) * peers.n; Gc = Ga + da.total; }
   if (B >= 1024 && !mega)                // dW levels run split-K with fp32 atomics: the gradient buffer must start at zero
     D4PG_CUDA_OK(cudaMemsetAsync(Ga, 0, size_t(da.total + dc.total) * sizeof(float), st));
   if (rows) {
@@ -381,7 +387,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   }
   if (chain || rows) {                    // every dW of the step as ONE grouped launch
     GemmWideBatch& gw = L->dw_batch;
-    gemm_wide_begin(gw);
+    gemm_wide_begin(gw, peer_mode ? peers.flag[peers.rank] : nullptr);   // its last CTA signals the peers
     gemm_wide_add(gw, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], lc[2], Gc + dc.b_off[2], H, H, B));
     gemm_wide_add(gw, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], lc[1], Gc + dc.b_off[1], H, H, B));
     gemm_wide_add(gw, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], la[2], Ga + da.b_off[2], H, H, B));
@@ -437,12 +443,24 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   }
 
   // 6. data-parallel gradient exchange: ONE all-reduce over the flat [P_a + P_c] buffer
-  if (c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
+  // every rank's half of this step must be complete before Adam sums them: the chain plans signal from the dW
+  // kernel and wait inside the Adam kernel; the level plan (several dW launches) uses a small barrier launch
+  const bool inline_sync = peer_mode && (chain || rows);
+  if (peer_mode && !inline_sync) RUN(comm_peer_barrier(L->comm, st));
+  else if (!peer_mode && c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
 
   // 7. Adam (actor + critic), sync (identity), Polyak -- one launch, two segments
   AdamArgs aa{};
-  aa.seg[0] = AdamSeg{b.actor, Ga, b.adam_m_actor, b.adam_v_actor, b.actor_target, da.total, 0.f, 0};
-  aa.seg[1] = AdamSeg{b.critic, Gc, b.adam_m_critic, b.adam_v_critic, b.critic_target, dc.total, 0.f, 1};
+  aa.seg[0] = AdamSeg{b.actor, Ga, b.adam_m_actor, b.adam_v_actor, b.actor_target, da.total, nullptr, 0, 0.f, 0};
+  aa.seg[1] = AdamSeg{b.critic, Gc, b.adam_m_critic, b.adam_v_critic, b.critic_target, dc.total, nullptr, 0, 0.f, 1};
+  if (peer_mode) {                                              // sum of the ranks' halves, also stored in the caller's buffer
+    aa.npeers = peers.world;
+    for (int r = 0; r < peers.world; ++r) aa.peer_g[r] = peers.x[r] + int64_t(gpar) * peers.n;
+    aa.seg[0].g_out = b.grad_actor; aa.seg[0].g_off = 0;
+    aa.seg[1].g_out = b.grad_critic; aa.seg[1].g_off = da.total;
+    aa.my_flags = inline_sync ? peers.flag[peers.rank] : nullptr; aa.rank = peers.rank;
+    for (int r = 0; r < peers.world; ++r) aa.peer_wait[r] = peers.flag[r];
+  }
   aa.nseg = 2;
   aa.w1 = float(1.0 - c.beta1); aa.w2 = float(1.0 - c.beta2); aa.beta2 = float(c.beta2); aa.eps = float(c.adam_eps);
   aa.tau = float(c.tau); aa.one_minus_tau = float(1.0 - c.tau); aa.grad_scale = 1.0f; aa.clock = w.clock;
@@ -549,7 +567,8 @@ extern "C" int32_t d4pg_learner_step(d4pg_learner_t* L, d4pg_stream_t stream) {
     if (rc == D4PG_OK) commit_variant(L, par);
     return rc;
   }
-  const int v = prefetching(L->cfg) ? par * 2 + (cold ? 1 : 0) : 0;
+  // without the prefetch pipeline the only per-step variation is the gradient half of the peer exchange
+  const int v = prefetching(L->cfg) ? par * 2 + (cold ? 1 : 0) : int(L->steps_done & 1);
   if (!L->graph_ready[v]) {
     D4PG_REQUIRE(st != nullptr, D4PG_EINVAL, "d4pg_learner_step: graph capture needs a non-default stream");
     cudaGraph_t graph = nullptr;

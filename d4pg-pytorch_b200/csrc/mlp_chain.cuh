@@ -58,8 +58,11 @@ struct GemmWideBatch {
   GemmProblem p[GEMM_WIDE_MAX];
   int n, total_tiles, pdl;
   unsigned long long* trace;
+  // data parallel over peer memory: the last CTA to finish publishes "this rank's gradient half is complete"
+  // ([0] published step count, [1] local step count, [2] CTA ticket), see comm.cu
+  unsigned long long* peer_flags;
 };
-void gemm_wide_begin(GemmWideBatch& b);
+void gemm_wide_begin(GemmWideBatch& b, unsigned long long* peer_flags = nullptr);
 void gemm_wide_add(GemmWideBatch& b, const GemmProblem& p);
 int gemm_wide_launch(GemmWideBatch& b, cudaStream_t st);
 

@@ -109,6 +109,8 @@ class _Learner(object):
             raise _lib.D4PGError("train() called before any transition was added to the replay buffer")
         store.flush()
         h = C.c_void_p()
+        if ddpg.comm is not None and cfg.world_size > 1 and not cfg.persistent:
+            ddpg.comm.setup_peers(Pa + Pc)            # fused all-reduce over peer memory (collective call)
         comm = ddpg.comm.handle if ddpg.comm is not None else None
         _lib.check(L.d4pg_learner_create(C.byref(cfg), C.byref(buf), store.handle, comm, C.byref(h)), "d4pg_learner_create")
         self.handle = h

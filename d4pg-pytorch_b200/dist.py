@@ -56,6 +56,37 @@ class Comm(object):
         _lib.check(_lib.lib().d4pg_comm_create(uid2, self.rank, self.world_size, C.byref(h)), "d4pg_comm_create")
         self.handle = h
 
+    def setup_peers(self, n_floats):
+        """Fused all-reduce over peer memory (one node): allocate this rank's exchange block, gather the CUDA IPC
+        handles of all ranks, map them.  Collective (every rank must call it); falls back to the NCCL all-reduce --
+        on every rank -- if any rank cannot export or map (D4PG_COMM_PEER=0 disables it)."""
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.lib()
+        if self.world_size <= 1 or self.world_size > 8 or L.d4pg_comm_peer_ready(self.handle):
+            return bool(L.d4pg_comm_peer_ready(self.handle))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        ok = os.environ.get("D4PG_COMM_PEER", "1") != "0"
+        mine = (C.c_uint8 * 64)()
+        if ok and L.d4pg_comm_peer_alloc(self.handle, int(n_floats), mine) != 0:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return False
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev)
+        parts = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(self.world_size)]
+        dist.all_gather(parts, t)
+        blob = b"".join(bytes(p.cpu().tolist()) for p in parts)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        ok = L.d4pg_comm_peer_open(self.handle, arr) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            raise _lib.D4PGError("CUDA IPC mapping of the peer exchange buffers failed on some rank: %s (set D4PG_COMM_PEER=0)"
+                                 % L.d4pg_last_error().decode())
+        return True
+
     def allreduce_sum_(self, flat):
         from . import _lib
         _lib.check(_lib.lib().d4pg_comm_allreduce_sum(self.handle, _lib.ptr(flat), flat.numel(), _lib.stream_ptr()),

@@ -290,6 +290,14 @@ int32_t d4pg_comm_unique_id(uint8_t* id128);                       /* ncclGetUni
 int32_t d4pg_comm_create(const uint8_t* id128, int32_t rank, int32_t world, d4pg_comm_t** out);
 int32_t d4pg_comm_destroy(d4pg_comm_t* c);
 int32_t d4pg_comm_allreduce_sum(d4pg_comm_t* c, float* buf, int64_t n, d4pg_stream_t stream);
+/* Fused gradient all-reduce over peer memory (one node, <= 8 ranks) instead of the NCCL kernel: every rank allocates
+ * an exchange block ([2][n_floats] gradient halves + flags) and exports it with CUDA IPC (64-byte handle); after the
+ * handles of all ranks were gathered (rank order) every rank maps them.  A learner created with such a communicator
+ * writes its dW into its own half, a flag barrier orders the ranks, and the fused Adam kernel sums all ranks' halves
+ * (fixed rank order: replicas stay bit-identical) while it updates the parameters. */
+int32_t d4pg_comm_peer_alloc(d4pg_comm_t* c, int64_t n_floats, uint8_t* handle64);
+int32_t d4pg_comm_peer_open(d4pg_comm_t* c, const uint8_t* all_handles /* world x 64 bytes */);
+int32_t d4pg_comm_peer_ready(const d4pg_comm_t* c);
 
 /* Debug: %globaltimer (ns) phase stamps written by CTA 0 of the most recent tcgen05 GEMM launch when
  * the environment variable D4PG_TC_TRACE is set; the persistent step kernel writes one stamp per
