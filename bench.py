@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def summary(self):
         if not self.samples:
@@ -215,7 +215,6 @@ def gpu_main(args):
         e1.record(stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    sampler.stop_flag = True
     kernels = dd.kernels_per_step()
     lc, la = dd.last_losses()
     assert np.isfinite(lc) and np.isfinite(la)
@@ -302,6 +301,7 @@ def gpu_main(args):
     barrier()
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
+    sampler.stop_flag = True                        # clocks were sampled through both timed regions
     del dd
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
@@ -338,7 +338,7 @@ def gpu_main(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CFG))
