@@ -145,15 +145,49 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int bid, Sample
       } else if (a.state->pristine) {
         // tree of Python floats: mass and the descent are fp64 (all node values are integers)
         double mass = __dmul_rn(u, double(total_s));
-        while (i < a.cap) {
-          const double left = double((2 * i < 2 * top_end) ? top_s[2 * i] : __ldcg(a.sum + 2 * i));
+        while (i < a.cap && 2 * i < 2 * top_end) {                    // levels staged in shared memory
+          const double left = double(top_s[2 * i]);
           if (left > mass) i = 2 * i;                                 // strict, :144
+          else { mass = __dsub_rn(mass, left); i = 2 * i + 1; }
+        }
+        // below: THREE levels per L2 round trip -- the 7 left children the next three decisions can ask for are
+        // fetched together; the comparisons and subtractions are the same ones, in the same order
+        while (4 * i < a.cap) {
+          const float* V = a.sum;
+          const float l1 = __ldcg(V + 2 * i), l20 = __ldcg(V + 4 * i), l21 = __ldcg(V + 4 * i + 2);
+          const float l30 = __ldcg(V + 8 * i), l31 = __ldcg(V + 8 * i + 2), l32 = __ldcg(V + 8 * i + 4), l33 = __ldcg(V + 8 * i + 6);
+          const bool r1 = !(double(l1) > mass); if (r1) mass = __dsub_rn(mass, double(l1));
+          const float l2 = r1 ? l21 : l20;
+          const bool r2 = !(double(l2) > mass); if (r2) mass = __dsub_rn(mass, double(l2));
+          const float l3 = r1 ? (r2 ? l33 : l32) : (r2 ? l31 : l30);
+          const bool r3 = !(double(l3) > mass); if (r3) mass = __dsub_rn(mass, double(l3));
+          i = 8 * i + 4 * int(r1) + 2 * int(r2) + int(r3);
+        }
+        while (i < a.cap) {
+          const double left = double(__ldcg(a.sum + 2 * i));
+          if (left > mass) i = 2 * i;
           else { mass = __dsub_rn(mass, left); i = 2 * i + 1; }
         }
       } else {
         float mass = __fmul_rn(__double2float_rn(u), total_s);         // weak float * np.float32
+        while (i < a.cap && 2 * i < 2 * top_end) {
+          const float left = top_s[2 * i];
+          if (left > mass) i = 2 * i;
+          else { mass = __fsub_rn(mass, left); i = 2 * i + 1; }
+        }
+        while (4 * i < a.cap) {
+          const float* V = a.sum;
+          const float l1 = __ldcg(V + 2 * i), l20 = __ldcg(V + 4 * i), l21 = __ldcg(V + 4 * i + 2);
+          const float l30 = __ldcg(V + 8 * i), l31 = __ldcg(V + 8 * i + 2), l32 = __ldcg(V + 8 * i + 4), l33 = __ldcg(V + 8 * i + 6);
+          const bool r1 = !(l1 > mass); if (r1) mass = __fsub_rn(mass, l1);
+          const float l2 = r1 ? l21 : l20;
+          const bool r2 = !(l2 > mass); if (r2) mass = __fsub_rn(mass, l2);
+          const float l3 = r1 ? (r2 ? l33 : l32) : (r2 ? l31 : l30);
+          const bool r3 = !(l3 > mass); if (r3) mass = __fsub_rn(mass, l3);
+          i = 8 * i + 4 * int(r1) + 2 * int(r2) + int(r3);
+        }
         while (i < a.cap) {
-          const float left = (2 * i < 2 * top_end) ? top_s[2 * i] : __ldcg(a.sum + 2 * i);
+          const float left = __ldcg(a.sum + 2 * i);
           if (left > mass) i = 2 * i;
           else { mass = __fsub_rn(mass, left); i = 2 * i + 1; }
         }
