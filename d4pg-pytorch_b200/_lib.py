@@ -62,6 +62,7 @@ _P = C.c_void_p
 _PROTOS = {
     "d4pg_last_error": (C.c_char_p, []),
     "d4pg_version": (C.c_int32, []),
+    "d4pg_struct_size": (C.c_int32, [C.c_int32]),
     "d4pg_device_sm": (C.c_int32, []),
     "d4pg_actor_layout": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(NetLayout)]),
     "d4pg_critic_layout": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(NetLayout)]),

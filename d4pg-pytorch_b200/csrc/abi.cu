@@ -77,6 +77,15 @@ using namespace d4pg;
 
 extern "C" const char* d4pg_last_error(void) { return g_err; }
 extern "C" int32_t d4pg_version(void) { return 100; }   /* 0.1.0 */
+/* sizeof of the structs that cross the ABI by pointer: a binding whose mirror has another size is out of date */
+extern "C" int32_t d4pg_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return int32_t(sizeof(d4pg_learner_config_t));
+    case 1: return int32_t(sizeof(d4pg_learner_buffers_t));
+    case 2: return int32_t(sizeof(d4pg_net_layout_t));
+    default: return -1;
+  }
+}
 
 extern "C" int32_t d4pg_device_sm(void) {
   int dev = 0, major = 0, minor = 0;

@@ -32,6 +32,18 @@ def test_library_exports_every_declared_symbol():
     assert L.d4pg_version() >= 100
 
 
+def test_struct_mirrors_have_the_c_sizes():
+    """The ctypes mirrors of the structs passed by pointer must have exactly the C sizes (a stale mirror would make
+    the library read garbage configuration)."""
+    import ctypes as C
+    from d4pg_b200 import _lib
+    L = _lib.lib()
+    assert L.d4pg_struct_size(0) == C.sizeof(_lib.LearnerConfig)
+    assert L.d4pg_struct_size(1) == C.sizeof(_lib.LearnerBuffers)
+    assert L.d4pg_struct_size(2) == C.sizeof(_lib.NetLayout)
+    assert L.d4pg_struct_size(99) == -1
+
+
 def test_no_compute_without_gpu_fails_loudly():
     import d4pg_b200
     if torch.cuda.is_available():
