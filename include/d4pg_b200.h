@@ -39,10 +39,10 @@ extern "C" {
 typedef void* d4pg_stream_t;   /* cudaStream_t */
 
 const char* d4pg_last_error(void);
-int32_t     d4pg_version(void);
+int32_t     d4pg_version(void);            /* 10000*major + 100*minor + patch */
 /* sizeof of the structs that cross this ABI by pointer (0 d4pg_learner_config_t, 1 d4pg_learner_buffers_t,
  * 2 d4pg_net_layout_t; -1 otherwise): lets a binding verify that its mirror of the struct is current */
-int32_t d4pg_struct_size(int32_t which);            /* 10000*major + 100*minor + patch */
+int32_t     d4pg_struct_size(int32_t which);
 /* compute capability of the current device as 10*major+minor (100 on B200), or <0 */
 int32_t     d4pg_device_sm(void);
 
