@@ -224,9 +224,12 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     RUN(launch_mlp_rows(ra, st));
   } else if (chain) {
     // 2'. the three forward chains of the step as ONE cluster launch (mlp_chain.cu):
-    //   T: actor_target(s') -> critic_target(s', .)      ddpg.py:205-206
-    //   Q: critic(s, a)                                   ddpg.py:208
-    //   P: actor(s) -> critic(s, actor(s))                ddpg.py:236-238 (fc1 of the critic is recomputed: K=|s|)
+    //   chain 0  T: actor_target(s') -> critic_target(s', .)      ddpg.py:205-206
+    //   chain 1  P: actor(s) -> critic(s, actor(s))                ddpg.py:236-238 (fc1 of the critic is recomputed: K=|s|)
+    //   chain 2  Q: critic(s, a)                                   ddpg.py:208
+    // The block scheduler fills SMs in launch order: the two 8-layer chains come first so that each of their CTAs
+    // gets an SM of its own, and the short 4-layer chain is the one that doubles up (measured with %smid: in the
+    // order T,Q,P 38 SMs hosted a T and a P CTA while 52 SMs hosted a lone Q CTA; forward launch 49 us)
     ChainArgs& ca = L->chain_fwd_args;
     chain_args_begin(ca, B, w.xchg, c.precision);
     ChainSlot sl; int at3, ct1, q1, a3, c1;
@@ -239,19 +242,19 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     sl = chain_fwd(Wct + dc.w_off[2], lc[2], Wct + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[1], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 0, sl);
     sl = chain_fwd(Wct + dc.w_off[3], lc[3], Wct + dc.b_off[3], N, H, EPI_BIAS, w.out[1], Np, 0); chain_src_plane(sl, t); chain_add(ca, 0, sl);
 
-    sl = chain_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, w.h1[2], H, 1); chain_src_global(sl, w.s, Sp); q1 = chain_add(ca, 1, sl);
-    sl = chain_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[2], H, 1); chain_src_plane(sl, q1); chain_src2_global(sl, H, w.a, Ap); t = chain_add(ca, 1, sl);
-    sl = chain_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[2], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 1, sl);
-    sl = chain_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[2], Np, 0); chain_src_plane(sl, t); chain_add(ca, 1, sl);
+    sl = chain_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, w.h1[2], H, 1); chain_src_global(sl, w.s, Sp); q1 = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[2], H, 1); chain_src_plane(sl, q1); chain_src2_global(sl, H, w.a, Ap); t = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[2], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 2, sl);
+    sl = chain_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[2], Np, 0); chain_src_plane(sl, t); chain_add(ca, 2, sl);
 
-    sl = chain_fwd(Wa + da.w_off[0], la[0], Wa + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[3], H, 1); chain_src_global(sl, w.s, Sp); t = chain_add(ca, 2, sl);
-    sl = chain_fwd(Wa + da.w_off[1], la[1], Wa + da.b_off[1], H, H, EPI_BIAS, w.h2[3], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 2, sl);
-    sl = chain_fwd(Wa + da.w_off[2], la[2], Wa + da.b_off[2], H, H, EPI_BIAS_RELU, w.h3[3], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 2, sl);
-    sl = chain_fwd(Wa + da.w_off[3], la[3], Wa + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[3], Ap, 1); chain_src_plane(sl, t); a3 = chain_add(ca, 2, sl);
-    sl = chain_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, 1); chain_src_global(sl, w.s, Sp); c1 = chain_add(ca, 2, sl);
-    sl = chain_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[4], H, 1); chain_src_plane(sl, c1); chain_src2_plane(sl, H, a3); t = chain_add(ca, 2, sl);
-    sl = chain_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[4], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 2, sl);
-    sl = chain_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[4], Np, 0); chain_src_plane(sl, t); chain_add(ca, 2, sl);
+    sl = chain_fwd(Wa + da.w_off[0], la[0], Wa + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[3], H, 1); chain_src_global(sl, w.s, Sp); t = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wa + da.w_off[1], la[1], Wa + da.b_off[1], H, H, EPI_BIAS, w.h2[3], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wa + da.w_off[2], la[2], Wa + da.b_off[2], H, H, EPI_BIAS_RELU, w.h3[3], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wa + da.w_off[3], la[3], Wa + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[3], Ap, 1); chain_src_plane(sl, t); a3 = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, 1); chain_src_global(sl, w.s, Sp); c1 = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[4], H, 1); chain_src_plane(sl, c1); chain_src2_plane(sl, H, a3); t = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[4], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 1, sl);
+    sl = chain_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[4], Np, 0); chain_src_plane(sl, t); chain_add(ca, 1, sl);
     RUN(launch_mlp_chain(ca, st));
   } else {
   // 2. forward level 1: fc1 of actor_target(s'), critic_target(s'), critic(s), actor(s)

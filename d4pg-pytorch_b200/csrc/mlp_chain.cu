@@ -315,6 +315,11 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
   unsigned long long* tr0 = (args.trace && int(blockIdx.x) == args.trace_cta && tid == 0) ? args.trace : nullptr;
   const long long clk0 = clock64();
   step_stamp(args.step_trace, args.step_slot);
+  if (args.step_trace && args.step_slot == 1 && tid == 0 && blockIdx.x < 256) {   // forward launch: which SM runs which CTA
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    reinterpret_cast<unsigned char*>(args.step_trace + (128 - STEP_TRACE_BASE))[blockIdx.x] = (unsigned char)smid;
+  }
   for (int l = 0; l < ns; ++l) {
     const ChainSlot& S = args.slot[chain][l];
     const bool has_tile = n0 < S.N;

@@ -17,8 +17,8 @@ dd.replayBuffer.add_batch(rng.randn(n, S).astype(np.float32), rng.uniform(-1, 1,
                           -rng.rand(n), rng.randn(n, S).astype(np.float32), np.zeros(n, bool))
 dd.train_n(50)
 torch.cuda.synchronize()
-out = (C.c_ulonglong * 128)()
-_lib.check(_lib.lib().d4pg_debug_trace_read(out, 128), "trace")
+out = (C.c_ulonglong * 256)()
+_lib.check(_lib.lib().d4pg_debug_trace_read(out, 256), "trace")
 names = {0: "sample (cold)", 1: "fwd chains", 2: "heads", 3: "tree update [side]", 4: "sample t+1 [side]", 5: "dX chains", 6: "dW", 7: "adam"}
 ev = [(out[96 + k], out[112 + k], names[k]) for k in names if out[96 + k]]
 t0 = min(e[0] for e in ev if e[2] != "sample (cold)")
@@ -37,3 +37,11 @@ for base, nm in ((0, "fwd launch"), (48, "dX launch")):
         if l and st[0] <= out[base + 6 * (l - 1)]: break
         if st[0] == 0: break
         print("  %s slot %d @%6d: " % (nm, l, st[0] - t0) + " ".join("+%d" % (st[i] - st[i - 1]) for i in range(1, 6) if st[i] > st[i-1] and st[i] - st[i-1] < 10**8))
+
+import collections
+raw = bytes(C.cast(out, C.POINTER(C.c_ubyte * (256 * 8))).contents)[128 * 8:128 * 8 + 192]
+sm = collections.defaultdict(list)
+for cta, s_ in enumerate(raw):
+    sm[s_].append("TPQ"[cta // 64])
+pat = collections.Counter("".join(sorted(v)) for v in sm.values())
+print("forward launch: CTAs per SM by chain (T = target, Q = critic, P = policy):", dict(pat), " SMs used:", len(sm))
