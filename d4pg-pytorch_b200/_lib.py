@@ -113,6 +113,7 @@ _PROTOS = {
     "d4pg_comm_peer_alloc": (C.c_int32, [_P, C.c_int64, _P]),
     "d4pg_comm_peer_open": (C.c_int32, [_P, _P]),
     "d4pg_comm_peer_ready": (C.c_int32, [_P]),
+    "d4pg_comm_peer_disable": (C.c_int32, [_P]),
     "d4pg_comm_allreduce_sum": (C.c_int32, [_P, _P, C.c_int64, _P]),
 }
 EXPORTED_SYMBOLS = sorted(_PROTOS)

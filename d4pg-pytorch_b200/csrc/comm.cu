@@ -197,3 +197,13 @@ extern "C" int32_t d4pg_comm_peer_open(d4pg_comm_t* c, const uint8_t* all_handle
   return D4PG_OK;
 }
 extern "C" int32_t d4pg_comm_peer_ready(const d4pg_comm_t* c) { return (c && c->peer_ready) ? 1 : 0; }
+/* some rank could not map its peers: every rank drops back to the NCCL all-reduce */
+extern "C" int32_t d4pg_comm_peer_disable(d4pg_comm_t* c) {
+  D4PG_REQUIRE(c, D4PG_EINVAL, "d4pg_comm_peer_disable: null handle");
+  c->peer_ready = false;
+  for (int i = 0; i < D4PG_MAX_PEERS; ++i) {
+    if (c->peer_base[i]) { cudaIpcCloseMemHandle(c->peer_base[i]); c->peer_base[i] = nullptr; }
+    c->peer_x[i] = nullptr; c->peer_flag[i] = nullptr;
+  }
+  return D4PG_OK;
+}

@@ -82,9 +82,9 @@ class Comm(object):
         ok = L.d4pg_comm_peer_open(self.handle, arr) == 0
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            raise _lib.D4PGError("CUDA IPC mapping of the peer exchange buffers failed on some rank: %s (set D4PG_COMM_PEER=0)"
-                                 % L.d4pg_last_error().decode())
+        if int(flag.item()) == 0:                  # e.g. no CUDA IPC between the ranks' containers: NCCL path on every rank
+            L.d4pg_comm_peer_disable(self.handle)
+            return False
         return True
 
     def allreduce_sum_(self, flat):

@@ -301,6 +301,7 @@ int32_t d4pg_comm_allreduce_sum(d4pg_comm_t* c, float* buf, int64_t n, d4pg_stre
 int32_t d4pg_comm_peer_alloc(d4pg_comm_t* c, int64_t n_floats, uint8_t* handle64);
 int32_t d4pg_comm_peer_open(d4pg_comm_t* c, const uint8_t* all_handles /* world x 64 bytes */);
 int32_t d4pg_comm_peer_ready(const d4pg_comm_t* c);
+int32_t d4pg_comm_peer_disable(d4pg_comm_t* c);      /* collective decision: fall back to the NCCL all-reduce */
 
 /* Debug: %globaltimer (ns) phase stamps written by CTA 0 of the most recent tcgen05 GEMM launch when
  * the environment variable D4PG_TC_TRACE is set; the persistent step kernel writes one stamp per
