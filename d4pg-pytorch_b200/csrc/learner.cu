@@ -17,6 +17,7 @@
 #include "gemm_ffma.cuh"
 #include "adam.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -190,6 +191,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   GemmBatch g;
   const int plan = step_plan(c);
   const bool chain = plan == 1, rows = plan == 2;
+  static const bool no_pre = getenv("D4PG_NO_PRE") != nullptr;          // A/B switch
+  const bool pre_ok = chain && c.precision == 0 && A <= 8 && !no_pre;   // pre-layers: fp32 tile, |a| <= 8
   if (rows) {
     // 2''. the same three chains, row-owner form (mlp_rows.cu): a CTA carries 5-8 rows through a whole chain
     RowsArgs& ra = L->rows_fwd_args;
@@ -232,13 +235,24 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     // order T,Q,P 38 SMs hosted a T and a P CTA while 52 SMs hosted a lone Q CTA; forward launch 49 us)
     ChainArgs& ca = L->chain_fwd_args;
     chain_args_begin(ca, B, w.xchg, c.precision);
-    ChainSlot sl; int at3, ct1, q1, a3, c1;
+    ChainSlot sl; int at3 = -1, ct1, q1, a3 = -1, c1;
+    (void)at3; (void)a3;
     sl = chain_fwd(Wat + da.w_off[0], la[0], Wat + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[0], H, 1); chain_src_global(sl, w.s2, Sp); int t = chain_add(ca, 0, sl);
     sl = chain_fwd(Wat + da.w_off[1], la[1], Wat + da.b_off[1], H, H, EPI_BIAS, w.h2[0], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 0, sl);
     sl = chain_fwd(Wat + da.w_off[2], la[2], Wat + da.b_off[2], H, H, EPI_BIAS_RELU, w.h3[0], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 0, sl);
+    // the 6-wide actor fc3 is a PRE-LAYER of the critic's fc2 slot (every CTA computes it for its 32 rows) instead of
+    // a slot of its own, when it fits (|a| <= 8, fp32 tile); otherwise it is a slot that publishes 8 plane rows
+    const int t22 = t;
+    if (pre_ok) {
+      sl = chain_fwd(Wct + dc.w_off[0], lc[0], Wct + dc.b_off[0], H, S, EPI_BIAS_RELU, w.h1[1], H, 1); chain_src_global(sl, w.s2, Sp); ct1 = chain_add(ca, 0, sl);
+      sl = chain_fwd(Wct + dc.w_off[1], lc[1], Wct + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[1], H, 1); chain_src_plane(sl, ct1);
+      chain_pre_layer(sl, Wat + da.w_off[3], la[3], Wat + da.b_off[3], nullptr, 0, A, H, EPI_BIAS_TANH, w.out[0], Ap, t22, H, false);
+      t = chain_add(ca, 0, sl);
+    } else {
     sl = chain_fwd(Wat + da.w_off[3], la[3], Wat + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[0], Ap, 1); chain_src_plane(sl, t); at3 = chain_add(ca, 0, sl);
     sl = chain_fwd(Wct + dc.w_off[0], lc[0], Wct + dc.b_off[0], H, S, EPI_BIAS_RELU, w.h1[1], H, 1); chain_src_global(sl, w.s2, Sp); ct1 = chain_add(ca, 0, sl);
     sl = chain_fwd(Wct + dc.w_off[1], lc[1], Wct + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[1], H, 1); chain_src_plane(sl, ct1); chain_src2_plane(sl, H, at3); t = chain_add(ca, 0, sl);
+    }
     sl = chain_fwd(Wct + dc.w_off[2], lc[2], Wct + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[1], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 0, sl);
     sl = chain_fwd(Wct + dc.w_off[3], lc[3], Wct + dc.b_off[3], N, H, EPI_BIAS, w.out[1], Np, 0); chain_src_plane(sl, t); chain_add(ca, 0, sl);
 
@@ -250,9 +264,17 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     sl = chain_fwd(Wa + da.w_off[0], la[0], Wa + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[3], H, 1); chain_src_global(sl, w.s, Sp); t = chain_add(ca, 1, sl);
     sl = chain_fwd(Wa + da.w_off[1], la[1], Wa + da.b_off[1], H, H, EPI_BIAS, w.h2[3], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 1, sl);
     sl = chain_fwd(Wa + da.w_off[2], la[2], Wa + da.b_off[2], H, H, EPI_BIAS_RELU, w.h3[3], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 1, sl);
+    const int a22 = t;
+    if (pre_ok) {
+      sl = chain_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, 1); chain_src_global(sl, w.s, Sp); c1 = chain_add(ca, 1, sl);
+      sl = chain_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[4], H, 1); chain_src_plane(sl, c1);
+      chain_pre_layer(sl, Wa + da.w_off[3], la[3], Wa + da.b_off[3], nullptr, 0, A, H, EPI_BIAS_TANH, w.out[3], Ap, a22, H, false);
+      t = chain_add(ca, 1, sl);
+    } else {
     sl = chain_fwd(Wa + da.w_off[3], la[3], Wa + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[3], Ap, 1); chain_src_plane(sl, t); a3 = chain_add(ca, 1, sl);
     sl = chain_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, 1); chain_src_global(sl, w.s, Sp); c1 = chain_add(ca, 1, sl);
     sl = chain_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[4], H, 1); chain_src_plane(sl, c1); chain_src2_plane(sl, H, a3); t = chain_add(ca, 1, sl);
+    }
     sl = chain_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[4], H, 1); chain_src_plane(sl, t); t = chain_add(ca, 1, sl);
     sl = chain_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[4], Np, 0); chain_src_plane(sl, t); chain_add(ca, 1, sl);
     RUN(launch_mlp_chain(ca, st));
@@ -382,8 +404,14 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
 
     sl = chain_dx(Wc + dc.w_off[3], lc[3], H, N, EPI_RELU_MASK, w.h3[4], H, w.p_dz22, H, 1); chain_src_global(sl, w.dlogits_pi, Np); t = chain_add(cb, 1, sl);
     sl = chain_dx(Wc + dc.w_off[2], lc[2], H, H, EPI_RELU_MASK, w.h2[4], H, w.p_dz2, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
+    if (pre_ok) {      // d action (6 wide) as a pre-layer of the step through actor fc3
+      sl = chain_dx(Wa + da.w_off[3], la[3], H, A, EPI_RELU_MASK, w.h3[3], H, w.a_dz22, H, 1);
+      chain_pre_layer(sl, Wc + dc.w_off[1] + H, lc[1], nullptr, w.out[3], Ap, A, H, EPI_TANH_MASK, w.a_dz3, Ap, t, H, true);
+      t = chain_add(cb, 1, sl);
+    } else {
     sl = chain_dx(Wc + dc.w_off[1] + H, lc[1], A, H, EPI_TANH_MASK, w.out[3], Ap, w.a_dz3, Ap, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
     sl = chain_dx(Wa + da.w_off[3], la[3], H, A, EPI_RELU_MASK, w.h3[3], H, w.a_dz22, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
+    }
     sl = chain_dx(Wa + da.w_off[2], la[2], H, H, EPI_NONE, nullptr, 0, w.a_dh2, H, 1); chain_src_plane(sl, t); t = chain_add(cb, 1, sl);
     sl = chain_dx(Wa + da.w_off[1], la[1], H, H, EPI_RELU_MASK, w.h1[3], H, w.a_dz1, H, 0); chain_src_plane(sl, t); chain_add(cb, 1, sl);
     RUN(launch_mlp_chain(cb, st));

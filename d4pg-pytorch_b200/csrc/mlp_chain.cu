@@ -16,6 +16,7 @@
 #include "gemm_ffma_dev.cuh"
 #include "mlp_chain.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace d4pg {
 
@@ -69,10 +70,14 @@ __device__ __forceinline__ void fill_from_plane(float* As, int kbase, const floa
 }
 // the CTA's 32-column weight slice of one slot, all of K at once
 template <bool SWZ>
+__device__ __forceinline__ void fetch_weights(float* Ws, const float* __restrict__ W, int ldw, int N, int K, int mode, int n0, int tid);
+template <bool SWZ>
 __device__ __forceinline__ void fetch_weights(float* Ws, const ChainSlot& S, int n0, int tid) {
-  const int K = S.K, N = S.N, ldw = S.ldw;
-  const float* __restrict__ W = S.W;
-  if (S.mode == GEMM_FWD) {                      // rows j = n0..n0+31 of W[N][ldw], K floats each
+  fetch_weights<SWZ>(Ws, S.W, S.ldw, S.N, S.K, S.mode, n0, tid);
+}
+template <bool SWZ>
+__device__ __forceinline__ void fetch_weights(float* Ws, const float* __restrict__ W, int ldw, int N, int K, int mode, int n0, int tid) {
+  if (mode == GEMM_FWD) {                      // rows j = n0..n0+31 of W[N][ldw], K floats each
     const int kq = (K + 3) >> 2, P = chain_wpitch(K);
     const int j = tid >> 3;                      // 8 threads per weight row
     if (n0 + j < N) {
@@ -194,9 +199,14 @@ __device__ __forceinline__ void chain_tile_mma(const ChainSlot& S, float* As, co
   }
 }
 
+struct TileDesc { int N, K, epi; float* C; int ldc; };
+__device__ __forceinline__ TileDesc tile_of(const ChainSlot& S) { return TileDesc{S.N, S.K, S.epi, S.C, S.ldc}; }
+
+// As: the A operand (k-major, 32 rows); red: the 8-warp reduce buffer (aliases the slot's A plane, which is dead by then);
+// sout: optional shared-memory k-major copy of the output (pre-layers)
 template <int MODE>
-__device__ __forceinline__ void chain_tile(const ChainSlot& S, float* As, const float* Ws, int m0, int n0, int B, float* xout,
-                                           const float (&eop)[4], unsigned long long* tr) {
+__device__ __forceinline__ void chain_tile(const TileDesc& S, const float* As, float* red, const float* Ws, int m0, int n0, int B,
+                                           float* xout, float* sout, const float (&eop)[4], unsigned long long* tr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = (lane >> 3) * 8, c0 = (lane & 7) * 4, l7 = lane & 7;
   const int N = S.N, K = S.K;
@@ -255,7 +265,6 @@ __device__ __forceinline__ void chain_tile(const ChainSlot& S, float* As, const 
 
   // cross-warp reduction in fixed order.  Buffer column c' = 4*(lane&7) + jj holds output column
   // (FWD) (lane&7) + 8*jj / (DX) c' itself.
-  float* red = As;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     *reinterpret_cast<float4*>(&red[(warp * BM + r0 + i) * BN + c0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -290,6 +299,7 @@ __device__ __forceinline__ void chain_tile(const ChainSlot& S, float* As, const 
       if (C) C[size_t(gi) * ldc + gj] = x;
     } else x = 0.f;                                   // rows past the batch stay finite in the planes
     if (xout) xout[gj * CHAIN_ROWS + orow] = x;
+    if (sout) sout[gj * CHAIN_ROWS + orow] = x;
   }
 }
 
@@ -337,13 +347,37 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
     }
     if (l > 0) cluster_wait();                        // previous slot's planes are visible; smem is free
     CTRACE(1);
+    if (PREC == 0 && S.has_pre && has_tile) {
+      // ---- pre-layer: <= 8 columns, every CTA computes all of them for the cluster's 32 rows --------------------
+      float* Wp = W0 + ((l + 1) & 1) * wf;            // the next slot's weight buffer is still free
+      fetch_weights<SWZ>(Wp, S.pre_W, S.pre_ldw, S.pre_N, S.pre_K, S.mode, 0, tid);
+      fill_from_plane<SWZ>(As, 0, planes + size_t(S.pre_src) * CHAIN_PLANE, S.pre_K, tid);
+      cp_async_commit();
+      float pe[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const int gi = m0 + (tid >> 3);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int gj = (S.mode == GEMM_FWD) ? (tid & 7) + 8 * cc : (tid & 7) * 4 + cc;
+          if (gj < S.pre_N && gi < B)
+            pe[cc] = (S.mode == GEMM_FWD) ? __ldg(S.pre_bias + gj) : __ldg(S.pre_aux + size_t(gi) * S.pre_ldaux + gj);
+        }
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+      const TileDesc D{S.pre_N, S.pre_K, S.pre_epi, rank == 0 ? S.pre_C : nullptr, S.pre_ldc};
+      float* sout = As + S.pre_row * CHAIN_ROWS;      // outside the reduce buffer (rows 0..255)
+      if (S.mode == GEMM_FWD) chain_tile<GEMM_FWD>(D, As, As, Wp, m0, 0, B, nullptr, sout, pe, nullptr);
+      else chain_tile<GEMM_DX>(D, As, As, Wp, m0, 0, B, nullptr, sout, pe, nullptr);
+      __syncthreads();                                // reduce buffer dead, pre-layer output in place
+    }
     if (has_tile) {
       const int K = S.K, K1 = S.K1;
       if (S.src >= 0) fill_from_plane<SWZ>(As, 0, planes + size_t(S.src) * CHAIN_PLANE, K1, tid);
-      else fill_from_rows<SWZ>(As, 0, S.Ag, S.ldag, m0, B, K1, tid);
+      else if (S.src == -1) fill_from_rows<SWZ>(As, 0, S.Ag, S.ldag, m0, B, K1, tid);
       if (K > K1) {
         if (S.src2 >= 0) fill_from_plane<SWZ>(As, K1, planes + size_t(S.src2) * CHAIN_PLANE, K - K1, tid);
-        else fill_from_rows<SWZ>(As, K1, S.A2g, S.lda2g, m0, B, K - K1, tid);
+        else if (S.src2 == -1) fill_from_rows<SWZ>(As, K1, S.A2g, S.lda2g, m0, B, K - K1, tid);
       }
     }
     cp_async_commit();
@@ -356,8 +390,10 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs args) {
     if (has_tile) {
       float* xout = S.publish ? planes + size_t(l) * CHAIN_PLANE : nullptr;
       if (PREC == 0) {
-        if (S.mode == GEMM_FWD) chain_tile<GEMM_FWD>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
-        else chain_tile<GEMM_DX>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
+        const TileDesc D = tile_of(S);
+        const float* Am = As + S.a_row0 * CHAIN_ROWS;
+        if (S.mode == GEMM_FWD) chain_tile<GEMM_FWD>(D, Am, As, W0 + (l & 1) * wf, m0, n0, B, xout, nullptr, eop, tr);
+        else chain_tile<GEMM_DX>(D, Am, As, W0 + (l & 1) * wf, m0, n0, B, xout, nullptr, eop, tr);
       } else {
         if (S.mode == GEMM_FWD) chain_tile_mma<GEMM_FWD, PREC>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
         else chain_tile_mma<GEMM_DX, PREC>(S, As, W0 + (l & 1) * wf, m0, n0, B, xout, eop, tr);
@@ -389,7 +425,7 @@ int chain_add(ChainArgs& a, int c, const ChainSlot& s) {
   if (c >= a.nchains) a.nchains = c + 1;
   const int l = a.nslots[c]++;
   a.slot[c][l] = s;
-  const int af = int(align4(int64_t(s.K) * CHAIN_ROWS));
+  const int af = int(align4(int64_t(s.has_pre ? std::max(s.K, s.pre_row + 8) : s.K) * CHAIN_ROWS));
   const int wf = s.mode == GEMM_FWD ? BN * chain_wpitch(s.K) : int(align4(int64_t(s.K) * BN));
   if (af > a.a_floats) a.a_floats = af;
   if (wf > a.w_floats) a.w_floats = wf;
@@ -412,6 +448,13 @@ void chain_src_global(ChainSlot& s, const float* Ag, int ldag) { s.Ag = Ag; s.ld
 void chain_src_plane(ChainSlot& s, int slot) { s.src = slot; }
 void chain_src2_global(ChainSlot& s, int K1, const float* A2g, int lda2g) { s.K1 = K1; s.A2g = A2g; s.lda2g = lda2g; s.src2 = -1; }
 void chain_src2_plane(ChainSlot& s, int K1, int slot) { s.K1 = K1; s.src2 = slot; }
+void chain_pre_layer(ChainSlot& s, const float* W, int ldw, const float* bias, const float* aux, int ldaux, int N, int K, int epi,
+                     float* C, int ldc, int src_slot, int pre_row, bool whole_operand) {
+  s.has_pre = 1; s.pre_W = W; s.pre_ldw = ldw; s.pre_bias = bias; s.pre_aux = aux; s.pre_ldaux = ldaux;
+  s.pre_N = N; s.pre_K = K; s.pre_epi = epi; s.pre_C = C; s.pre_ldc = ldc; s.pre_src = src_slot; s.pre_row = pre_row;
+  if (whole_operand) { s.src = -2; s.K1 = s.K; s.a_row0 = pre_row; }     // DX: the pre-layer IS the A operand
+  else { s.src2 = -2; s.K1 = s.K - N; s.a_row0 = 0; }                     // FWD: the pre-layer is the concatenated tail
+}
 
 int launch_mlp_chain(ChainArgs& a, cudaStream_t st) {
   D4PG_REQUIRE(a.nchains > 0 && a.nchains <= CHAIN_MAX, D4PG_EINVAL, "launch_mlp_chain: %d chains", a.nchains);
@@ -422,8 +465,15 @@ int launch_mlp_chain(ChainArgs& a, cudaStream_t st) {
       D4PG_REQUIRE(s.N > 0 && s.N <= CHAIN_CLUSTER * BN, D4PG_ENOTSUP, "launch_mlp_chain: layer width %d > %d", s.N, CHAIN_CLUSTER * BN);
       D4PG_REQUIRE(s.ldw % 4 == 0 && (reinterpret_cast<uintptr_t>(s.W) & 15) == 0, D4PG_EINVAL, "launch_mlp_chain: weights must be 16-B pitched");
       D4PG_REQUIRE(s.src < l && s.src2 < l, D4PG_EINVAL, "launch_mlp_chain: slot %d reads a later plane", l);
-      D4PG_REQUIRE(s.src >= 0 || (s.Ag && s.ldag % 4 == 0 && s.ldag >= s.K1), D4PG_EINVAL, "launch_mlp_chain: bad global A source");
-      D4PG_REQUIRE(s.K == s.K1 || s.src2 >= 0 || (s.A2g && s.lda2g % 4 == 0 && s.lda2g >= s.K - s.K1), D4PG_EINVAL, "launch_mlp_chain: bad second A source");
+      D4PG_REQUIRE(s.src >= 0 || s.src == -2 || (s.Ag && s.ldag % 4 == 0 && s.ldag >= s.K1), D4PG_EINVAL, "launch_mlp_chain: bad global A source");
+      D4PG_REQUIRE(s.K == s.K1 || s.src2 >= 0 || s.src2 == -2 || (s.A2g && s.lda2g % 4 == 0 && s.lda2g >= s.K - s.K1), D4PG_EINVAL, "launch_mlp_chain: bad second A source");
+      D4PG_REQUIRE((s.src != -2 && s.src2 != -2) || s.has_pre, D4PG_EINVAL, "launch_mlp_chain: slot %d expects a pre-layer", l);
+      if (s.has_pre) {
+        D4PG_REQUIRE(a.precision == 0, D4PG_ENOTSUP, "launch_mlp_chain: pre-layers exist for the fp32 tile only");
+        D4PG_REQUIRE(s.pre_N > 0 && s.pre_N <= 8 && s.pre_K <= D4PG_HIDDEN && s.pre_row >= D4PG_HIDDEN && s.pre_src >= 0 && s.pre_src < l &&
+                     a.slot[c][s.pre_src].publish && a.slot[c][s.pre_src].N >= s.pre_K && s.pre_ldw % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(s.pre_W) & 15) == 0, D4PG_EINVAL, "launch_mlp_chain: bad pre-layer in slot %d", l);
+      }
       D4PG_REQUIRE(s.src < 0 || (a.slot[c][s.src].publish && a.slot[c][s.src].N >= s.K1), D4PG_EINVAL, "launch_mlp_chain: slot %d reads an unpublished plane", l);
       D4PG_REQUIRE(s.K == s.K1 || s.src2 < 0 || (a.slot[c][s.src2].publish && a.slot[c][s.src2].N >= s.K - s.K1), D4PG_EINVAL, "launch_mlp_chain: slot %d reads an unpublished plane", l);
     }

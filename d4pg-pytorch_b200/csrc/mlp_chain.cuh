@@ -24,6 +24,14 @@ struct ChainSlot {
   int src, src2;                  // exchange-plane slot of the first / second A source (-1: global)
   int mode, epi;                  // GEMM_FWD / GEMM_DX, GemmEpi
   int publish;                    // 1: also store the output tile k-major for later slots
+  // Optional PRE-LAYER (fp32 path): a layer at most 8 columns wide (actor fc3, the d-action step of the policy
+  // backward) that every CTA of the cluster evaluates redundantly at the start of this slot, from plane `pre_src`,
+  // into rows [pre_row, pre_row + pre_N) of its own A operand -- instead of a slot of its own (barrier + exchange
+  // for a 32 x 6 result).  src2 == -2 (FWD: the pre-layer is the concatenated tail) or src == -2 with a_row0 =
+  // pre_row (DX: the pre-layer is the whole A operand).  Rank 0 also stores it row-major to pre_C.
+  int has_pre, pre_src, pre_row, a_row0;
+  const float* pre_W; const float* pre_bias; const float* pre_aux; float* pre_C;
+  int pre_ldw, pre_ldaux, pre_ldc, pre_N, pre_K, pre_epi;
 };
 
 struct ChainArgs {
@@ -50,6 +58,8 @@ void chain_src_global(ChainSlot& s, const float* Ag, int ldag);
 void chain_src_plane(ChainSlot& s, int slot);
 void chain_src2_global(ChainSlot& s, int K1, const float* A2g, int lda2g);
 void chain_src2_plane(ChainSlot& s, int K1, int slot);
+void chain_pre_layer(ChainSlot& s, const float* W, int ldw, const float* bias, const float* aux, int ldaux, int N, int K, int epi,
+                     float* C, int ldc, int src_slot, int pre_row, bool whole_operand);
 int launch_mlp_chain(ChainArgs& a, cudaStream_t st);
 
 // dW level of the whole step in one launch (up to 12 problems, no TMA descriptors in the parameters)
