@@ -38,6 +38,32 @@ def main():
                 rng.rand(n) < 0.05)
     dd.replayBuffer.add_batch(*shard(rank))
 
+    if os.environ.get("D4PG_DP_MODE") == "device":
+        # the benchmark's configuration: device-side sampling, prefetch pipeline, 4-step graphs, gradient exchange fused
+        # into the dW / Adam kernels.  Replicas must stay bit-identical through replays, adds and single steps.
+        torch.manual_seed(0)
+        dv = d4pg.DDPG(17, 6, memory_size=n, batch_size=B, critic_dist_info=info, comm=comm, precision=precision,
+                       sampling="device", philox_seed=100 + rank)
+        dv.assign_global_optimizer(d4pg.SharedAdam(dv.actor.parameters(), lr=1e-3), d4pg.SharedAdam(dv.critic.parameters(), lr=1e-3))
+        dv.replayBuffer.add_batch(*shard(rank))
+        for phase in range(3):
+            dv.train_n(11)
+            dv.train()
+            dv.replayBuffer.add_batch(*[x[:37] for x in shard(rank + 10 * (phase + 1))])     # invalidates the prefetched batch
+            dv.train()
+            lc, la = dv.last_losses()
+            assert np.isfinite(lc) and np.isfinite(la)
+            flat = torch.cat([dv.actor.flat_params(), dv.critic.flat_params(), dv.actor_target.flat_params(),
+                              dv.critic_target.flat_params()])
+            ref = flat.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(flat, ref), "device-sampling replicas diverged in phase %d on rank %d" % (phase, rank)
+        dist.barrier()
+        if rank == 0:
+            print("DP_OK world=%d precision=%s mode=device kernels/step=%d" % (world, precision, dv.kernels_per_step()))
+        dist.destroy_process_group()
+        return
+
     oracle_bufs, lo = None, None
     if rank == 0:
         oracle_bufs = []

@@ -19,3 +19,14 @@ def test_data_parallel_two_ranks_match_single_big_batch_oracle(precision):
            "--master-port", "29517", os.path.join(ROOT, "tests", "dp_worker.py")]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_data_parallel_device_sampling_replicas_stay_identical():
+    """The benchmark's DP configuration (device sampling + prefetch + fused peer-memory gradient exchange)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, D4PG_PRECISION="fp32", D4PG_DP_MODE="device")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(ROOT, "tests", "dp_worker.py")]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "DP_OK" in r.stdout and "mode=device" in r.stdout, r.stdout[-3000:]
