@@ -202,7 +202,13 @@ def gpu_main(args):
 
     # ---- value: inputs resident in HBM, device-side sampling, CUDA-graph replay -------------
     dd = make("device")
-    dd.train_n(max(args.warmup, 3))
+    # untimed warm-up: at least W steps, issued so that every CUDA-graph variant of the step (cold / warm, both halves of
+    # the double-buffered batch, the 4-step replay graphs) is captured and instantiated before the timed region
+    warm_done = 0
+    for n in (1, 4, 1, 4, 1):
+        dd.train_n(n); warm_done += n
+    if max(args.warmup, 3) > warm_done:
+        dd.train_n(max(args.warmup, 3) - warm_done); warm_done = max(args.warmup, 3)
     stream = dd._learner.stream
     sampler = ClockSampler(local)
     barrier()
@@ -314,7 +320,7 @@ def gpu_main(args):
                              r["done"], args.config, len(os.sched_getaffinity(0)), len(os.sched_getaffinity(0)))}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": warm_done, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.config, "batch_per_gpu": B, "global_batch": B * world, "obs_dim": cfg["obs"],
                            "act_dim": cfg["act"], "n_atoms": cfg["atoms"], "replay_capacity_per_gpu": cap,
