@@ -38,6 +38,35 @@ __device__ __forceinline__ void row_softmax(const float* __restrict__ logits, in
   for (int t = 0; t < NT; ++t) p[t] = p[t] / s;
 }
 
+// the same softmax on logits already in registers (rows whose loads were issued early)
+template <int NT>
+__device__ __forceinline__ void row_load(const float* __restrict__ logits, int N, int lane, float (&x)[NT], bool probs) {
+#pragma unroll
+  for (int t = 0; t < NT; ++t) { const int k = lane + 32 * t; x[t] = (k < N) ? __ldg(logits + k) : (probs ? 0.f : -INFINITY); }
+}
+template <int NT>
+__device__ __forceinline__ void row_softmax_x(const float (&x)[NT], int N, int lane, float (&p)[NT], bool already_probs) {
+  if (already_probs) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) p[t] = x[t];
+    return;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) mx = fmaxf(mx, x[t]);
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int k = lane + 32 * t;
+    p[t] = (k < N) ? expf(x[t] - mx) : 0.f;
+    s += p[t];
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int t = 0; t < NT; ++t) p[t] = p[t] / s;
+}
+
 // per-warp shared tables of one row (3.5 KB per warp)
 struct HeadsWarpSmem {
   double wl[D4PG_MAX_ATOMS];
@@ -47,17 +76,24 @@ struct HeadsWarpSmem {
   int u[D4PG_MAX_ATOMS];
 };
 
-// one batch row, executed by one warp
+// one batch row, executed by one warp.  parts: 1 = critic part (projection, CE loss, td, priority, d/d q-logits),
+// 2 = policy head, 3 = both.  The two parts are independent, so the standalone kernel gives them to different warps;
+// all global loads of a part are issued up front (three dependent round trips became one).
 template <int MODE, int NT>
-__device__ __forceinline__ void heads_row(const HeadsArgs& a, int row, int lane, HeadsWarpSmem& ws) {
+__device__ __forceinline__ void heads_row(const HeadsArgs& a, int row, int lane, HeadsWarpSmem& ws, int parts = 3) {
   const int N = a.N;
   const size_t ro = size_t(row) * a.ld;
+  if (parts & 1) {
 
   // ---- target distribution ------------------------------------------------------------
-  float p[NT];
-  row_softmax(a.target_logits + ro, N, lane, p, (a.flags & D4PG_PROJ_TARGET_IS_PROBS) != 0);
+  float p[NT], xt[NT], xq[NT];
+  const bool t_probs = (a.flags & D4PG_PROJ_TARGET_IS_PROBS) != 0, q_probs = (a.flags & D4PG_PROJ_Q_IS_PROBS) != 0;
+  row_load(a.target_logits + ro, N, lane, xt, t_probs);
+  row_load(a.q_logits + ro, N, lane, xq, q_probs);
   const double r = a.rewards[row];
   const bool done = a.dones[row] != 0;
+  const float isw = a.is_weights ? __ldg(a.is_weights + row) : 1.f;
+  row_softmax_x(xt, N, lane, p, t_probs);
 
   float mk[NT];
 #pragma unroll
@@ -154,10 +190,9 @@ __device__ __forceinline__ void heads_row(const HeadsArgs& a, int row, int lane,
 
   // ---- online critic: CE loss, TD proxy, priority, d loss / d logits -------------------
   float q[NT];
-  row_softmax(a.q_logits + ro, N, lane, q, (a.flags & D4PG_PROJ_Q_IS_PROBS) != 0);
+  row_softmax_x(xq, N, lane, q, q_probs);
   float ce = 0.f, mq = 0.f, sq = 0.f;
   float gq[NT];
-  const float isw = a.is_weights ? __ldg(a.is_weights + row) : 1.f;
   const float gscale = a.grad_scale * isw;
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
@@ -189,8 +224,10 @@ __device__ __forceinline__ void heads_row(const HeadsArgs& a, int row, int lane,
     if (a.prio) a.prio[row] = (a.ce_priority ? -ce : fabsf(tdv)) + float(a.prio_eps);   // np.abs(f32) + 1e-6 (f32)
   }
 
+  }   // parts & 1
+
   // ---- policy head: -E_q[z] and its logit gradient --------------------------------------
-  if (a.pi_logits) {
+  if ((parts & 2) && a.pi_logits) {
     float qp[NT];
     row_softmax(a.pi_logits + ro, N, lane, qp);
     float ez = 0.f;
@@ -218,9 +255,10 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
   pdl_trigger(a.pdl);
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * HEAD_WARPS + warp;
+  const int g = blockIdx.x * HEAD_WARPS + warp;            // warps [0, B): critic part of row g; [B, 2B): policy head of row g - B
   step_stamp(a.trace, 2);
-  if (row < a.B) heads_row<MODE, NT>(a, row, lane, ws[warp]);
+  if (g < a.B) heads_row<MODE, NT>(a, g, lane, ws[warp], 1);
+  else if (g < 2 * a.B) heads_row<MODE, NT>(a, g - a.B, lane, ws[warp], 2);
   step_stamp(a.trace, 2 + 16);
   if (a.sampler_clock && blockIdx.x == 0 && threadIdx.x == 0) {
     a.sampler_clock->s_adam_step += 1; a.sampler_clock->s_beta_t += 1; a.sampler_clock->s_steps_done += 1;
