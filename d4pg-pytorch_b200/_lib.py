@@ -42,7 +42,7 @@ class LearnerConfig(C.Structure):
         ("prio_eps", C.c_double),
         ("precision", C.c_int32), ("sample_mode", C.c_int32),
         ("philox_seed", C.c_uint64),
-        ("world_size", C.c_int32), ("use_graph", C.c_int32), ("persistent", C.c_int32),
+        ("world_size", C.c_int32), ("use_graph", C.c_int32),
         ("loss_flags", C.c_int32), ("chain", C.c_int32), ("prefetch", C.c_int32),
     ]
 
@@ -85,7 +85,11 @@ _PROTOS = {
     "d4pg_replay_reduce": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P]),
     "d4pg_replay_find_prefixsum": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
     "d4pg_replay_set_leaves": (C.c_int32, [_P, C.c_int32, _P, _P, _P, _P]),
-    "d4pg_replay_set_len": (C.c_int32, [_P, C.c_int64, C.c_int64, C.c_int32]),
+    "d4pg_nstep_returns": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_double, _P, _P]),
+    "d4pg_replay_add_nstep": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, C.c_double, _P, C.c_int32, _P]),
+    "d4pg_her_relabel": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                     C.c_double, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "d4pg_replay_set_len": (C.c_int32, [_P, C.c_int64, C.c_int64, C.c_int32, _P]),
     "d4pg_actor_forward": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, _P]),
     "d4pg_critic_forward": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P]),
     "d4pg_adam_polyak": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -97,7 +101,7 @@ _PROTOS = {
     "d4pg_learner_destroy": (C.c_int32, [_P]),
     "d4pg_learner_step": (C.c_int32, [_P, _P]),
     "d4pg_learner_run": (C.c_int32, [_P, C.c_int32, _P]),
-    "d4pg_learner_set_host_buffers": (C.c_int32, [_P, _P, _P, _P]),
+    "d4pg_learner_step_host_mt": (C.c_int32, [_P, _P, _P, _P]),
     "d4pg_learner_step_host": (C.c_int32, [_P, _P, _P, _P, _P]),
     "d4pg_learner_read_losses": (C.c_int32, [_P, _P, _P]),
     "d4pg_learner_tensor": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
@@ -107,6 +111,7 @@ _PROTOS = {
     "d4pg_learner_set_counters": (C.c_int32, [_P, C.c_int64, C.c_int64, _P]),
     "d4pg_debug_tc_trace": (C.c_int32, [_P]),
     "d4pg_debug_trace_read": (C.c_int32, [_P, C.c_int32]),
+    "d4pg_debug_watchdog": (C.c_int32, [_P]),
     "d4pg_comm_unique_id": (C.c_int32, [_P]),
     "d4pg_comm_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "d4pg_comm_destroy": (C.c_int32, [_P]),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libd4pg_sm100.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["abi.cu", "proj_loss.cu", "replay.cu", "gemm_ffma.cu", "gemm_tc.cu", "adam.cu", "step_mega.cu", "mlp_chain.cu", "mlp_rows.cu", "learner.cu", "comm.cu"]
+SOURCES = ["abi.cu", "proj_loss.cu", "replay.cu", "gemm_ffma.cu", "gemm_tc.cu", "adam.cu", "mlp_chain.cu", "mlp_tc_chain.cu", "learner.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 

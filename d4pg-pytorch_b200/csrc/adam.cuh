@@ -10,7 +10,7 @@ struct LearnerClock {
   int64_t adam_step;     // completed Adam steps (state['step'] before this step)
   int64_t beta_t;        // LinearSchedule.t
   int64_t steps_done;    // Philox counter / bookkeeping
-  int64_t mega_epoch;    // completed persistent-kernel steps (base of its grid-barrier targets)
+  int64_t reserved;
   // derived per-step scalars: written by the sample kernel, read by later kernels of the step
   float beta;            // PER beta for this step's IS weights
   float neg_step_size[2];   // -(lr/bc1) for actor, critic

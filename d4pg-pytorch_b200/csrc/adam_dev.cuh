@@ -1,4 +1,4 @@
-// Device code of the fused Adam + Polyak update (shared by adam.cu and the persistent step kernel).
+// Device code of the fused Adam + Polyak update.
 #pragma once
 #include "adam.cuh"
 

@@ -1,4 +1,4 @@
-// Device code of the exact-fp32 grouped GEMM (shared by gemm_ffma.cu and the persistent step kernel).
+// Device code of the exact-fp32 grouped GEMM.
 #pragma once
 #include "gemm_ffma.cuh"
 

@@ -547,7 +547,7 @@ static bool prepare_v2(GemmBatch& b) {
 static unsigned long long* g_trace = nullptr;
 unsigned long long* debug_trace_buffer() {
   static const bool tracing = getenv("D4PG_TC_TRACE") != nullptr;
-  if (tracing && !g_trace) { cudaMalloc(&g_trace, 256 * sizeof(unsigned long long)); cudaMemset(g_trace, 0, 256 * 8); }
+  if (tracing && !g_trace) { cudaMalloc(&g_trace, 512 * sizeof(unsigned long long)); cudaMemset(g_trace, 0, 512 * 8); }
   return tracing ? g_trace : nullptr;
 }
 void gemm_tc_prepare(GemmBatch& b) {
@@ -591,7 +591,7 @@ int gemm_tc_batch_launch(const GemmBatch& b, int passes, cudaStream_t st) {
 
 // debug: %globaltimer (ns) phase stamps of CTA 0 of the last gemm_tc2 launch (D4PG_TC_TRACE=1)
 extern "C" int32_t d4pg_debug_trace_read(unsigned long long* out, int32_t n) {
-  if (!d4pg::g_trace || !out || n < 1 || n > 256) return D4PG_ESTATE;
+  if (!d4pg::g_trace || !out || n < 1 || n > 512) return D4PG_ESTATE;
   D4PG_CUDA_OK(cudaMemcpy(out, d4pg::g_trace, size_t(n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return D4PG_OK;
 }

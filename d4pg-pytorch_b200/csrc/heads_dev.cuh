@@ -1,5 +1,5 @@
 // Device code of the fused projection / loss / priority / logit-gradient row kernel
-// (shared by proj_loss.cu and the persistent step kernel).
+// (included by proj_loss.cu).
 #pragma once
 #include "internal.cuh"
 

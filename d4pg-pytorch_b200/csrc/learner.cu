@@ -23,9 +23,8 @@
 #include <vector>
 
 #include "internal.cuh"
-#include "step_mega.cuh"
 #include "mlp_chain.cuh"
-#include "mlp_rows.cuh"
+#include "mlp_tc_chain.cuh"
 
 namespace d4pg {
 
@@ -39,7 +38,6 @@ struct Workspace {
   // backward
   float *c_dz22, *c_dz2, *c_dz1, *p_dz22, *p_dz2, *a_dz3, *a_dz22, *a_dh2, *a_dz1;
   LearnerClock* clock;
-  unsigned long long* barrier;     // grid-barrier counter of the persistent step kernel
   float* xchg;                     // exchange planes of the cluster-fused chain kernels (chain mode)
   // prefetch pipeline: the second half of the double-buffered batch, and the sampler's own index / weight buffers
   float *s_b, *a_b, *s2_b; double* r_b; uint8_t* done_b;
@@ -71,8 +69,7 @@ static Workspace carve(float* base, int B, int S, int A, int N, bool chain, bool
   w.a_dz3 = take(int64_t(B) * Ap); w.a_dz22 = take(int64_t(B) * H); w.a_dh2 = take(int64_t(B) * H);
   w.a_dz1 = take(int64_t(B) * H);
   w.clock = reinterpret_cast<LearnerClock*>(take(sizeof(LearnerClock) / 4 + 4));
-  w.barrier = reinterpret_cast<unsigned long long*>(take(64));   // [0] arrival counter, [16] release flag (own line)
-  w.xchg = chain ? take(chain_xchg_floats(B)) : nullptr;
+  w.xchg = chain ? take(std::max(chain_xchg_floats(B), tcc_xchg_floats(B))) : nullptr;
   if (prefetch) {
     w.s_b = take(int64_t(B) * Sp); w.a_b = take(int64_t(B) * Ap); w.s2_b = take(int64_t(B) * Sp);
     w.r_b = reinterpret_cast<double*>(take(int64_t(B) * 2));
@@ -105,24 +102,78 @@ struct d4pg_learner {
   int kernels_per_step;
   // profiling (d4pg_learner_profile_step): CUDA-event pair around every launch of an eager step
   cudaStream_t side; cudaEvent_t ev_fork, ev_join;
-  MegaParams mega;
   ChainArgs chain_fwd_args, chain_bwd_args;
-  RowsArgs rows_fwd_args, rows_bwd_args;
+  // tcgen05 chains (precision >= 1): library-owned weight images + the per-step pack / chain descriptors
+  uint8_t* tcc_images; TccPackArgs tcc_pack; int tcc_use[32]; bool tcc_ok;
+  TccArgs tcc_fwd_args, tcc_bwd_args;
   GemmWideBatch dw_batch;
-  // host-facing step (caller-owned pinned buffers, d4pg_learner_set_host_buffers)
-  double* host_u; int32_t* host_pos; float* host_losses; cudaEvent_t ev_in, ev_out;
+  // host-facing step: library-owned pinned staging, double-buffered by step parity (a buffer is rewritten only after
+  // the H2D copy out of it, two steps earlier, has completed)
+  double* host_u[2]; int32_t* host_pos[2]; float* host_losses; cudaEvent_t ev_in, ev_out, ev_h2d[2];
+  int64_t host_steps;
   bool profiling;
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> ev_name;
+  std::vector<int> ev_reps;        // how many times the launch between the event pair was repeated
 };
 
-// step plan: 0 = one grouped launch per dependency level, 1 = cluster-fused chains (mlp_chain.cu),
-// 2 = row-owner chains (mlp_rows.cu).  The chain plans pay off while the batch fits one wave of clusters: measured
+// step plan: 0 = one grouped launch per dependency level, 1 = cluster-fused chains (mlp_chain.cu exact fp32 /
+// mlp_tc_chain.cu tcgen05).  The chain plans pay off while the batch fits one wave of clusters: measured
 // on B200, batch 1024 (config 3) 409 us with chains vs 320 us per level, batch 4096 (config 5) 906 vs 733 us
 // (tcgen05 levels), so batches above 512 rows always run plan 0.
 static int step_plan(const d4pg_learner_config_t& c) { return c.batch > 512 ? 0 : c.chain; }
 // prefetch pipeline: batch t+1 is sampled on a side branch of step t (device-side sampling only)
-static bool prefetching(const d4pg_learner_config_t& c) { return c.prefetch != 0 && c.sample_mode == 1 && !c.persistent; }
+static bool prefetching(const d4pg_learner_config_t& c) { return c.prefetch != 0 && c.sample_mode == 1; }
+
+// weight matrices as the tcgen05 chains consume them (F = forward image, D = transposed image for dX)
+enum { U_A_F1, U_A_F2, U_A_F22, U_A_F3, U_A_D3, U_A_D22, U_A_D2, U_AT_F1, U_AT_F2, U_AT_F22, U_AT_F3,
+       U_C_F1, U_C_F2, U_C_F22, U_C_F3, U_C_D3, U_C_D22, U_C_D2H, U_C_D2A, U_CT_F1, U_CT_F2, U_CT_F22, U_CT_F3, U_COUNT };
+
+// tcgen05 chains need |s| <= 32 (one resident input chunk), |a| <= 32 (one K-tail chunk) and <= 256 atoms
+static bool tcc_shapes_ok(const d4pg_learner_config_t& c) {
+  return c.chain == 1 && c.batch <= 512 && c.precision >= 1 && c.obs_dim <= 32 && c.act_dim <= 32 && c.n_atoms <= 256;
+}
+static int tcc_setup(d4pg_learner* L) {
+  L->tcc_ok = false; L->tcc_images = nullptr;
+  const d4pg_learner_config_t& c = L->cfg;
+  static const bool off = getenv("D4PG_NO_TCC") != nullptr;      // A/B switch: mma.sync chain tiles instead
+  if (!tcc_shapes_ok(c) || off) return D4PG_OK;
+  const d4pg_learner_buffers_t& b = L->buf;
+  const NetDims& da = L->da; const NetDims& dc = L->dc;
+  const int S = c.obs_dim, A = c.act_dim, N = c.n_atoms, H = D4PG_HIDDEN;
+  TccPackArgs& pk = L->tcc_pack;
+  tcc_pack_begin(pk, nullptr);
+  auto add = [&](int id, const float* W, int ldw, int mode, int rows, int K) { L->tcc_use[id] = tcc_pack_add(pk, W, ldw, mode, rows, K); };
+  const float* Wn[2] = {b.actor, b.actor_target};
+  for (int t = 0; t < 2; ++t) {
+    const int base = t ? U_AT_F1 : U_A_F1;
+    add(base + 0, Wn[t] + da.w_off[0], da.ld[0], GEMM_FWD, H, S);
+    add(base + 1, Wn[t] + da.w_off[1], da.ld[1], GEMM_FWD, H, H);
+    add(base + 2, Wn[t] + da.w_off[2], da.ld[2], GEMM_FWD, H, H);
+    add(base + 3, Wn[t] + da.w_off[3], da.ld[3], GEMM_FWD, A, H);
+  }
+  add(U_A_D3, b.actor + da.w_off[3], da.ld[3], GEMM_DX, H, A);
+  add(U_A_D22, b.actor + da.w_off[2], da.ld[2], GEMM_DX, H, H);
+  add(U_A_D2, b.actor + da.w_off[1], da.ld[1], GEMM_DX, H, H);
+  const float* Wm[2] = {b.critic, b.critic_target};
+  for (int t = 0; t < 2; ++t) {
+    const int base = t ? U_CT_F1 : U_C_F1;
+    add(base + 0, Wm[t] + dc.w_off[0], dc.ld[0], GEMM_FWD, H, S);
+    add(base + 1, Wm[t] + dc.w_off[1], dc.ld[1], GEMM_FWD, H, H + A);      // K = [h1 (256) | action]: 8 chunks + a tail chunk
+    add(base + 2, Wm[t] + dc.w_off[2], dc.ld[2], GEMM_FWD, H, H);
+    add(base + 3, Wm[t] + dc.w_off[3], dc.ld[3], GEMM_FWD, N, H);
+  }
+  add(U_C_D3, b.critic + dc.w_off[3], dc.ld[3], GEMM_DX, H, N);
+  add(U_C_D22, b.critic + dc.w_off[2], dc.ld[2], GEMM_DX, H, H);
+  add(U_C_D2H, b.critic + dc.w_off[1], dc.ld[1], GEMM_DX, H, H);
+  add(U_C_D2A, b.critic + dc.w_off[1] + H, dc.ld[1], GEMM_DX, A, H);
+  for (int i = 0; i < U_COUNT; ++i) D4PG_REQUIRE(L->tcc_use[i] >= 0, D4PG_ENOTSUP, "tcc_setup: too many weight images");
+  D4PG_CUDA_OK(cudaMalloc(&L->tcc_images, size_t(tcc_pack_bytes(pk))));
+  pk.dst = L->tcc_images;
+  (void)tcc_watchdog_device();                         // allocate outside of any stream capture
+  L->tcc_ok = true;
+  return D4PG_OK;
+}
 
 // idempotent launches (pure functions of their inputs) are repeated in profile mode
 constexpr int PROFILE_REPS = 16;
@@ -143,30 +194,18 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   const int Sp = pitch4(S), Ap = pitch4(A), Np = pitch4(N);          // activation row pitches
   const int* la = da.ld; const int* lc = dc.ld;                        // weight row pitches per layer
   int rc; int nk = 0;
-  const bool mega = c.persistent != 0;
-  MegaParams* mp = mega ? &L->mega : nullptr;
-  int n_levels = 0;
-  if (mega) { mp->n_fwd = 0; mp->n_bwd = 0; }
-  // a GEMM level is either launched or (persistent kernel) recorded as a phase
-#define LEVEL(gb)                                                                           \
-  do {                                                                                      \
-    if (mega) {                                                                             \
-      D4PG_REQUIRE(n_levels < MEGA_MAX_LEVELS, D4PG_ENOTSUP, "too many GEMM levels");       \
-      for (int _i = 0; _i < (gb).n; ++_i) { (gb).p[_i].ksplit = 1; (gb).p[_i].kslice = (gb).p[_i].K; } \
-      gemm_batch_retile(gb, 32, 32);            /* no split-K inside the persistent kernel */ \
-      GemmBatchLite& lv = mp->level[n_levels++];                                            \
-      for (int _i = 0; _i < (gb).n; ++_i) lv.p[_i] = (gb).p[_i];                            \
-      lv.n = (gb).n; lv.total_tiles = (gb).total_tiles;                                     \
-    } else RUN(gemm_launch(gb, c.precision, st));                                           \
-  } while (0)
+#define LEVEL(gb) RUN(gemm_launch(gb, c.precision, st))
 #define RUN(expr)                                                                          \
   do {                                                                                     \
     if (L->profiling) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);    \
-      std::string nm0(#expr); const bool rep = nm0.rfind("gemm_launch", 0) == 0 || nm0.rfind("launch_heads", 0) == 0 || nm0.rfind("launch_mlp_chain", 0) == 0 || nm0.rfind("launch_mlp_rows", 0) == 0; \
+      std::string nm0(#expr);                                                              \
+      /* the loss kernel also advances the sampler clock under the prefetch pipeline: not idempotent there */ \
+      const bool rep = nm0.rfind("gemm_launch", 0) == 0 || (nm0.rfind("launch_heads", 0) == 0 && !pf) || \
+                       nm0.rfind("launch_mlp_chain", 0) == 0 || nm0.rfind("launch_mlp_tc_chain", 0) == 0; \
       cudaEventRecord(e0, st); rc = (expr);                                                \
       for (int _r = 1; rep && _r < PROFILE_REPS && rc == 0; ++_r) rc = (expr);             \
       cudaEventRecord(e1, st);                                                             \
-      L->ev.push_back(e0); L->ev.push_back(e1);                                            \
+      L->ev.push_back(e0); L->ev.push_back(e1); L->ev_reps.push_back(rep ? PROFILE_REPS : 1); \
       std::string nm(#expr); L->ev_name.push_back(nm.substr(0, nm.find('('))); }           \
     else rc = (expr);                                                                      \
     if (rc) return rc;                                                                     \
@@ -177,11 +216,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   //    scalars (Adam bias corrections, PER beta, Philox counter) from the learner clock.
   ClockParams cp{c.lr_actor, c.lr_critic, c.beta1, c.beta2, c.per_beta0, c.per_beta_final,
                  c.per_beta_iters > 0 ? c.per_beta_iters : 1};
-  if (mega)
-    learner_sample_args(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
-                        (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
-                        c.philox_seed, w.clock, cp, b.idx, b.weights, w.s, w.a, w.r, w.s2, w.done, Sp, Ap, mp->sample);
-  else if (!pf || cold)
+  if (!pf || cold)
     RUN(learner_sample(L->replay, B, c.prioritized, c.sample_mode == 0 ? b.uniforms : nullptr,
                        (c.sample_mode == 0 && !c.prioritized) ? b.positions : nullptr,
                        c.philox_seed, w.clock, cp,
@@ -190,41 +225,63 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   const float* Wa = b.actor; const float* Wat = b.actor_target; const float* Wc = b.critic; const float* Wct = b.critic_target;
   GemmBatch g;
   const int plan = step_plan(c);
-  const bool chain = plan == 1, rows = plan == 2;
+  const bool tcc = plan == 1 && c.precision >= 1 && L->tcc_ok;       // tcgen05 cluster chains
+  const bool chain = plan == 1 && !tcc;
   static const bool no_pre = getenv("D4PG_NO_PRE") != nullptr;          // A/B switch
   const bool pre_ok = chain && c.precision == 0 && A <= 8 && !no_pre;   // pre-layers: fp32 tile, |a| <= 8
-  if (rows) {
-    // 2''. the same three chains, row-owner form (mlp_rows.cu): a CTA carries 5-8 rows through a whole chain
-    RowsArgs& ra = L->rows_fwd_args;
-    rows_args_begin(ra, B, S, A);
-    rows_chain_input(ra, 0, w.s2, Sp, S);
-    rows_add(ra, 0, rows_fwd(Wat + da.w_off[0], la[0], Wat + da.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, XB_IN, XB_PING, 0));
-    rows_add(ra, 0, rows_fwd(Wat + da.w_off[1], la[1], Wat + da.b_off[1], H, H, EPI_BIAS, nullptr, H, XB_PING, XB_PONG, 0));
-    rows_add(ra, 0, rows_fwd(Wat + da.w_off[2], la[2], Wat + da.b_off[2], H, H, EPI_BIAS_RELU, nullptr, H, XB_PONG, XB_PING, 0));
-    rows_add(ra, 0, rows_fwd(Wat + da.w_off[3], la[3], Wat + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[0], Ap, XB_PING, XB_CAT, H));
-    rows_add(ra, 0, rows_fwd(Wct + dc.w_off[0], lc[0], Wct + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, XB_IN, XB_CAT, 0));
-    rows_add(ra, 0, rows_fwd(Wct + dc.w_off[1], lc[1], Wct + dc.b_off[1], H, H + A, EPI_BIAS_RELU, nullptr, H, XB_CAT, XB_PING, 0));
-    rows_add(ra, 0, rows_fwd(Wct + dc.w_off[2], lc[2], Wct + dc.b_off[2], H, H, EPI_BIAS_RELU, nullptr, H, XB_PING, XB_PONG, 0));
-    rows_add(ra, 0, rows_fwd(Wct + dc.w_off[3], lc[3], Wct + dc.b_off[3], N, H, EPI_BIAS, w.out[1], Np, XB_PONG, -1, 0));
-
-    rows_chain_input(ra, 1, w.s, Sp, S);
-    rows_chain_input2(ra, 1, w.a, Ap, A, H);
-    rows_add(ra, 1, rows_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, w.h1[2], H, XB_IN, XB_CAT, 0));
-    rows_add(ra, 1, rows_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[2], H, XB_CAT, XB_PING, 0));
-    rows_add(ra, 1, rows_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[2], H, XB_PING, XB_PONG, 0));
-    rows_add(ra, 1, rows_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[2], Np, XB_PONG, -1, 0));
-
-    rows_chain_input(ra, 2, w.s, Sp, S);
-    rows_add(ra, 2, rows_fwd(Wa + da.w_off[0], la[0], Wa + da.b_off[0], H, S, EPI_BIAS_RELU, w.h1[3], H, XB_IN, XB_PING, 0));
-    rows_add(ra, 2, rows_fwd(Wa + da.w_off[1], la[1], Wa + da.b_off[1], H, H, EPI_BIAS, w.h2[3], H, XB_PING, XB_PONG, 0));
-    rows_add(ra, 2, rows_fwd(Wa + da.w_off[2], la[2], Wa + da.b_off[2], H, H, EPI_BIAS_RELU, w.h3[3], H, XB_PONG, XB_PING, 0));
-    rows_add(ra, 2, rows_fwd(Wa + da.w_off[3], la[3], Wa + da.b_off[3], A, H, EPI_BIAS_TANH, w.out[3], Ap, XB_PING, XB_CAT, H));
-    rows_add(ra, 2, rows_fwd(Wc + dc.w_off[0], lc[0], Wc + dc.b_off[0], H, S, EPI_BIAS_RELU, nullptr, H, XB_IN, XB_CAT, 0));
-    rows_add(ra, 2, rows_fwd(Wc + dc.w_off[1], lc[1], Wc + dc.b_off[1], H, H + A, EPI_BIAS_RELU, w.h2[4], H, XB_CAT, XB_PING, 0));
-    rows_add(ra, 2, rows_fwd(Wc + dc.w_off[2], lc[2], Wc + dc.b_off[2], H, H, EPI_BIAS_RELU, w.h3[4], H, XB_PING, XB_PONG, 0));
-    rows_add(ra, 2, rows_fwd(Wc + dc.w_off[3], lc[3], Wc + dc.b_off[3], N, H, EPI_BIAS, w.out[4], Np, XB_PONG, -1, 0));
-    if ((rc = rows_finalize(ra)) != 0) return rc;
-    RUN(launch_mlp_rows(ra, st));
+  if (tcc) {
+    // 2''. the same three forward chains on the tensor cores (mlp_tc_chain.cu): clusters of 8 CTAs own 64 rows,
+    // every layer a tcgen05.mma tile.  The hi/lo weight images are re-packed first (Adam / Polyak changed them).
+    RUN(launch_tcc_pack(L->tcc_pack, st));
+    const TccPackArgs& pk = L->tcc_pack; const int* U = L->tcc_use;
+    TccArgs& fa = L->tcc_fwd_args;
+    tcc_args_begin(fa, B, reinterpret_cast<uint8_t*>(w.xchg), c.precision == 1 ? 3 : 1); fa.step_slot = 1;
+    int l, p1, p2, pa;
+    // chain 0  T: actor_target(s') -> critic_target(s', .)   (fc1 of both networks share the resident s' chunk)
+    tcc_chain_x0(fa, 0, w.s2, Sp, S);
+    l = tcc_slot_begin(fa, 0); tcc_slot_src_x(fa, 0, l);
+    p1 = tcc_slot_group(fa, 0, l, pk, U[U_AT_F1], EPI_BIAS_RELU, Wat + da.b_off[0], nullptr, 0, nullptr, H, 1);
+    p2 = tcc_slot_group(fa, 0, l, pk, U[U_CT_F1], EPI_BIAS_RELU, Wct + dc.b_off[0], nullptr, 0, nullptr, H, 1);
+    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
+    p1 = tcc_slot_group(fa, 0, l, pk, U[U_AT_F2], EPI_BIAS, Wat + da.b_off[1], nullptr, 0, nullptr, H, 1);
+    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
+    p1 = tcc_slot_group(fa, 0, l, pk, U[U_AT_F22], EPI_BIAS_RELU, Wat + da.b_off[2], nullptr, 0, nullptr, H, 1);
+    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
+    pa = tcc_slot_group(fa, 0, l, pk, U[U_AT_F3], EPI_BIAS_TANH, Wat + da.b_off[3], nullptr, 0, w.out[0], Ap, 1);
+    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p2, 8); tcc_slot_src_plane(fa, 0, l, pa, 1);
+    p1 = tcc_slot_group(fa, 0, l, pk, U[U_CT_F2], EPI_BIAS_RELU, Wct + dc.b_off[1], nullptr, 0, nullptr, H, 1);
+    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
+    p1 = tcc_slot_group(fa, 0, l, pk, U[U_CT_F22], EPI_BIAS_RELU, Wct + dc.b_off[2], nullptr, 0, nullptr, H, 1);
+    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
+    tcc_slot_group(fa, 0, l, pk, U[U_CT_F3], EPI_BIAS, Wct + dc.b_off[3], nullptr, 0, w.out[1], Np, 0);
+    // chain 1  P: actor(s) -> critic(s, actor(s))
+    tcc_chain_x0(fa, 1, w.s, Sp, S);
+    l = tcc_slot_begin(fa, 1); tcc_slot_src_x(fa, 1, l);
+    p1 = tcc_slot_group(fa, 1, l, pk, U[U_A_F1], EPI_BIAS_RELU, Wa + da.b_off[0], nullptr, 0, w.h1[3], H, 1);
+    p2 = tcc_slot_group(fa, 1, l, pk, U[U_C_F1], EPI_BIAS_RELU, Wc + dc.b_off[0], nullptr, 0, nullptr, H, 1);
+    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
+    p1 = tcc_slot_group(fa, 1, l, pk, U[U_A_F2], EPI_BIAS, Wa + da.b_off[1], nullptr, 0, w.h2[3], H, 1);
+    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
+    p1 = tcc_slot_group(fa, 1, l, pk, U[U_A_F22], EPI_BIAS_RELU, Wa + da.b_off[2], nullptr, 0, w.h3[3], H, 1);
+    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
+    pa = tcc_slot_group(fa, 1, l, pk, U[U_A_F3], EPI_BIAS_TANH, Wa + da.b_off[3], nullptr, 0, w.out[3], Ap, 1);
+    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p2, 8); tcc_slot_src_plane(fa, 1, l, pa, 1);
+    p1 = tcc_slot_group(fa, 1, l, pk, U[U_C_F2], EPI_BIAS_RELU, Wc + dc.b_off[1], nullptr, 0, w.h2[4], H, 1);
+    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
+    p1 = tcc_slot_group(fa, 1, l, pk, U[U_C_F22], EPI_BIAS_RELU, Wc + dc.b_off[2], nullptr, 0, w.h3[4], H, 1);
+    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
+    tcc_slot_group(fa, 1, l, pk, U[U_C_F3], EPI_BIAS, Wc + dc.b_off[3], nullptr, 0, w.out[4], Np, 0);
+    // chain 2  Q: critic(s, a): the resident chunk holds s for fc1, then the replay actions (fc2's K tail)
+    tcc_chain_x0(fa, 2, w.s, Sp, S);
+    l = tcc_slot_begin(fa, 2); tcc_slot_src_x(fa, 2, l); tcc_slot_reconvert_x(fa, 2, l, w.a, Ap, A);
+    p1 = tcc_slot_group(fa, 2, l, pk, U[U_C_F1], EPI_BIAS_RELU, Wc + dc.b_off[0], nullptr, 0, w.h1[2], H, 1);
+    l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8); tcc_slot_src_x(fa, 2, l);
+    p1 = tcc_slot_group(fa, 2, l, pk, U[U_C_F2], EPI_BIAS_RELU, Wc + dc.b_off[1], nullptr, 0, w.h2[2], H, 1);
+    l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8);
+    p1 = tcc_slot_group(fa, 2, l, pk, U[U_C_F22], EPI_BIAS_RELU, Wc + dc.b_off[2], nullptr, 0, w.h3[2], H, 1);
+    l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8);
+    tcc_slot_group(fa, 2, l, pk, U[U_C_F3], EPI_BIAS, Wc + dc.b_off[3], nullptr, 0, w.out[2], Np, 0);
+    RUN(launch_mlp_tc_chain(fa, st));
   } else if (chain) {
     // 2'. the three forward chains of the step as ONE cluster launch (mlp_chain.cu):
     //   chain 0  T: actor_target(s') -> critic_target(s', .)      ddpg.py:205-206
@@ -334,15 +391,11 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   ha.is_weights = ((c.loss_flags & 1) && c.prioritized) ? bwts : nullptr;
   ha.sampler_clock = pf ? w.clock : nullptr;          // sample(t) is done, sample(t+1) not yet launched
   ha.ce_priority = (c.loss_flags & 2) ? 1 : 0;
-  if (mega) { mp->heads = ha; mp->heads_mode = c.proj_mode; mp->n_fwd = n_levels; }
-  else RUN(launch_heads(ha, c.proj_mode, st));
+  RUN(launch_heads(ha, c.proj_mode, st));
 
   // 4. priorities into the trees (ddpg.py:252-255): independent of the backward pass, so it runs
   //    on a forked branch (side stream -> parallel graph branch) and joins before the step ends
-  if (mega) {
-    mp->do_tree = c.prioritized ? 1 : 0;
-    if (c.prioritized) tree_update_args(L->replay, B, b.idx, b.prio, mp->tree);
-  } else if (c.prioritized || pf) {
+  if (c.prioritized || pf) {
     D4PG_CUDA_OK(cudaEventRecord(L->ev_fork, st));
     D4PG_CUDA_OK(cudaStreamWaitEvent(L->side, L->ev_fork, 0));
     if (pf) {                                          // the caller-visible copies of this step's indices / IS weights
@@ -370,25 +423,35 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   const bool peer_mode = c.world_size > 1 && comm_peer_info(L->comm, &peers);
   const int gpar = pf ? par : int(L->steps_done & 1);
   if (peer_mode) { Ga = peers.x[peers.rank] + int64_t(gpar) * peers.n; Gc = Ga + da.total; }
-  if (B >= 1024 && !mega)                // dW levels run split-K with fp32 atomics: the gradient buffer must start at zero
+  if (B >= 1024)                // dW levels run split-K with fp32 atomics: the gradient buffer must start at zero
     D4PG_CUDA_OK(cudaMemsetAsync(Ga, 0, size_t(da.total + dc.total) * sizeof(float), st));
-  if (rows) {
-    // 5''. both dX chains, row-owner form
-    RowsArgs& rb = L->rows_bwd_args;
-    rows_args_begin(rb, B, S, A); rb.trace_base = 2 * ROWS_MAX_LAYERS + 8;
-    rows_chain_input(rb, 0, w.dlogits_q, Np, N);
-    rows_add(rb, 0, rows_dx(Wc + dc.w_off[3], lc[3], H, N, EPI_RELU_MASK, w.h3[2], H, w.c_dz22, H, XB_IN, XB_PING, 0));
-    rows_add(rb, 0, rows_dx(Wc + dc.w_off[2], lc[2], H, H, EPI_RELU_MASK, w.h2[2], H, w.c_dz2, H, XB_PING, XB_PONG, 0));
-    rows_add(rb, 0, rows_dx(Wc + dc.w_off[1], lc[1], H, H, EPI_RELU_MASK, w.h1[2], H, w.c_dz1, H, XB_PONG, -1, 0));
-    rows_chain_input(rb, 1, w.dlogits_pi, Np, N);
-    rows_add(rb, 1, rows_dx(Wc + dc.w_off[3], lc[3], H, N, EPI_RELU_MASK, w.h3[4], H, nullptr, H, XB_IN, XB_PING, 0));
-    rows_add(rb, 1, rows_dx(Wc + dc.w_off[2], lc[2], H, H, EPI_RELU_MASK, w.h2[4], H, nullptr, H, XB_PING, XB_PONG, 0));
-    rows_add(rb, 1, rows_dx(Wc + dc.w_off[1] + H, lc[1], A, H, EPI_TANH_MASK, w.out[3], Ap, w.a_dz3, Ap, XB_PONG, XB_PING, 0));
-    rows_add(rb, 1, rows_dx(Wa + da.w_off[3], la[3], H, A, EPI_RELU_MASK, w.h3[3], H, w.a_dz22, H, XB_PING, XB_PONG, 0));
-    rows_add(rb, 1, rows_dx(Wa + da.w_off[2], la[2], H, H, EPI_NONE, nullptr, 0, w.a_dh2, H, XB_PONG, XB_PING, 0));
-    rows_add(rb, 1, rows_dx(Wa + da.w_off[1], la[1], H, H, EPI_RELU_MASK, w.h1[3], H, w.a_dz1, H, XB_PING, -1, 0));
-    if ((rc = rows_finalize(rb)) != 0) return rc;
-    RUN(launch_mlp_rows(rb, st));
+  if (tcc) {
+    // 5''. both dX chains on the tensor cores (transposed weight images; masks applied by the epilogue)
+    const TccPackArgs& pk = L->tcc_pack; const int* U = L->tcc_use;
+    TccArgs& ba = L->tcc_bwd_args;
+    tcc_args_begin(ba, B, reinterpret_cast<uint8_t*>(w.xchg), c.precision == 1 ? 3 : 1); ba.step_slot = 5;
+    int l, p1;
+    tcc_chain_pre(ba, 0, w.dlogits_q, Np, N);                     // C: critic loss
+    l = tcc_slot_begin(ba, 0); tcc_slot_src_pre(ba, 0, l);
+    p1 = tcc_slot_group(ba, 0, l, pk, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[2], H, w.c_dz22, H, 1);
+    l = tcc_slot_begin(ba, 0); tcc_slot_src_plane(ba, 0, l, p1, 8);
+    p1 = tcc_slot_group(ba, 0, l, pk, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[2], H, w.c_dz2, H, 1);
+    l = tcc_slot_begin(ba, 0); tcc_slot_src_plane(ba, 0, l, p1, 8);
+    tcc_slot_group(ba, 0, l, pk, U[U_C_D2H], EPI_RELU_MASK, nullptr, w.h1[2], H, w.c_dz1, H, 0);
+    tcc_chain_pre(ba, 1, w.dlogits_pi, Np, N);                    // P: policy loss (PRE-update critic weights)
+    l = tcc_slot_begin(ba, 1); tcc_slot_src_pre(ba, 1, l);
+    p1 = tcc_slot_group(ba, 1, l, pk, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[4], H, nullptr, H, 1);
+    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
+    p1 = tcc_slot_group(ba, 1, l, pk, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[4], H, nullptr, H, 1);
+    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
+    p1 = tcc_slot_group(ba, 1, l, pk, U[U_C_D2A], EPI_TANH_MASK, nullptr, w.out[3], Ap, w.a_dz3, Ap, 1);
+    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 1);
+    p1 = tcc_slot_group(ba, 1, l, pk, U[U_A_D3], EPI_RELU_MASK, nullptr, w.h3[3], H, w.a_dz22, H, 1);
+    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
+    p1 = tcc_slot_group(ba, 1, l, pk, U[U_A_D22], EPI_NONE, nullptr, nullptr, 0, w.a_dh2, H, 1);
+    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
+    tcc_slot_group(ba, 1, l, pk, U[U_A_D2], EPI_RELU_MASK, nullptr, w.h1[3], H, w.a_dz1, H, 0);
+    RUN(launch_mlp_tc_chain(ba, st));
   }
   if (chain) {
     // 5'. both dX chains as ONE cluster launch, then every dW of the step as ONE grouped launch
@@ -416,7 +479,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     sl = chain_dx(Wa + da.w_off[1], la[1], H, H, EPI_RELU_MASK, w.h1[3], H, w.a_dz1, H, 0); chain_src_plane(sl, t); chain_add(cb, 1, sl);
     RUN(launch_mlp_chain(cb, st));
   }
-  if (chain || rows) {                    // every dW of the step as ONE grouped launch
+  if (chain || tcc) {                     // every dW of the step as ONE grouped launch
     GemmWideBatch& gw = L->dw_batch;
     gemm_wide_begin(gw, peer_mode ? peers.flag[peers.rank] : nullptr);   // its last CTA signals the peers
     gemm_wide_add(gw, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], lc[2], Gc + dc.b_off[2], H, H, B));
@@ -476,7 +539,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   // 6. data-parallel gradient exchange: ONE all-reduce over the flat [P_a + P_c] buffer
   // every rank's half of this step must be complete before Adam sums them: the chain plans signal from the dW
   // kernel and wait inside the Adam kernel; the level plan (several dW launches) uses a small barrier launch
-  const bool inline_sync = peer_mode && (chain || rows);
+  const bool inline_sync = peer_mode && (chain || tcc);
   if (peer_mode && !inline_sync) RUN(comm_peer_barrier(L->comm, st));
   else if (!peer_mode && c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
 
@@ -498,14 +561,8 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   aa.pipe_slot = pf ? par : -1;
   // tail slice of the same launch: reported batch-mean losses + advance the device clock
   aa.loss_rows = w.loss_rows; aa.pi_rows = w.pi_rows; aa.B = B; aa.inv_count = 1.0f / float(B); aa.loss_out = b.losses;
-  if (mega) {
-    mp->n_bwd = n_levels - mp->n_fwd;
-    mp->adam = aa; mp->clock = w.clock; mp->barrier = w.barrier; mp->trace = debug_trace_buffer();
-    RUN(launch_step_mega(*mp, st));
-  } else {
-    RUN(launch_adam(aa, st));
-    if (c.prioritized || pf) D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join, 0));
-  }
+  RUN(launch_adam(aa, st));
+  if (c.prioritized || pf) D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join, 0));
 #undef LEVEL
 #undef RUN
   L->kernels_per_step = nk;
@@ -527,11 +584,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   D4PG_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, D4PG_ENOTSUP,
                "d4pg_learner_create: precision %d unknown (0 fp32 FFMA, 1 3xTF32 tcgen05, 2 TF32 tcgen05)", cfg->precision);
   D4PG_REQUIRE(cfg->world_size <= 1 || comm, D4PG_EINVAL, "d4pg_learner_create: world_size>1 needs a communicator");
-  D4PG_REQUIRE(!cfg->persistent || (cfg->precision == 0 && cfg->world_size <= 1), D4PG_ENOTSUP,
-               "d4pg_learner_create: the persistent step kernel needs precision 0 and a single GPU");
-  D4PG_REQUIRE(cfg->chain >= 0 && cfg->chain <= 2, D4PG_EINVAL, "d4pg_learner_create: chain must be 0, 1 or 2");
-  D4PG_REQUIRE(!cfg->chain || !cfg->persistent, D4PG_ENOTSUP, "d4pg_learner_create: the fused chain kernels exclude persistent");
-  D4PG_REQUIRE(cfg->chain != 2 || cfg->precision == 0, D4PG_ENOTSUP, "d4pg_learner_create: the row-owner chains are fp32 only");
+  D4PG_REQUIRE(cfg->chain == 0 || cfg->chain == 1, D4PG_EINVAL, "d4pg_learner_create: chain must be 0 or 1");
   D4PG_REQUIRE(buf->actor && buf->actor_target && buf->critic && buf->critic_target && buf->grad_actor && buf->grad_critic &&
                buf->adam_m_actor && buf->adam_v_actor && buf->adam_m_critic && buf->adam_v_critic &&
                buf->idx && buf->prio && buf->td && buf->losses && buf->workspace, D4PG_EINVAL,
@@ -552,7 +605,20 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   L->steps_done = 0; L->kernels_per_step = 0;
   L->profiling = false;
   (void)debug_trace_buffer();          // allocate outside of any stream capture
-  L->host_u = nullptr; L->host_pos = nullptr; L->host_losses = nullptr; L->ev_in = nullptr; L->ev_out = nullptr;
+  if (int rc = tcc_setup(L)) { delete L; return rc; }
+  L->host_steps = 0; L->host_losses = nullptr; L->ev_in = nullptr; L->ev_out = nullptr;
+  for (int i = 0; i < 2; ++i) { L->host_u[i] = nullptr; L->host_pos[i] = nullptr; L->ev_h2d[i] = nullptr; }
+  {
+    const size_t nb = size_t(cfg->batch);
+    bool ok = cudaEventCreateWithFlags(&L->ev_in, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&L->ev_out, cudaEventDisableTiming) == cudaSuccess &&
+              cudaHostAlloc(reinterpret_cast<void**>(&L->host_losses), 4 * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&L->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaHostAlloc(reinterpret_cast<void**>(&L->host_u[i]), nb * sizeof(double), cudaHostAllocDefault) == cudaSuccess &&
+           cudaHostAlloc(reinterpret_cast<void**>(&L->host_pos[i]), nb * sizeof(int32_t), cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) { set_error("d4pg_learner_create: pinned staging allocation failed"); delete L; return D4PG_ECUDA; }
+  }
   if (cudaStreamCreateWithFlags(&L->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -570,8 +636,15 @@ extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   for (int i = 0; i < 4; ++i) if (L->graph_exec[i]) cudaGraphExecDestroy(L->graph_exec[i]);
   for (int i = 0; i < 2; ++i) if (L->multi_exec[i]) cudaGraphExecDestroy(L->multi_exec[i]);
   cudaEventDestroy(L->ev_fork); cudaEventDestroy(L->ev_join); cudaStreamDestroy(L->side);
+  if (L->tcc_images) cudaFree(L->tcc_images);
   if (L->ev_in) cudaEventDestroy(L->ev_in);
   if (L->ev_out) cudaEventDestroy(L->ev_out);
+  if (L->host_losses) cudaFreeHost(L->host_losses);
+  for (int i = 0; i < 2; ++i) {
+    if (L->ev_h2d[i]) cudaEventDestroy(L->ev_h2d[i]);
+    if (L->host_u[i]) cudaFreeHost(L->host_u[i]);
+    if (L->host_pos[i]) cudaFreeHost(L->host_pos[i]);
+  }
   delete L;
   return D4PG_OK;
 }
@@ -618,31 +691,32 @@ extern "C" int32_t d4pg_learner_step(d4pg_learner_t* L, d4pg_stream_t stream) {
   return D4PG_OK;
 }
 
-extern "C" int32_t d4pg_learner_set_host_buffers(d4pg_learner_t* L, double* pinned_uniforms, int32_t* pinned_positions,
-                                                 float* pinned_losses) {
-  D4PG_REQUIRE(L && pinned_losses, D4PG_EINVAL, "d4pg_learner_set_host_buffers: null argument");
-  L->host_u = pinned_uniforms; L->host_pos = pinned_positions; L->host_losses = pinned_losses;
-  if (!L->ev_in) D4PG_CUDA_OK(cudaEventCreateWithFlags(&L->ev_in, cudaEventDisableTiming));
-  if (!L->ev_out) D4PG_CUDA_OK(cudaEventCreateWithFlags(&L->ev_out, cudaEventDisableTiming));
-  return D4PG_OK;
-}
-
-extern "C" int32_t d4pg_learner_step_host(d4pg_learner_t* L, const double* uniforms, const int32_t* positions,
-                                          d4pg_stream_t caller_stream, d4pg_stream_t learner_stream) {
-  D4PG_REQUIRE(L && L->ev_in, D4PG_ESTATE, "d4pg_learner_step_host: call d4pg_learner_set_host_buffers first");
+// The host-facing step: stage this step's host inputs in pinned memory, H2D, the step, order the caller after it.
+static int step_host_common(d4pg_learner_t* L, const double* uniforms, const uint32_t* mt_words, const int32_t* positions,
+                            d4pg_stream_t caller_stream, d4pg_stream_t learner_stream) {
   cudaStream_t cs = as_stream(caller_stream), ls = as_stream(learner_stream);
   const int B = L->cfg.batch;
+  const int par = int(L->host_steps & 1);
   D4PG_CUDA_OK(cudaEventRecord(L->ev_in, cs));                 // adds / weight loads issued by the caller
   D4PG_CUDA_OK(cudaStreamWaitEvent(ls, L->ev_in, 0));
-  if (uniforms) {
-    D4PG_REQUIRE(L->host_u && L->buf.uniforms, D4PG_ESTATE, "d4pg_learner_step_host: no uniforms buffers");
-    if (uniforms != L->host_u) memcpy(L->host_u, uniforms, size_t(B) * sizeof(double));
-    D4PG_CUDA_OK(cudaMemcpyAsync(L->buf.uniforms, L->host_u, size_t(B) * sizeof(double), cudaMemcpyHostToDevice, ls));
-  }
-  if (positions) {
-    D4PG_REQUIRE(L->host_pos && L->buf.positions, D4PG_ESTATE, "d4pg_learner_step_host: no positions buffers");
-    if (positions != L->host_pos) memcpy(L->host_pos, positions, size_t(B) * sizeof(int32_t));
-    D4PG_CUDA_OK(cudaMemcpyAsync(L->buf.positions, L->host_pos, size_t(B) * sizeof(int32_t), cudaMemcpyHostToDevice, ls));
+  if (uniforms || mt_words || positions) {
+    if (L->host_steps >= 2) D4PG_CUDA_OK(cudaEventSynchronize(L->ev_h2d[par]));   // the copy out of this buffer, two steps ago
+    if (uniforms || mt_words) {
+      D4PG_REQUIRE(L->buf.uniforms, D4PG_ESTATE, "d4pg_learner_step_host: no device uniforms buffer");
+      double* u = L->host_u[par];
+      if (uniforms) memcpy(u, uniforms, size_t(B) * sizeof(double));
+      else                                                     // CPython random.random(): (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53
+        for (int i = 0; i < B; ++i)
+          u[i] = (double(mt_words[2 * i] >> 5) * 67108864.0 + double(mt_words[2 * i + 1] >> 6)) * (1.0 / 9007199254740992.0);
+      D4PG_CUDA_OK(cudaMemcpyAsync(L->buf.uniforms, u, size_t(B) * sizeof(double), cudaMemcpyHostToDevice, ls));
+    }
+    if (positions) {
+      D4PG_REQUIRE(L->buf.positions, D4PG_ESTATE, "d4pg_learner_step_host: no device positions buffer");
+      memcpy(L->host_pos[par], positions, size_t(B) * sizeof(int32_t));
+      D4PG_CUDA_OK(cudaMemcpyAsync(L->buf.positions, L->host_pos[par], size_t(B) * sizeof(int32_t), cudaMemcpyHostToDevice, ls));
+    }
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_h2d[par], ls));
+    ++L->host_steps;
   }
   int rc = d4pg_learner_step(L, learner_stream);
   if (rc) return rc;
@@ -651,8 +725,20 @@ extern "C" int32_t d4pg_learner_step_host(d4pg_learner_t* L, const double* unifo
   return D4PG_OK;
 }
 
+extern "C" int32_t d4pg_learner_step_host(d4pg_learner_t* L, const double* uniforms, const int32_t* positions,
+                                          d4pg_stream_t caller_stream, d4pg_stream_t learner_stream) {
+  D4PG_REQUIRE(L, D4PG_EINVAL, "d4pg_learner_step_host: null handle");
+  return step_host_common(L, uniforms, nullptr, positions, caller_stream, learner_stream);
+}
+
+extern "C" int32_t d4pg_learner_step_host_mt(d4pg_learner_t* L, const uint32_t* mt_words,
+                                             d4pg_stream_t caller_stream, d4pg_stream_t learner_stream) {
+  D4PG_REQUIRE(L && mt_words, D4PG_EINVAL, "d4pg_learner_step_host_mt: null argument");
+  return step_host_common(L, nullptr, mt_words, nullptr, caller_stream, learner_stream);
+}
+
 extern "C" int32_t d4pg_learner_read_losses(d4pg_learner_t* L, float* out4, d4pg_stream_t learner_stream) {
-  D4PG_REQUIRE(L && out4 && L->host_losses, D4PG_ESTATE, "d4pg_learner_read_losses: call d4pg_learner_set_host_buffers first");
+  D4PG_REQUIRE(L && out4, D4PG_EINVAL, "d4pg_learner_read_losses: null argument");
   cudaStream_t ls = as_stream(learner_stream);
   D4PG_CUDA_OK(cudaMemcpyAsync(L->host_losses, L->buf.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, ls));
   D4PG_CUDA_OK(cudaStreamSynchronize(ls));
@@ -700,7 +786,7 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
                                              float* ms_out, char* names_out, int32_t name_stride, int32_t* n_out) {
   D4PG_REQUIRE(L && ms_out && n_out && max_launches > 0, D4PG_EINVAL, "d4pg_learner_profile_step: bad arguments");
   cudaStream_t st = as_stream(stream);
-  L->profiling = true; L->ev.clear(); L->ev_name.clear();
+  L->profiling = true; L->ev.clear(); L->ev_name.clear(); L->ev_reps.clear();
   int par; bool cold;
   next_variant(L, &par, &cold);
   int rc = enqueue_step(L, st, par, cold);
@@ -712,7 +798,7 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
   for (int i = 0; i < n; ++i) {
     float ms = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, L->ev[2 * i], L->ev[2 * i + 1]);
-    if (L->ev_name[i] == "gemm_launch" || L->ev_name[i] == "launch_heads" || L->ev_name[i] == "launch_mlp_chain" || L->ev_name[i] == "launch_mlp_rows") ms /= float(PROFILE_REPS);
+    ms /= float(L->ev_reps[i]);
     if (i < max_launches) {
       ms_out[i] = ms;
       if (names_out && name_stride > 1) {
@@ -722,7 +808,7 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
     }
     cudaEventDestroy(L->ev[2 * i]); cudaEventDestroy(L->ev[2 * i + 1]);
   }
-  L->ev.clear(); L->ev_name.clear();
+  L->ev.clear(); L->ev_name.clear(); L->ev_reps.clear();
   if (e != cudaSuccess) { set_error("d4pg_learner_profile_step: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
   return rc;
 }
@@ -737,7 +823,6 @@ extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_ste
   c.s_adam_step = adam_step; c.s_beta_t = beta_t; c.s_steps_done = adam_step;
   L->prefetch_valid = false;                          // a prefetched batch was drawn with the old counters
   D4PG_CUDA_OK(cudaMemcpyAsync(L->ws.clock, &c, sizeof(c), cudaMemcpyHostToDevice, as_stream(stream)));
-  D4PG_CUDA_OK(cudaMemsetAsync(L->ws.barrier, 0, 64 * sizeof(float), as_stream(stream)));
   D4PG_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
   return D4PG_OK;
 }
@@ -755,7 +840,13 @@ extern "C" int32_t d4pg_learner_tensor(d4pg_learner_t* L, const char* name, void
       {"m", w.m, B * Np, Np}, {"q_probs", w.q_probs, B * Np, Np}, {"target_probs", w.target_probs, B * Np, Np},
       {"dlogits_q", w.dlogits_q, B * Np, Np}, {"dlogits_pi", w.dlogits_pi, B * Np, Np},
       {"actor_out", w.out[3], B * Ap, Ap}, {"actor_target_out", w.out[0], B * Ap, Ap},
-      {"loss_rows", w.loss_rows, B, 1}, {"pi_rows", w.pi_rows, B, 1}};
+      {"loss_rows", w.loss_rows, B, 1}, {"pi_rows", w.pi_rows, B, 1},
+      {"h1_c", w.h1[2], B * 256, 256}, {"h2_c", w.h2[2], B * 256, 256}, {"h3_c", w.h3[2], B * 256, 256},
+      {"h1_a", w.h1[3], B * 256, 256}, {"h2_a", w.h2[3], B * 256, 256}, {"h3_a", w.h3[3], B * 256, 256},
+      {"h2_p", w.h2[4], B * 256, 256}, {"h3_p", w.h3[4], B * 256, 256},
+      {"c_dz22", w.c_dz22, B * 256, 256}, {"c_dz2", w.c_dz2, B * 256, 256}, {"c_dz1", w.c_dz1, B * 256, 256},
+      {"a_dz3", w.a_dz3, B * Ap, Ap}, {"a_dz22", w.a_dz22, B * 256, 256}, {"a_dh2", w.a_dh2, B * 256, 256},
+      {"a_dz1", w.a_dz1, B * 256, 256}};
   for (const E& e : table)
     if (strcmp(e.n, name) == 0) { *ptr = e.p; *count = e.c; *ld = e.ld; return D4PG_OK; }
   set_error("d4pg_learner_tensor: unknown tensor '%s'", name);

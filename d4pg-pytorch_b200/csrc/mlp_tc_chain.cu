@@ -1,0 +1,579 @@
+// tcgen05 cluster chains: every dependent layer of an actor/critic network chain in ONE launch, each layer a
+// tcgen05.mma (UTCHMMA) tile with a TMEM accumulator, operands brought in by TMA bulk copies.
+//
+// Reference ops: actor.forward / critic.forward (models.py:32-41,76-88) for the five forward passes of
+// DDPG.train (ddpg.py:205-208,236) and the two backward passes of ddpg.py:230,242 (dX only; dW is gemm_wide).
+//
+// Decomposition.  A thread-block CLUSTER of 8 CTAs owns 64 batch rows (UMMA M = 64) for a whole chain.  CTA r
+// owns output features [32r, 32r+32) of every 256-wide layer (UMMA N = 32), so a layer is eight 64x32xK tiles
+// and the layer-to-layer dependency is an all-gather of the 64x256 activation plane inside the cluster.
+//
+// Precision.  3xTF32: x = hi + lo, hi = x with the low 13 mantissa bits cleared, lo = tf32(x - hi);
+// D += Al*Bh + Ah*Bl + Ah*Bh with fp32 accumulation in TMEM (~2^-21 relative, meets the 1e-5 parity bar).
+// Nothing is split on the critical path:
+//   * weights: hi/lo parts are PRE-PACKED once per step (tcc_pack_kernel, right after Adam changed them) into the
+//     exact shared-memory image the MMA reads (K-major SWIZZLE_128B, 32x32 blocks) -- for the backward pass the
+//     transposed image -- so a CTA's weight slice of a layer is ONE contiguous cp.async.bulk;
+//   * activations: the epilogue that PRODUCES a layer output (tcgen05.ld -> bias/ReLU/tanh/mask) writes it three
+//     times: row-major fp32 (for the loss kernel / dW), and as hi and lo images of its 64x32 tile = K-chunk r of
+//     the next layer's A operand, already swizzled.  The consumers fetch chunk c with one 16-KB cp.async.bulk.
+//
+// Per CTA: warp 0 = loader (one lane issues every bulk copy: weight slice one slot ahead, A chunks into an
+// 8-deep ring, completion on mbarriers by byte count), warp 1 = TMEM owner + the single MMA-issuing lane (12
+// tcgen05.mma per 32-deep chunk and group; tcgen05.commit releases ring buffers and signals the accumulator),
+// warps 2..9 = epilogue (lane quarter = warp % 4, 16 accumulator columns each).  A slot boundary is a cluster
+// barrier (arrive.release / wait.acquire): outputs in L2 are visible, ring and weight buffers are free.
+#include "mlp_tc_chain.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+namespace d4pg {
+
+using namespace tc;
+
+// shared-memory map (bytes from the 1024-B aligned base)
+constexpr uint32_t TCC_OFF_RING = 0;
+constexpr uint32_t TCC_OFF_X = TCC_RING * TCC_A_CHUNK;
+constexpr uint32_t TCC_OFF_W = TCC_OFF_X + TCC_A_CHUNK;
+constexpr uint32_t TCC_OFF_BAR = TCC_OFF_W + TCC_MAX_CHUNKS * TCC_W_CHUNK;
+constexpr uint32_t TCC_SMEM = TCC_OFF_BAR + 256 + 1024;      // barriers + alignment slack
+constexpr int TCC_TMEM_COLS = 64;
+constexpr int TCC_TRACE_PER_SLOT = 8;
+
+__device__ __forceinline__ void tcc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tcc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned tcc_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned long long tcc_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// 1-D bulk copy global -> this CTA's shared memory, completion by byte count on an mbarrier
+__device__ __forceinline__ void tcc_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Watchdog: every mbarrier wait of this kernel is bounded (~2 s of SM clocks).  A protocol bug then ends the launch
+// with a trap and a record in HOST-mapped memory (readable after the context died: d4pg_debug_watchdog) instead of
+// hanging the GPU.  record[0] = 1, [1] = code | slot << 8 | rank << 16 | parity << 24 | block << 32, [2] = seq / nact.
+__device__ __forceinline__ void tcc_wait(uint64_t* bar, uint32_t parity, unsigned long long* dbg, unsigned code, unsigned aux) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  bool recorded = false;
+  while (!mbar_try_wait(bar, parity)) {
+    const long long dt = clock64() - t0;
+    if (dt > 4000000000ll && !recorded) {
+      recorded = true;
+      if (dbg) {
+        if (atomicCAS(dbg, 0ull, 1ull) == 0ull) {           // the first wait that timed out anywhere
+          dbg[1] = (unsigned long long)code | ((unsigned long long)parity << 24) | ((unsigned long long)blockIdx.x << 32);
+          dbg[2] = aux;
+        }
+        const unsigned kind = code & 0xFFu;                 // and the first one of every kind (5 kinds, 2 words each)
+        if (kind < 6 && atomicCAS(dbg + 4 + 2 * kind, 0ull, 1ull) == 0ull) {
+          dbg[4 + 2 * kind] = (unsigned long long)code | ((unsigned long long)parity << 24) | ((unsigned long long)blockIdx.x << 32);
+          dbg[5 + 2 * kind] = aux;
+        }
+        __threadfence_system();
+      }
+    }
+    if (dt > 5000000000ll) __trap();                        // every stuck waiter had time to leave its record
+  }
+}
+#define TCC_CODE(kind, slot, rank) (unsigned(kind) | (unsigned(slot) << 8) | (unsigned(rank) << 16))
+enum { WD_LOADER_EMPTY = 1, WD_LOADER_DFULL = 2, WD_MMA_WFULL = 3, WD_MMA_FULL = 4, WD_EPI_DFULL = 5 };
+
+// generic-proxy writes (shared AND global) -> ordered before later async-proxy (TMA / tensor core) accesses
+__device__ __forceinline__ void tcc_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// 32 lanes x 16 columns of fp32 accumulators
+__device__ __forceinline__ void tcc_tmem_ld16(uint32_t taddr, float (&r)[16]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float4 tcc_hi4(float4 v) { return make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w)); }
+__device__ __forceinline__ float4 tcc_lo4(float4 v, float4 h) {
+  return make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
+}
+
+// [64 rows x 32 k] chunk of a row-major fp32 array -> hi / lo SWIZZLE_128B K-major images (256 epilogue threads)
+__device__ __forceinline__ void tcc_convert_chunk(uint8_t* dst, const float* __restrict__ src, int ld, int k0, int ncols,
+                                                  int m0, int B, int et) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int e = et + p * 256, row = e >> 3, u = e & 7, k = k0 + (u << 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + row < B && k < ncols) {
+      v = __ldg(reinterpret_cast<const float4*>(src + size_t(m0 + row) * ld + k));     // ld is a multiple of 4 >= ncols
+      if (k + 1 >= ncols) v.y = 0.f;
+      if (k + 2 >= ncols) v.z = 0.f;
+      if (k + 3 >= ncols) v.w = 0.f;
+    }
+    const float4 h = tcc_hi4(v);
+    const uint32_t off = sw128_kmajor_off(row, u << 2);
+    *reinterpret_cast<float4*>(dst + off) = h;
+    *reinterpret_cast<float4*>(dst + TCC_A_HALF + off) = tcc_lo4(v, h);
+  }
+}
+
+__device__ __forceinline__ bool tcc_group_active(const TccSlot& S, int g, int n0) { return g < S.ngroups && n0 < S.g[g].N; }
+__device__ __forceinline__ bool tcc_slot_active(const TccSlot& S, int n0) { return tcc_group_active(S, 0, n0) || tcc_group_active(S, 1, n0); }
+
+// loader lane: the CTA's weight slices of one slot -> W buffer (one bulk copy per group)
+__device__ __forceinline__ void tcc_issue_weights(const TccSlot& S, int rank, int n0, uint8_t* Wb, uint64_t* wfull, int flags) {
+  const uint32_t gbytes = uint32_t(S.nchunks) * TCC_W_CHUNK;
+  uint32_t bytes = 0;
+#pragma unroll
+  for (int g = 0; g < TCC_MAX_GROUPS; ++g)
+    if (tcc_group_active(S, g, n0)) bytes += gbytes;
+  mbar_expect_tx(wfull, bytes);
+#pragma unroll
+  for (int g = 0; g < TCC_MAX_GROUPS; ++g)
+    if (tcc_group_active(S, g, n0)) {
+      if (flags & 1) {                           // debugging: one copy per chunk
+        for (int c = 0; c < S.nchunks; ++c)
+          tcc_bulk_load(Wb + g * gbytes + c * TCC_W_CHUNK, S.g[g].wimg + size_t(rank) * gbytes + size_t(c) * TCC_W_CHUNK, TCC_W_CHUNK, wfull);
+      } else tcc_bulk_load(Wb + g * gbytes, S.g[g].wimg + size_t(rank) * gbytes, gbytes, wfull);
+    }
+}
+
+__global__ void __cluster_dims__(TCC_CLUSTER, 1, 1) __launch_bounds__(TCC_THREADS, 1)
+mlp_tc_chain_kernel(const __grid_constant__ TccArgs args) {
+  extern __shared__ uint8_t tcc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tcc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem + TCC_OFF_RING;
+  uint8_t* Xb = smem + TCC_OFF_X;
+  uint8_t* Wb = smem + TCC_OFF_W;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TCC_OFF_BAR);
+  uint64_t* full = bars;                 // [TCC_RING]  bytes of a ring buffer have landed
+  uint64_t* empty = bars + TCC_RING;     // [TCC_RING]  MMAs reading a ring buffer have completed
+  uint64_t* wfull = bars + 2 * TCC_RING; // weight slices of the current slot have landed
+  uint64_t* dfull = wfull + 1;           // all MMAs of the current slot have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = int(tcc_ctarank());
+  const int cid = blockIdx.x / TCC_CLUSTER;
+  const int chain = cid / args.row_blocks, rb = cid - chain * args.row_blocks;
+  const int m0 = rb * TCC_ROWS, B = args.B;
+  const TccChain& CH = args.chain[chain];
+  const int ns = CH.nslots;
+  const int n0 = rank * TCC_BN;
+  uint8_t* planes = args.xchg + (size_t(chain) * args.row_blocks + rb) * (size_t(TCC_PLANES) * TCC_PLANE_BYTES);
+  const int npre = CH.pre ? (CH.precols + TCC_KC - 1) / TCC_KC : 0;
+  const int passes = args.passes;
+  unsigned long long* tr0 = (args.trace && int(blockIdx.x) == args.trace_cta) ? args.trace : nullptr;
+  step_stamp(args.step_trace, args.step_slot);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2 * TCC_RING + 2; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TCC_TMEM_COLS);
+  if (warp >= 2) {
+    const int et = tid - 64;
+    if (CH.x0) tcc_convert_chunk(Xb, CH.x0, CH.x0ld, 0, CH.x0cols, m0, B, et);
+    for (int p = 0; p < npre; ++p) tcc_convert_chunk(ring + p * TCC_A_CHUNK, CH.pre, CH.preld, p * TCC_KC, CH.precols, m0, B, et);
+    fence_proxy_async();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+  // the pre-converted chunks occupy ring uses 0..npre-1: complete the first phase of their `full` barriers so that
+  // ring phases stay in step with the sequence numbers (the MMA issuer waits on them like on a loaded chunk)
+  if (tid == 0)
+    for (int p = 0; p < npre; ++p) mbar_arrive(&full[p]);
+
+  // per-role state (only the owning role uses its copy)
+  int seq = (warp == 0) ? npre : 0;      // ring chunks issued (loader) / consumed (MMA issuer)
+  int nact = 0;                          // slots this CTA took part in so far: phase of wfull / dfull
+  if (warp == 0 && lane == 0 && tcc_slot_active(CH.slot[0], n0)) tcc_issue_weights(CH.slot[0], rank, n0, Wb, wfull, args.flags);
+
+  for (int l = 0; l < ns; ++l) {
+    const TccSlot& S = CH.slot[l];
+    const bool act0 = tcc_group_active(S, 0, n0), act1 = tcc_group_active(S, 1, n0);
+    const bool active = act0 || act1;
+    unsigned long long* tr = tr0 ? tr0 + TCC_TRACE_PER_SLOT * l : nullptr;
+
+    if (warp == 0) {
+      // ============================== loader ==========================================================
+      if (lane == 0) {
+        if (tr) tr[0] = tcc_gtime();
+        if (active) {
+          tcc_fence_proxy_async_all();           // the cluster's generic-proxy stores (acquired above) -> TMA reads
+          for (int c = 0; c < S.nchunks; ++c) {
+            const TccChunk ch = S.ch[c];
+            if (ch.kind == TCC_SRC_X) continue;
+            if (ch.kind == TCC_SRC_IMG) {
+              const int buf = seq % TCC_RING;
+              if (seq >= TCC_RING) tcc_wait(&empty[buf], ((seq / TCC_RING) - 1) & 1, args.watchdog, TCC_CODE(WD_LOADER_EMPTY, l, rank), seq);
+              mbar_expect_tx(&full[buf], TCC_A_CHUNK);
+              tcc_bulk_load(ring + buf * TCC_A_CHUNK, planes + size_t(ch.plane) * TCC_PLANE_BYTES + size_t(ch.chunk) * TCC_A_CHUNK,
+                            TCC_A_CHUNK, &full[buf]);
+              ++seq;
+            }                                     // TCC_SRC_PRE: converted at kernel start, already counted
+          }
+        }
+        if (tr) tr[1] = tcc_gtime();
+        // next slot's weights travel while this slot's epilogue and the barrier run
+        if (l + 1 < ns && tcc_slot_active(CH.slot[l + 1], n0)) {
+          if (active) tcc_wait(dfull, nact & 1, args.watchdog, TCC_CODE(WD_LOADER_DFULL, l, rank), nact);  // this slot's MMAs no longer read the weight buffer
+          tcc_issue_weights(CH.slot[l + 1], rank, n0, Wb, wfull, args.flags);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ============================== MMA issuer ======================================================
+      if (lane == 0 && active) {
+        const uint32_t idesc = make_idesc(FMT_TF32, false, false, TCC_ROWS, TCC_BN);
+        const uint64_t tmpl = make_smem_desc(0, 16, 1024, 2);
+        const uint32_t gstride = (uint32_t(S.nchunks) * TCC_W_CHUNK) >> 4;
+        const uint32_t w_base = smem_u32(Wb) >> 4;
+        tcc_wait(wfull, nact & 1, args.watchdog, TCC_CODE(WD_MMA_WFULL, l, rank), nact);
+        if (tr) tr[2] = tcc_gtime();
+        for (int c = 0; c < S.nchunks; ++c) {
+          const TccChunk ch = S.ch[c];
+          uint32_t a_hi;
+          int buf = 0;
+          if (ch.kind == TCC_SRC_X) a_hi = smem_u32(Xb) >> 4;
+          else {
+            buf = seq % TCC_RING;
+            tcc_wait(&full[buf], (seq / TCC_RING) & 1, args.watchdog, TCC_CODE(WD_MMA_FULL, l, rank), seq);
+            a_hi = smem_u32(ring + buf * TCC_A_CHUNK) >> 4;
+          }
+          if (tr && c == 0) tr[3] = tcc_gtime();
+          tc_fence_after_sync();
+          const uint32_t a_lo = a_hi + (TCC_A_HALF >> 4);
+#pragma unroll
+          for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
+            if (!(g == 0 ? act0 : act1)) continue;
+            const uint32_t b_hi = w_base + g * gstride + uint32_t(c) * (TCC_W_CHUNK >> 4), b_lo = b_hi + (TCC_W_HALF >> 4);
+            const uint32_t d = tmem_d + uint32_t(g * TCC_BN);
+            if (passes > 1) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) mma_tf32(d, tmpl + (a_lo + 2 * ks), tmpl + (b_hi + 2 * ks), idesc, (c | ks) != 0);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) mma_tf32(d, tmpl + (a_hi + 2 * ks), tmpl + (b_lo + 2 * ks), idesc, true);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) mma_tf32(d, tmpl + (a_hi + 2 * ks), tmpl + (b_hi + 2 * ks), idesc, true);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) mma_tf32(d, tmpl + (a_hi + 2 * ks), tmpl + (b_hi + 2 * ks), idesc, (c | ks) != 0);
+            }
+          }
+          if (ch.kind != TCC_SRC_X) { mma_commit(&empty[buf]); ++seq; }
+        }
+        mma_commit(dfull);
+        if (tr) tr[4] = tcc_gtime();
+      }
+      __syncwarp();
+    } else {
+      // ============================== epilogue ========================================================
+      const int et = tid - 64;
+      const int q = warp & 3, half = (warp - 2) >> 2;
+      const int row = 16 * q + lane;                       // UMMA M = 64: row m lives in TMEM lane (m % 16) + 32 (m / 16)
+      const int gi = m0 + row;
+      const bool lane_ok = lane < 16, row_ok = lane_ok && gi < B;
+      if (active) {
+        // this thread's epilogue operands do not depend on the chain: fetch them before the accumulator is ready
+        float eop[TCC_MAX_GROUPS][16];
+#pragma unroll
+        for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) eop[g][j] = 0.f;
+          if (!(g == 0 ? act0 : act1)) continue;
+          const TccGroup& G = S.g[g];
+          const int npad = (G.N + 3) & ~3;
+          const bool fwd = G.epi == EPI_BIAS || G.epi == EPI_BIAS_RELU || G.epi == EPI_BIAS_TANH;
+          const bool msk = G.epi == EPI_RELU_MASK || G.epi == EPI_TANH_MASK;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int gj = n0 + half * 16 + 4 * i;
+            if (gj >= npad) continue;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (fwd) v = __ldg(reinterpret_cast<const float4*>(G.bias + gj));
+            else if (msk && row_ok) v = __ldg(reinterpret_cast<const float4*>(G.aux + size_t(gi) * G.ldaux + gj));
+            eop[g][4 * i] = v.x; eop[g][4 * i + 1] = v.y; eop[g][4 * i + 2] = v.z; eop[g][4 * i + 3] = v.w;
+          }
+        }
+        tcc_wait(dfull, nact & 1, args.watchdog, TCC_CODE(WD_EPI_DFULL, l, rank), nact);
+        tc_fence_after_sync();
+        if (tr && et == 0) tr[5] = tcc_gtime();
+#pragma unroll
+        for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
+          if (!(g == 0 ? act0 : act1)) continue;
+          const TccGroup& G = S.g[g];
+          float r[16];
+          tcc_tmem_ld16(tmem_d + (uint32_t(32 * q) << 16) + uint32_t(g * TCC_BN + half * 16), r);
+          const int epi = G.epi;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int gj = n0 + half * 16 + j;
+            float x = r[j];
+            const float e = eop[g][j];
+            switch (epi) {
+              case EPI_BIAS: x += e; break;
+              case EPI_BIAS_RELU: x = fmaxf(x + e, 0.f); break;
+              case EPI_BIAS_TANH: x = tanhf(x + e); break;
+              case EPI_RELU_MASK: x = (e > 0.f) ? x : 0.f; break;
+              case EPI_TANH_MASK: x *= (1.f - e * e); break;
+              default: break;
+            }
+            r[j] = (row_ok && gj < G.N) ? x : 0.f;       // pad rows / columns stay zero in the images
+          }
+          if (lane_ok) {
+            if (G.pub >= 0) {                              // K-chunk `rank` of the consumers' A operand, hi and lo images
+              uint8_t* img = planes + size_t(G.pub) * TCC_PLANE_BYTES + size_t(rank) * TCC_A_CHUNK;
+              const uint32_t rbase = uint32_t((row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 v = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+                const float4 h = tcc_hi4(v);
+                const uint32_t off = rbase + uint32_t((((half * 4 + i) ^ (row & 7)) & 7) << 4);
+                *reinterpret_cast<float4*>(img + off) = h;
+                *reinterpret_cast<float4*>(img + TCC_A_HALF + off) = tcc_lo4(v, h);
+              }
+            }
+            if (G.C && row_ok) {
+              const int npad = (G.N + 3) & ~3;
+              float* crow = G.C + size_t(gi) * G.ldc;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int gj = n0 + half * 16 + 4 * i;
+                if (gj < npad) *reinterpret_cast<float4*>(crow + gj) = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+              }
+            }
+          }
+        }
+        tc_fence_before_sync();                            // accumulator reads done before the next slot's MMAs overwrite it
+      }
+      // the resident X chunk is re-used for another array (critic fc2's action columns) once this slot's MMAs are done
+      if (S.xsrc) {
+        if (!active) { /* X was not read in this slot */ }
+        tcc_convert_chunk(Xb, S.xsrc, S.xld, 0, S.xcols, m0, B, et);
+      }
+      tcc_fence_proxy_async_all();                         // image stores (global) and X (shared) -> async proxy readers
+      if (tr && et == 0) tr[6] = tcc_gtime();
+    }
+    if (active) ++nact;
+    if (l + 1 < ns) {
+      tcc_cluster_arrive();
+      tcc_cluster_wait();
+      if (tr && tid == 0) tr[7] = tcc_gtime();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, TCC_TMEM_COLS);
+  step_stamp(args.step_trace, args.step_slot + 16);
+}
+
+// ---- weight packing -------------------------------------------------------------------------------------
+// One CTA per 32x32 block: 256 threads, one float4 of hi and lo each.
+__global__ void __launch_bounds__(256) tcc_pack_kernel(const __grid_constant__ TccPackArgs args) {
+  int ui = 0;
+#pragma unroll 1
+  for (int i = 1; i < args.n; ++i)
+    if (int(blockIdx.x) >= args.use[i].block_begin) ui = i;
+  const TccPackUse& U = args.use[ui];
+  const int blk = blockIdx.x - U.block_begin;
+  const int slice = blk / U.nchunks, chunk = blk - slice * U.nchunks;
+  uint8_t* dst = args.dst + U.dst_off + size_t(blk) * TCC_W_CHUNK;
+  const int tid = threadIdx.x;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  int j, u;
+  if (U.mode == GEMM_FWD) {
+    j = tid >> 3; u = tid & 7;                               // consecutive threads: consecutive 16-B units of a W row
+    const int n = slice * TCC_BN + j, k = chunk * TCC_KC + 4 * u;
+    if (n < U.N && k < U.K) {
+      v = __ldg(reinterpret_cast<const float4*>(U.W + size_t(n) * U.ldw + k));   // row pitch is a multiple of 4 floats
+      if (k + 1 >= U.K) v.y = 0.f;
+      if (k + 2 >= U.K) v.z = 0.f;
+      if (k + 3 >= U.K) v.w = 0.f;
+    }
+  } else {
+    j = tid & 31; u = tid >> 5;                              // consecutive threads: consecutive columns n of a W row (coalesced)
+    const int n = slice * TCC_BN + j, k = chunk * TCC_KC + 4 * u;
+    if (n < U.N) {
+      if (k < U.K) v.x = __ldg(U.W + size_t(k) * U.ldw + n);
+      if (k + 1 < U.K) v.y = __ldg(U.W + size_t(k + 1) * U.ldw + n);
+      if (k + 2 < U.K) v.z = __ldg(U.W + size_t(k + 2) * U.ldw + n);
+      if (k + 3 < U.K) v.w = __ldg(U.W + size_t(k + 3) * U.ldw + n);
+    }
+  }
+  const float4 h = tcc_hi4(v);
+  const uint32_t off = sw128_kmajor_off(j, 4 * u);
+  *reinterpret_cast<float4*>(dst + off) = h;
+  *reinterpret_cast<float4*>(dst + TCC_W_HALF + off) = tcc_lo4(v, h);
+}
+
+static unsigned long long* g_tcc_watchdog_host = nullptr;
+// allocated once per process, outside of any stream capture (tcc users call this at create time)
+unsigned long long* tcc_watchdog_device() {
+  static bool tried = false;
+  static unsigned long long* dev = nullptr;
+  if (!tried) {
+    tried = true;
+    unsigned long long* host = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&host), 128, cudaHostAllocMapped) == cudaSuccess) {
+      memset(host, 0, 128);
+      if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), host, 0) != cudaSuccess) dev = nullptr;
+      g_tcc_watchdog_host = host;
+    }
+    (void)cudaGetLastError();
+  }
+  return dev;
+}
+}  // namespace d4pg
+// the watchdog record of the tcgen05 chain kernel (host-mapped memory: readable after a trapped launch killed the context)
+extern "C" int32_t d4pg_debug_watchdog(unsigned long long* out16) {
+  if (!out16) return D4PG_EINVAL;
+  for (int i = 0; i < 16; ++i) out16[i] = d4pg::g_tcc_watchdog_host ? d4pg::g_tcc_watchdog_host[i] : 0ull;
+  return D4PG_OK;
+}
+namespace d4pg {
+
+void tcc_pack_begin(TccPackArgs& p, uint8_t* dst) { p.n = 0; p.total_blocks = 0; p.dst = dst; }
+int tcc_pack_add(TccPackArgs& p, const float* W, int ldw, int mode, int N, int K) {
+  if (p.n >= TCC_MAX_USES) return -1;
+  TccPackUse& u = p.use[p.n];
+  u.W = W; u.ldw = ldw; u.mode = mode; u.N = N; u.K = K;
+  u.nslices = cdiv(N, TCC_BN); u.nchunks = cdiv(K, TCC_KC);
+  u.block_begin = p.total_blocks;
+  u.dst_off = (long long)(p.total_blocks) * TCC_W_CHUNK;
+  p.total_blocks += u.nslices * u.nchunks;
+  return p.n++;
+}
+long long tcc_pack_bytes(const TccPackArgs& p) { return (long long)(p.total_blocks) * TCC_W_CHUNK; }
+int launch_tcc_pack(const TccPackArgs& p, cudaStream_t st) {
+  D4PG_REQUIRE(p.n > 0 && p.dst, D4PG_EINVAL, "launch_tcc_pack: nothing to pack");
+  tcc_pack_kernel<<<p.total_blocks, 256, 0, st>>>(p);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+// ---- chain construction -----------------------------------------------------------------------------------
+int64_t tcc_xchg_floats(int B) {
+  return int64_t(TCC_MAX_CHAINS) * cdiv(B, TCC_ROWS) * TCC_PLANES * (TCC_PLANE_BYTES / 4);
+}
+void tcc_args_begin(TccArgs& a, int B, uint8_t* xchg, int passes) {
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.row_blocks = cdiv(B, TCC_ROWS); a.xchg = xchg; a.passes = passes;
+}
+void tcc_chain_x0(TccArgs& a, int c, const float* src, int ld, int cols) {
+  a.chain[c].x0 = src; a.chain[c].x0ld = ld; a.chain[c].x0cols = cols;
+}
+void tcc_chain_pre(TccArgs& a, int c, const float* src, int ld, int cols) {
+  a.chain[c].pre = src; a.chain[c].preld = ld; a.chain[c].precols = cols;
+}
+int tcc_slot_begin(TccArgs& a, int c) {
+  if (c >= a.nchains) a.nchains = c + 1;
+  TccChain& ch = a.chain[c];
+  const int l = ch.nslots++;
+  if (l < TCC_MAX_SLOTS) { ch.slot[l] = TccSlot{}; ch.slot[l].g[0].pub = ch.slot[l].g[1].pub = -1; }
+  return l;
+}
+static void tcc_push_chunk(TccSlot& s, int kind, int plane, int chunk) {
+  if (s.nchunks < TCC_MAX_CHUNKS) s.ch[s.nchunks] = TccChunk{short(kind), short(plane), short(chunk), 0};
+  ++s.nchunks;
+}
+void tcc_slot_src_x(TccArgs& a, int c, int slot) { tcc_push_chunk(a.chain[c].slot[slot], TCC_SRC_X, 0, 0); }
+void tcc_slot_src_pre(TccArgs& a, int c, int slot) {
+  const int n = cdiv(a.chain[c].precols, TCC_KC);
+  for (int i = 0; i < n; ++i) tcc_push_chunk(a.chain[c].slot[slot], TCC_SRC_PRE, 0, i);
+}
+void tcc_slot_src_plane(TccArgs& a, int c, int slot, int plane, int nchunks) {
+  for (int i = 0; i < nchunks; ++i) tcc_push_chunk(a.chain[c].slot[slot], TCC_SRC_IMG, plane, i);
+}
+void tcc_slot_reconvert_x(TccArgs& a, int c, int slot, const float* src, int ld, int cols) {
+  TccSlot& s = a.chain[c].slot[slot];
+  s.xsrc = src; s.xld = ld; s.xcols = cols;
+}
+int tcc_slot_group(TccArgs& a, int c, int slot, const TccPackArgs& pk, int use, int epi, const float* bias,
+                   const float* aux, int ldaux, float* C, int ldc, int publish) {
+  TccChain& ch = a.chain[c];
+  TccSlot& s = ch.slot[slot];
+  const int gi = s.ngroups++;
+  if (gi >= TCC_MAX_GROUPS) return -1;
+  TccGroup& g = s.g[gi];
+  const TccPackUse& u = pk.use[use];
+  g.wimg = tcc_image(pk, use); g.bias = bias; g.aux = aux; g.ldaux = ldaux; g.C = C; g.ldc = ldc;
+  g.N = u.N; g.epi = epi; g.kchunks = u.nchunks;
+  g.pub = publish ? ch.nplanes++ : -1;
+  return g.pub;
+}
+
+int launch_mlp_tc_chain(TccArgs& a, cudaStream_t st) {
+  D4PG_REQUIRE(a.nchains > 0 && a.nchains <= TCC_MAX_CHAINS, D4PG_EINVAL, "launch_mlp_tc_chain: %d chains", a.nchains);
+  D4PG_REQUIRE(a.passes == 1 || a.passes == 3, D4PG_EINVAL, "launch_mlp_tc_chain: passes %d", a.passes);
+  for (int c = 0; c < a.nchains; ++c) {
+    const TccChain& ch = a.chain[c];
+    D4PG_REQUIRE(ch.nslots > 0 && ch.nslots <= TCC_MAX_SLOTS, D4PG_EINVAL, "launch_mlp_tc_chain: chain %d has %d slots", c, ch.nslots);
+    D4PG_REQUIRE(ch.nplanes <= TCC_PLANES, D4PG_ENOTSUP, "launch_mlp_tc_chain: chain %d publishes %d planes", c, ch.nplanes);
+    D4PG_REQUIRE(!ch.x0 || (ch.x0cols <= TCC_KC && ch.x0ld % 4 == 0 && ch.x0ld >= ch.x0cols), D4PG_ENOTSUP, "launch_mlp_tc_chain: bad X source");
+    D4PG_REQUIRE(!ch.pre || (ch.precols <= TCC_RING * TCC_KC && ch.preld % 4 == 0 && ch.preld >= ch.precols), D4PG_ENOTSUP,
+                 "launch_mlp_tc_chain: bad first-slot source");
+    int planes_seen = 0;
+    for (int l = 0; l < ch.nslots; ++l) {
+      const TccSlot& s = ch.slot[l];
+      D4PG_REQUIRE(s.ngroups >= 1 && s.ngroups <= TCC_MAX_GROUPS, D4PG_EINVAL, "launch_mlp_tc_chain: slot %d has %d groups", l, s.ngroups);
+      D4PG_REQUIRE(s.nchunks >= 1 && s.nchunks <= TCC_MAX_CHUNKS && s.ngroups * s.nchunks <= TCC_MAX_CHUNKS, D4PG_ENOTSUP,
+                   "launch_mlp_tc_chain: slot %d: %d groups x %d chunks exceed the weight buffer", l, s.ngroups, s.nchunks);
+      int nring = 0;
+      for (int i = 0; i < s.nchunks; ++i) {
+        const TccChunk& k = s.ch[i];
+        if (k.kind == TCC_SRC_IMG) D4PG_REQUIRE(k.plane >= 0 && k.plane < planes_seen && k.chunk < TCC_CLUSTER, D4PG_EINVAL,
+                                                 "launch_mlp_tc_chain: slot %d reads plane %d before it is published", l, k.plane);
+        if (k.kind == TCC_SRC_PRE) D4PG_REQUIRE(l == 0 && ch.pre && k.chunk == nring, D4PG_EINVAL, "launch_mlp_tc_chain: pre chunks belong to slot 0, in order");
+        if (k.kind == TCC_SRC_X) D4PG_REQUIRE(ch.x0 != nullptr, D4PG_EINVAL, "launch_mlp_tc_chain: slot %d reads X but the chain has none", l);
+        if (k.kind != TCC_SRC_X) ++nring;
+      }
+      for (int g = 0; g < s.ngroups; ++g) {
+        const TccGroup& G = s.g[g];
+        D4PG_REQUIRE(G.N > 0 && G.N <= TCC_CLUSTER * TCC_BN && G.wimg, D4PG_ENOTSUP, "launch_mlp_tc_chain: group width %d", G.N);
+        D4PG_REQUIRE(G.kchunks == s.nchunks, D4PG_EINVAL, "launch_mlp_tc_chain: chain %d slot %d: A operand has %d chunks, the weight image %d", c, l, s.nchunks, G.kchunks);
+        D4PG_REQUIRE(!G.C || (G.ldc % 4 == 0 && G.ldc >= ((G.N + 3) & ~3) && (reinterpret_cast<uintptr_t>(G.C) & 15) == 0), D4PG_EINVAL,
+                     "launch_mlp_tc_chain: output pitch");
+        const bool fwd = G.epi == EPI_BIAS || G.epi == EPI_BIAS_RELU || G.epi == EPI_BIAS_TANH;
+        const bool msk = G.epi == EPI_RELU_MASK || G.epi == EPI_TANH_MASK;
+        D4PG_REQUIRE(!fwd || (G.bias && (reinterpret_cast<uintptr_t>(G.bias) & 15) == 0), D4PG_EINVAL, "launch_mlp_tc_chain: bias");
+        D4PG_REQUIRE(!msk || (G.aux && G.ldaux % 4 == 0 && (reinterpret_cast<uintptr_t>(G.aux) & 15) == 0), D4PG_EINVAL, "launch_mlp_tc_chain: mask operand");
+        if (G.pub >= 0) ++planes_seen;
+      }
+      if (l == 0 && ch.pre) D4PG_REQUIRE(s.g[0].N > (TCC_CLUSTER - 1) * TCC_BN, D4PG_ENOTSUP, "launch_mlp_tc_chain: the first slot must span the cluster");
+    }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    D4PG_CUDA_OK(cudaFuncSetAttribute(mlp_tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TCC_SMEM)));
+    D4PG_CUDA_OK(cudaFuncSetAttribute(mlp_tc_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared)));
+    attr_set = true;
+  }
+  a.watchdog = tcc_watchdog_device();
+  { const char* e = getenv("D4PG_TCC_FLAGS"); a.flags = e ? atoi(e) : 0; }
+  unsigned long long* dbg = debug_trace_buffer();
+  a.trace = dbg ? dbg + (a.step_slot == 5 ? 256 : 0) : nullptr;
+  a.step_trace = dbg ? dbg + STEP_TRACE_BASE : nullptr;
+  { const char* e = getenv("D4PG_TRACE_CTA"); a.trace_cta = e ? atoi(e) : 0; if (a.trace_cta >= a.nchains * a.row_blocks * TCC_CLUSTER) a.trace_cta = 0; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.nchains * a.row_blocks * TCC_CLUSTER); cfg.blockDim = dim3(TCC_THREADS);
+  cfg.dynamicSmemBytes = TCC_SMEM; cfg.stream = st;
+  cfg.attrs = nullptr; cfg.numAttrs = 0;              // cluster shape is compiled in (__cluster_dims__)
+  D4PG_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_tc_chain_kernel, a));
+  return D4PG_OK;
+}
+
+}  // namespace d4pg

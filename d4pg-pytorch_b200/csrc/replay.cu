@@ -391,6 +391,113 @@ extern "C" int32_t d4pg_replay_set_staging(d4pg_replay_t* h, void* pinned_host, 
   return D4PG_OK;
 }
 
+// ---- device-side ingest: n-step return accumulation at insert (replay_memory.py:38-45) ------------------------
+// Transition i of an episode of T steps: (s_i, a_i, sum_{k<n} gamma^k r_{i+k}, s'_{i+n-1}, done_{i+n-1}).  Only the
+// reward needs arithmetic -- s'/done are the same arrays shifted by n-1 rows -- and it is the reference's own
+// left-to-right f64 loop (`cum += exp_gamma * r; exp_gamma *= gamma`) with explicit _rn ops (no FMA contraction).
+__global__ void nstep_returns_kernel(const double* __restrict__ rew, int64_t T, int n, double gamma, double* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i + n > T) return;
+  double cum = 0.0, eg = 1.0;
+  for (int k = 0; k < n; ++k) {
+    cum = __dadd_rn(cum, __dmul_rn(eg, rew[i + k]));
+    eg = __dmul_rn(eg, gamma);
+  }
+  out[i] = cum;
+}
+
+extern "C" int32_t d4pg_nstep_returns(const double* rew, int64_t T, int32_t n_steps, double gamma, double* out,
+                                      d4pg_stream_t stream) {
+  D4PG_REQUIRE(rew && out && T > 0 && n_steps >= 1, D4PG_EINVAL, "d4pg_nstep_returns: bad arguments");
+  if (T < n_steps) return D4PG_OK;                        // the reference adds nothing before step n-1 (:38)
+  const int64_t m = T - n_steps + 1;
+  nstep_returns_kernel<<<unsigned((m + 255) / 256), 256, 0, as_stream(stream)>>>(rew, T, n_steps, gamma, out);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_replay_add_nstep(d4pg_replay_t* h, int64_t T, const float* obs, const float* act, const double* rew,
+                                         const float* obs2, const uint8_t* done, int32_t n_steps, double gamma,
+                                         double* rew_scratch, int32_t prioritized, d4pg_stream_t stream) {
+  D4PG_REQUIRE(h && obs && act && rew && obs2 && done && rew_scratch && T > 0 && n_steps >= 1, D4PG_EINVAL,
+               "d4pg_replay_add_nstep: bad arguments");
+  if (T < n_steps) return D4PG_OK;
+  int rc = d4pg_nstep_returns(rew, T, n_steps, gamma, rew_scratch, stream);
+  if (rc) return rc;
+  const int64_t shift = n_steps - 1;
+  return d4pg_replay_add(h, T - shift, obs, act, rew_scratch, obs2 + shift * h->obs_dim, done + shift, prioritized, stream);
+}
+
+// ---- device-side ingest: hindsight relabelling (main.py:154-184, "future" strategy) ------------------------------
+// Episode of T goal-conditioned steps: obs/obs_next [T, So] f32, goal [T, G] f64 (the desired goal of every step),
+// ag_next [T, G] f64 (achieved goal of the NEXT state), act [T, A], rew [T] f64, done [T].  Output rows, in the
+// reference's order: for every t the original transition (s = obs_t || goal_t, s' = obs_next_t || goal_t), directly
+// followed -- where select[t] != 0 -- by its relabelled copy with the achieved goal of step future[t] >= t as the goal,
+// reward = -(||ag_next_t - goal'||_2 > threshold) (the sparse gym-robotics compute_reward, f64, sqrt of the
+// left-to-right sum of squares like np.linalg.norm(axis=-1)) and done = (reward == 0).  select / future are the
+// caller's random draws (np.random.uniform() < her_ratio, np.random.randint(t, T): main.py:166,170), `dst_row[t]` the
+// exclusive prefix count of output rows.  The reference stores the relabelled copy with the LAST action of the rollout
+// (`action`, main.py:184, not the step's own `a`): her_action_mode 0 reproduces that, 1 uses a_t.
+struct HerArgs {
+  const float* obs; const float* obs_next; const double* goal; const double* ag_next; const float* act;
+  const double* rew; const uint8_t* done; const uint8_t* select; const int32_t* future; const int32_t* dst_row;
+  int T, So, G, A, action_mode; double threshold;
+  float* o_s; float* o_a; double* o_r; float* o_s2; uint8_t* o_d;
+};
+__global__ void her_relabel_kernel(const HerArgs a) {
+  const int t = blockIdx.x;
+  if (t >= a.T) return;
+  const int S = a.So + a.G, row = a.dst_row[t];
+  const bool sel = a.select[t] != 0;
+  const int f = sel ? a.future[t] : t;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const bool is_obs = j < a.So;
+    const float so = is_obs ? a.obs[size_t(t) * a.So + j] : float(a.goal[size_t(t) * a.G + (j - a.So)]);
+    const float sn = is_obs ? a.obs_next[size_t(t) * a.So + j] : so;
+    a.o_s[size_t(row) * S + j] = so;
+    a.o_s2[size_t(row) * S + j] = sn;
+    if (sel) {
+      const float g2 = is_obs ? 0.f : float(a.ag_next[size_t(f) * a.G + (j - a.So)]);
+      a.o_s[size_t(row + 1) * S + j] = is_obs ? so : g2;
+      a.o_s2[size_t(row + 1) * S + j] = is_obs ? sn : g2;
+    }
+  }
+  for (int j = threadIdx.x; j < a.A; j += blockDim.x) {
+    a.o_a[size_t(row) * a.A + j] = a.act[size_t(t) * a.A + j];
+    if (sel) a.o_a[size_t(row + 1) * a.A + j] = a.act[size_t(a.action_mode ? t : a.T - 1) * a.A + j];
+  }
+  if (threadIdx.x == 0) {
+    a.o_r[row] = a.rew[t];
+    a.o_d[row] = a.done[t];
+    if (sel) {
+      double ss = 0.0;
+      for (int j = 0; j < a.G; ++j) {
+        const double d = __dsub_rn(a.ag_next[size_t(t) * a.G + j], a.ag_next[size_t(f) * a.G + j]);
+        ss = __dadd_rn(ss, __dmul_rn(d, d));
+      }
+      const double r = (__dsqrt_rn(ss) > a.threshold) ? -1.0 : -0.0;     // -(d > threshold), as gym-robotics returns it
+      a.o_r[row + 1] = r;
+      a.o_d[row + 1] = (r == 0.0) ? 1 : 0;
+    }
+  }
+}
+
+extern "C" int32_t d4pg_her_relabel(int32_t T, int32_t obs_dim, int32_t goal_dim, int32_t act_dim,
+                                    const float* obs, const float* obs_next, const double* goal, const double* ag_next,
+                                    const float* act, const double* rew, const uint8_t* done,
+                                    const uint8_t* select, const int32_t* future, const int32_t* dst_row,
+                                    double threshold, int32_t her_action_mode,
+                                    float* out_s, float* out_a, double* out_r, float* out_s2, uint8_t* out_d,
+                                    d4pg_stream_t stream) {
+  D4PG_REQUIRE(T > 0 && obs_dim > 0 && goal_dim > 0 && act_dim > 0 && obs && obs_next && goal && ag_next && act && rew && done &&
+               select && future && dst_row && out_s && out_a && out_r && out_s2 && out_d, D4PG_EINVAL, "d4pg_her_relabel: bad arguments");
+  HerArgs a{obs, obs_next, goal, ag_next, act, rew, done, select, future, dst_row, T, obs_dim, goal_dim, act_dim,
+            her_action_mode ? 1 : 0, threshold, out_s, out_a, out_r, out_s2, out_d};
+  her_relabel_kernel<<<T, 64, 0, as_stream(stream)>>>(a);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
 extern "C" int32_t d4pg_replay_add_host(d4pg_replay_t* h, int64_t n, const float* obs, const float* act, const double* rew,
                                         const float* obs2, const uint8_t* done, int32_t prioritized, d4pg_stream_t stream) {
   if (h) ++h->gen;
@@ -417,12 +524,12 @@ extern "C" int32_t d4pg_replay_add_host(d4pg_replay_t* h, int64_t n, const float
 extern "C" int64_t d4pg_replay_len(const d4pg_replay_t* h) { return h ? h->len : -1; }
 extern "C" int64_t d4pg_replay_next_idx(const d4pg_replay_t* h) { return h ? h->next_idx : -1; }
 
-extern "C" int32_t d4pg_replay_set_len(d4pg_replay_t* h, int64_t len, int64_t next_idx, int32_t pristine) {
+extern "C" int32_t d4pg_replay_set_len(d4pg_replay_t* h, int64_t len, int64_t next_idx, int32_t pristine, d4pg_stream_t stream) {
   if (h) ++h->gen;
   D4PG_REQUIRE(h && len >= 0 && len <= h->size && next_idx >= 0 && next_idx < h->size, D4PG_EINVAL,
                "d4pg_replay_set_len: out of range");
   h->len = len; h->next_idx = next_idx; h->pristine = pristine ? 1 : 0;
-  state_set_kernel<<<1, 1>>>(reinterpret_cast<ReplayState*>(h->state), len, next_idx, h->pristine);
+  state_set_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<ReplayState*>(h->state), len, next_idx, h->pristine);
   D4PG_LAUNCH_OK();
   return D4PG_OK;
 }

@@ -1,4 +1,4 @@
-// Device code of the GPU-resident prioritized replay (shared by replay.cu and the persistent step kernel).
+// Device code of the GPU-resident prioritized replay.
 #pragma once
 #include "internal.cuh"
 #include "adam.cuh"
@@ -239,7 +239,7 @@ struct TreeArgs {
 };
 constexpr int TREE_THREADS = 1024;
 
-// executed by ONE CTA of NT threads (1024 standalone, 256 inside the persistent step kernel)
+// executed by ONE CTA of NT threads
 template <int MODE, int NT>
 __device__ __forceinline__ void tree_write_body(const TreeArgs& a, float* red) {
   const int t = threadIdx.x;
@@ -366,6 +366,7 @@ __device__ __forceinline__ void tree_update_fast_body(const TreeArgs& a, unsigne
       }
     }
   }
+  __syncthreads();                                            // every sharer of a duplicated leaf has read its winner
   if (act) a.scratch[p] = -1;
 #pragma unroll 1
   for (int lvl = 0; lvl <= L; ++lvl) {

@@ -71,12 +71,9 @@ class _Learner(object):
         cfg.world_size = ddpg.comm.world_size if ddpg.comm is not None else 1
         cfg.use_graph = 1 if ddpg.use_graph else 0
         cfg.loss_flags = (1 if ddpg.importance_weighted else 0) | (2 if ddpg.priority == "ce" else 0)
-        cfg.persistent = 1 if (ddpg.persistent and ddpg.precision == "fp32" and cfg.world_size == 1) else 0
-        plan = {"levels": 0, "cluster": 1, "rows": 2, False: 0, True: 1, 0: 0, 1: 1, 2: 2}[ddpg.chain]
-        if cfg.persistent or (plan == 2 and ddpg.precision != "fp32"):
-            plan = 0
-        cfg.chain = plan                    # tf32x3 / tf32: plan 1 = mma.sync chain tiles, plan 0 = tcgen05 per level
-        cfg.prefetch = 1 if (ddpg.prefetch and cfg.sample_mode == 1 and not cfg.persistent) else 0
+        # plan 1: fp32 = FFMA chain tiles; tf32x3 / tf32 = tcgen05 chain tiles (mlp_tc_chain.cu); plan 0: one launch per level
+        cfg.chain = {"levels": 0, "cluster": 1, False: 0, True: 1, 0: 0, 1: 1}[ddpg.chain]
+        cfg.prefetch = 1 if (ddpg.prefetch and cfg.sample_mode == 1) else 0
         self.cfg = cfg
         nws = L.d4pg_learner_workspace_floats(C.byref(cfg))
         f32 = torch.float32
@@ -88,9 +85,6 @@ class _Learner(object):
         self.prio = torch.zeros(B, dtype=f32, device=dev)
         self.td = torch.zeros(B, dtype=f32, device=dev)
         self.losses = torch.zeros(4, dtype=f32, device=dev)
-        self.host_u = torch.zeros(B, dtype=torch.float64, pin_memory=True)
-        self.host_pos = torch.zeros(B, dtype=torch.int32, pin_memory=True)
-        self.host_losses = torch.zeros(4, dtype=f32, pin_memory=True)
         buf = _lib.LearnerBuffers()
         buf.actor, buf.actor_target = g.actor.flat_params().data_ptr(), ddpg.actor_target.flat_params().data_ptr()
         buf.critic, buf.critic_target = g.critic.flat_params().data_ptr(), ddpg.critic_target.flat_params().data_ptr()
@@ -109,7 +103,7 @@ class _Learner(object):
             raise _lib.D4PGError("train() called before any transition was added to the replay buffer")
         store.flush()
         h = C.c_void_p()
-        if ddpg.comm is not None and cfg.world_size > 1 and not cfg.persistent:
+        if ddpg.comm is not None and cfg.world_size > 1:
             ddpg.comm.setup_peers(Pa + Pc)            # fused all-reduce over peer memory (collective call)
         comm = ddpg.comm.handle if ddpg.comm is not None else None
         _lib.check(L.d4pg_learner_create(C.byref(cfg), C.byref(buf), store.handle, comm, C.byref(h)), "d4pg_learner_create")
@@ -119,14 +113,9 @@ class _Learner(object):
         self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
         self.step_host = L.d4pg_learner_step_host
+        self.step_host_mt = L.d4pg_learner_step_host_mt
         self.read_losses = L.d4pg_learner_read_losses
-        self.host_u_np = self.host_u.numpy()
-        self.host_pos_np = self.host_pos.numpy()
-        self.u_ptr = C.c_void_p(self.host_u.data_ptr())
-        self.pos_ptr = C.c_void_p(self.host_pos.data_ptr())
         self.losses_out = (C.c_float * 4)()
-        _lib.check(L.d4pg_learner_set_host_buffers(h, self.u_ptr, self.pos_ptr, C.c_void_p(self.host_losses.data_ptr())),
-                   "d4pg_learner_set_host_buffers")
         if opt_a.step_count or (ddpg.prioritized_replay and ddpg.beta_schedule.t):
             _lib.check(L.d4pg_learner_set_counters(h, opt_a.step_count,
                                                    ddpg.beta_schedule.t if ddpg.prioritized_replay else 0,
@@ -166,7 +155,7 @@ class DDPG:
                  critic_dist_info=None, n_steps=1,
                  # ---- B200 build extensions (keyword-only in spirit; reference callers never pass them)
                  device=None, sampling="reference", projection="reference", precision="fp32",
-                 use_graph=True, philox_seed=0, comm=None, persistent=False, chain="cluster", prefetch=True,
+                 use_graph=True, philox_seed=0, comm=None, chain="cluster", prefetch=True,
                  importance_weighted=False, priority="reference"):
         self.gamma = gamma
         self.n_steps = n_steps
@@ -181,9 +170,8 @@ class DDPG:
         assert precision in ("fp32", "tf32x3", "tf32")
         self.sampling, self.projection, self.precision = sampling, projection, precision
         self.use_graph, self.philox_seed, self.comm = use_graph, philox_seed, comm
-        self.persistent = persistent        # one cooperative kernel per step (fp32, single GPU)
-        # step plan of the MLP passes (fp32): "cluster" (default) cluster-fused layer chains, "rows" row-owner
-        # chains with TMA-multicast weight streaming (correct, measured slower), "levels" one launch per level
+        # step plan of the MLP passes: "cluster" (default) cluster-fused layer chains (exact FFMA tiles for fp32,
+        # tcgen05 tiles for tf32x3 / tf32), "levels" one launch per dependency level
         self.chain = chain
         # device-side sampling only: step t already samples batch t+1 behind its own backward pass (identical results)
         self.prefetch = prefetch
@@ -318,18 +306,17 @@ class DDPG:
         if store._n_staged:
             store.flush()
         B = self.batch_size
-        u_ptr = pos_ptr = None
-        if self.sampling == "reference":
-            if self.prioritized_replay:
-                rnd = random.random                                       # random.random() x B, in order, as
-                L.host_u_np[:] = [rnd() for _ in range(B)]                # prioritized_replay_memory.py:262
-                u_ptr = L.u_ptr
-            else:
-                L.host_pos_np[:] = self.replayBuffer.sample_positions(B)
-                pos_ptr = L.pos_ptr
         # one library call: order after the caller's stream, H2D of this step's host inputs, the step's
         # CUDA graph on the learner stream, order the caller's stream after it
-        rc = L.step_host(L.handle, u_ptr, pos_ptr, _lib.raw_stream(L.dev_index), L.stream_ptr)
+        if self.sampling == "reference" and self.prioritized_replay:
+            # B x random.random() in order (prioritized_replay_memory.py:262): the 2*B raw MT19937 words are drawn in
+            # one call -- same generator state afterwards -- and turned into the doubles by the library
+            rc = L.step_host_mt(L.handle, random.randbytes(8 * B), _lib.raw_stream(L.dev_index), L.stream_ptr)
+        elif self.sampling == "reference":
+            pos = np.ascontiguousarray(self.replayBuffer.sample_positions(B), dtype=np.int32)
+            rc = L.step_host(L.handle, None, pos.ctypes.data, _lib.raw_stream(L.dev_index), L.stream_ptr)
+        else:
+            rc = L.step_host(L.handle, None, None, _lib.raw_stream(L.dev_index), L.stream_ptr)
         if rc:
             _lib.check(rc, "d4pg_learner_step_host")
         if self.prioritized_replay:
@@ -388,11 +375,9 @@ class DDPG:
         with torch.cuda.stream(L.stream):
             if self.sampling == "reference":
                 if self.prioritized_replay:
-                    L.host_u.numpy()[:] = [random.random() for _ in range(self.batch_size)]
-                    L.uniforms.copy_(L.host_u, non_blocking=True)
+                    L.uniforms.copy_(torch.tensor([random.random() for _ in range(self.batch_size)], dtype=torch.float64))
                 else:
-                    L.host_pos.numpy()[:] = self.replayBuffer.sample_positions(self.batch_size)
-                    L.positions.copy_(L.host_pos, non_blocking=True)
+                    L.positions.copy_(torch.as_tensor(np.asarray(self.replayBuffer.sample_positions(self.batch_size), dtype=np.int32)))
             _lib.check(_lib.lib().d4pg_learner_profile_step(L.handle, C.c_void_p(L.stream.cuda_stream), cap, ms, names,
                                                             stride, C.byref(n)), "d4pg_learner_profile_step")
         if self.prioritized_replay:

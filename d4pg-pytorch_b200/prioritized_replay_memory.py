@@ -202,6 +202,81 @@ class _DeviceReplay(object):
             hi = min(n, lo + self.size)
             self._add_device(hi - lo, [t[lo:hi] for t in args])
 
+    def _episode_to_device(self, s, a, r, s2, done):
+        self.flush()
+        s = torch.as_tensor(s, dtype=torch.float32)
+        if s.dim() == 1:
+            s = s.view(1, -1)
+        T = s.shape[0]
+        a = torch.as_tensor(a, dtype=torch.float32).reshape(T, -1)
+        if self.handle is None:
+            self._allocate(s.shape[1], a.shape[1])
+        dev = self.device
+        return T, [s.to(dev).contiguous(), a.to(dev).contiguous(),
+                   torch.as_tensor(r, dtype=torch.float64).reshape(T).to(dev).contiguous(),
+                   torch.as_tensor(s2, dtype=torch.float32).reshape(T, -1).to(dev).contiguous(),
+                   torch.as_tensor(done).reshape(T).to(torch.uint8).to(dev).contiguous()]
+
+    def add_episode_nstep(self, s, a, r, s2, done, n_steps, gamma):
+        """One episode of T consecutive steps with the n-step return accumulated ON THE DEVICE at insert
+        (replay_memory.py:38-45): transition i = (s_i, a_i, sum_k gamma^k r_{i+k}, s'_{i+n-1}, done_{i+n-1})."""
+        T, args = self._episode_to_device(s, a, r, s2, done)
+        n_steps = int(n_steps)
+        if T < n_steps:
+            return 0
+        m = T - n_steps + 1
+        if m > self.size:
+            raise _lib.D4PGError("add_episode_nstep: episode longer than the buffer")
+        scratch = torch.empty(T, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().d4pg_replay_add_nstep(self.handle, T, *[_lib.ptr(t) for t in args], n_steps, float(gamma),
+                                                    _lib.ptr(scratch), 1 if self.prioritized else 0, _lib.stream_ptr()),
+                   "d4pg_replay_add_nstep")
+        self._len = int(_lib.lib().d4pg_replay_len(self.handle))
+        self._next_idx = int(_lib.lib().d4pg_replay_next_idx(self.handle))
+        return m
+
+    def add_her_episode(self, obs, obs_next, goal, ag_next, act, rew, done, her_ratio=0.8, threshold=0.05,
+                        her_action="reference", rng=None):
+        """Hindsight relabelling of one goal-conditioned episode on the device (main.py:154-184): every transition is
+        stored, and with probability `her_ratio` also a copy whose goal is the achieved goal of a uniformly chosen
+        FUTURE step (reward recomputed as the sparse -(distance > threshold), done = reward == 0).  The random draws
+        are made on the host in the reference's order (np.random.uniform() then np.random.randint(t, T) per step)."""
+        rng = np.random if rng is None else rng
+        obs = np.ascontiguousarray(obs, dtype=np.float32)
+        T, So = obs.shape
+        goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(T, -1)
+        G = goal.shape[1]
+        act = np.ascontiguousarray(act, dtype=np.float32).reshape(T, -1)
+        A = act.shape[1]
+        select = np.zeros(T, dtype=np.uint8)
+        future = np.arange(T, dtype=np.int32)
+        for t in range(T):
+            if rng.uniform() < her_ratio:                                                   # main.py:166
+                select[t] = 1
+                future[t] = rng.randint(t, T)                                               # main.py:170
+        counts = 1 + select.astype(np.int64)
+        dst = (np.cumsum(counts) - counts).astype(np.int32)
+        n_out = int(counts.sum())
+        if self.handle is None:
+            self._allocate(So + G, A)
+        if n_out > self.size:
+            raise _lib.D4PGError("add_her_episode: episode longer than the buffer")
+        self.flush()
+        dev = self.device
+        up = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x, dtype=dt)).to(dev)
+        ins = [up(obs, np.float32), up(np.asarray(obs_next).reshape(T, So), np.float32), up(goal, np.float64),
+               up(np.asarray(ag_next).reshape(T, G), np.float64), up(act, np.float32), up(np.asarray(rew).reshape(T), np.float64),
+               up(np.asarray(done).reshape(T).astype(np.uint8), np.uint8), up(select, np.uint8), up(future, np.int32),
+               up(dst, np.int32)]
+        outs = [torch.empty(n_out, So + G, dtype=torch.float32, device=dev), torch.empty(n_out, A, dtype=torch.float32, device=dev),
+                torch.empty(n_out, dtype=torch.float64, device=dev), torch.empty(n_out, So + G, dtype=torch.float32, device=dev),
+                torch.empty(n_out, dtype=torch.uint8, device=dev)]
+        _lib.check(_lib.lib().d4pg_her_relabel(T, So, G, A, *[_lib.ptr(t) for t in ins], float(threshold),
+                                               0 if her_action == "reference" else 1, *[_lib.ptr(t) for t in outs],
+                                               _lib.stream_ptr()), "d4pg_her_relabel")
+        self._add_device(n_out, outs)
+        return n_out
+
     def _add_device(self, n, tensors):
         _lib.check(_lib.lib().d4pg_replay_add(self.handle, n, *[_lib.ptr(t) for t in tensors],
                                               1 if self.prioritized else 0, _lib.stream_ptr()), "d4pg_replay_add")
@@ -272,6 +347,10 @@ class _DeviceReplay(object):
         pr = torch.as_tensor(np.asarray(priorities, dtype=np.float32)).to(self.device) if not torch.is_tensor(priorities) \
             else priorities.to(device=self.device, dtype=torch.float32)
         assert idx.numel() == pr.numel()                                                   # :328
+        if idx.numel():
+            # the reference's per-element asserts (:330-331); an unchecked index would be a stray device write into the trees
+            assert bool((pr > 0).all()), "priorities must be > 0"
+            assert bool(((idx >= 0) & (idx < len(self))).all()), "index out of range"
         _lib.check(_lib.lib().d4pg_replay_update_priorities(self.handle, idx.numel(), _lib.ptr(idx), _lib.ptr(pr),
                                                             _lib.stream_ptr()), "d4pg_replay_update_priorities")
 
@@ -400,6 +479,15 @@ class ReplayBuffer(object):
             self._store.add_batch_host(obs_t, action, reward, obs_tp1, done)
         else:
             self._store.add_batch(obs_t, action, reward, obs_tp1, done)
+
+    def add_episode(self, obs, action, reward, obs_next, done, n_steps=1, gamma=0.99):
+        """One episode of consecutive steps; the n-step return is accumulated on the device at insert
+        (the arithmetic of replay_memory.py:38-45).  Returns the number of transitions inserted."""
+        return self._store.add_episode_nstep(obs, action, reward, obs_next, done, n_steps, gamma)
+
+    def add_her_episode(self, obs, obs_next, goal, achieved_goal_next, action, reward, done, **kw):
+        """Hindsight relabelling on the device (main.py:154-184); see _DeviceReplay.add_her_episode."""
+        return self._store.add_her_episode(obs, obs_next, goal, achieved_goal_next, action, reward, done, **kw)
 
     def _encode_sample(self, idxes):
         return _to_host_batch(self._store.gather(idxes))

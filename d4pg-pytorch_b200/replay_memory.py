@@ -39,30 +39,33 @@ class Replay(object):
         else:
             self._store.add_batch(state, action, reward, next_state, done)
 
+    def add_episode(self, states, actions, rewards, next_states, dones):
+        """One episode of consecutive steps; the n-step return (self.n_steps, self.gamma) is accumulated on the device
+        at insert -- the arithmetic of initialize() below / replay_memory.py:38-45."""
+        return self._store.add_episode_nstep(states, actions, rewards, next_states, dones, self.n_steps, self.gamma)
+
     def initialize(self, init_length):
-        """Random-policy filler with n-step return accumulation at insert time
-        (replay_memory.py:21-59).  Needs a gym-style `env`; host-side glue only."""
+        """Random-policy filler with n-step return accumulation at insert time (replay_memory.py:21-59).  Needs a
+        gym-style `env`.  The rollout is host glue; every finished (or cut-off) episode goes to the device in one
+        `add_episode` call, which forms the n-step transitions there.  The reference stops the moment the buffer holds
+        `init_length` transitions, possibly mid-episode: the last episode is truncated to the steps it had taken."""
         env = self.env
-        state = env.reset()
-        states, actions, rewards = [], [], []
         while len(self) < init_length:
-            action = np.random.uniform(-1.0, 1.0, size=env.action_space.shape)
-            next_state, reward, done, _ = env.step(action)
-            states.append(state)
-            actions.append(action)
-            rewards.append(reward)
-            if len(rewards) >= self.n_steps:
-                window = rewards[-self.n_steps:]
-                ret, disc = 0.0, 1
-                for rw in window:
-                    ret += disc * rw
-                    disc *= self.gamma
-                self.add(np.asarray(states[-self.n_steps]).reshape(-1), actions[-self.n_steps], ret, next_state, done)
-            if done:
-                state = env.reset()
-                states, actions, rewards = [], [], []
-            else:
+            state = env.reset()
+            states, actions, rewards, nexts, dones = [], [], [], [], []
+            have = len(self)
+            while True:
+                action = np.random.uniform(-1.0, 1.0, size=env.action_space.shape)
+                next_state, reward, done, _ = env.step(action)
+                states.append(np.asarray(state).reshape(-1)); actions.append(action); rewards.append(reward)
+                nexts.append(np.asarray(next_state).reshape(-1)); dones.append(done)
+                added = max(0, len(rewards) - self.n_steps + 1)               # transitions this episode contributes so far
+                if have + added >= init_length or done:
+                    break
                 state = next_state
+            if len(rewards) >= self.n_steps:
+                self.add_episode(np.stack(states), np.stack(actions), np.asarray(rewards, dtype=np.float64), np.stack(nexts),
+                                 np.asarray(dones))
 
     def sample_positions(self, batch_size):
         return random.sample(range(len(self)), batch_size)                 # replay_memory.py:67

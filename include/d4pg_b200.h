@@ -137,6 +137,33 @@ int32_t d4pg_replay_set_staging(d4pg_replay_t* h, void* pinned_host, void* devic
 int32_t d4pg_replay_add_host(d4pg_replay_t* h, int64_t n, const float* obs, const float* act, const double* rew,
                              const float* obs2, const uint8_t* done, int32_t prioritized, d4pg_stream_t stream);
 
+/* Device-side ingest with n-step return accumulation at insert (replay_memory.py:38-45).  The arrays hold ONE episode
+ * of T consecutive steps, resident on the device; transition i = (s_i, a_i, sum_{k<n} gamma^k r_{i+k}, s'_{i+n-1},
+ * done_{i+n-1}) for i <= T-n is inserted (nothing when T < n, like the reference before step n-1).  The return is the
+ * reference's left-to-right f64 loop, bit for bit.  `rew_scratch` f64 [T] is caller-owned device scratch.
+ * d4pg_nstep_returns is the arithmetic alone: out[i], i <= T-n. */
+int32_t d4pg_nstep_returns(const double* rew, int64_t T, int32_t n_steps, double gamma, double* out, d4pg_stream_t stream);
+int32_t d4pg_replay_add_nstep(d4pg_replay_t* h, int64_t T, const float* obs, const float* act, const double* rew,
+                              const float* obs2, const uint8_t* done, int32_t n_steps, double gamma,
+                              double* rew_scratch, int32_t prioritized, d4pg_stream_t stream);
+
+/* Hindsight-experience relabelling on the device (main.py:154-184, "future" strategy) as a gather kernel that produces
+ * the rows d4pg_replay_add then inserts.  Episode of T goal-conditioned steps: obs / obs_next f32 [T, obs_dim], goal
+ * f64 [T, goal_dim] (desired goal of every step), ag_next f64 [T, goal_dim] (achieved goal of the next state), act f32
+ * [T, act_dim], rew f64 [T], done u8 [T].  select u8 [T] / future i32 [T] are the caller's draws
+ * (np.random.uniform() < her_ratio; np.random.randint(t, T)), dst_row i32 [T] = exclusive prefix sum of (1 + select).
+ * Output rows (state width obs_dim + goal_dim): the original transition of step t, then -- if selected -- its copy with
+ * goal' = ag_next[future[t]], reward = -(||ag_next[t] - goal'||_2 > threshold) in f64 (the sparse gym-robotics
+ * compute_reward) and done = (reward == 0).  her_action_mode 0 keeps the reference's behaviour of storing the rollout's
+ * LAST action with the relabelled copy (main.py:184 uses `action`, not the step's `a`); 1 stores a_t. */
+int32_t d4pg_her_relabel(int32_t T, int32_t obs_dim, int32_t goal_dim, int32_t act_dim,
+                         const float* obs, const float* obs_next, const double* goal, const double* ag_next,
+                         const float* act, const double* rew, const uint8_t* done,
+                         const uint8_t* select, const int32_t* future, const int32_t* dst_row,
+                         double threshold, int32_t her_action_mode,
+                         float* out_s, float* out_a, double* out_r, float* out_s2, uint8_t* out_d,
+                         d4pg_stream_t stream);
+
 /* _sample_proportional + IS weights + _encode_sample (:258-313,189-199).
  *   uniforms [B] f64 in [0,1): the reference's random.random() draws; NULL = device Philox
  *   (seed, counter) stream.  mass = u * sum(0,len-1) with the reference's association and
@@ -165,13 +192,13 @@ int32_t d4pg_replay_find_prefixsum(d4pg_replay_t* h, int32_t n, const double* ma
 /* raw leaf write + parent recompute for n (idx, value) pairs: SegmentTree.__setitem__ (:98-108) */
 int32_t d4pg_replay_set_leaves(d4pg_replay_t* h, int32_t n, const int32_t* idx, const float* sum_vals,
                                const float* min_vals, d4pg_stream_t stream);
-/* host-visible bookkeeping the drop-in needs after a host-side restore */
-int32_t d4pg_replay_set_len(d4pg_replay_t* h, int64_t len, int64_t next_idx, int32_t pristine);
+/* host-visible bookkeeping the drop-in needs after a host-side restore (stream-ordered like every other mutator) */
+int32_t d4pg_replay_set_len(d4pg_replay_t* h, int64_t len, int64_t next_idx, int32_t pristine, d4pg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Actor / critic forward (inference entry points).  Replace actor.forward (models.py:32-41)
  * and critic.forward (models.py:76-88).  `params` = flat buffer in d4pg_*_layout order.
- * `workspace` f32 [3*B*256] scratch.  precision: 0 fp32 (FFMA), 1 3xTF32 tcgen05, 2 bf16 tcgen05.
+ * `workspace` f32 [3*B*256] scratch.  precision: 0 fp32 (FFMA), 1 3xTF32 tcgen05 (fp32-accurate), 2 one TF32 tcgen05 pass.
  * ------------------------------------------------------------------------------------- */
 int32_t d4pg_actor_forward(const float* params, int32_t obs_dim, int32_t act_dim,
                            const float* s, int32_t B, float* action, float* workspace,
@@ -209,21 +236,20 @@ typedef struct {
   int32_t prioritized;        /* 1 = PrioritizedReplayBuffer path, 0 = uniform Replay path */
   double  per_beta0, per_beta_final; int64_t per_beta_iters;   /* LinearSchedule, ddpg.py:81-86 */
   double  prio_eps;           /* ddpg.py:87 */
-  int32_t precision;          /* 0 fp32 FFMA, 1 3xTF32 tcgen05, 2 bf16 tcgen05 */
+  int32_t precision;          /* 0 exact fp32 FFMA, 1 3xTF32 tcgen05 (hi/lo split, fp32-accurate: meets the 1e-5 parity bar),
+                                 2 one TF32 tcgen05 pass (not parity-grade) */
   int32_t sample_mode;        /* 0 = caller uniforms/positions (parity), 1 = device Philox */
   uint64_t philox_seed;
   int32_t world_size;         /* >1: gradients are averaged over ranks before Adam */
   int32_t use_graph;          /* 1 = capture the step into a CUDA graph */
-  int32_t persistent;         /* 1 = run the step as ONE cooperative kernel with grid barriers (precision 0 only) */
   int32_t loss_flags;         /* corrected-semantics switches, 0 = reference behaviour:
                                  1 = importance-weighted critic CE (the reference samples the weights but
                                      ignores them, ddpg.py:217), 2 = priority = CE_i + eps instead of
                                      |sum_j m_ij q_ij| + eps (ddpg.py:221-222,253) */
   int32_t chain;              /* step plan of the MLP passes (batches above 512 rows always use plan 0): 0 = one grouped launch per dependency
                                  level (18 kernels/step); 1 = cluster-fused layer chains: forward passes, dX passes
-                                 and all dW are ONE launch each (7 kernels/step, bit-identical to 0); 2 = row-owner
-                                 chains: a CTA carries a few batch rows through a whole chain, weights streamed
-                                 (7 kernels/step; same fp32 dot products in a different summation order) */
+                                 and all dW are ONE launch each (7 kernels/step; precision 0: FFMA tiles, bit-identical
+                                 to plan 0; precision 1/2: tcgen05 tiles, 64-row clusters, pre-packed hi/lo weight images) */
   int32_t prefetch;           /* 1 (sample_mode 1 only): step t samples batch t+1 on a side branch, right after its own
                                  priorities are in the trees, while its backward pass and Adam still run.  Same
                                  Philox counters and the same trees as sampling at the start of step t+1, so results
@@ -256,15 +282,20 @@ int32_t d4pg_learner_destroy(d4pg_learner_t* h);
 /* One gradient step.  Everything is stream-ordered; results land in buf->losses etc. */
 int32_t d4pg_learner_step(d4pg_learner_t* h, d4pg_stream_t stream);
 /* Host-facing step: everything `DDPG.train()` needs per call in ONE library call.
- *   d4pg_learner_set_host_buffers: caller-owned PINNED host buffers: uniforms f64[B], positions i32[B], losses f32[4]
  *   d4pg_learner_step_host: order the learner stream after `caller_stream`, copy this step's host inputs
- *     (uniforms for prioritized replay / positions for uniform replay; NULL with device-side sampling)
- *     to the device, run the step on `learner_stream`, order `caller_stream` after it.
+ *     (uniforms f64[B] for prioritized replay / positions i32[B] for uniform replay; NULL with device-side sampling)
+ *     to the device, run the step on `learner_stream`, order `caller_stream` after it.  The inputs may live in
+ *     ordinary host memory and may be reused as soon as the call returns: they are staged in library-owned pinned
+ *     buffers (allocated by d4pg_learner_create, double-buffered by step parity, a buffer is rewritten only after the
+ *     H2D copy out of it has completed).
+ *   d4pg_learner_step_host_mt: the same for prioritized replay, taking the 2*B raw 32-bit MT19937 outputs of
+ *     `random.randbytes(8*B)` instead of B doubles: uniform i = ((w[2i] >> 5) * 2^26 + (w[2i+1] >> 6)) / 2^53, which is
+ *     CPython's random.random() -- the draws of prioritized_replay_memory.py:262, same generator state afterwards.
  *   d4pg_learner_read_losses: D2H of {critic loss, actor loss, -, -} and wait for it (the step's result). */
-int32_t d4pg_learner_set_host_buffers(d4pg_learner_t* h, double* pinned_uniforms, int32_t* pinned_positions,
-                                      float* pinned_losses);
 int32_t d4pg_learner_step_host(d4pg_learner_t* h, const double* uniforms, const int32_t* positions,
                                d4pg_stream_t caller_stream, d4pg_stream_t learner_stream);
+int32_t d4pg_learner_step_host_mt(d4pg_learner_t* h, const uint32_t* mt_words,
+                                  d4pg_stream_t caller_stream, d4pg_stream_t learner_stream);
 int32_t d4pg_learner_read_losses(d4pg_learner_t* h, float* out4, d4pg_stream_t learner_stream);
 /* n_steps back-to-back gradient steps without returning to the caller in between (device-side
  * sampling keeps advancing; caller-supplied uniforms/positions would be reused). */
@@ -304,11 +335,16 @@ int32_t d4pg_comm_peer_ready(const d4pg_comm_t* c);
 int32_t d4pg_comm_peer_disable(d4pg_comm_t* c);      /* collective decision: fall back to the NCCL all-reduce */
 
 /* Debug: %globaltimer (ns) phase stamps written by CTA 0 of the most recent tcgen05 GEMM launch when
- * the environment variable D4PG_TC_TRACE is set; the persistent step kernel writes one stamp per
- * phase boundary instead (out16 = 32 x uint64, host memory). */
+ * the environment variable D4PG_TC_TRACE is set (out16 = 32 x uint64, host memory). */
 int32_t d4pg_debug_tc_trace(unsigned long long* out16);
-/* first n (<= 128) stamps of the same buffer: the chain kernels write 6 per layer slot of CTA 0 */
+/* first n (<= 512) stamps of the same buffer: the chain kernels write 6-8 per layer slot of one CTA */
 int32_t d4pg_debug_trace_read(unsigned long long* out, int32_t n);
+/* Watchdog record of the tcgen05 chain kernels (16 x uint64, host memory): every mbarrier wait inside them is bounded;
+ * a wait that times out traps the launch and leaves {1, code | slot<<8 | rank<<16 | parity<<24 | block<<32, aux, ...}
+ * in host-mapped memory, readable here even after the failed launch invalidated the context; words [4 + 2k, 5 + 2k] hold
+ * the first timed-out wait of kind k = 1..5 (loader: ring buffer free / accumulator done, MMA: weights / A chunk landed,
+ * epilogue: accumulator done).  All zero = never fired. */
+int32_t d4pg_debug_watchdog(unsigned long long* out16);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,8 @@
-"""Import the UNMODIFIED reference (/root/reference) behind the compat shim.
+"""Import the UNMODIFIED reference behind the compat shim: from /root/reference where it exists (the build
+container), else from `oracle/_ref/` -- the same modules byte-compiled by oracle/build_ref.py, which travel to the GPU
+box as build output (bench.py's CPU arm; the `-m gpu` tests never need them).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Only usable where
-/root/reference exists (the build container); the GPU box never has it.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 Shim items (each verified by running the reference here):
   1. SharedAdam `state['step']` must be a 0-d tensor for torch>=2 (shared_adam.py:11).
@@ -14,14 +15,27 @@ import os
 import sys
 
 REFERENCE_PATH = os.environ.get("D4PG_REFERENCE_PATH", "/root/reference")
+COMPILED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 class ReferenceBreakpoint(RuntimeError):
     """Raised where the reference would have dropped into pdb."""
 
 
-def available():
+def source_available():
     return os.path.isfile(os.path.join(REFERENCE_PATH, "ddpg.py"))
+
+
+def compiled_available():
+    return os.path.isfile(os.path.join(COMPILED_PATH, "ddpg.pyc"))
+
+
+def available():
+    return source_available() or compiled_available()
+
+
+def import_path():
+    return REFERENCE_PATH if source_available() else COMPILED_PATH
 
 
 _cached = None
@@ -33,7 +47,8 @@ def load():
     if _cached is not None:
         return _cached
     if not available():
-        raise RuntimeError("reference not present at %s" % REFERENCE_PATH)
+        raise RuntimeError("reference not present at %s nor compiled under %s" % (REFERENCE_PATH, COMPILED_PATH))
+    ref_path = import_path()
     import types
     import numpy as np
     import torch
@@ -56,14 +71,14 @@ def load():
     names = ["utils", "models", "random_process", "replay_memory",
              "prioritized_replay_memory", "shared_adam", "ddpg"]
     saved = {n: sys.modules.pop(n) for n in names if n in sys.modules}
-    sys.path.insert(0, REFERENCE_PATH)
+    sys.path.insert(0, ref_path)
     try:
         mods = {}
         import importlib
         for n in names:
             mods[n] = importlib.import_module(n)
     finally:
-        sys.path.remove(REFERENCE_PATH)
+        sys.path.remove(ref_path)
         for n in names:
             m = sys.modules.pop(n, None)
             if m is not None:

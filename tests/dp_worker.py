@@ -104,6 +104,10 @@ def main():
                 assert np.abs(p - all_prio[r].cpu().numpy()).max() <= 1e-5
                 oracle_bufs[r].update_priorities(batches[r][6], all_prio[r].cpu().numpy())
             assert abs(losses[0].item() / world - float(out["loss_critic"])) <= 1e-5
+            for net, grads in ((dd.actor, out["grads_actor"]), (dd.critic, out["grads_critic"])):      # the rank-order SUM of the shards' gradients
+                for k in O.PARAM_ORDER:
+                    gk = net.named_grad_views()[k].cpu()
+                    assert (gk - grads[k]).abs().max().item() <= 1e-5, (t, k, (gk - grads[k]).abs().max().item())
             for k in O.PARAM_ORDER:
                 for mine, refw in ((dd.actor.state_dict()[k], lo.actor[k]), (dd.critic.state_dict()[k], lo.critic[k])):
                     err = (mine.cpu() - refw).abs()

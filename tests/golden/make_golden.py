@@ -177,11 +177,9 @@ def compact(out, key, arr):
                                        np.abs(flat.astype(np.float64)).sum(), flat.size])
 
 
-def gen_train(ref, tag, obs_dim, act_dim, info, B, mem, n_fill, per, steps, term_p, seed):
-    """`steps` consecutive DDPG.train() calls (ddpg.py:200-255) from a saved state."""
-    out = {}
-    g, l, oa, oc = ref_shim.make_learner_pair(obs_dim, act_dim, info, B, mem,
-                                              prioritized_replay=per, seed=seed)
+def train_data(seed, n_fill, obs_dim, act_dim, term_p):
+    """The transitions of a train_*.npz fixture (also used by the tests to REGENERATE them when a fixture stores
+    only the seed: numpy's RandomState streams are stable across versions)."""
     rng = np.random.RandomState(seed + 1)
     S = rng.randn(n_fill, obs_dim).astype(np.float32)
     A = rng.uniform(-1, 1, (n_fill, act_dim)).astype(np.float32)
@@ -189,11 +187,25 @@ def gen_train(ref, tag, obs_dim, act_dim, info, B, mem, n_fill, per, steps, term
     S2 = rng.randn(n_fill, obs_dim).astype(np.float32)
     # terminal rows get non-integer rewards only (no H6 mixing)
     D = rng.rand(n_fill) < term_p
+    return S, A, R, S2, D
+
+
+def gen_train(ref, tag, obs_dim, act_dim, info, B, mem, n_fill, per, steps, term_p, seed, n_steps=1, store_data=True):
+    """`steps` consecutive DDPG.train() calls (ddpg.py:200-255) from a saved state."""
+    out = {}
+    g, l, oa, oc = ref_shim.make_learner_pair(obs_dim, act_dim, info, B, mem,
+                                              prioritized_replay=per, seed=seed, n_steps=n_steps)
+    S, A, R, S2, D = train_data(seed, n_fill, obs_dim, act_dim, term_p)
     for i in range(n_fill):
         l.replayBuffer.add(S[i], A[i], float(R[i]), S2[i], bool(D[i]))
     out["meta"] = np.array([obs_dim, act_dim, info["n_atoms"], B, mem, n_fill, int(per), steps])
     out["dist"] = np.array([info["v_min"], info["v_max"]])
-    out["S"], out["A"], out["R"], out["S2"], out["D"] = S, A, R, S2, D
+    out["n_steps"] = np.array(n_steps)
+    if store_data:
+        out["S"], out["A"], out["R"], out["S2"], out["D"] = S, A, R, S2, D
+    else:                                   # big fixtures: the tests regenerate the transitions from the seed
+        out["term_p"] = np.array(term_p)
+        compact(out, "S", S); compact(out, "R", R)
     # initial weights are re-creatable from `seed` (oracle.init_actor/init_critic consume
     # the RNG exactly like models.py); the subsample pins them
     out["seed"] = np.array(seed)
@@ -251,8 +263,11 @@ def gen_train(ref, tag, obs_dim, act_dim, info, B, mem, n_fill, per, steps, term
         out["loss_critic_%d" % t] = (-(m * torch.log(q + 1e-10)).sum(dim=1).mean()).numpy()   # ddpg.py:217
         z = torch.from_numpy(l.bin_centers).float()
         out["loss_actor_%d" % t] = (-torch.from_numpy(qs[1]).matmul(z).mean()).numpy()       # ddpg.py:238
-        out["target_probs_%d" % t], out["m_%d" % t] = rec["tz"], rec["m"]
-        out["q_%d" % t], out["q_pi_%d" % t] = qs[0], qs[1]
+        for key, arr in (("target_probs_%d" % t, rec["tz"]), ("m_%d" % t, rec["m"]), ("q_%d" % t, qs[0]), ("q_pi_%d" % t, qs[1])):
+            if store_data:
+                out[key] = arr
+            else:
+                compact(out, key, arr)
         if per:
             out["idx_%d" % t], out["prio_%d" % t] = rec["idx"], rec["prio"]
             s, mn = dump_tree(l.replayBuffer)
@@ -295,9 +310,32 @@ def gen_init(ref):
     print("init.npz:", len(out), "arrays")
 
 
+def gen_baseline_sizes(ref):
+    """Fixtures at the BASELINE.json sizes: c2 as configured (B=256), config-3 shapes
+    (|s|=376, |a|=17, B=1024, small capacity), config-5 shapes (101 atoms, n_steps=5; train() at B=256 -- the live
+    projection is reproject2 with gamma) and the n-step projection at B=4096."""
+    gen_train(ref, "per_c2_b256", 17, 6, INFO51, 256, 2048, 2048, True, 3, 0.05, seed=21, store_data=False)
+    gen_train(ref, "per_c3_b1024", 376, 17, INFO51, 1024, 2048, 2048, True, 2, 0.05, seed=22, store_data=False)
+    gen_train(ref, "per_c5_b256", 17, 6, INFO101, 256, 2048, 2048, True, 2, 0.05, seed=23, n_steps=5, store_data=False)
+    rng = np.random.RandomState(4096)
+    B = 4096
+    p = softmax_rows(rng, B, 101, sharp=2.0)
+    r = (40.0 * (rng.rand(B) - 0.5)).astype(np.float32).astype(np.float64)
+    done = rng.rand(B) < 0.05
+    out = {"seed": np.array(4096), "B": np.array(B)}
+    compact(out, "probs", p); compact(out, "r", r)
+    out["done_count"] = np.array(int(done.sum()))
+    compact(out, "m", ref_project(ref, INFO101, 0.99, 5, p, r, done, live=False))
+    np.savez_compressed(os.path.join(HERE, "projection_c5_b4096.npz"), **out)
+    print("projection_c5_b4096.npz:", len(out), "arrays")
+
+
 def main():
     ref = ref_shim.load()
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "baseline":      # only the BASELINE-size fixtures (added in round 2)
+        gen_baseline_sizes(ref)
+        return
     gen_projection(ref)
     gen_tree(ref)
     gen_init(ref)
@@ -307,6 +345,7 @@ def main():
     gen_train(ref, "per_part", 17, 6, INFO51, 16, 1000, 333, True, 3, 0.0, seed=12)
     # config 1: Pendulum dims, uniform replay_memory.py
     gen_train(ref, "uniform_c1", 3, 1, INFO_PEND, 64, 500, 400, False, 3, 0.0, seed=13)
+    gen_baseline_sizes(ref)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,15 @@ def test_projection_nstep_vs_golden(d4pg):
         assert np.abs(m.astype(np.float64) - g[k + "_m"]).max() <= 1e-6     # tolerance: 1e-5 allowed, 1e-6 asserted
 
 
+def test_projection_nstep_config5_size_vs_golden(d4pg):
+    """B=4096, 101 atoms, n_steps=5: the reference's reproj_categorical_dist (ddpg.py:122-140) run at the BASELINE size."""
+    g, p, r, done = H.projection_c5_inputs()
+    m, bl, bu = _proj(d4pg, p, r, done, -150.0, 150.0, 101, 0.99 ** 5, 1)
+    _, ol, ou = O.project_nstep(p, r, done, -150.0, 150.0, 101, 0.99, 5, return_bins=True)
+    assert np.array_equal(bl, ol) and np.array_equal(bu, ou)
+    H.check_compact(g, "m", m.astype(np.float64), 1e-6)
+
+
 def test_projection_full_size_properties(d4pg):
     """Config-5 size (B=4096, N=101): rows sum to sum(p) (mass conservation), non-negative."""
     rng = np.random.RandomState(9)

@@ -14,14 +14,15 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", persistent=False, chain=True):
+def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", chain=True):
     obs_dim, act_dim, N, B, mem, n_fill, per, steps = [int(x) for x in g["meta"]]
     v_min, v_max = [float(x) for x in g["dist"]]
     info = {"type": "categorical", "v_min": v_min, "v_max": v_max, "n_atoms": N}
     seed = int(g["seed"])
     torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
     kw = dict(memory_size=mem, batch_size=B, critic_dist_info=info, prioritized_replay=bool(per),
-              use_graph=use_graph, sampling=sampling, precision=precision, persistent=persistent, chain=chain)
+              use_graph=use_graph, sampling=sampling, precision=precision, chain=chain,
+              n_steps=int(g["n_steps"]) if "n_steps" in g.files else 1)
     glob = d4pg.DDPG(obs_dim, act_dim, **kw)               # main.py:382-385
     oa = d4pg.SharedAdam(glob.actor.parameters(), lr=1e-3)
     oc = d4pg.SharedAdam(glob.critic.parameters(), lr=1e-3)
@@ -32,26 +33,35 @@ def _build(d4pg, g, use_graph, sampling="reference", precision="fp32", persisten
     for k in H.NAMES:   # same seed -> same initial weights as the reference run
         H.check_compact(g, "init_actor_" + k, loc.actor.state_dict()[k].cpu().numpy(), 0.0)
         H.check_compact(g, "init_critic_" + k, loc.critic.state_dict()[k].cpu().numpy(), 0.0)
+    S, A, R, S2, D = H.train_data(g)
     for i in range(n_fill):
-        loc.replayBuffer.add(g["S"][i], g["A"][i], float(g["R"][i]), g["S2"][i], bool(g["D"][i]))
+        loc.replayBuffer.add(S[i], A[i], float(R[i]), S2[i], bool(D[i]))
     return glob, loc, oa, oc, (obs_dim, act_dim, N, B, mem, n_fill, per, steps, v_min, v_max)
 
 
-@pytest.mark.parametrize("tag", ["per_c2", "per_part", "uniform_c1"])
-@pytest.mark.parametrize("use_graph,precision", [(False, "fp32"), (True, "fp32"), (True, "rows"), (True, "levels"), (True, "mma_tf32x3"), (False, "mma_tf32x3"), (True, "tf32x3"),
-                          (True, "mega"), (False, "mega")])
+CASES = [(tag, ug, pr) for tag in ("per_c2", "per_part", "uniform_c1")
+         for ug, pr in ((False, "fp32"), (True, "fp32"), (True, "levels"), (True, "tf32x3"), (False, "tf32x3"), (True, "tf32x3_levels"))]
+# reference-generated fixtures at the BASELINE.json sizes: config 2 as benchmarked (B=256), config-3 shapes (|s|=376,
+# |a|=17, B=1024: one launch per level), config-5 shapes (101 atoms, n_steps=5)
+CASES += [("per_c2_b256", True, "fp32"), ("per_c2_b256", True, "tf32x3"), ("per_c2_b256", False, "tf32x3"),
+          ("per_c5_b256", True, "fp32"), ("per_c5_b256", True, "tf32x3"),
+          ("per_c3_b1024", True, "levels"), ("per_c3_b1024", True, "tf32x3_levels")]
+
+
+@pytest.mark.parametrize("tag,use_graph,precision", CASES)
 def test_train_steps_vs_reference_golden(tag, use_graph, precision):
-    """precision fp32 = exact-FFMA kernels as cluster-fused layer chains (the default step plan); rows = the
-    row-owner chains (TMA-multicast weight stream); levels = one grouped launch per dependency level; mma_tf32x3 =
-    the cluster chains with the mma.sync 3xTF32 tile (tensor cores, fp32-accurate); tf32x3 = tcgen05 tensor cores
-    with the 3xTF32 split.  All must meet the same 1e-5 bar against the reference's fp32 CPU results."""
+    """precision fp32 = exact-FFMA kernels as cluster-fused layer chains; levels = the same tiles, one grouped launch per
+    dependency level; tf32x3 = the cluster chains on tcgen05 tensor cores with the 3xTF32 split (mlp_tc_chain.cu, the
+    benchmarked plan); tf32x3_levels = tcgen05 3xTF32, one launch per level.  All must meet the same 1e-5 bar against
+    the reference's fp32 CPU results."""
     import d4pg_b200 as d4pg
     g = H.load("train_%s.npz" % tag)
-    persistent = precision == "mega"          # fp32 kernels as phases of ONE cooperative kernel per step
-    chain = {"fp32": "cluster", "rows": "rows", "mma_tf32x3": "cluster"}.get(precision, "levels")
-    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision="fp32" if precision in ("mega", "levels", "rows") else ("tf32x3" if precision == "mma_tf32x3" else precision),
-                                     persistent=persistent, chain=chain)
+    chain = {"fp32": "cluster", "tf32x3": "cluster"}.get(precision, "levels")
+    glob, loc, oa, oc, meta = _build(d4pg, g, use_graph, precision={"levels": "fp32", "tf32x3_levels": "tf32x3"}.get(precision, precision),
+                                     chain=chain)
     obs_dim, act_dim, N, B, mem, n_fill, per, steps, v_min, v_max = meta
+    data = H.train_data(g)
+    stats = {"grad_rel_l2": 0.0, "param_outlier_frac": 0.0, "param_max_err": 0.0}
     for t in range(steps):
         random.seed(9000 + t)                       # same generator state as the reference run
         loc.train(glob)
@@ -61,17 +71,14 @@ def test_train_steps_vs_reference_golden(tag, use_graph, precision):
         lc, la = loc.last_losses()
         assert abs(lc - float(g["loss_critic_%d" % t])) <= TOL
         assert abs(la - float(g["loss_actor_%d" % t])) <= TOL * max(1.0, abs(la))
-        tp = loc.debug_tensor("target_probs", (B, N)).cpu().numpy()
-        m = loc.debug_tensor("m", (B, N)).cpu().numpy()
-        q = loc.debug_tensor("q_probs", (B, N)).cpu().numpy()
-        assert np.abs(tp - g["target_probs_%d" % t]).max() <= TOL
-        assert np.abs(m - g["m_%d" % t]).max() <= TOL
-        assert np.abs(q - g["q_%d" % t]).max() <= TOL
+        H.check_compact(g, "target_probs_%d" % t, loc.debug_tensor("target_probs", (B, N)).cpu().numpy(), TOL)
+        H.check_compact(g, "m_%d" % t, loc.debug_tensor("m", (B, N)).cpu().numpy(), TOL)
+        H.check_compact(g, "q_%d" % t, loc.debug_tensor("q_probs", (B, N)).cpu().numpy(), TOL)
         # gathered batch is bit-exact
         r = loc.debug_tensor("r", None, torch.float64).cpu().numpy()
-        assert np.array_equal(r, g["R"][idx])
+        assert np.array_equal(r, data[2][idx])
         s = loc.debug_tensor("s", (B, obs_dim)).cpu().numpy()
-        assert np.array_equal(s, g["S"][idx])
+        assert np.array_equal(s, data[0][idx])
         if per:
             assert np.abs(info["prio"].cpu().numpy() - g["prio_%d" % t]).max() <= TOL
             # leaves = (reference priority)**0.6 vs (our priority, <=1e-5 away)**0.6: compare loosely,
@@ -87,8 +94,10 @@ def test_train_steps_vs_reference_golden(tag, use_graph, precision):
                 gk = gviews[k].cpu().numpy().reshape(-1)
                 H.check_compact(g, "g_%s_%s_%d" % (name, k, t), gk, TOL)
                 ref, mine = H.golden_vec(g, "g_%s_%s_%d" % (name, k, t), gk)
-                assert H.rel_l2(mine, ref) <= 1e-4, (name, k, t, H.rel_l2(mine, ref))
-                H.check_params(g, "%s_%s_%d" % (name, k, t), net.state_dict()[k].cpu().numpy())
+                rl = H.rel_l2(mine, ref)
+                assert rl <= 1e-4, (name, k, t, rl)
+                stats["grad_rel_l2"] = max(stats["grad_rel_l2"], rl)
+                H.check_params(g, "%s_%s_%d" % (name, k, t), net.state_dict()[k].cpu().numpy(), stats=stats)
         # local == global (ddpg.py:247)
         assert torch.equal(loc.actor.flat_params(), glob.actor.flat_params())
     t = steps - 1
@@ -100,6 +109,10 @@ def test_train_steps_vs_reference_golden(tag, use_graph, precision):
     for prm, k in zip(glob.critic.parameters(), H.NAMES):
         H.check_compact(g, "adam_v_critic_%s_%d" % (k, t), oc.state[prm]["exp_avg_sq"].cpu().numpy().reshape(-1), 1e-6)
     assert loc.kernels_per_step() > 0
+    # observed slack inside the tolerances: a regression shows up here before it fails
+    print("\n[parity %s graph=%s %s] worst gradient rel-L2 %.2e (bar 1e-4), post-Adam parameters: max err %.2e (bar 2.5e-4), "
+          "worst fraction of elements off by > 1e-5: %.4f (bar 0.1)" % (tag, use_graph, precision, stats["grad_rel_l2"],
+                                                                         stats["param_max_err"], stats["param_outlier_frac"]))
 
 
 @pytest.mark.parametrize("B,obs_dim,act_dim,N", [(256, 17, 6, 51), (96, 376, 17, 51), (40, 3, 1, 101)])
@@ -131,46 +144,6 @@ def test_chain_equals_levels(B, obs_dim, act_dim, N):
                     torch.tensor(dd.last_losses())))
     for a, b in zip(*out):
         assert torch.equal(a, b)
-
-
-@pytest.mark.parametrize("B,obs_dim,act_dim,N", [(256, 17, 6, 51), (96, 376, 17, 51), (37, 3, 1, 101), (512, 17, 6, 51)])
-def test_rows_chain_vs_levels(B, obs_dim, act_dim, N):
-    """The row-owner chain kernels compute the same fp32 dot products in a different summation order:
-    after one device-sampled step the sampled batch, losses, logits and priorities agree with the
-    level-by-level launches to rounding, every gradient to 1e-5 relative L2."""
-    import d4pg_b200 as d4pg
-    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": N}
-    n_fill = 2048
-    rng = np.random.RandomState(12)
-    S = rng.randn(n_fill, obs_dim).astype(np.float32); A = rng.uniform(-1, 1, (n_fill, act_dim)).astype(np.float32)
-    R = (-3 * rng.rand(n_fill)).astype(np.float32).astype(np.float64); S2 = rng.randn(n_fill, obs_dim).astype(np.float32)
-    D = rng.rand(n_fill) < 0.05
-    out = {}
-    for chain in ("rows", "levels"):
-        torch.manual_seed(6); np.random.seed(6); random.seed(6)
-        dd = d4pg.DDPG(obs_dim, act_dim, memory_size=n_fill, batch_size=B, critic_dist_info=info, sampling="device",
-                       philox_seed=78, chain=chain)
-        dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3),
-                                   d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
-        dd.replayBuffer.add_batch(S, A, R, S2, D)
-        dd.train()
-        torch.cuda.synchronize()
-        assert dd.kernels_per_step() == (8 if chain == "rows" else 19)      # + the first step's own sample launch
-        g = {("a", k): v.clone() for k, v in dd.actor.named_grad_views().items()}
-        g.update({("c", k): v.clone() for k, v in dd.critic.named_grad_views().items()})
-        out[chain] = dict(idx=dd.last_batch_info()["idx"].clone(), prio=dd.last_batch_info()["prio"].clone(),
-                          losses=np.array(dd.last_losses()), grads=g,
-                          q=dd.debug_tensor("q_probs", (B, N)).clone(), m=dd.debug_tensor("m", (B, N)).clone(),
-                          act=dd.debug_tensor("actor_out", (B, act_dim)).clone())
-    a, b = out["rows"], out["levels"]
-    assert torch.equal(a["idx"], b["idx"])
-    assert np.abs(a["losses"] - b["losses"]).max() <= 1e-5 * max(1.0, np.abs(b["losses"]).max())
-    for k in ("q", "m", "act", "prio"):
-        assert (a[k] - b[k]).abs().max().item() <= 2e-6, k
-    for k in a["grads"]:
-        ga, gb = a["grads"][k].double().reshape(-1), b["grads"][k].double().reshape(-1)
-        rel = (ga - gb).norm().item() / max(gb.norm().item(), 1e-30)
-        assert rel <= 1e-5, (k, rel)
 
 
 @pytest.mark.parametrize("prioritized", [True, False])
@@ -372,3 +345,72 @@ def test_config3_shapes_batch1024_split_k(precision):
                 # exact-fp32 summation orders differ by 2e-4..2e-3 relative (measured, split-K atomics included); 3xTF32 adds 2^-21 per layer
                 rel_tol = 5e-3 if precision == "fp32" else 2e-2
                 assert H.rel_l2(gk.numpy(), grads[k].numpy()) <= rel_tol, (k, H.rel_l2(gk.numpy(), grads[k].numpy()))
+
+
+def _philox_uniform53(seed, counter, lane):
+    """Host restatement of Philox::uniform53 (csrc/common.cuh): Philox4x32-10, counter (lo, hi, lane, 0x9E3779B9),
+    key = seed; 53-bit uniform built like CPython's random.random() from two 32-bit outputs."""
+    M0, M1, MASK = 0xD2511F53, 0xCD9E8D57, 0xFFFFFFFF
+    c = [counter & MASK, (counter >> 32) & MASK, lane & MASK, 0x9E3779B9]
+    k0, k1 = seed & MASK, (seed >> 32) & MASK
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c[3] ^ k1) & MASK, p0 & MASK]
+        k0, k1 = (k0 + 0x9E3779B9) & MASK, (k1 + 0xBB67AE85) & MASK
+    return ((c[0] >> 5) * 67108864.0 + (c[1] >> 6)) * (1.0 / 9007199254740992.0)
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_device_sampling_mode_pinned_to_oracle(precision):
+    """The BENCHMARKED sampling mode (sampling="device", prefetch pipeline on): step t draws Philox(seed, counter=t,
+    lane=row) on the device.  The same uniforms, recomputed on the host, go through the oracle's
+    _sample_proportional / IS-weight code (prioritized_replay_memory.py:258-313) on a copy of the device trees:
+    indices must be bit-exact and weights within rtol 1e-5 -- across warm (prefetched) steps, an add_batch that
+    discards the prefetched batch, and the len-1 exclusion of a partially filled buffer.  Fails if the device descent,
+    the beta clock, the Philox counter or the sum(0, len-1) association drifts."""
+    import d4pg_b200 as d4pg
+    B, obs_dim, act_dim, N = 64, 17, 6, 51
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": N}
+    cap, seed = 4096, 0x1234567812345
+    rng = np.random.RandomState(31)
+
+    def chunk(n):
+        return (rng.randn(n, obs_dim).astype(np.float32), rng.uniform(-1, 1, (n, act_dim)).astype(np.float32),
+                (-3 * rng.rand(n)).astype(np.float32).astype(np.float64), rng.randn(n, obs_dim).astype(np.float32),
+                rng.rand(n) < 0.05)
+    torch.manual_seed(9); np.random.seed(9); random.seed(9)
+    dd = d4pg.DDPG(obs_dim, act_dim, memory_size=cap, batch_size=B, critic_dist_info=info, sampling="device",
+                   philox_seed=seed, prefetch=True, precision=precision)
+    dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3), d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
+    ob = O.PrioritizedReplayOracle(cap, 0.6, obs_dim, act_dim)
+    sched = O.LinearScheduleOracle(100000, 1.0, 0.4)
+    st = dd.replayBuffer._store
+
+    def adopt_device_trees():                       # index parity is asserted GIVEN identical tree contents
+        torch.cuda.synchronize()
+        ob.sum.value[:] = st.sum_tree.cpu().numpy()
+        ob.min.value[:] = st.min_tree.cpu().numpy()
+    t = 0
+    for phase, n_new, steps in ((0, 1500, 4), (1, 700, 3), (2, 2100, 3)):     # 1500 -> 2200 (partial) -> wraps to full
+        data = chunk(n_new)
+        dd.replayBuffer.add_batch(*data)
+        ob.add_batch(*data)
+        adopt_device_trees()
+        for _ in range(steps):
+            dd.train()
+            info_t = dd.last_batch_info()
+            idx = info_t["idx"].cpu().numpy()
+            us = [_philox_uniform53(seed, t, i) for i in range(B)]
+            want = ob.sample_indices(us)
+            assert np.array_equal(idx, want), "step %d (phase %d): device-sampled indices differ from the oracle" % (t, phase)
+            if len(ob) < cap:
+                assert idx.max() <= len(ob) - 2 + 1                      # sum(0, len-1): the mass never reaches past slot len-1 (:262)
+            w = ob.is_weights(want, sched.value())
+            np.testing.assert_allclose(info_t["weights"].cpu().numpy(), np.asarray(w, dtype=np.float64), rtol=1e-5)
+            s = dd.debug_tensor("s", (B, obs_dim)).cpu().numpy()
+            assert np.array_equal(s, ob.obs[want])                       # the gathered rows of those indices
+            ob.pristine = False                                          # update_priorities ran on the device (:332-333)
+            ob.max_priority_is_f32 = True
+            ob.max_priority = float(st.state[0].item())
+            adopt_device_trees()                                         # tree after this step's priorities (what step t+1's sample saw)
+            t += 1

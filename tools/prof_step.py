@@ -9,7 +9,7 @@ info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": N}
 n = 1 << 20
 chain = int(os.environ.get("CHAIN", "1"))
 dd = d4pg.DDPG(S, A, memory_size=n, batch_size=B, critic_dist_info=info, sampling="device", use_graph=False,
-               chain={0: "levels", 1: "cluster", 2: "rows"}[chain], precision=os.environ.get("PRECISION", "fp32"))
+               chain={0: "levels", 1: "cluster"}[chain], precision=os.environ.get("PRECISION", "fp32"))
 dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3), d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
 rng = np.random.RandomState(0)
 dd.replayBuffer.add_batch(rng.randn(n, S).astype(np.float32), rng.uniform(-1, 1, (n, A)).astype(np.float32),
