@@ -33,13 +33,12 @@ namespace d4pg {
 using namespace tc;
 
 // shared-memory map (bytes from the 1024-B aligned base)
-constexpr uint32_t TCC_OFF_RING = 0;
-constexpr uint32_t TCC_OFF_X = TCC_RING * TCC_A_CHUNK;
-constexpr uint32_t TCC_OFF_W = TCC_OFF_X + TCC_A_CHUNK;
+constexpr uint32_t TCC_OFF_A = 0;
+constexpr uint32_t TCC_OFF_W = TCC_ABUFS * TCC_A_CHUNK;
 constexpr uint32_t TCC_OFF_BAR = TCC_OFF_W + TCC_MAX_CHUNKS * TCC_W_CHUNK;
 constexpr uint32_t TCC_SMEM = TCC_OFF_BAR + 256 + 1024;      // barriers + alignment slack
-constexpr int TCC_TMEM_COLS = 64;
-constexpr int TCC_TRACE_PER_SLOT = 8;
+constexpr int TCC_TMEM_COLS = TCC_MAX_GROUPS * 2 * TCC_BN; // one 128-lane x 64-column fp32 accumulator per group
+constexpr int TCC_TRACE_PER_SLOT = 12;
 
 __device__ __forceinline__ void tcc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tcc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -86,12 +85,37 @@ __device__ __forceinline__ void tcc_wait(uint64_t* bar, uint32_t parity, unsigne
   }
 }
 #define TCC_CODE(kind, slot, rank) (unsigned(kind) | (unsigned(slot) << 8) | (unsigned(rank) << 16))
-enum { WD_LOADER_EMPTY = 1, WD_LOADER_DFULL = 2, WD_MMA_WFULL = 3, WD_MMA_FULL = 4, WD_EPI_DFULL = 5 };
+enum { WD_LOADER_DFULL = 2, WD_MMA_WFULL = 3, WD_MMA_FULL = 4, WD_EPI_DFULL = 5 };
 
 // generic-proxy writes (shared AND global) -> ordered before later async-proxy (TMA / tensor core) accesses
 __device__ __forceinline__ void tcc_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// 32 lanes x 16 columns of fp32 accumulators
+// The MMA-issuing code runs WARP-UNIFORM (all 32 lanes execute the loop with identical values, so descriptors live in
+// uniform registers) and only the instruction is predicated on an elected lane: measured on B200 (tests/probe/
+// mma_probe2.cu) 25 cycles per 64x32x8 tcgen05.mma this way vs 50 from a single-lane branch and 150+ with per-thread
+// integer arithmetic (R2UR round trips) in the loop.
+// The descriptors are passed as their LOW words (start address >> 4 | LBO << 16); the high word of a K-major
+// SWIZZLE_128B descriptor (SBO = 1024, version 1, layout 2) is the constant 0x40004040, so the compiler moves two
+// instead of four values into uniform registers per instruction.
+constexpr uint32_t TCC_DESC_HI = 0x40004040u;
+constexpr uint32_t TCC_DESC_LO = 1u << 16;                 // LBO = 16 bytes (unused by swizzled K-major layouts)
+__device__ __forceinline__ void tcc_mma_elect(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(TCC_DESC_HI) : "memory");
+}
+__device__ __forceinline__ void tcc_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 16 columns of fp32 accumulators (no wait: several loads may be in flight, then tcc_tmem_ld_wait)
 __device__ __forceinline__ void tcc_tmem_ld16(uint32_t taddr, float (&r)[16]) {
   uint32_t* u = reinterpret_cast<uint32_t*>(r);
   asm volatile(
@@ -100,8 +124,8 @@ __device__ __forceinline__ void tcc_tmem_ld16(uint32_t taddr, float (&r)[16]) {
       : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
         "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tcc_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float4 tcc_hi4(float4 v) { return make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w)); }
 __device__ __forceinline__ float4 tcc_lo4(float4 v, float4 h) {
@@ -153,13 +177,12 @@ __global__ void __cluster_dims__(TCC_CLUSTER, 1, 1) __launch_bounds__(TCC_THREAD
 mlp_tc_chain_kernel(const __grid_constant__ TccArgs args) {
   extern __shared__ uint8_t tcc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tcc_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem + TCC_OFF_RING;
-  uint8_t* Xb = smem + TCC_OFF_X;
+  uint8_t* Ab = smem + TCC_OFF_A;        // [TCC_ABUFS] A-chunk buffers; buffer 8 doubles as the resident X chunk
+  uint8_t* Xb = Ab + 8 * TCC_A_CHUNK;
   uint8_t* Wb = smem + TCC_OFF_W;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TCC_OFF_BAR);
-  uint64_t* full = bars;                 // [TCC_RING]  bytes of a ring buffer have landed
-  uint64_t* empty = bars + TCC_RING;     // [TCC_RING]  MMAs reading a ring buffer have completed
-  uint64_t* wfull = bars + 2 * TCC_RING; // weight slices of the current slot have landed
+  uint64_t* full = bars;                 // [TCC_ABUFS]  bytes of the copy that starts at this buffer have landed
+  uint64_t* wfull = bars + TCC_ABUFS;    // weight slices of the current slot have landed
   uint64_t* dfull = wfull + 1;           // all MMAs of the current slot have completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
 
@@ -178,27 +201,26 @@ mlp_tc_chain_kernel(const __grid_constant__ TccArgs args) {
   step_stamp(args.step_trace, args.step_slot);
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * TCC_RING + 2; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < TCC_ABUFS + 2; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TCC_TMEM_COLS);
   if (warp >= 2) {
     const int et = tid - 64;
     if (CH.x0) tcc_convert_chunk(Xb, CH.x0, CH.x0ld, 0, CH.x0cols, m0, B, et);
-    for (int p = 0; p < npre; ++p) tcc_convert_chunk(ring + p * TCC_A_CHUNK, CH.pre, CH.preld, p * TCC_KC, CH.precols, m0, B, et);
+    for (int p = 0; p < npre; ++p) tcc_convert_chunk(Ab + p * TCC_A_CHUNK, CH.pre, CH.preld, p * TCC_KC, CH.precols, m0, B, et);
     fence_proxy_async();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
-  // the pre-converted chunks occupy ring uses 0..npre-1: complete the first phase of their `full` barriers so that
-  // ring phases stay in step with the sequence numbers (the MMA issuer waits on them like on a loaded chunk)
+
+  // the pre-converted chunks: complete the first phase of their `full` barriers (the MMA issuer waits on them like on a copy)
   if (tid == 0)
     for (int p = 0; p < npre; ++p) mbar_arrive(&full[p]);
-
-  // per-role state (only the owning role uses its copy)
-  int seq = (warp == 0) ? npre : 0;      // ring chunks issued (loader) / consumed (MMA issuer)
+  // per-role state.  fph: bit b = parity of the NEXT completion of full[b] this thread will wait for (MMA issuer)
+  uint32_t fph = 0;
   int nact = 0;                          // slots this CTA took part in so far: phase of wfull / dfull
   if (warp == 0 && lane == 0 && tcc_slot_active(CH.slot[0], n0)) tcc_issue_weights(CH.slot[0], rank, n0, Wb, wfull, args.flags);
 
@@ -207,86 +229,95 @@ mlp_tc_chain_kernel(const __grid_constant__ TccArgs args) {
     const bool act0 = tcc_group_active(S, 0, n0), act1 = tcc_group_active(S, 1, n0);
     const bool active = act0 || act1;
     unsigned long long* tr = tr0 ? tr0 + TCC_TRACE_PER_SLOT * l : nullptr;
+    bool arrived = false;                  // this thread already arrived on the slot's cluster barrier (hi epilogue warps)
 
     if (warp == 0) {
       // ============================== loader ==========================================================
+      // Every A buffer is free here: the previous slot's MMAs completed before anyone passed the cluster barrier.
       if (lane == 0) {
         if (tr) tr[0] = tcc_gtime();
-        if (active) {
-          tcc_fence_proxy_async_all();           // the cluster's generic-proxy stores (acquired above) -> TMA reads
-          for (int c = 0; c < S.nchunks; ++c) {
-            const TccChunk ch = S.ch[c];
-            if (ch.kind == TCC_SRC_X) continue;
-            if (ch.kind == TCC_SRC_IMG) {
-              const int buf = seq % TCC_RING;
-              if (seq >= TCC_RING) tcc_wait(&empty[buf], ((seq / TCC_RING) - 1) & 1, args.watchdog, TCC_CODE(WD_LOADER_EMPTY, l, rank), seq);
-              mbar_expect_tx(&full[buf], TCC_A_CHUNK);
-              tcc_bulk_load(ring + buf * TCC_A_CHUNK, planes + size_t(ch.plane) * TCC_PLANE_BYTES + size_t(ch.chunk) * TCC_A_CHUNK,
-                            TCC_A_CHUNK, &full[buf]);
-              ++seq;
-            }                                     // TCC_SRC_PRE: converted at kernel start, already counted
+        if (active && S.nloads > 0) {
+          // the cluster's generic-proxy stores to the planes (acquired by the barrier above) -> this thread's TMA reads
+          if (args.flags & 4) tcc_fence_proxy_async_all(); else asm volatile("fence.proxy.async.global;" ::: "memory");
+          for (int i = 0; i < S.nloads; ++i) {
+            const TccLoad L = S.ld[i];
+            const uint32_t bytes = uint32_t(L.count) * TCC_A_CHUNK;
+            mbar_expect_tx(&full[L.buf0], bytes);
+            tcc_bulk_load(Ab + L.buf0 * TCC_A_CHUNK, planes + size_t(L.plane) * TCC_PLANE_BYTES + size_t(L.chunk0) * TCC_A_CHUNK,
+                          bytes, &full[L.buf0]);
           }
         }
         if (tr) tr[1] = tcc_gtime();
         // next slot's weights travel while this slot's epilogue and the barrier run
         if (l + 1 < ns && tcc_slot_active(CH.slot[l + 1], n0)) {
-          if (active) tcc_wait(dfull, nact & 1, args.watchdog, TCC_CODE(WD_LOADER_DFULL, l, rank), nact);  // this slot's MMAs no longer read the weight buffer
+          if (active) tcc_wait(dfull, nact & 1, args.watchdog, TCC_CODE(WD_LOADER_DFULL, l, rank), nact);  // the weight buffer is free
           tcc_issue_weights(CH.slot[l + 1], rank, n0, Wb, wfull, args.flags);
         }
       }
       __syncwarp();
     } else if (warp == 1) {
-      // ============================== MMA issuer ======================================================
-      if (lane == 0 && active) {
-        const uint32_t idesc = make_idesc(FMT_TF32, false, false, TCC_ROWS, TCC_BN);
-        const uint64_t tmpl = make_smem_desc(0, 16, 1024, 2);
-        const uint32_t gstride = (uint32_t(S.nchunks) * TCC_W_CHUNK) >> 4;
-        const uint32_t w_base = smem_u32(Wb) >> 4;
-        tcc_wait(wfull, nact & 1, args.watchdog, TCC_CODE(WD_MMA_WFULL, l, rank), nact);
-        if (tr) tr[2] = tcc_gtime();
-        for (int c = 0; c < S.nchunks; ++c) {
-          const TccChunk ch = S.ch[c];
-          uint32_t a_hi;
-          int buf = 0;
-          if (ch.kind == TCC_SRC_X) a_hi = smem_u32(Xb) >> 4;
-          else {
-            buf = seq % TCC_RING;
-            tcc_wait(&full[buf], (seq / TCC_RING) & 1, args.watchdog, TCC_CODE(WD_MMA_FULL, l, rank), seq);
-            a_hi = smem_u32(ring + buf * TCC_A_CHUNK) >> 4;
+      // ============================== MMA issuer (warp-uniform, elected lane issues) =====================
+      if (active) {
+        // ONE instruction per 8-deep k-step computes all partial products of the 3xTF32 split: the A chunk holds the hi
+        // image (64 rows) directly followed by the lo image (64 rows) = a 128-row operand, the weight chunk hi (32 rows)
+        // then lo (32 rows) = a 64-row operand.  D[128 x 64] = [Ah; Al] . [Bh; Bl]^T: rows 0-63 / columns 0-31 = Ah.Bh,
+        // columns 32-63 = Ah.Bl, rows 64-127 / columns 0-31 = Al.Bh (and Al.Bl, ~2^-22 relative, unused).  4 MMAs per
+        // chunk instead of 12: the issue rate of tcgen05.mma (~50 cycles with fresh descriptors) is what bounds a slot.
+        const uint32_t idesc = make_idesc(FMT_TF32, false, false, 2 * TCC_ROWS, 2 * TCC_BN);
+        // (TCC_DESC_HI << 32 | TCC_DESC_LO) == make_smem_desc(0, 16, 1024, 2)
+        const int nch = S.nchunks, boff = S.boff;
+        const uint32_t wait_mask = S.wait_mask;
+        const uint32_t gstride = (uint32_t(nch) * TCC_W_CHUNK) >> 4;
+        const uint32_t w_base = (smem_u32(Wb) >> 4) | TCC_DESC_LO;
+        const uint32_t a_base = ((smem_u32(Ab) >> 4) + uint32_t(boff) * (TCC_A_CHUNK >> 4)) | TCC_DESC_LO;
+        // lane 0 waits, the warp re-converges on __syncwarp: the issue code below then runs provably converged, which is
+        // what lets the compiler keep descriptors in the uniform datapath instead of R2UR round trips per instruction
+        if (lane == 0) {
+          tcc_wait(wfull, nact & 1, args.watchdog, TCC_CODE(WD_MMA_WFULL, l, rank), nact);
+          if (tr) tr[2] = tcc_gtime();
+        }
+        __syncwarp();
+        // Chunk c of the slot's K lives in A buffer c + boff (checked at launch) and every index below derives from
+        // kernel parameters and the loop counter only.
+        for (int c = 0; c < nch; ++c) {
+          if ((wait_mask >> c) & 1u) {                    // first chunk of a bulk copy / a pre-converted chunk
+            const int b = c + boff;
+            if (lane == 0) {
+              tcc_wait(&full[b], (fph >> b) & 1u, args.watchdog, TCC_CODE(WD_MMA_FULL, l, rank), b);
+              if (tr && c == 0) tr[3] = tcc_gtime();
+            }
+            fph ^= 1u << b;
+            __syncwarp();
           }
-          if (tr && c == 0) tr[3] = tcc_gtime();
           tc_fence_after_sync();
-          const uint32_t a_lo = a_hi + (TCC_A_HALF >> 4);
+          const uint32_t a_d = a_base + uint32_t(c) * (TCC_A_CHUNK >> 4);
+          const uint32_t acc = c != 0;
 #pragma unroll
           for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
             if (!(g == 0 ? act0 : act1)) continue;
-            const uint32_t b_hi = w_base + g * gstride + uint32_t(c) * (TCC_W_CHUNK >> 4), b_lo = b_hi + (TCC_W_HALF >> 4);
-            const uint32_t d = tmem_d + uint32_t(g * TCC_BN);
-            if (passes > 1) {
+            const uint32_t b_d = w_base + g * gstride + uint32_t(c) * (TCC_W_CHUNK >> 4);
+            const uint32_t d0 = tmem_d + uint32_t(g * 2 * TCC_BN);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) mma_tf32(d, tmpl + (a_lo + 2 * ks), tmpl + (b_hi + 2 * ks), idesc, (c | ks) != 0);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) mma_tf32(d, tmpl + (a_hi + 2 * ks), tmpl + (b_lo + 2 * ks), idesc, true);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) mma_tf32(d, tmpl + (a_hi + 2 * ks), tmpl + (b_hi + 2 * ks), idesc, true);
-            } else {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) mma_tf32(d, tmpl + (a_hi + 2 * ks), tmpl + (b_hi + 2 * ks), idesc, (c | ks) != 0);
-            }
+            for (int ks = 0; ks < 4; ++ks) tcc_mma_elect(d0, a_d + 2 * ks, b_d + 2 * ks, idesc, ks ? 1u : acc);
           }
-          if (ch.kind != TCC_SRC_X) { mma_commit(&empty[buf]); ++seq; }
         }
-        mma_commit(dfull);
-        if (tr) tr[4] = tcc_gtime();
+        tcc_commit_elect(dfull);
+        if (tr && lane == 0) tr[4] = tcc_gtime();
       }
       __syncwarp();
     } else {
       // ============================== epilogue ========================================================
+      // TMEM lane quarter q = warp % 4.  Quarters 0/1 hold accumulator rows 0-63 (A hi image: Ah.Bh | Ah.Bl), quarters
+      // 2/3 rows 64-127 (A lo image: Al.Bh): the "lo" warp of a pair hands its 32 x 16 partial sums to the "hi" warp
+      // through shared memory (A buffer g: free, every MMA of the slot has completed), which adds the three partial
+      // products, applies the epilogue and stores.  Pair = (q, q + 2) of one 16-column half: named barrier 1 + half * 2 + (q & 1).
       const int et = tid - 64;
       const int q = warp & 3, half = (warp - 2) >> 2;
-      const int row = 16 * q + lane;                       // UMMA M = 64: row m lives in TMEM lane (m % 16) + 32 (m / 16)
+      const bool hi_warp = q < 2;
+      const int row = 32 * (q & 1) + lane;                 // batch row inside the cluster's 64-row block
       const int gi = m0 + row;
-      const bool lane_ok = lane < 16, row_ok = lane_ok && gi < B;
+      const bool row_ok = gi < B;
+      constexpr int SCP = 36;                              // scratch row pitch in floats (16-B aligned, spreads the banks)
       if (active) {
         // this thread's epilogue operands do not depend on the chain: fetch them before the accumulator is ready
         float eop[TCC_MAX_GROUPS][16];
@@ -294,7 +325,7 @@ mlp_tc_chain_kernel(const __grid_constant__ TccArgs args) {
         for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) eop[g][j] = 0.f;
-          if (!(g == 0 ? act0 : act1)) continue;
+          if (!hi_warp || !(g == 0 ? act0 : act1)) continue;
           const TccGroup& G = S.g[g];
           const int npad = (G.N + 3) & ~3;
           const bool fwd = G.epi == EPI_BIAS || G.epi == EPI_BIAS_RELU || G.epi == EPI_BIAS_TANH;
@@ -312,67 +343,145 @@ mlp_tc_chain_kernel(const __grid_constant__ TccArgs args) {
         tcc_wait(dfull, nact & 1, args.watchdog, TCC_CODE(WD_EPI_DFULL, l, rank), nact);
         tc_fence_after_sync();
         if (tr && et == 0) tr[5] = tcc_gtime();
+        // the resident X chunk is re-used for another array (critic fc2's action columns) now that this slot's MMAs are
+        // done -- before any thread arrives on the slot's barrier
+        if (S.xsrc) {
+          tcc_convert_chunk(Xb, S.xsrc, S.xld, 0, S.xcols, m0, B, et);
+          fence_proxy_async();                             // shared-memory writes -> the tensor core's async-proxy reads
+        }
+        const uint32_t tq = tmem_d + (uint32_t(32 * q) << 16) + uint32_t(half * 16);
+        if (!hi_warp) {
+          // ---- lo rows: Al.Bh partial sums -> scratch ---------------------------------------------------------
 #pragma unroll
-        for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
-          if (!(g == 0 ? act0 : act1)) continue;
-          const TccGroup& G = S.g[g];
-          float r[16];
-          tcc_tmem_ld16(tmem_d + (uint32_t(32 * q) << 16) + uint32_t(g * TCC_BN + half * 16), r);
-          const int epi = G.epi;
+          for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
+            if (!(g == 0 ? act0 : act1)) continue;
+            float t[16];
+            tcc_tmem_ld16(tq + uint32_t(g * 2 * TCC_BN), t);
+            tcc_tmem_ld_wait();
+            float* sc = reinterpret_cast<float*>(Ab + g * TCC_A_CHUNK) + row * SCP + half * 16;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int gj = n0 + half * 16 + j;
-            float x = r[j];
-            const float e = eop[g][j];
-            switch (epi) {
-              case EPI_BIAS: x += e; break;
-              case EPI_BIAS_RELU: x = fmaxf(x + e, 0.f); break;
-              case EPI_BIAS_TANH: x = tanhf(x + e); break;
-              case EPI_RELU_MASK: x = (e > 0.f) ? x : 0.f; break;
-              case EPI_TANH_MASK: x *= (1.f - e * e); break;
-              default: break;
-            }
-            r[j] = (row_ok && gj < G.N) ? x : 0.f;       // pad rows / columns stay zero in the images
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sc + 4 * i) = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
           }
-          if (lane_ok) {
-            if (G.pub >= 0) {                              // K-chunk `rank` of the consumers' A operand, hi and lo images
-              uint8_t* img = planes + size_t(G.pub) * TCC_PLANE_BYTES + size_t(rank) * TCC_A_CHUNK;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + half * 2 + (q & 1)) : "memory");
+        } else {
+          // ---- hi rows: Ah.Bh + Ah.Bl (TMEM) + Al.Bh (scratch), epilogue, stores -----------------------------------
+          float r[TCC_MAX_GROUPS][16], r2[TCC_MAX_GROUPS][16];
+#pragma unroll
+          for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
+            if (!(g == 0 ? act0 : act1)) continue;
+            tcc_tmem_ld16(tq + uint32_t(g * 2 * TCC_BN), r[g]);
+            tcc_tmem_ld16(tq + uint32_t(g * 2 * TCC_BN + TCC_BN), r2[g]);
+          }
+          tcc_tmem_ld_wait();
+          if (tr && et == 64) tr[6] = tcc_gtime();
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + half * 2 + (q & 1)) : "memory");
+          bool any_pub = false;
+#pragma unroll
+          for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
+            if (!(g == 0 ? act0 : act1)) continue;
+            const TccGroup& G = S.g[g];
+            const float* sc = reinterpret_cast<const float*>(Ab + g * TCC_A_CHUNK) + row * SCP + half * 16;
+            const int epi = G.epi;
+            float x16[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = *reinterpret_cast<const float4*>(sc + 4 * i);
+              x16[4 * i] = t.x; x16[4 * i + 1] = t.y; x16[4 * i + 2] = t.z; x16[4 * i + 3] = t.w;
+            }
+            // the epilogue kind is decided ONCE per group, around whole loops (a per-element switch compiles to an
+            // indirect branch per element: 32 BRX per group cost 1.7 us of a 5 us slot)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x16[j] = (r2[g][j] + x16[j]) + r[g][j];   // the two small cross terms first, then the leading product
+            if (epi == EPI_BIAS || epi == EPI_BIAS_RELU || epi == EPI_BIAS_TANH) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x16[j] += eop[g][j];
+              if (epi == EPI_BIAS_RELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x16[j] = fmaxf(x16[j], 0.f);
+              } else if (epi == EPI_BIAS_TANH) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (n0 + half * 16 + j < G.N) x16[j] = tanhf(x16[j]);             // warp-uniform guard: the 6 action columns only
+              }
+            } else if (epi == EPI_RELU_MASK) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x16[j] = (eop[g][j] > 0.f) ? x16[j] : 0.f;
+            } else if (epi == EPI_TANH_MASK) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x16[j] *= (1.f - eop[g][j] * eop[g][j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int gj = n0 + half * 16 + j;
+              x16[j] = (row_ok && gj < G.N) ? x16[j] : 0.f; // pad rows / columns stay zero in the images
+              r[g][j] = x16[j];                            // kept for the row-major store after the barrier arrive
+            }
+            if (G.pub >= 0) {
+              // K-chunk `rank` of the consumers' A operand: the hi and lo images of this 64 x 32 tile are ONE contiguous
+              // 16-KB block of the plane -> staged in shared memory (A buffer 2 + g, free) in the image layout and
+              // written with a single TMA bulk store (scattered 16-B st.global cost 32 L2 transactions per warp store)
+              any_pub = true;
+              uint8_t* stg = Ab + (2 + g) * TCC_A_CHUNK;
               const uint32_t rbase = uint32_t((row >> 3) * 1024 + (row & 7) * 128);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 v = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+                const float4 v = make_float4(x16[4 * i], x16[4 * i + 1], x16[4 * i + 2], x16[4 * i + 3]);
                 const float4 h = tcc_hi4(v);
                 const uint32_t off = rbase + uint32_t((((half * 4 + i) ^ (row & 7)) & 7) << 4);
-                *reinterpret_cast<float4*>(img + off) = h;
-                *reinterpret_cast<float4*>(img + TCC_A_HALF + off) = tcc_lo4(v, h);
+                *reinterpret_cast<float4*>(stg + off) = h;
+                *reinterpret_cast<float4*>(stg + TCC_A_HALF + off) = tcc_lo4(v, h);
               }
             }
+          }
+          if (tr && et == 64) tr[7] = tcc_gtime();
+          if (any_pub) {                                   // uniform over the hi warps (depends on the slot only)
+            fence_proxy_async();                           // staged tiles (generic proxy) -> TMA store (async proxy)
+            asm volatile("bar.sync 5, 128;" ::: "memory"); // the four hi warps
+            if (et == 64) {
+#pragma unroll
+              for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
+                if (!(g == 0 ? act0 : act1) || S.g[g].pub < 0) continue;
+                uint8_t* img = planes + size_t(S.g[g].pub) * TCC_PLANE_BYTES + size_t(rank) * TCC_A_CHUNK;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(img), "r"(smem_u32(Ab + (2 + g) * TCC_A_CHUNK)), "r"(TCC_A_CHUNK) : "memory");
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // writes complete: visible before the barrier arrive
+            }
+          }
+          if (tr && et == 64) tr[8] = tcc_gtime();
+          tc_fence_before_sync();                          // accumulator reads done before the next slot's MMAs overwrite it
+          // The row-major outputs are read by later kernels only: they are stored AFTER this thread's barrier arrive, so
+          // the cluster does not wait for them to drain.
+          if (l + 1 < ns) { tcc_cluster_arrive(); arrived = true; }
+#pragma unroll
+          for (int g = 0; g < TCC_MAX_GROUPS; ++g) {
+            if (!(g == 0 ? act0 : act1)) continue;
+            const TccGroup& G = S.g[g];
             if (G.C && row_ok) {
               const int npad = (G.N + 3) & ~3;
               float* crow = G.C + size_t(gi) * G.ldc;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int gj = n0 + half * 16 + 4 * i;
-                if (gj < npad) *reinterpret_cast<float4*>(crow + gj) = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+                if (gj < npad) *reinterpret_cast<float4*>(crow + gj) = make_float4(r[g][4 * i], r[g][4 * i + 1], r[g][4 * i + 2], r[g][4 * i + 3]);
               }
             }
           }
         }
         tc_fence_before_sync();                            // accumulator reads done before the next slot's MMAs overwrite it
       }
-      // the resident X chunk is re-used for another array (critic fc2's action columns) once this slot's MMAs are done
-      if (S.xsrc) {
-        if (!active) { /* X was not read in this slot */ }
+      if (!active && S.xsrc) {                             // (an inactive CTA did not read X in this slot)
         tcc_convert_chunk(Xb, S.xsrc, S.xld, 0, S.xcols, m0, B, et);
+        fence_proxy_async();
       }
-      tcc_fence_proxy_async_all();                         // image stores (global) and X (shared) -> async proxy readers
-      if (tr && et == 0) tr[6] = tcc_gtime();
+      if (tr && et == 0) tr[9] = tcc_gtime();
     }
     if (active) ++nact;
     if (l + 1 < ns) {
-      tcc_cluster_arrive();
+      if (!arrived) tcc_cluster_arrive();
       tcc_cluster_wait();
-      if (tr && tid == 0) tr[7] = tcc_gtime();
+      if (tr && tid == 0) tr[10] = tcc_gtime();
     }
   }
   tc_fence_before_sync();
@@ -519,28 +628,60 @@ int tcc_slot_group(TccArgs& a, int c, int slot, const TccPackArgs& pk, int use, 
 int launch_mlp_tc_chain(TccArgs& a, cudaStream_t st) {
   D4PG_REQUIRE(a.nchains > 0 && a.nchains <= TCC_MAX_CHAINS, D4PG_EINVAL, "launch_mlp_tc_chain: %d chains", a.nchains);
   D4PG_REQUIRE(a.passes == 1 || a.passes == 3, D4PG_EINVAL, "launch_mlp_tc_chain: passes %d", a.passes);
+  static const int gmax = [] { const char* e = getenv("D4PG_TCC_GROUP"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   for (int c = 0; c < a.nchains; ++c) {
-    const TccChain& ch = a.chain[c];
+    TccChain& ch = a.chain[c];
+    bool x_clobbered = false;
     D4PG_REQUIRE(ch.nslots > 0 && ch.nslots <= TCC_MAX_SLOTS, D4PG_EINVAL, "launch_mlp_tc_chain: chain %d has %d slots", c, ch.nslots);
     D4PG_REQUIRE(ch.nplanes <= TCC_PLANES, D4PG_ENOTSUP, "launch_mlp_tc_chain: chain %d publishes %d planes", c, ch.nplanes);
     D4PG_REQUIRE(!ch.x0 || (ch.x0cols <= TCC_KC && ch.x0ld % 4 == 0 && ch.x0ld >= ch.x0cols), D4PG_ENOTSUP, "launch_mlp_tc_chain: bad X source");
-    D4PG_REQUIRE(!ch.pre || (ch.precols <= TCC_RING * TCC_KC && ch.preld % 4 == 0 && ch.preld >= ch.precols), D4PG_ENOTSUP,
+    D4PG_REQUIRE(!ch.pre || (ch.precols <= 8 * TCC_KC && ch.preld % 4 == 0 && ch.preld >= ch.precols), D4PG_ENOTSUP,
                  "launch_mlp_tc_chain: bad first-slot source");
     int planes_seen = 0;
     for (int l = 0; l < ch.nslots; ++l) {
-      const TccSlot& s = ch.slot[l];
+      TccSlot& s = ch.slot[l];
       D4PG_REQUIRE(s.ngroups >= 1 && s.ngroups <= TCC_MAX_GROUPS, D4PG_EINVAL, "launch_mlp_tc_chain: slot %d has %d groups", l, s.ngroups);
       D4PG_REQUIRE(s.nchunks >= 1 && s.nchunks <= TCC_MAX_CHUNKS && s.ngroups * s.nchunks <= TCC_MAX_CHUNKS, D4PG_ENOTSUP,
                    "launch_mlp_tc_chain: slot %d: %d groups x %d chunks exceed the weight buffer", l, s.ngroups, s.nchunks);
+      // A buffers are direct-mapped: the j-th non-resident chunk of a slot lives in buffer j (0..7); a 9th one takes
+      // buffer 8, the resident X chunk's, if this slot does not read X (and X is dead from then on).  Consecutive
+      // chunks of one plane in consecutive buffers travel as ONE bulk copy (at most `gmax` chunks each, so that the
+      // MMAs of the first chunks overlap the arrival of the rest).
       int nring = 0;
+      bool uses_x = false;
+      for (int i = 0; i < s.nchunks; ++i) uses_x = uses_x || s.ch[i].kind == TCC_SRC_X;
+      s.nloads = 0;
       for (int i = 0; i < s.nchunks; ++i) {
-        const TccChunk& k = s.ch[i];
+        TccChunk& k = s.ch[i];
         if (k.kind == TCC_SRC_IMG) D4PG_REQUIRE(k.plane >= 0 && k.plane < planes_seen && k.chunk < TCC_CLUSTER, D4PG_EINVAL,
                                                  "launch_mlp_tc_chain: slot %d reads plane %d before it is published", l, k.plane);
-        if (k.kind == TCC_SRC_PRE) D4PG_REQUIRE(l == 0 && ch.pre && k.chunk == nring, D4PG_EINVAL, "launch_mlp_tc_chain: pre chunks belong to slot 0, in order");
-        if (k.kind == TCC_SRC_X) D4PG_REQUIRE(ch.x0 != nullptr, D4PG_EINVAL, "launch_mlp_tc_chain: slot %d reads X but the chain has none", l);
-        if (k.kind != TCC_SRC_X) ++nring;
+        if (k.kind == TCC_SRC_PRE) D4PG_REQUIRE(l == 0 && ch.pre && k.chunk == nring && nring < 8, D4PG_EINVAL, "launch_mlp_tc_chain: pre chunks belong to slot 0, in order");
+        if (k.kind == TCC_SRC_X) {
+          D4PG_REQUIRE(ch.x0 != nullptr && !x_clobbered, D4PG_EINVAL, "launch_mlp_tc_chain: slot %d reads X but the chain has none (or it was overwritten)", l);
+          k.buf = 8;
+          continue;
+        }
+        if (nring < 8) k.buf = short(nring);
+        else {
+          D4PG_REQUIRE(nring == 8 && !uses_x && k.kind == TCC_SRC_IMG, D4PG_ENOTSUP, "launch_mlp_tc_chain: slot %d needs more than 9 A buffers", l);
+          k.buf = 8; x_clobbered = true;
+        }
+        ++nring;
+        if (k.kind == TCC_SRC_IMG) {
+          TccLoad* cur = s.nloads ? &s.ld[s.nloads - 1] : nullptr;
+          if (cur && cur->plane == k.plane && cur->chunk0 + cur->count == k.chunk && cur->buf0 + cur->count == k.buf && cur->count < gmax) ++cur->count;
+          else s.ld[s.nloads++] = TccLoad{k.plane, k.chunk, k.buf, 1};
+        }
       }
+      s.nacc = 1;
+      // MMA-side view: chunk c <-> A buffer c + boff, wait on full[c + boff] where a copy (or a pre-converted chunk) starts
+      s.boff = s.ch[0].buf;
+      s.wait_mask = 0;
+      for (int i = 0; i < s.nchunks; ++i) {
+        D4PG_REQUIRE(s.ch[i].buf == s.boff + i, D4PG_ENOTSUP, "launch_mlp_tc_chain: slot %d: chunk %d is not in A buffer %d", l, i, s.boff + i);
+        if (s.ch[i].kind == TCC_SRC_PRE) s.wait_mask |= 1u << i;
+      }
+      for (int i = 0; i < s.nloads; ++i) s.wait_mask |= 1u << (s.ld[i].buf0 - s.boff);
       for (int g = 0; g < s.ngroups; ++g) {
         const TccGroup& G = s.g[g];
         D4PG_REQUIRE(G.N > 0 && G.N <= TCC_CLUSTER * TCC_BN && G.wimg, D4PG_ENOTSUP, "launch_mlp_tc_chain: group width %d", G.N);
@@ -565,7 +706,7 @@ int launch_mlp_tc_chain(TccArgs& a, cudaStream_t st) {
   a.watchdog = tcc_watchdog_device();
   { const char* e = getenv("D4PG_TCC_FLAGS"); a.flags = e ? atoi(e) : 0; }
   unsigned long long* dbg = debug_trace_buffer();
-  a.trace = dbg ? dbg + (a.step_slot == 5 ? 256 : 0) : nullptr;
+  a.trace = dbg ? dbg + (a.step_slot == 5 ? 384 : 256) : nullptr;
   a.step_trace = dbg ? dbg + STEP_TRACE_BASE : nullptr;
   { const char* e = getenv("D4PG_TRACE_CTA"); a.trace_cta = e ? atoi(e) : 0; if (a.trace_cta >= a.nchains * a.row_blocks * TCC_CLUSTER) a.trace_cta = 0; }
   cudaLaunchConfig_t cfg{};

@@ -9,7 +9,7 @@ constexpr int TCC_ROWS = 64;          // batch rows owned by one cluster (= UMMA
 constexpr int TCC_CLUSTER = 8;        // CTAs per cluster: CTA r owns output features [32r, 32r+32) of a layer
 constexpr int TCC_BN = 32;            // UMMA N of one group
 constexpr int TCC_KC = 32;            // k per chunk (one 128-B SWIZZLE_128B row of tf32)
-constexpr int TCC_RING = 8;           // A-chunk ring buffers per CTA
+constexpr int TCC_ABUFS = 9;          // A-chunk buffers per CTA: 0..7 one per K chunk of a 256-wide plane, 8 = the resident / tail chunk
 constexpr int TCC_MAX_SLOTS = 8, TCC_MAX_CHAINS = 3, TCC_MAX_GROUPS = 2, TCC_MAX_CHUNKS = 9, TCC_PLANES = 8;
 constexpr uint32_t TCC_A_HALF = TCC_ROWS * 128, TCC_A_CHUNK = 2 * TCC_A_HALF;      // hi image then lo image
 constexpr uint32_t TCC_W_HALF = TCC_BN * 128, TCC_W_CHUNK = 2 * TCC_W_HALF;
@@ -27,12 +27,17 @@ struct TccGroup {
   int N, epi, kchunks;           // kchunks: K chunks of the weight image (= the slot's A chunk count)
   int pub;                        // plane the output is published to for later slots (-1: none)
 };
-struct TccChunk { short kind, plane, chunk, pad; };
+struct TccChunk { short kind, plane, chunk, buf; };      // buf: A buffer the chunk occupies (assigned at launch)
+// one bulk copy: `count` consecutive chunks of a plane into consecutive A buffers, completion on full[buf0]
+struct TccLoad { short plane, chunk0, buf0, count; };
 // One layer slot: every group contracts the same A operand (the chunk list) with its own weights.
 struct TccSlot {
   TccGroup g[TCC_MAX_GROUPS];
   TccChunk ch[TCC_MAX_CHUNKS];
-  int ngroups, nchunks;
+  TccLoad ld[TCC_MAX_CHUNKS];
+  int ngroups, nchunks, nloads;
+  int nacc;                              // TMEM accumulators per group (1)
+  int boff; unsigned wait_mask;          // MMA issuer: chunk c <-> A buffer c + boff; bit c: wait on full[c + boff] first
   const float* xsrc; int xld, xcols;     // after this slot's MMAs: re-convert the resident X chunk from this array
 };
 struct TccChain {

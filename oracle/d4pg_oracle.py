@@ -376,6 +376,45 @@ class PrioritizedReplayOracle:
         self.pristine = False
 
 
+def nstep_transitions(states, actions, rewards, next_states, dones, n_steps, gamma):
+    """replay_memory.py:31-45 for ONE episode: at every step t >= n-1 the reference adds
+    (s_{t-n+1}, a_{t-n+1}, sum_k gamma^k r_{t-n+1+k}, s'_t, done_t); the return is accumulated left to right in
+    Python floats (`cum_reward += exp_gamma * r; exp_gamma *= gamma`).  Returns the list of added tuples."""
+    out = []
+    T = len(rewards)
+    for t in range(n_steps - 1, T):
+        cum, eg = 0., 1
+        for k in range(t - n_steps + 1, t + 1):
+            cum += eg * rewards[k]
+            eg *= gamma
+        i = t - n_steps + 1
+        out.append((np.asarray(states[i]).reshape(-1), actions[i], cum, next_states[t], dones[t]))
+    return out
+
+
+def her_relabel(obs, obs_next, goal, ag_next, act, rew, done, select, future, threshold, last_action):
+    """main.py:154-184 for one episode whose rollout did not succeed (`args.her and not done`), "future" strategy.
+    PARITY UNPINNED: main.py cannot be imported here (gym / pybullet_envs / tensorboard-pytorch are absent), so this
+    is a restatement of the listed lines only; `select[t]` stands for `np.random.uniform() < her_ratio` (:166),
+    `future[t]` for `np.random.randint(t, len(episode_buffer))` (:170), the reward for the sparse gym-robotics
+    `env.compute_reward` = -(||achieved - goal||_2 > distance_threshold).  The relabelled copy is stored with `action`,
+    the LAST action of the rollout loop (:184 -- not the step's own `a`), passed here as `last_action`."""
+    rows = []
+    T = len(rew)
+    for t in range(T):
+        s = np.concatenate((obs[t], goal[t]))
+        s_n = np.concatenate((obs_next[t], goal[t]))
+        rows.append((s, act[t], rew[t], s_n, bool(done[t])))                                 # :160-163
+        if select[t]:
+            dummy_goal = ag_next[future[t]]                                                 # :170-171
+            her_s = np.concatenate((obs[t], dummy_goal))
+            her_sn = np.concatenate((obs_next[t], dummy_goal))
+            d = np.linalg.norm(np.asarray(ag_next[t], dtype=np.float64) - np.asarray(dummy_goal, dtype=np.float64), axis=-1)
+            her_r = -float(d > threshold)                                                   # :177
+            rows.append((her_s, last_action, her_r, her_sn, her_r == 0.))                   # :182-184
+    return rows
+
+
 class LinearScheduleOracle:
     """prioritized_replay_memory.py:5-29 (post-incrementing beta schedule)."""
 

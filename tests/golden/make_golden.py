@@ -19,6 +19,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import ref_shim  # noqa: E402
+from tests.helpers import ScriptedEnv  # noqa: E402
 
 INFO51 = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": 51}
 INFO101 = {"type": "categorical", "v_min": -150.0, "v_max": 150.0, "n_atoms": 101}
@@ -310,6 +311,27 @@ def gen_init(ref):
     print("init.npz:", len(out), "arrays")
 
 
+def gen_nstep(ref):
+    """Replay.initialize (replay_memory.py:21-59): n-step return accumulation at insert, n_steps=5."""
+    out = {}
+    env = ScriptedEnv()
+    np.random.seed(321)
+    rp = ref.replay_memory.Replay(64, env, n_steps=5, gamma=0.99)
+    rp.initialize(init_length=40)
+    out["meta"] = np.array([5, 40, len(rp.buffer), len(env.log)])
+    out["gamma"] = np.array(0.99)
+    out["buf_s"] = np.stack([np.asarray(b[0], dtype=np.float64).reshape(-1) for b in rp.buffer])
+    out["buf_a"] = np.stack([np.asarray(b[1], dtype=np.float64) for b in rp.buffer])
+    out["buf_r"] = np.array([b[2] for b in rp.buffer], dtype=np.float64)
+    out["buf_s2"] = np.stack([np.asarray(b[3], dtype=np.float64) for b in rp.buffer])
+    out["buf_d"] = np.array([bool(b[4]) for b in rp.buffer])
+    for i, e in enumerate(env.log):
+        for k in ("s", "a", "r", "s2", "d"):
+            out["ep%d_%s" % (i, k)] = np.asarray(e[k])
+    np.savez_compressed(os.path.join(HERE, "nstep_init.npz"), **out)
+    print("nstep_init.npz:", len(out), "arrays,", len(rp.buffer), "transitions from", len(env.log), "episodes")
+
+
 def gen_baseline_sizes(ref):
     """Fixtures at the BASELINE.json sizes: c2 as configured (B=256), config-3 shapes
     (|s|=376, |a|=17, B=1024, small capacity), config-5 shapes (101 atoms, n_steps=5; train() at B=256 -- the live
@@ -336,6 +358,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "baseline":      # only the BASELINE-size fixtures (added in round 2)
         gen_baseline_sizes(ref)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "nstep":
+        gen_nstep(ref)
+        return
     gen_projection(ref)
     gen_tree(ref)
     gen_init(ref)
@@ -346,6 +371,7 @@ def main():
     # config 1: Pendulum dims, uniform replay_memory.py
     gen_train(ref, "uniform_c1", 3, 1, INFO_PEND, 64, 500, 400, False, 3, 0.0, seed=13)
     gen_baseline_sizes(ref)
+    gen_nstep(ref)
 
 
 if __name__ == "__main__":

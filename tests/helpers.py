@@ -14,6 +14,38 @@ def load(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
+class ScriptedEnv(object):
+    """Deterministic gym-style env for replay_memory.py:21-59 (Replay.initialize): float32-representable states,
+    Python-float rewards, scripted episode lengths (some shorter than n_steps)."""
+    LENGTHS = [7, 3, 12, 5, 4, 9, 30]
+
+    class _Space(object):
+        shape = (2,)
+    action_space = _Space()
+
+    def __init__(self):
+        self.ep = -1
+        self.log = []                       # per episode: dict of lists
+
+    def reset(self):
+        self.ep += 1
+        self.t = 0
+        self.state = np.array([0.25 * (self.ep + 1), -0.5, 1.0 + self.ep], dtype=np.float32).astype(np.float64)
+        self.log.append(dict(s=[], a=[], r=[], s2=[], d=[]))
+        return self.state
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float64)
+        nxt = (0.875 * self.state + np.array([a[0], a[1], 0.125 * self.t])).astype(np.float32).astype(np.float64)
+        reward = float(-np.abs(self.state).sum() + 0.1 * a[0])
+        done = self.t == self.LENGTHS[self.ep % len(self.LENGTHS)] - 1
+        e = self.log[-1]
+        e["s"].append(self.state.copy()); e["a"].append(a.copy()); e["r"].append(reward); e["s2"].append(nxt.copy()); e["d"].append(done)
+        self.state = nxt
+        self.t += 1
+        return nxt, reward, done, {}
+
+
 def train_data(g):
     """(S, A, R, S2, D) of a train_*.npz fixture: stored, or -- big fixtures -- regenerated from the seed with the
     recipe of tests/golden/make_golden.py:train_data and checked against the stored subsample / checksums."""

@@ -40,6 +40,21 @@ def test_projection_nstep_config5_size_matches_reference():
     H.check_compact(g, "m", m, 0.0)
 
 
+def test_nstep_accumulation_at_insert_matches_reference_initialize():
+    """replay_memory.py:21-59 run on a scripted env (tests/golden/make_golden.py:gen_nstep): the restatement of its
+    n-step accumulation reproduces the reference buffer, returns bit for bit."""
+    g = H.load("nstep_init.npz")
+    n_steps, init_length, n_buf, n_eps = [int(x) for x in g["meta"]]
+    rows = []
+    for i in range(n_eps):
+        e = [g["ep%d_%s" % (i, k)] for k in ("s", "a", "r", "s2", "d")]
+        rows += O.nstep_transitions(e[0], e[1], [float(x) for x in e[2]], e[3], e[4], n_steps, float(g["gamma"]))
+    assert len(rows) == n_buf
+    assert np.array_equal(np.stack([r[0] for r in rows]), g["buf_s"]) and np.array_equal(np.stack([r[1] for r in rows]), g["buf_a"])
+    assert np.array_equal(np.array([r[2] for r in rows]), g["buf_r"])
+    assert np.array_equal(np.stack([r[3] for r in rows]), g["buf_s2"]) and np.array_equal(np.array([bool(r[4]) for r in rows]), g["buf_d"])
+
+
 def _replay(g, name):
     size, n_fill, B, rounds = [int(x) for x in g[name + "_meta"]]
     buf = O.PrioritizedReplayOracle(size, 0.6, 2, 1)

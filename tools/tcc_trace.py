@@ -21,15 +21,15 @@ dd.train_n(20)
 torch.cuda.synchronize()
 out = (C.c_ulonglong * 512)()
 _lib.check(_lib.lib().d4pg_debug_trace_read(out, 512), "trace")
-names = ["start", "a_issued", "w_landed", "a0_landed", "mma_issued", "acc_done", "stored", "barrier"]
-for base, nm, ns in ((0, "forward launch, traced CTA's chain", 8), (256, "backward launch, traced CTA's chain", 8)):
+names = ["start", "a_issued", "w_landed", "a0_landed", "mma_issued", "acc_done", "tmem_ld", "math", "img_st", "epi_end", "barrier", "-"]
+for base, nm, ns in ((256, "forward launch, traced CTA's chain", 8), (384, "backward launch, traced CTA's chain", 8)):
     t0 = out[base]
     print(nm)
     for l in range(ns):
-        st = [out[base + 8 * l + i] for i in range(8)]
+        st = [out[base + 12 * l + i] for i in range(12)]
         if st[0] == 0:
             break
-        print("  slot %d @%6d ns: " % (l, st[0] - t0) + "  ".join("%s %+d" % (names[i], st[i] - st[0]) for i in range(1, 8) if st[i]))
+        print("  slot %d @%6d ns: " % (l, st[0] - t0) + "  ".join("%s %+d" % (names[i], st[i] - st[0]) for i in range(1, 11) if st[i]))
 st = [out[96 + i] for i in range(32)]
 print("step timeline (entry, exit) ns relative to the forward launch:")
 for k, nm in ((0, "sample"), (1, "fwd chains"), (2, "heads"), (3, "tree update"), (4, "sample t+1"), (5, "dX chains"), (6, "dW"), (7, "adam")):
