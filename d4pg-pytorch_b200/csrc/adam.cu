@@ -58,6 +58,7 @@ extern "C" int32_t d4pg_adam_polyak(float* p, const float* g, float* m, float* v
   const double bc1 = 1.0 - pow(beta1, double(step));
   const double bc2 = 1.0 - pow(beta2, double(step));
   a.seg[0] = AdamSeg{p, g, m, v, target, n, nullptr, 0, float(-(lr / bc1)), -1};
+  a.seg[0].nimg = 0;
   a.nseg = 1;
   a.w1 = float(1.0 - beta1); a.w2 = float(1.0 - beta2); a.beta2 = float(beta2); a.eps = float(eps);
   a.bc2_sqrt = float(sqrt(bc2)); a.tau = float(tau); a.one_minus_tau = float(1.0 - tau);

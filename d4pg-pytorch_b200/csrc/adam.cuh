@@ -55,12 +55,57 @@ __device__ __forceinline__ float clock_beta(const LearnerClock* c, const ClockPa
 }
 
 constexpr int D4PG_MAX_PEERS = 8;
-struct PeerInfo { int world, rank; int64_t n; float* x[D4PG_MAX_PEERS]; unsigned long long* flag[D4PG_MAX_PEERS]; };
+// Cross-rank signals are PUSHED: a rank that finished a phase stores its step count into slot [its rank] of every rank's
+// inbox (one posted NVLink store each, after a system-scope fence), and waiters poll their own LOCAL inbox -- one one-way
+// NVLink latency per hop instead of a remote-polling round trip.  Flag block of a rank, per signal kind k (64 u64 apart):
+// [0] unused, [1] local count of this rank's own completions, [2] CTA ticket, [8 + r] inbox slot written by rank r.
+struct PeerSignal {
+  unsigned long long* local;                   // this rank's block for the signal kind
+  unsigned long long* inbox[8];                // inbox[p] = &(rank p's block)[8 + my_rank]
+  int world;
+};
+// called by thread 0 of every CTA of the producing kernel after a __syncthreads(): the last CTA publishes
+__device__ __forceinline__ void peer_signal_last_cta(const PeerSignal& s, unsigned nblocks) {
+  __threadfence();
+  unsigned long long* f = s.local;
+  if (atomicAdd(f + 2, 1ull) == nblocks - 1) {
+    f[2] = 0ull;
+    const unsigned long long v = f[1] + 1ull;
+    f[1] = v;
+    __threadfence_system();
+    for (int p = 0; p < s.world; ++p) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(s.inbox[p]), "l"(v) : "memory");
+  }
+}
+// threads 0..world-1 of a CTA poll the LOCAL inbox until every rank published >= this rank's own count; then __syncthreads
+__device__ __forceinline__ void peer_wait_all(const unsigned long long* block, int world) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    const unsigned long long target = __ldcg(block + 1);
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(block + 8 + r) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
 
+// x[r]: rank r's [2][n] gradient halves; red[r]: rank r's [n] REDUCED gradient (every slice written by the rank that owns
+// it); flag[r] / flag2[r]: "gradient half of step k complete" / "my slice of step k is reduced and pushed to everyone"
+struct PeerInfo {
+  int world, rank; int64_t n;
+  float* x[D4PG_MAX_PEERS]; float* red[D4PG_MAX_PEERS];
+  unsigned long long* flag[D4PG_MAX_PEERS]; unsigned long long* flag2[D4PG_MAX_PEERS];
+};
+
+// tcgen05 chains (mlp_tc_chain.cu): the updated weights are ALSO written as the tensor cores' forward operand images
+// (hi / lo tf32 parts, 32 x 32 K-major SWIZZLE_128B blocks), for the online network and -- the Polyak output -- its
+// target, so that the next step's forward chains need no separate pack launch.  One entry per weight matrix.
+struct AdamImgLayer { int64_t w_off, w_end; int ld, nchunks; uint8_t* img; uint8_t* img_t; };
 struct AdamSeg {
   float* p; const float* g; float* m; float* v; float* target; int64_t n;
   float* g_out; int64_t g_off;                 // peer mode: the summed gradient is also stored here; offset in the exchange half
   float neg_step_size; int clock_slot;        // clock_slot >= 0: read -step_size from the device clock
+  AdamImgLayer imgl[4]; int nimg;              // nimg = 0: no images
 };
 struct AdamArgs {
   AdamSeg seg[2]; int nseg;
@@ -70,9 +115,11 @@ struct AdamArgs {
   // fused all-reduce: g = sum over ranks r = 0..npeers-1 (fixed order: identical on every rank) of peer_g[r][g_off + i],
   // read over NVLink from IPC-mapped peer memory; the ranks were synchronised by comm_peer_barrier
   const float* peer_g[D4PG_MAX_PEERS]; int npeers;
+  int peer_reduced;                           // 1: seg.g already holds the reduced gradient (reduce-scatter + all-gather ran before);
+                                              //    only wait for every rank's "slice pushed" flag.  0: sum the ranks' halves here
   // non-null: wait inside the kernel until every rank published step count >= this rank's local one
   // (the signal came from the dW kernel's last CTA); null: a barrier launch already ordered the ranks
-  const unsigned long long* peer_wait[D4PG_MAX_PEERS]; const unsigned long long* my_flags; int rank;
+  const unsigned long long* my_flags; int rank;   // this rank's flag block of the awaited signal kind (local inbox inside)
   int pipe_slot;                              // >= 0: the step's scalars are in this slot of the clock (prefetch pipeline)
   // fused tail (learner): deterministic batch means of the per-row losses -> out[0], out[1]
   const float* loss_rows; const float* pi_rows; int B; float inv_count; float* loss_out;

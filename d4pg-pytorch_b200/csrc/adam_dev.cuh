@@ -1,6 +1,7 @@
 // Device code of the fused Adam + Polyak update.
 #pragma once
 #include "adam.cuh"
+#include "tc_common.cuh"
 
 namespace d4pg {
 
@@ -47,21 +48,10 @@ __device__ __forceinline__ void adam_segment(const AdamArgs& a, int seg, int bx,
   float4* v4 = reinterpret_cast<float4*>(s.v);
   float4* t4 = reinterpret_cast<float4*>(s.target);
   float4* go4 = reinterpret_cast<float4*>(s.g_out);
-  if (a.npeers > 0 && a.my_flags) {                       // every peer's gradient half of this step is complete
-    const int r = threadIdx.x;
-    if (r < a.npeers && r != a.rank) {
-      const unsigned long long target = __ldcg(a.my_flags + 1);
-      unsigned long long v;
-      do {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.peer_wait[r]) : "memory");
-        if (v < target) __nanosleep(32);
-      } while (v < target);
-    }
-    __syncthreads();
-  }
+  if (a.npeers > 0 && a.my_flags) peer_wait_all(a.my_flags, a.npeers);   // every rank signalled this step (local inbox)
   for (int64_t i = bx * int64_t(256) + threadIdx.x; i < n4; i += int64_t(gx) * 256) {
     float4 g;
-    if (a.npeers > 0) {
+    if (a.npeers > 0 && !a.peer_reduced) {
       g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < D4PG_MAX_PEERS; ++r)
@@ -70,7 +60,10 @@ __device__ __forceinline__ void adam_segment(const AdamArgs& a, int seg, int bx,
           g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
         }
       if (go4) go4[i] = g;
-    } else g = g4[i];
+    } else {
+      g = (a.npeers > 0) ? __ldcg(g4 + i) : g4[i];          // peer mode: written by remote ranks, bypass L1
+      if (go4) go4[i] = g;
+    }
     float4 p = p4[i], m = m4[i], v = v4[i];
     float4 t = s.target ? t4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x; float* tt = &t.x;
@@ -85,6 +78,26 @@ __device__ __forceinline__ void adam_segment(const AdamArgs& a, int seg, int bx,
     }
     p4[i] = p; m4[i] = m; v4[i] = v;
     if (s.target) t4[i] = t;
+    if (s.nimg) {                                             // forward operand images of the tcgen05 chains
+      const int64_t e = i << 2;
+#pragma unroll
+      for (int L = 0; L < 4; ++L) {
+        if (L >= s.nimg || e < s.imgl[L].w_off || e >= s.imgl[L].w_end) continue;
+        const AdamImgLayer& I = s.imgl[L];
+        const int rel = int(e - I.w_off), n = rel / I.ld, k = rel - n * I.ld;     // row pitch is a multiple of 4: one float4 = 4 k of one row
+        const uint32_t off = uint32_t(((n >> 5) * I.nchunks + (k >> 5)) * 8192) + tc::sw128_kmajor_off(n & 31, k & 31);
+        const float4 ph = make_float4(tc::tf32_hi(p.x), tc::tf32_hi(p.y), tc::tf32_hi(p.z), tc::tf32_hi(p.w));
+        *reinterpret_cast<float4*>(I.img + off) = ph;
+        *reinterpret_cast<float4*>(I.img + 4096 + off) =
+            make_float4(tc::tf32_lo(p.x, ph.x), tc::tf32_lo(p.y, ph.y), tc::tf32_lo(p.z, ph.z), tc::tf32_lo(p.w, ph.w));
+        if (I.img_t) {
+          const float4 th = make_float4(tc::tf32_hi(t.x), tc::tf32_hi(t.y), tc::tf32_hi(t.z), tc::tf32_hi(t.w));
+          *reinterpret_cast<float4*>(I.img_t + off) = th;
+          *reinterpret_cast<float4*>(I.img_t + 4096 + off) =
+              make_float4(tc::tf32_lo(t.x, th.x), tc::tf32_lo(t.y, th.y), tc::tf32_lo(t.z, th.z), tc::tf32_lo(t.w, th.w));
+        }
+      }
+    }
   }
 }
 

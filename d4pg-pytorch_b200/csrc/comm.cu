@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <algorithm>
 
 using d4pg::D4PG_MAX_PEERS;
 using d4pg::PeerInfo;
@@ -65,7 +66,8 @@ int load_nccl() {
 struct d4pg_comm {
   ncclComm_t comm; int rank, world;
   // ---- fused all-reduce over peer memory (d4pg_comm_peer_*) ----------------------------------------------------
-  // One cudaMalloc block per rank, exported with CUDA IPC: [2][n] gradient halves (double buffer) + a flag line.
+  // One cudaMalloc block per rank, exported with CUDA IPC: [2][n] gradient halves (double buffer), [n] reduced
+  // gradient, two flag lines (256 B apart).
   float* xbuf; int64_t xn; unsigned long long* flags;       // local block
   void* peer_base[D4PG_MAX_PEERS];                          // opened IPC mappings (nullptr for self)
   float* peer_x[D4PG_MAX_PEERS]; unsigned long long* peer_flag[D4PG_MAX_PEERS];
@@ -73,42 +75,83 @@ struct d4pg_comm {
 };
 
 namespace d4pg {
-// "my gradient half of this step is complete" + "wait until every peer's is": thread 0 bumps this rank's step
-// counter and publishes it (release, system scope); lane r polls rank r's counter over NVLink (acquire).
-// The counters only ever grow and every rank runs the same number of steps, so no reset is ever needed.
-__global__ void peer_barrier_kernel(unsigned long long* my_flags, PeerInfo info) {
-  __shared__ unsigned long long target;
-  if (threadIdx.x == 0) {
-    const unsigned long long t = my_flags[1] + 1ull;
-    my_flags[1] = t;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(my_flags), "l"(t) : "memory");
-    target = t;
-  }
+// "my gradient half of this step is complete" + "wait until every peer's is" as a launch of its own (the level plan has
+// several dW launches): one CTA publishes, then polls its local inbox.
+__global__ void peer_barrier_kernel(PeerSignal sig) {
+  if (threadIdx.x == 0) peer_signal_last_cta(sig, 1u);
   __syncthreads();
-  const int r = threadIdx.x;
-  if (r < info.world && r != info.rank) {
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(info.flag[r]) : "memory");
-      if (v < target) __nanosleep(64);
-    } while (v < target);
-  }
-  __syncthreads();
+  peer_wait_all(sig.local, sig.world);
   __threadfence_system();
+}
+
+PeerSignal comm_peer_signal(const PeerInfo& info, int kind) {
+  PeerSignal s{};
+  s.world = info.world;
+  s.local = info.flag[info.rank] + kind * 64;
+  for (int p = 0; p < info.world; ++p) s.inbox[p] = info.flag[p] + kind * 64 + 8 + info.rank;
+  return s;
 }
 
 bool comm_peer_info(d4pg_comm* c, PeerInfo* out) {
   if (!c || !c->peer_ready) return false;
   if (!out) return true;
   out->world = c->world; out->rank = c->rank; out->n = c->xn;
-  for (int r = 0; r < c->world; ++r) { out->x[r] = c->peer_x[r]; out->flag[r] = c->peer_flag[r]; }
+  for (int r = 0; r < c->world; ++r) {
+    out->x[r] = c->peer_x[r]; out->red[r] = c->peer_x[r] + 2 * c->xn;
+    out->flag[r] = c->peer_flag[r]; out->flag2[r] = c->peer_flag[r] + 64;
+  }
   return true;
 }
 int comm_peer_barrier(d4pg_comm* c, cudaStream_t st) {
   PeerInfo info{};
   D4PG_REQUIRE(comm_peer_info(c, &info), D4PG_ESTATE, "comm_peer_barrier: peers are not open");
-  peer_barrier_kernel<<<1, 32, 0, st>>>(c->flags, info);
+  peer_barrier_kernel<<<1, 32, 0, st>>>(comm_peer_signal(info, 0));
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
+// ---- reduce-scatter + all-gather over peer memory ---------------------------------------------------------------
+// Rank r owns slice r of the flat gradient.  After every rank's dW published flag1 for this step, rank r reads slice r of
+// all N halves (N-1 of them over NVLink), sums them IN RANK ORDER and stores the result into slice r of every rank's
+// reduced buffer (N-1 remote stores).  Every element is reduced by exactly one rank, so all replicas consume the same
+// bits.  Per rank: (N-1)/N x 1.15 MB in and out, instead of pulling all N halves (N x 1.15 MB in).  The last CTA
+// publishes flag2; the fused Adam kernel waits for all ranks' flag2 and then streams its LOCAL reduced buffer.
+struct PeerRSArgs {
+  int world, rank; int64_t n4, lo4, hi4, half_off;
+  const float* g[D4PG_MAX_PEERS]; float* red[D4PG_MAX_PEERS];
+  const unsigned long long* my_f1;              // this rank's flag block of signal 0 (local inbox: every rank's dW is done)
+  d4pg::PeerSignal sig2;                        // signal 1: this rank's slice is reduced and pushed
+};
+__global__ void __launch_bounds__(256) peer_reduce_scatter_kernel(const PeerRSArgs a) {
+  d4pg::peer_wait_all(a.my_f1, a.world);
+  for (int64_t i = a.lo4 + int64_t(blockIdx.x) * 256 + threadIdx.x; i < a.hi4; i += int64_t(gridDim.x) * 256) {
+    float4 t[D4PG_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < D4PG_MAX_PEERS; ++r)
+      if (r < a.world) t[r] = __ldcg(reinterpret_cast<const float4*>(a.g[r] + a.half_off) + i);     // all loads in flight
+    float4 s = t[0];
+#pragma unroll
+    for (int r = 1; r < D4PG_MAX_PEERS; ++r)
+      if (r < a.world) { s.x += t[r].x; s.y += t[r].y; s.z += t[r].z; s.w += t[r].w; }
+#pragma unroll
+    for (int r = 0; r < D4PG_MAX_PEERS; ++r)
+      if (r < a.world) reinterpret_cast<float4*>(a.red[r])[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence_system(); d4pg::peer_signal_last_cta(a.sig2, gridDim.x); }
+}
+int comm_peer_reduce_scatter(d4pg_comm* c, int parity, cudaStream_t st) {
+  PeerInfo info{};
+  D4PG_REQUIRE(comm_peer_info(c, &info), D4PG_ESTATE, "comm_peer_reduce_scatter: peers are not open");
+  PeerRSArgs a{};
+  a.world = info.world; a.rank = info.rank; a.n4 = info.n >> 2;
+  const int64_t per = (a.n4 + info.world - 1) / info.world;
+  a.lo4 = std::min<int64_t>(a.n4, per * info.rank); a.hi4 = std::min<int64_t>(a.n4, a.lo4 + per);
+  a.half_off = int64_t(parity) * info.n;
+  for (int r = 0; r < info.world; ++r) { a.g[r] = info.x[r]; a.red[r] = info.red[r]; }
+  a.my_f1 = info.flag[info.rank]; a.sig2 = comm_peer_signal(info, 1);
+  const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(296, (a.hi4 - a.lo4 + 255) / 256)));
+  peer_reduce_scatter_kernel<<<blocks, 256, 0, st>>>(a);
   D4PG_LAUNCH_OK();
   return D4PG_OK;
 }
@@ -169,11 +212,11 @@ extern "C" int32_t d4pg_comm_peer_alloc(d4pg_comm_t* c, int64_t n_floats, uint8_
   D4PG_REQUIRE(c->world <= D4PG_MAX_PEERS, D4PG_ENOTSUP, "d4pg_comm_peer_alloc: at most %d ranks (one node)", D4PG_MAX_PEERS);
   D4PG_REQUIRE(!c->xbuf, D4PG_ESTATE, "d4pg_comm_peer_alloc: already allocated");
   const int64_t n = (n_floats + 31) & ~int64_t(31);
-  const size_t bytes = size_t(2 * n) * sizeof(float) + 256;
+  const size_t bytes = size_t(3 * n) * sizeof(float) + 1024;  // [2][n] halves + [n] reduced + two flag blocks of 512 B
   D4PG_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&c->xbuf), bytes));
   D4PG_CUDA_OK(cudaMemset(c->xbuf, 0, bytes));
   D4PG_CUDA_OK(cudaDeviceSynchronize());
-  c->xn = n; c->flags = reinterpret_cast<unsigned long long*>(c->xbuf + 2 * n);
+  c->xn = n; c->flags = reinterpret_cast<unsigned long long*>(c->xbuf + 3 * n);
   cudaIpcMemHandle_t h;
   static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
   D4PG_CUDA_OK(cudaIpcGetMemHandle(&h, c->xbuf));
@@ -191,7 +234,7 @@ extern "C" int32_t d4pg_comm_peer_open(d4pg_comm_t* c, const uint8_t* all_handle
     D4PG_CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
     c->peer_base[r] = base;
     c->peer_x[r] = static_cast<float*>(base);
-    c->peer_flag[r] = reinterpret_cast<unsigned long long*>(static_cast<float*>(base) + 2 * c->xn);
+    c->peer_flag[r] = reinterpret_cast<unsigned long long*>(static_cast<float*>(base) + 3 * c->xn);
   }
   c->peer_ready = true;
   return D4PG_OK;

@@ -53,19 +53,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_wide_kernel(const __grid
     gemm_dw_tile_async<false>(P, smem, tm * BM, tn * BN, tn, 0, P.K);
   }
   step_stamp(batch.trace, 6 + 16);
-  if (batch.peer_flags) {                                // gradients of this rank complete -> tell the peers (system scope)
+  if (batch.has_peer_sig) {                              // gradients of this rank complete -> tell the peers (system scope)
     __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      unsigned long long* f = batch.peer_flags;
-      if (atomicAdd(f + 2, 1ull) == gridDim.x - 1) {
-        f[2] = 0ull;
-        const unsigned long long v = f[1] + 1ull;
-        f[1] = v;
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
-      }
-    }
+    if (threadIdx.x == 0) peer_signal_last_cta(batch.peer_sig, gridDim.x);
   }
   pdl_trigger_end(batch.pdl);
 }
@@ -131,7 +121,10 @@ void gemm_batch_retile(GemmBatch& b, int bm, int bn) {
     b.total_tiles += p.tiles_m * p.tiles_n * p.ksplit;
   }
 }
-void gemm_wide_begin(GemmWideBatch& b, unsigned long long* peer_flags) { b.n = 0; b.total_tiles = 0; b.pdl = 0; b.trace = nullptr; b.peer_flags = peer_flags; }
+void gemm_wide_begin(GemmWideBatch& b, const PeerSignal* sig) {
+  b.n = 0; b.total_tiles = 0; b.pdl = 0; b.trace = nullptr; b.has_peer_sig = sig ? 1 : 0;
+  if (sig) b.peer_sig = *sig;
+}
 void gemm_wide_add(GemmWideBatch& b, const GemmProblem& pin) {
   if (b.n >= GEMM_WIDE_MAX) { b.n = GEMM_WIDE_MAX + 1; return; }      // reported by gemm_wide_launch
   GemmProblem p = pin;

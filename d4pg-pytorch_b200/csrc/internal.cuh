@@ -37,6 +37,10 @@ void trace_set_side_stream(cudaStream_t s);     // changes whenever the caller m
 int comm_allreduce(d4pg_comm* c, float* buf, int64_t n, cudaStream_t st);
 // fused all-reduce over IPC-mapped peer memory (comm.cu): x[r] = rank r's [2][n] gradient halves
 bool comm_peer_info(d4pg_comm* c, PeerInfo* out);
+PeerSignal comm_peer_signal(const PeerInfo& info, int kind);    // kind 0: gradient half complete, 1: reduced slice pushed
 int comm_peer_barrier(d4pg_comm* c, cudaStream_t st);
+// reduce-scatter + all-gather of the step's gradient over peer memory: this rank sums ITS slice of every rank's half
+// `parity` (rank order) and pushes the result into every rank's reduced buffer; publishes flag2 when done
+int comm_peer_reduce_scatter(d4pg_comm* c, int parity, cudaStream_t st);
 
 }  // namespace d4pg

@@ -104,7 +104,10 @@ struct d4pg_learner {
   cudaStream_t side; cudaEvent_t ev_fork, ev_join;
   ChainArgs chain_fwd_args, chain_bwd_args;
   // tcgen05 chains (precision >= 1): library-owned weight images + the per-step pack / chain descriptors
-  uint8_t* tcc_images; TccPackArgs tcc_pack; int tcc_use[32]; bool tcc_ok;
+  // weight images: forward ones (packed at the start of a graph launch, then kept current by the Adam kernel) and the
+  // transposed ones of the dX chains (packed every step on the side branch, off the critical path)
+  uint8_t* tcc_images; TccPackArgs tcc_pack_fwd, tcc_pack_dx; TccImage tcc_img[32]; bool tcc_ok;
+  cudaEvent_t ev_fork2, ev_join2;
   TccArgs tcc_fwd_args, tcc_bwd_args;
   GemmWideBatch dw_batch;
   // host-facing step: library-owned pinned staging, double-buffered by step parity (a buffer is rewritten only after
@@ -141,9 +144,13 @@ static int tcc_setup(d4pg_learner* L) {
   const d4pg_learner_buffers_t& b = L->buf;
   const NetDims& da = L->da; const NetDims& dc = L->dc;
   const int S = c.obs_dim, A = c.act_dim, N = c.n_atoms, H = D4PG_HIDDEN;
-  TccPackArgs& pk = L->tcc_pack;
-  tcc_pack_begin(pk, nullptr);
-  auto add = [&](int id, const float* W, int ldw, int mode, int rows, int K) { L->tcc_use[id] = tcc_pack_add(pk, W, ldw, mode, rows, K); };
+  TccPackArgs& pf = L->tcc_pack_fwd; TccPackArgs& pd = L->tcc_pack_dx;
+  tcc_pack_begin(pf, nullptr); tcc_pack_begin(pd, nullptr);
+  int use_of[U_COUNT]; bool is_dx[U_COUNT];
+  auto add = [&](int id, const float* W, int ldw, int mode, int rows, int K) {
+    is_dx[id] = mode == GEMM_DX;
+    use_of[id] = tcc_pack_add(is_dx[id] ? pd : pf, W, ldw, mode, rows, K);
+  };
   const float* Wn[2] = {b.actor, b.actor_target};
   for (int t = 0; t < 2; ++t) {
     const int base = t ? U_AT_F1 : U_A_F1;
@@ -167,9 +174,13 @@ static int tcc_setup(d4pg_learner* L) {
   add(U_C_D22, b.critic + dc.w_off[2], dc.ld[2], GEMM_DX, H, H);
   add(U_C_D2H, b.critic + dc.w_off[1], dc.ld[1], GEMM_DX, H, H);
   add(U_C_D2A, b.critic + dc.w_off[1] + H, dc.ld[1], GEMM_DX, A, H);
-  for (int i = 0; i < U_COUNT; ++i) D4PG_REQUIRE(L->tcc_use[i] >= 0, D4PG_ENOTSUP, "tcc_setup: too many weight images");
-  D4PG_CUDA_OK(cudaMalloc(&L->tcc_images, size_t(tcc_pack_bytes(pk))));
-  pk.dst = L->tcc_images;
+  for (int i = 0; i < U_COUNT; ++i) D4PG_REQUIRE(use_of[i] >= 0, D4PG_ENOTSUP, "tcc_setup: too many weight images");
+  const long long fwd_bytes = tcc_pack_bytes(pf), all_bytes = fwd_bytes + tcc_pack_bytes(pd);
+  D4PG_CUDA_OK(cudaMalloc(&L->tcc_images, size_t(all_bytes)));
+  D4PG_CUDA_OK(cudaMemset(L->tcc_images, 0, size_t(all_bytes)));
+  tcc_pack_set_base(pf, L->tcc_images, 0);
+  tcc_pack_set_base(pd, L->tcc_images, fwd_bytes);
+  for (int i = 0; i < U_COUNT; ++i) L->tcc_img[i] = tcc_image(is_dx[i] ? pd : pf, use_of[i]);
   (void)tcc_watchdog_device();                         // allocate outside of any stream capture
   L->tcc_ok = true;
   return D4PG_OK;
@@ -179,7 +190,9 @@ static int tcc_setup(d4pg_learner* L) {
 constexpr int PROFILE_REPS = 16;
 
 // par: half of the double-buffered batch this step trains on; cold: sample it first (no valid prefetch)
-static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
+// pack_fwd: re-pack the forward weight images first (start of a graph launch / eager step: the caller may have changed
+// the parameters); later steps of one multi-step graph rely on the images the previous step's Adam kernel wrote
+static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bool pack_fwd = true) {
   const d4pg_learner_config_t& c = L->cfg;
   const d4pg_learner_buffers_t& b = L->buf;
   Workspace w = L->ws;                               // local copy: the batch pointers follow `par`
@@ -232,55 +245,60 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   if (tcc) {
     // 2''. the same three forward chains on the tensor cores (mlp_tc_chain.cu): clusters of 8 CTAs own 64 rows,
     // every layer a tcgen05.mma tile.  The hi/lo weight images are re-packed first (Adam / Polyak changed them).
-    RUN(launch_tcc_pack(L->tcc_pack, st));
-    const TccPackArgs& pk = L->tcc_pack; const int* U = L->tcc_use;
+    if (pack_fwd) RUN(launch_tcc_pack(L->tcc_pack_fwd, st));
+    // the transposed images of the dX chains are needed ~35 us from now: packed on the side branch
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_fork2, st));
+    D4PG_CUDA_OK(cudaStreamWaitEvent(L->side, L->ev_fork2, 0));
+    RUN(launch_tcc_pack(L->tcc_pack_dx, L->side));
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_join2, L->side));
+    const TccImage* U = L->tcc_img;
     TccArgs& fa = L->tcc_fwd_args;
     tcc_args_begin(fa, B, reinterpret_cast<uint8_t*>(w.xchg), c.precision == 1 ? 3 : 1); fa.step_slot = 1;
     int l, p1, p2, pa;
     // chain 0  T: actor_target(s') -> critic_target(s', .)   (fc1 of both networks share the resident s' chunk)
     tcc_chain_x0(fa, 0, w.s2, Sp, S);
     l = tcc_slot_begin(fa, 0); tcc_slot_src_x(fa, 0, l);
-    p1 = tcc_slot_group(fa, 0, l, pk, U[U_AT_F1], EPI_BIAS_RELU, Wat + da.b_off[0], nullptr, 0, nullptr, H, 1);
-    p2 = tcc_slot_group(fa, 0, l, pk, U[U_CT_F1], EPI_BIAS_RELU, Wct + dc.b_off[0], nullptr, 0, nullptr, H, 1);
+    p1 = tcc_slot_group(fa, 0, l, U[U_AT_F1], EPI_BIAS_RELU, Wat + da.b_off[0], nullptr, 0, nullptr, H, 1);
+    p2 = tcc_slot_group(fa, 0, l, U[U_CT_F1], EPI_BIAS_RELU, Wct + dc.b_off[0], nullptr, 0, nullptr, H, 1);
     l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    p1 = tcc_slot_group(fa, 0, l, pk, U[U_AT_F2], EPI_BIAS, Wat + da.b_off[1], nullptr, 0, nullptr, H, 1);
+    p1 = tcc_slot_group(fa, 0, l, U[U_AT_F2], EPI_BIAS, Wat + da.b_off[1], nullptr, 0, nullptr, H, 1);
     l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    p1 = tcc_slot_group(fa, 0, l, pk, U[U_AT_F22], EPI_BIAS_RELU, Wat + da.b_off[2], nullptr, 0, nullptr, H, 1);
+    p1 = tcc_slot_group(fa, 0, l, U[U_AT_F22], EPI_BIAS_RELU, Wat + da.b_off[2], nullptr, 0, nullptr, H, 1);
     l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    pa = tcc_slot_group(fa, 0, l, pk, U[U_AT_F3], EPI_BIAS_TANH, Wat + da.b_off[3], nullptr, 0, w.out[0], Ap, 1);
+    pa = tcc_slot_group(fa, 0, l, U[U_AT_F3], EPI_BIAS_TANH, Wat + da.b_off[3], nullptr, 0, w.out[0], Ap, 1);
     l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p2, 8); tcc_slot_src_plane(fa, 0, l, pa, 1);
-    p1 = tcc_slot_group(fa, 0, l, pk, U[U_CT_F2], EPI_BIAS_RELU, Wct + dc.b_off[1], nullptr, 0, nullptr, H, 1);
+    p1 = tcc_slot_group(fa, 0, l, U[U_CT_F2], EPI_BIAS_RELU, Wct + dc.b_off[1], nullptr, 0, nullptr, H, 1);
     l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    p1 = tcc_slot_group(fa, 0, l, pk, U[U_CT_F22], EPI_BIAS_RELU, Wct + dc.b_off[2], nullptr, 0, nullptr, H, 1);
+    p1 = tcc_slot_group(fa, 0, l, U[U_CT_F22], EPI_BIAS_RELU, Wct + dc.b_off[2], nullptr, 0, nullptr, H, 1);
     l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    tcc_slot_group(fa, 0, l, pk, U[U_CT_F3], EPI_BIAS, Wct + dc.b_off[3], nullptr, 0, w.out[1], Np, 0);
+    tcc_slot_group(fa, 0, l, U[U_CT_F3], EPI_BIAS, Wct + dc.b_off[3], nullptr, 0, w.out[1], Np, 0);
     // chain 1  P: actor(s) -> critic(s, actor(s))
     tcc_chain_x0(fa, 1, w.s, Sp, S);
     l = tcc_slot_begin(fa, 1); tcc_slot_src_x(fa, 1, l);
-    p1 = tcc_slot_group(fa, 1, l, pk, U[U_A_F1], EPI_BIAS_RELU, Wa + da.b_off[0], nullptr, 0, w.h1[3], H, 1);
-    p2 = tcc_slot_group(fa, 1, l, pk, U[U_C_F1], EPI_BIAS_RELU, Wc + dc.b_off[0], nullptr, 0, nullptr, H, 1);
+    p1 = tcc_slot_group(fa, 1, l, U[U_A_F1], EPI_BIAS_RELU, Wa + da.b_off[0], nullptr, 0, w.h1[3], H, 1);
+    p2 = tcc_slot_group(fa, 1, l, U[U_C_F1], EPI_BIAS_RELU, Wc + dc.b_off[0], nullptr, 0, nullptr, H, 1);
     l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    p1 = tcc_slot_group(fa, 1, l, pk, U[U_A_F2], EPI_BIAS, Wa + da.b_off[1], nullptr, 0, w.h2[3], H, 1);
+    p1 = tcc_slot_group(fa, 1, l, U[U_A_F2], EPI_BIAS, Wa + da.b_off[1], nullptr, 0, w.h2[3], H, 1);
     l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    p1 = tcc_slot_group(fa, 1, l, pk, U[U_A_F22], EPI_BIAS_RELU, Wa + da.b_off[2], nullptr, 0, w.h3[3], H, 1);
+    p1 = tcc_slot_group(fa, 1, l, U[U_A_F22], EPI_BIAS_RELU, Wa + da.b_off[2], nullptr, 0, w.h3[3], H, 1);
     l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    pa = tcc_slot_group(fa, 1, l, pk, U[U_A_F3], EPI_BIAS_TANH, Wa + da.b_off[3], nullptr, 0, w.out[3], Ap, 1);
+    pa = tcc_slot_group(fa, 1, l, U[U_A_F3], EPI_BIAS_TANH, Wa + da.b_off[3], nullptr, 0, w.out[3], Ap, 1);
     l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p2, 8); tcc_slot_src_plane(fa, 1, l, pa, 1);
-    p1 = tcc_slot_group(fa, 1, l, pk, U[U_C_F2], EPI_BIAS_RELU, Wc + dc.b_off[1], nullptr, 0, w.h2[4], H, 1);
+    p1 = tcc_slot_group(fa, 1, l, U[U_C_F2], EPI_BIAS_RELU, Wc + dc.b_off[1], nullptr, 0, w.h2[4], H, 1);
     l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    p1 = tcc_slot_group(fa, 1, l, pk, U[U_C_F22], EPI_BIAS_RELU, Wc + dc.b_off[2], nullptr, 0, w.h3[4], H, 1);
+    p1 = tcc_slot_group(fa, 1, l, U[U_C_F22], EPI_BIAS_RELU, Wc + dc.b_off[2], nullptr, 0, w.h3[4], H, 1);
     l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    tcc_slot_group(fa, 1, l, pk, U[U_C_F3], EPI_BIAS, Wc + dc.b_off[3], nullptr, 0, w.out[4], Np, 0);
+    tcc_slot_group(fa, 1, l, U[U_C_F3], EPI_BIAS, Wc + dc.b_off[3], nullptr, 0, w.out[4], Np, 0);
     // chain 2  Q: critic(s, a): the resident chunk holds s for fc1, then the replay actions (fc2's K tail)
     tcc_chain_x0(fa, 2, w.s, Sp, S);
     l = tcc_slot_begin(fa, 2); tcc_slot_src_x(fa, 2, l); tcc_slot_reconvert_x(fa, 2, l, w.a, Ap, A);
-    p1 = tcc_slot_group(fa, 2, l, pk, U[U_C_F1], EPI_BIAS_RELU, Wc + dc.b_off[0], nullptr, 0, w.h1[2], H, 1);
+    p1 = tcc_slot_group(fa, 2, l, U[U_C_F1], EPI_BIAS_RELU, Wc + dc.b_off[0], nullptr, 0, w.h1[2], H, 1);
     l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8); tcc_slot_src_x(fa, 2, l);
-    p1 = tcc_slot_group(fa, 2, l, pk, U[U_C_F2], EPI_BIAS_RELU, Wc + dc.b_off[1], nullptr, 0, w.h2[2], H, 1);
+    p1 = tcc_slot_group(fa, 2, l, U[U_C_F2], EPI_BIAS_RELU, Wc + dc.b_off[1], nullptr, 0, w.h2[2], H, 1);
     l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8);
-    p1 = tcc_slot_group(fa, 2, l, pk, U[U_C_F22], EPI_BIAS_RELU, Wc + dc.b_off[2], nullptr, 0, w.h3[2], H, 1);
+    p1 = tcc_slot_group(fa, 2, l, U[U_C_F22], EPI_BIAS_RELU, Wc + dc.b_off[2], nullptr, 0, w.h3[2], H, 1);
     l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8);
-    tcc_slot_group(fa, 2, l, pk, U[U_C_F3], EPI_BIAS, Wc + dc.b_off[3], nullptr, 0, w.out[2], Np, 0);
+    tcc_slot_group(fa, 2, l, U[U_C_F3], EPI_BIAS, Wc + dc.b_off[3], nullptr, 0, w.out[2], Np, 0);
     RUN(launch_mlp_tc_chain(fa, st));
   } else if (chain) {
     // 2'. the three forward chains of the step as ONE cluster launch (mlp_chain.cu):
@@ -427,30 +445,31 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     D4PG_CUDA_OK(cudaMemsetAsync(Ga, 0, size_t(da.total + dc.total) * sizeof(float), st));
   if (tcc) {
     // 5''. both dX chains on the tensor cores (transposed weight images; masks applied by the epilogue)
-    const TccPackArgs& pk = L->tcc_pack; const int* U = L->tcc_use;
+    const TccImage* U = L->tcc_img;
+    D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join2, 0));       // transposed weight images are packed
     TccArgs& ba = L->tcc_bwd_args;
     tcc_args_begin(ba, B, reinterpret_cast<uint8_t*>(w.xchg), c.precision == 1 ? 3 : 1); ba.step_slot = 5;
     int l, p1;
     tcc_chain_pre(ba, 0, w.dlogits_q, Np, N);                     // C: critic loss
     l = tcc_slot_begin(ba, 0); tcc_slot_src_pre(ba, 0, l);
-    p1 = tcc_slot_group(ba, 0, l, pk, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[2], H, w.c_dz22, H, 1);
+    p1 = tcc_slot_group(ba, 0, l, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[2], H, w.c_dz22, H, 1);
     l = tcc_slot_begin(ba, 0); tcc_slot_src_plane(ba, 0, l, p1, 8);
-    p1 = tcc_slot_group(ba, 0, l, pk, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[2], H, w.c_dz2, H, 1);
+    p1 = tcc_slot_group(ba, 0, l, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[2], H, w.c_dz2, H, 1);
     l = tcc_slot_begin(ba, 0); tcc_slot_src_plane(ba, 0, l, p1, 8);
-    tcc_slot_group(ba, 0, l, pk, U[U_C_D2H], EPI_RELU_MASK, nullptr, w.h1[2], H, w.c_dz1, H, 0);
+    tcc_slot_group(ba, 0, l, U[U_C_D2H], EPI_RELU_MASK, nullptr, w.h1[2], H, w.c_dz1, H, 0);
     tcc_chain_pre(ba, 1, w.dlogits_pi, Np, N);                    // P: policy loss (PRE-update critic weights)
     l = tcc_slot_begin(ba, 1); tcc_slot_src_pre(ba, 1, l);
-    p1 = tcc_slot_group(ba, 1, l, pk, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[4], H, nullptr, H, 1);
+    p1 = tcc_slot_group(ba, 1, l, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[4], H, nullptr, H, 1);
     l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
-    p1 = tcc_slot_group(ba, 1, l, pk, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[4], H, nullptr, H, 1);
+    p1 = tcc_slot_group(ba, 1, l, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[4], H, nullptr, H, 1);
     l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
-    p1 = tcc_slot_group(ba, 1, l, pk, U[U_C_D2A], EPI_TANH_MASK, nullptr, w.out[3], Ap, w.a_dz3, Ap, 1);
+    p1 = tcc_slot_group(ba, 1, l, U[U_C_D2A], EPI_TANH_MASK, nullptr, w.out[3], Ap, w.a_dz3, Ap, 1);
     l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 1);
-    p1 = tcc_slot_group(ba, 1, l, pk, U[U_A_D3], EPI_RELU_MASK, nullptr, w.h3[3], H, w.a_dz22, H, 1);
+    p1 = tcc_slot_group(ba, 1, l, U[U_A_D3], EPI_RELU_MASK, nullptr, w.h3[3], H, w.a_dz22, H, 1);
     l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
-    p1 = tcc_slot_group(ba, 1, l, pk, U[U_A_D22], EPI_NONE, nullptr, nullptr, 0, w.a_dh2, H, 1);
+    p1 = tcc_slot_group(ba, 1, l, U[U_A_D22], EPI_NONE, nullptr, nullptr, 0, w.a_dh2, H, 1);
     l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
-    tcc_slot_group(ba, 1, l, pk, U[U_A_D2], EPI_RELU_MASK, nullptr, w.h1[3], H, w.a_dz1, H, 0);
+    tcc_slot_group(ba, 1, l, U[U_A_D2], EPI_RELU_MASK, nullptr, w.h1[3], H, w.a_dz1, H, 0);
     RUN(launch_mlp_tc_chain(ba, st));
   }
   if (chain) {
@@ -481,7 +500,9 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   }
   if (chain || tcc) {                     // every dW of the step as ONE grouped launch
     GemmWideBatch& gw = L->dw_batch;
-    gemm_wide_begin(gw, peer_mode ? peers.flag[peers.rank] : nullptr);   // its last CTA signals the peers
+    PeerSignal sig1{};
+    if (peer_mode) sig1 = comm_peer_signal(peers, 0);
+    gemm_wide_begin(gw, peer_mode ? &sig1 : nullptr);              // its last CTA signals the peers
     gemm_wide_add(gw, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], lc[2], Gc + dc.b_off[2], H, H, B));
     gemm_wide_add(gw, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], lc[1], Gc + dc.b_off[1], H, H, B));
     gemm_wide_add(gw, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], la[2], Ga + da.b_off[2], H, H, B));
@@ -540,7 +561,14 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
   // every rank's half of this step must be complete before Adam sums them: the chain plans signal from the dW
   // kernel and wait inside the Adam kernel; the level plan (several dW launches) uses a small barrier launch
   const bool inline_sync = peer_mode && (chain || tcc);
+  // exchange shape over peer memory: "pull" = one hop, every rank sums all N halves inside Adam (N x 1.15 MB inbound);
+  // "rs" = reduce-scatter + all-gather, two hops, ~2 MB per rank whatever N.  Measured on B200s: pull wins at 2 ranks
+  // (91.8 vs 104.8 us/step), rs from 4 ranks up.  D4PG_COMM_MODE=pull|rs overrides.
+  static const int comm_mode = [] { const char* e = getenv("D4PG_COMM_MODE"); return !e ? 0 : (e[0] == 'p' ? 1 : 2); }();
+  const bool peer_rs = peer_mode && (comm_mode == 2 || (comm_mode == 0 && c.world_size >= 4));
   if (peer_mode && !inline_sync) RUN(comm_peer_barrier(L->comm, st));
+  // reduce-scatter + all-gather over peer memory: each rank reduces its 1/N slice and pushes it to everyone
+  if (peer_rs) RUN(comm_peer_reduce_scatter(L->comm, gpar, st));
   else if (!peer_mode && c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
 
   // 7. Adam (actor + critic), sync (identity), Polyak -- one launch, two segments
@@ -553,9 +581,27 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
     aa.seg[0].g_out = b.grad_actor; aa.seg[0].g_off = 0;
     aa.seg[1].g_out = b.grad_critic; aa.seg[1].g_off = da.total;
     aa.my_flags = inline_sync ? peers.flag[peers.rank] : nullptr; aa.rank = peers.rank;
-    for (int r = 0; r < peers.world; ++r) aa.peer_wait[r] = peers.flag[r];
+    if (peer_rs) {                                              // the reduced gradient is local: wait for every rank's "slice pushed", then stream it
+      aa.peer_reduced = 1;
+      aa.seg[0].g = peers.red[peers.rank]; aa.seg[1].g = peers.red[peers.rank] + da.total;
+      aa.my_flags = peers.flag2[peers.rank];
+    }
   }
   aa.nseg = 2;
+  if (tcc) {                                                    // keep the forward weight images of the tcgen05 chains current
+    const TccImage* U = L->tcc_img;
+    const NetDims* nd[2] = {&da, &dc};
+    const int base[2] = {U_A_F1, U_C_F1}, tbase[2] = {U_AT_F1, U_CT_F1};
+    for (int sg = 0; sg < 2; ++sg) {
+      aa.seg[sg].nimg = 4;
+      for (int ly = 0; ly < 4; ++ly) {
+        AdamImgLayer& I = aa.seg[sg].imgl[ly];
+        I.w_off = nd[sg]->w_off[ly]; I.w_end = I.w_off + int64_t(nd[sg]->out[ly]) * nd[sg]->ld[ly];
+        I.ld = nd[sg]->ld[ly]; I.nchunks = U[base[sg] + ly].kchunks;
+        I.img = const_cast<uint8_t*>(U[base[sg] + ly].ptr); I.img_t = const_cast<uint8_t*>(U[tbase[sg] + ly].ptr);
+      }
+    }
+  }
   aa.w1 = float(1.0 - c.beta1); aa.w2 = float(1.0 - c.beta2); aa.beta2 = float(c.beta2); aa.eps = float(c.adam_eps);
   aa.tau = float(c.tau); aa.one_minus_tau = float(1.0 - c.tau); aa.grad_scale = 1.0f; aa.clock = w.clock;
   aa.pipe_slot = pf ? par : -1;
@@ -621,7 +667,9 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   }
   if (cudaStreamCreateWithFlags(&L->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
     set_error("d4pg_learner_create: stream/event creation failed"); delete L; return D4PG_ECUDA;
   }
   trace_set_side_stream(L->side);
@@ -635,7 +683,8 @@ extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   if (!L) return D4PG_OK;
   for (int i = 0; i < 4; ++i) if (L->graph_exec[i]) cudaGraphExecDestroy(L->graph_exec[i]);
   for (int i = 0; i < 2; ++i) if (L->multi_exec[i]) cudaGraphExecDestroy(L->multi_exec[i]);
-  cudaEventDestroy(L->ev_fork); cudaEventDestroy(L->ev_join); cudaStreamDestroy(L->side);
+  cudaEventDestroy(L->ev_fork); cudaEventDestroy(L->ev_join); cudaEventDestroy(L->ev_fork2); cudaEventDestroy(L->ev_join2);
+  cudaStreamDestroy(L->side);
   if (L->tcc_images) cudaFree(L->tcc_images);
   if (L->ev_in) cudaEventDestroy(L->ev_in);
   if (L->ev_out) cudaEventDestroy(L->ev_out);
@@ -748,7 +797,7 @@ extern "C" int32_t d4pg_learner_read_losses(d4pg_learner_t* L, float* out4, d4pg
 
 // Back-to-back steps with nothing in between: warm prefetch steps are replayed RUN_UNROLL at a time from one graph
 // (a graph launch boundary costs ~5 us of idle GPU; inside a graph consecutive steps are ordinary dependent nodes).
-constexpr int RUN_UNROLL = 4;
+constexpr int RUN_UNROLL = 8;
 extern "C" int32_t d4pg_learner_run(d4pg_learner_t* L, int32_t n_steps, d4pg_stream_t stream) {
   D4PG_REQUIRE(L && n_steps > 0, D4PG_EINVAL, "d4pg_learner_run: bad arguments");
   cudaStream_t st = as_stream(stream);
@@ -761,7 +810,7 @@ extern "C" int32_t d4pg_learner_run(d4pg_learner_t* L, int32_t n_steps, d4pg_str
         cudaGraph_t graph = nullptr;
         D4PG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         int rc = D4PG_OK;
-        for (int i = 0; i < RUN_UNROLL && rc == D4PG_OK; ++i) rc = enqueue_step(L, st, par ^ (i & 1), false);
+        for (int i = 0; i < RUN_UNROLL && rc == D4PG_OK; ++i) rc = enqueue_step(L, st, par ^ (i & 1), false, i == 0);
         cudaError_t e = cudaStreamEndCapture(st, &graph);
         if (rc != D4PG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) { set_error("d4pg_learner_run: end capture: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }

@@ -1,6 +1,7 @@
 // Cluster-fused MLP chains (exact fp32): a whole actor/critic network chain per launch.
 #pragma once
 #include "gemm_ffma.cuh"
+#include "adam.cuh"
 
 namespace d4pg {
 
@@ -70,9 +71,9 @@ struct GemmWideBatch {
   unsigned long long* trace;
   // data parallel over peer memory: the last CTA to finish publishes "this rank's gradient half is complete"
   // ([0] published step count, [1] local step count, [2] CTA ticket), see comm.cu
-  unsigned long long* peer_flags;
+  PeerSignal peer_sig; int has_peer_sig;
 };
-void gemm_wide_begin(GemmWideBatch& b, unsigned long long* peer_flags = nullptr);
+void gemm_wide_begin(GemmWideBatch& b, const PeerSignal* sig = nullptr);
 void gemm_wide_add(GemmWideBatch& b, const GemmProblem& p);
 int gemm_wide_launch(GemmWideBatch& b, cudaStream_t st);
 

@@ -567,6 +567,8 @@ int tcc_pack_add(TccPackArgs& p, const float* W, int ldw, int mode, int N, int K
   return p.n++;
 }
 long long tcc_pack_bytes(const TccPackArgs& p) { return (long long)(p.total_blocks) * TCC_W_CHUNK; }
+// the set's images start `first_byte` into the buffer `dst` (dst_off of every use is relative to the set's own start)
+void tcc_pack_set_base(TccPackArgs& p, uint8_t* dst, long long first_byte) { p.dst = dst + first_byte; }
 int launch_tcc_pack(const TccPackArgs& p, cudaStream_t st) {
   D4PG_REQUIRE(p.n > 0 && p.dst, D4PG_EINVAL, "launch_tcc_pack: nothing to pack");
   tcc_pack_kernel<<<p.total_blocks, 256, 0, st>>>(p);
@@ -611,16 +613,15 @@ void tcc_slot_reconvert_x(TccArgs& a, int c, int slot, const float* src, int ld,
   TccSlot& s = a.chain[c].slot[slot];
   s.xsrc = src; s.xld = ld; s.xcols = cols;
 }
-int tcc_slot_group(TccArgs& a, int c, int slot, const TccPackArgs& pk, int use, int epi, const float* bias,
+int tcc_slot_group(TccArgs& a, int c, int slot, const TccImage& img, int epi, const float* bias,
                    const float* aux, int ldaux, float* C, int ldc, int publish) {
   TccChain& ch = a.chain[c];
   TccSlot& s = ch.slot[slot];
   const int gi = s.ngroups++;
   if (gi >= TCC_MAX_GROUPS) return -1;
   TccGroup& g = s.g[gi];
-  const TccPackUse& u = pk.use[use];
-  g.wimg = tcc_image(pk, use); g.bias = bias; g.aux = aux; g.ldaux = ldaux; g.C = C; g.ldc = ldc;
-  g.N = u.N; g.epi = epi; g.kchunks = u.nchunks;
+  g.wimg = img.ptr; g.bias = bias; g.aux = aux; g.ldaux = ldaux; g.C = C; g.ldc = ldc;
+  g.N = img.N; g.epi = epi; g.kchunks = img.kchunks;
   g.pub = publish ? ch.nplanes++ : -1;
   return g.pub;
 }

@@ -73,10 +73,12 @@ struct TccPackArgs {
   uint8_t* dst;
 };
 void tcc_pack_begin(TccPackArgs& p, uint8_t* dst);
-// returns the use index; *bytes_out (optional) = image bytes of this use
+// returns the use index.  Several pack sets may share one image buffer: `first_block` = blocks already taken
 int tcc_pack_add(TccPackArgs& p, const float* W, int ldw, int mode, int N, int K);
+void tcc_pack_set_base(TccPackArgs& p, uint8_t* dst, long long first_byte);
 long long tcc_pack_bytes(const TccPackArgs& p);
-static inline const uint8_t* tcc_image(const TccPackArgs& p, int use) { return p.dst + p.use[use].dst_off; }
+struct TccImage { const uint8_t* ptr; int N, kchunks; };      // one packed weight image: N output rows, kchunks K chunks
+static inline TccImage tcc_image(const TccPackArgs& p, int use) { return TccImage{p.dst + p.use[use].dst_off, p.use[use].N, p.use[use].nchunks}; }
 int launch_tcc_pack(const TccPackArgs& p, cudaStream_t st);
 
 // ---- chain construction -----------------------------------------------------------------------------
@@ -91,7 +93,7 @@ void tcc_slot_src_pre(TccArgs& a, int c, int slot);                          // 
 void tcc_slot_src_plane(TccArgs& a, int c, int slot, int plane, int nchunks);
 void tcc_slot_reconvert_x(TccArgs& a, int c, int slot, const float* src, int ld, int cols);
 // add an output group; publish != 0 allocates a plane and returns its id (else -1)
-int tcc_slot_group(TccArgs& a, int c, int slot, const TccPackArgs& pk, int use, int epi, const float* bias,
+int tcc_slot_group(TccArgs& a, int c, int slot, const TccImage& img, int epi, const float* bias,
                    const float* aux, int ldaux, float* C, int ldc, int publish);
 int launch_mlp_tc_chain(TccArgs& a, cudaStream_t st);
 unsigned long long* tcc_watchdog_device();      // host-mapped watchdog record (allocate outside of stream capture)

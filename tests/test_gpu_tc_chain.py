@@ -45,7 +45,7 @@ def test_tc_chain_every_intermediate_vs_torch(B, S, A, N, graph):
          for k, net in (("a", dd.actor), ("at", dd.actor_target), ("c", dd.critic), ("ct", dd.critic_target))}
     dd.train()
     torch.cuda.synchronize()
-    assert dd.kernels_per_step() == 8            # sample, pack, fwd chains, loss, tree update, dX chains, dW, Adam
+    assert dd.kernels_per_step() == 9            # sample, pack fwd, pack dX (side branch), fwd chains, loss, tree update, dX chains, dW, Adam
     t = lambda name, w=None: dd.debug_tensor(name, (B, w) if w else None)
     s, a, s2 = _ref(t("s", S)), _ref(t("a", A)), _ref(t("s2", S))
     relu = torch.relu
