@@ -287,6 +287,7 @@ def gpu_main(args):
         regions.append(max_over_ranks(e0.elapsed_time(e1)))
     ms = float(np.median(regions))
     kernels = dd.kernels_per_step()
+    exchange = comm.exchange_mode() if comm is not None else "single"
     lc, la = dd.last_losses()
     assert np.isfinite(lc) and np.isfinite(la)
     ms_per_step = ms / args.steps
@@ -373,13 +374,16 @@ def gpu_main(args):
     h2d = B * 8 + n_new * ((2 * cfg["obs"] + cfg["act"]) * 4 + 8 + 1)
     d2h = 16
 
-    def e2e_step(i):
+    def e2e_step(i, first=False):
         lo = (i % 8) * n_new
         dd.replayBuffer.add_batch(*[p[lo:lo + n_new] for p in pin])      # H2D from pinned host memory
-        dd.train()                                                        # host MT19937 uniforms -> H2D
-        return dd.last_losses()                                           # D2H + sync
+        dd.train()                                                        # host MT19937 uniforms -> H2D; queues the D2H of its losses
+        # every step's result is read on the host, one step late: the read of step k-1 overlaps step k on the GPU
+        # (the last step's own result is read before the clock stops, below)
+        return None if first else dd.last_losses(lag=1)
     for i in range(max(args.warmup, 3)):
-        e2e_step(i)
+        e2e_step(i, first=(i == 0))
+    dd.last_losses()
     barrier()
     t0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,6 +391,8 @@ def gpu_main(args):
     e2e_steps = args.steps * max(1, args.repeats)      # same number of steps as the device-timed regions together
     for i in range(e2e_steps):
         e2e_step(i)
+    lc_e, la_e = dd.last_losses()                   # D2H result of the final step, inside the timed region
+    assert np.isfinite(lc_e) and np.isfinite(la_e)
     ev1.record()
     barrier()
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
@@ -407,12 +413,16 @@ def gpu_main(args):
                            "graph_capture_steps_before_warmup": capture_steps, "warmup_steps": max(args.warmup, 3)},
                 "replicas_identical": replicas_identical,
                 "implementation": {"step_plan": {1: "cluster chains", 0: "levels"}[args.chain],
+                           "gradient_exchange": exchange,
                            "precision": {"fp32": "exact fp32 FFMA tiles", "tf32x3": "3xTF32 on tcgen05 tensor cores (hi/lo split, fp32 accumulate in TMEM; meets the 1e-5 parity bar)", "tf32": "one TF32 tcgen05 pass (not parity-grade)"}[args.precision],
                            "l2": "inputs larger than L2: replay store %.0f MB + trees %.0f MB per GPU, rows sampled at "
                                  "random; parameters (%.1f MB) are L2-resident by design" % (
                                      cap * ((2 * cfg["obs"] + cfg["act"]) * 4 + 9) / 1e6, 16 * cap / 1e6 * 1.05, alg["P"] * 16 / 1e6)},
                 "clocks": sampler.summary(), "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d,
-                                                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+                                                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                                                     "how": "per step: add_batch of 256 new transitions from pinned host memory (H2D), train() with host-drawn "
+                                                            "MT19937 uniforms (H2D), its losses copied D2H; the host reads step k-1's losses while step k runs "
+                                                            "(DDPG.last_losses(lag=1)), the final step's before the clock stops"},
                 "gpu_launches": kernels * args.steps, "kernels_per_step": kernels,
                 "roofline": roofline, "roofline_step": step_roof, "launch_us_per_step": launch_breakdown,
                 "cpu_baseline": cpu, "losses": [lc, la]}

@@ -104,6 +104,7 @@ _PROTOS = {
     "d4pg_learner_step_host_mt": (C.c_int32, [_P, _P, _P, _P]),
     "d4pg_learner_step_host": (C.c_int32, [_P, _P, _P, _P, _P]),
     "d4pg_learner_read_losses": (C.c_int32, [_P, _P, _P]),
+    "d4pg_learner_fetch_losses": (C.c_int32, [_P, C.c_int32, _P]),
     "d4pg_learner_tensor": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "d4pg_learner_profile_step": (C.c_int32, [_P, _P, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "d4pg_learner_steps_done": (C.c_int64, [_P]),
@@ -120,6 +121,14 @@ _PROTOS = {
     "d4pg_comm_peer_ready": (C.c_int32, [_P]),
     "d4pg_comm_peer_disable": (C.c_int32, [_P]),
     "d4pg_comm_allreduce_sum": (C.c_int32, [_P, _P, C.c_int64, _P]),
+    "d4pg_comm_mc_supported": (C.c_int32, [_P]),
+    "d4pg_comm_mc_create": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
+    "d4pg_comm_mc_import": (C.c_int32, [_P, C.c_int32]),
+    "d4pg_comm_mc_add_device": (C.c_int32, [_P]),
+    "d4pg_comm_mc_bind": (C.c_int32, [_P]),
+    "d4pg_comm_mc_ready": (C.c_int32, [_P]),
+    "d4pg_comm_mc_disable": (C.c_int32, [_P]),
+    "d4pg_comm_mc_selftest": (C.c_int32, [_P, _P, _P, C.c_int64, _P]),
 }
 EXPORTED_SYMBOLS = sorted(_PROTOS)
 

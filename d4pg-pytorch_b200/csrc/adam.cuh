@@ -95,6 +95,9 @@ struct PeerInfo {
   int world, rank; int64_t n;
   float* x[D4PG_MAX_PEERS]; float* red[D4PG_MAX_PEERS];
   unsigned long long* flag[D4PG_MAX_PEERS]; unsigned long long* flag2[D4PG_MAX_PEERS];
+  // in-switch reduction (NVLS): mc = multicast mapping of every rank's [2][n] gradient buffer (multimem.ld_reduce on it
+  // returns the sum over the ranks), mc_uc = this rank's own buffer through an ordinary mapping; null when not set up
+  const float* mc; float* mc_uc;
 };
 
 // tcgen05 chains (mlp_tc_chain.cu): the updated weights are ALSO written as the tensor cores' forward operand images
@@ -115,6 +118,7 @@ struct AdamArgs {
   // fused all-reduce: g = sum over ranks r = 0..npeers-1 (fixed order: identical on every rank) of peer_g[r][g_off + i],
   // read over NVLink from IPC-mapped peer memory; the ranks were synchronised by comm_peer_barrier
   const float* peer_g[D4PG_MAX_PEERS]; int npeers;
+  const float* mc_g;                          // non-null: g = multimem.ld_reduce over all ranks at mc_g + g_off + i (NVSwitch sums)
   int peer_reduced;                           // 1: seg.g already holds the reduced gradient (reduce-scatter + all-gather ran before);
                                               //    only wait for every rank's "slice pushed" flag.  0: sum the ranks' halves here
   // non-null: wait inside the kernel until every rank published step count >= this rank's local one

@@ -51,7 +51,11 @@ __device__ __forceinline__ void adam_segment(const AdamArgs& a, int seg, int bx,
   if (a.npeers > 0 && a.my_flags) peer_wait_all(a.my_flags, a.npeers);   // every rank signalled this step (local inbox)
   for (int64_t i = bx * int64_t(256) + threadIdx.x; i < n4; i += int64_t(gx) * 256) {
     float4 g;
-    if (a.npeers > 0 && !a.peer_reduced) {
+    if (a.mc_g) {                                           // one instruction, one NVLink hop: the switch adds the N ranks' values
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(reinterpret_cast<const float4*>(a.mc_g + s.g_off) + i) : "memory");
+      if (go4) go4[i] = g;
+    } else if (a.npeers > 0 && !a.peer_reduced) {
       g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < D4PG_MAX_PEERS; ++r)

@@ -4,7 +4,9 @@
 // this is the synchronous-DP equivalent described in SURVEY.md section 8e.
 // NCCL is bound at run time (dlopen) so the .so has no link-time dependency on it.
 #include "internal.cuh"
+#include <cuda.h>          // driver-API types for the multicast (NVLS) objects; entry points are resolved at run time
 #include <dlfcn.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include <new>
@@ -72,6 +74,13 @@ struct d4pg_comm {
   void* peer_base[D4PG_MAX_PEERS];                          // opened IPC mappings (nullptr for self)
   float* peer_x[D4PG_MAX_PEERS]; unsigned long long* peer_flag[D4PG_MAX_PEERS];
   bool peer_ready;
+  // ---- in-switch reduction (NVLS): one multicast object over all ranks' gradient buffers (d4pg_comm_mc_*) -------------
+  // Every rank binds its own physical [2][n] gradient buffer to the same multicast object; `mc_ptr` is the multicast
+  // mapping (a multimem.ld_reduce on it returns the SUM over all ranks, computed by the NVSwitch), `mc_uc` the ordinary
+  // mapping of this rank's buffer (what its dW kernel writes).
+  CUmemGenericAllocationHandle mc_handle, mc_mem;
+  CUdeviceptr mc_ptr, mc_uc; size_t mc_size; int mc_dev;
+  bool mc_have_handle, mc_ready;
 };
 
 namespace d4pg {
@@ -96,6 +105,8 @@ bool comm_peer_info(d4pg_comm* c, PeerInfo* out) {
   if (!c || !c->peer_ready) return false;
   if (!out) return true;
   out->world = c->world; out->rank = c->rank; out->n = c->xn;
+  out->mc = c->mc_ready ? reinterpret_cast<const float*>(c->mc_ptr) : nullptr;
+  out->mc_uc = c->mc_ready ? reinterpret_cast<float*>(c->mc_uc) : nullptr;
   for (int r = 0; r < c->world; ++r) {
     out->x[r] = c->peer_x[r]; out->red[r] = c->peer_x[r] + 2 * c->xn;
     out->flag[r] = c->peer_flag[r]; out->flag2[r] = c->peer_flag[r] + 64;
@@ -183,6 +194,7 @@ extern "C" int32_t d4pg_comm_create(const uint8_t* id128, int32_t rank, int32_t 
   D4PG_REQUIRE(c, D4PG_EINVAL, "d4pg_comm_create: out of host memory");
   c->rank = rank; c->world = world;
   c->xbuf = nullptr; c->xn = 0; c->flags = nullptr; c->peer_ready = false;
+  c->mc_handle = 0; c->mc_mem = 0; c->mc_ptr = 0; c->mc_uc = 0; c->mc_size = 0; c->mc_dev = 0; c->mc_have_handle = false; c->mc_ready = false;
   for (int i = 0; i < D4PG_MAX_PEERS; ++i) { c->peer_base[i] = nullptr; c->peer_x[i] = nullptr; c->peer_flag[i] = nullptr; }
   ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
   if (r != 0) {
@@ -247,6 +259,169 @@ extern "C" int32_t d4pg_comm_peer_disable(d4pg_comm_t* c) {
   for (int i = 0; i < D4PG_MAX_PEERS; ++i) {
     if (c->peer_base[i]) { cudaIpcCloseMemHandle(c->peer_base[i]); c->peer_base[i] = nullptr; }
     c->peer_x[i] = nullptr; c->peer_flag[i] = nullptr;
+  }
+  return D4PG_OK;
+}
+
+// ---- in-switch reduction over NVLink / NVSwitch (NVLS multicast objects) ---------------------------------------------
+// Setup is collective and driven by the host binding (dist.py): every rank checks support; rank 0 creates the multicast
+// object and exports it as a POSIX file descriptor, the other ranks receive the descriptor over a Unix socket and import
+// it; every rank adds its device; after a barrier every rank creates its physical buffer, binds it and maps both views.
+namespace {
+struct DrvApi {
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+  CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
+  CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
+  CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+  CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false, tried = false;
+};
+DrvApi g_drv;
+bool load_drv() {
+  if (g_drv.tried) return g_drv.ok;
+  g_drv.tried = true;
+  bool ok = true;
+  auto get = [&](const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) ok = false;
+  };
+  get("cuDeviceGet", (void**)&g_drv.DeviceGet);
+  get("cuDeviceGetAttribute", (void**)&g_drv.DeviceGetAttribute);
+  get("cuMulticastGetGranularity", (void**)&g_drv.MulticastGetGranularity);
+  get("cuMulticastCreate", (void**)&g_drv.MulticastCreate);
+  get("cuMulticastAddDevice", (void**)&g_drv.MulticastAddDevice);
+  get("cuMulticastBindMem", (void**)&g_drv.MulticastBindMem);
+  get("cuMemExportToShareableHandle", (void**)&g_drv.MemExportToShareableHandle);
+  get("cuMemImportFromShareableHandle", (void**)&g_drv.MemImportFromShareableHandle);
+  get("cuMemCreate", (void**)&g_drv.MemCreate);
+  get("cuMemAddressReserve", (void**)&g_drv.MemAddressReserve);
+  get("cuMemMap", (void**)&g_drv.MemMap);
+  get("cuMemSetAccess", (void**)&g_drv.MemSetAccess);
+  get("cuMemGetAllocationGranularity", (void**)&g_drv.MemGetAllocationGranularity);
+  (void)cudaGetLastError();
+  g_drv.ok = ok;
+  return ok;
+}
+#define DRV_OK(expr)                                                                            \
+  do {                                                                                          \
+    CUresult _r = (expr);                                                                       \
+    if (_r != CUDA_SUCCESS) { d4pg::set_error("%s -> CUDA driver error %d", #expr, int(_r)); return D4PG_ECUDA; } \
+  } while (0)
+CUmulticastObjectProp mc_prop(int world, size_t size) {
+  CUmulticastObjectProp p{};
+  p.numDevices = unsigned(world); p.size = size; p.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR; p.flags = 0;
+  return p;
+}
+}  // namespace
+
+/* 1 if this rank's device supports multicast objects (NVSwitch system, driver with NVLS), else 0 */
+extern "C" int32_t d4pg_comm_mc_supported(d4pg_comm_t* c) {
+  if (!c || !load_drv()) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  CUdevice cd;
+  if (g_drv.DeviceGet(&cd, dev) != CUDA_SUCCESS) return 0;
+  int v = 0;
+  if (g_drv.DeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cd) != CUDA_SUCCESS) return 0;
+  c->mc_dev = dev;
+  return v ? 1 : 0;
+}
+static int mc_size_for(d4pg_comm* c, size_t* out) {
+  D4PG_REQUIRE(c->xn > 0, D4PG_ESTATE, "d4pg_comm_mc_*: call d4pg_comm_peer_alloc first (the exchange length comes from it)");
+  CUmulticastObjectProp p = mc_prop(c->world, 0);
+  size_t gran = 0;
+  p.size = size_t(2 * c->xn) * sizeof(float);
+  DRV_OK(g_drv.MulticastGetGranularity(&gran, &p, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  *out = ((size_t(2 * c->xn) * sizeof(float) + gran - 1) / gran) * gran;
+  return D4PG_OK;
+}
+/* rank 0: create the multicast object for [2][n] floats per rank and export it; *fd_out is a POSIX file descriptor */
+extern "C" int32_t d4pg_comm_mc_create(d4pg_comm_t* c, int32_t* fd_out) {
+  D4PG_REQUIRE(c && fd_out && load_drv(), D4PG_ENOTSUP, "d4pg_comm_mc_create: multicast API not available");
+  int rc = mc_size_for(c, &c->mc_size);
+  if (rc) return rc;
+  CUmulticastObjectProp p = mc_prop(c->world, c->mc_size);
+  DRV_OK(g_drv.MulticastCreate(&c->mc_handle, &p));
+  c->mc_have_handle = true;
+  int fd = -1;
+  DRV_OK(g_drv.MemExportToShareableHandle(&fd, c->mc_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  *fd_out = fd;
+  return D4PG_OK;
+}
+/* other ranks: import the object from the descriptor received from rank 0 (the descriptor is closed) */
+extern "C" int32_t d4pg_comm_mc_import(d4pg_comm_t* c, int32_t fd) {
+  D4PG_REQUIRE(c && fd >= 0 && load_drv(), D4PG_ENOTSUP, "d4pg_comm_mc_import: multicast API not available");
+  int rc = mc_size_for(c, &c->mc_size);
+  if (rc) return rc;
+  DRV_OK(g_drv.MemImportFromShareableHandle(&c->mc_handle, reinterpret_cast<void*>(static_cast<uintptr_t>(fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+  c->mc_have_handle = true;
+  close(fd);
+  return D4PG_OK;
+}
+/* every rank, after it holds the handle: join the multicast team (all ranks must have joined before anyone binds) */
+extern "C" int32_t d4pg_comm_mc_add_device(d4pg_comm_t* c) {
+  D4PG_REQUIRE(c && c->mc_have_handle, D4PG_ESTATE, "d4pg_comm_mc_add_device: no multicast handle");
+  CUdevice cd;
+  DRV_OK(g_drv.DeviceGet(&cd, c->mc_dev));
+  DRV_OK(g_drv.MulticastAddDevice(c->mc_handle, cd));
+  return D4PG_OK;
+}
+/* every rank, after a barrier: allocate this rank's physical gradient buffer, bind it, map the unicast and multicast views */
+extern "C" int32_t d4pg_comm_mc_bind(d4pg_comm_t* c) {
+  D4PG_REQUIRE(c && c->mc_have_handle && c->peer_ready, D4PG_ESTATE, "d4pg_comm_mc_bind: handle / peer block missing");
+  CUmemAllocationProp ap{};
+  ap.type = CU_MEM_ALLOCATION_TYPE_PINNED; ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ap.location.id = c->mc_dev;
+  ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t gran = 0;
+  DRV_OK(g_drv.MemGetAllocationGranularity(&gran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  D4PG_REQUIRE(c->mc_size % gran == 0 || gran % 4096 == 0, D4PG_ENOTSUP, "d4pg_comm_mc_bind: granularity mismatch");
+  const size_t size = ((c->mc_size + gran - 1) / gran) * gran;
+  DRV_OK(g_drv.MemCreate(&c->mc_mem, size, &ap, 0));
+  DRV_OK(g_drv.MulticastBindMem(c->mc_handle, 0, c->mc_mem, 0, c->mc_size, 0));
+  CUmemAccessDesc ad{};
+  ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ad.location.id = c->mc_dev; ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  DRV_OK(g_drv.MemAddressReserve(&c->mc_uc, size, gran, 0, 0));
+  DRV_OK(g_drv.MemMap(c->mc_uc, size, 0, c->mc_mem, 0));
+  DRV_OK(g_drv.MemSetAccess(c->mc_uc, size, &ad, 1));
+  DRV_OK(g_drv.MemAddressReserve(&c->mc_ptr, c->mc_size, gran, 0, 0));
+  DRV_OK(g_drv.MemMap(c->mc_ptr, c->mc_size, 0, c->mc_handle, 0));
+  DRV_OK(g_drv.MemSetAccess(c->mc_ptr, c->mc_size, &ad, 1));
+  D4PG_CUDA_OK(cudaMemset(reinterpret_cast<void*>(c->mc_uc), 0, size));
+  D4PG_CUDA_OK(cudaDeviceSynchronize());
+  c->mc_ready = true;
+  return D4PG_OK;
+}
+extern "C" int32_t d4pg_comm_mc_ready(const d4pg_comm_t* c) { return (c && c->mc_ready) ? 1 : 0; }
+/* collective decision of the binding: stop using the multicast path (the buffers stay mapped until destroy) */
+extern "C" int32_t d4pg_comm_mc_disable(d4pg_comm_t* c) { if (c) c->mc_ready = false; return D4PG_OK; }
+
+// self-test of the in-switch reduction: out[i] = multimem.ld_reduce over all ranks of (rank r's unicast buffer)[i]
+namespace d4pg {
+__global__ void mc_selftest_kernel(const float* mc, float* out, int n4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(reinterpret_cast<const float4*>(mc) + i) : "memory");
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+}  // namespace d4pg
+/* fill this rank's unicast buffer from `src` (n floats, device), or reduce: out[0..n) = sum over ranks (after a barrier) */
+extern "C" int32_t d4pg_comm_mc_selftest(d4pg_comm_t* c, const float* src, float* out, int64_t n, d4pg_stream_t stream) {
+  D4PG_REQUIRE(c && c->mc_ready && n > 0 && n % 4 == 0 && size_t(n) * 4 <= c->mc_size, D4PG_EINVAL, "d4pg_comm_mc_selftest: bad arguments");
+  cudaStream_t st = d4pg::as_stream(stream);
+  if (src) D4PG_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<void*>(c->mc_uc), src, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
+  if (out) {
+    d4pg::mc_selftest_kernel<<<unsigned((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float*>(c->mc_ptr), out, int(n / 4));
+    D4PG_LAUNCH_OK();
   }
   return D4PG_OK;
 }

@@ -114,6 +114,9 @@ struct d4pg_learner {
   // the H2D copy out of it, two steps earlier, has completed)
   double* host_u[2]; int32_t* host_pos[2]; float* host_losses; cudaEvent_t ev_in, ev_out, ev_h2d[2];
   int64_t host_steps;
+  // results of the host-facing steps: {critic loss, actor loss, -, -} of step k land in ring slot k & 1 (async D2H queued
+  // by the step itself), so a caller can read step k-1 while step k runs
+  float* loss_ring[2]; cudaEvent_t ev_loss[2]; int64_t loss_steps;
   bool profiling;
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> ev_name;
@@ -440,7 +443,12 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
   PeerInfo peers{};
   const bool peer_mode = c.world_size > 1 && comm_peer_info(L->comm, &peers);
   const int gpar = pf ? par : int(L->steps_done & 1);
-  if (peer_mode) { Ga = peers.x[peers.rank] + int64_t(gpar) * peers.n; Gc = Ga + da.total; }
+  const bool inline_sync_possible = chain || tcc;
+  static const bool mc_off = [] { const char* e = getenv("D4PG_COMM_MODE"); return e && e[0] != 'm'; }();
+  const bool use_mc_buf = peer_mode && peers.mc != nullptr && !mc_off && inline_sync_possible;
+  // this step's gradients go into this rank's half of the exchange buffer: the multicast-bound one when the in-switch
+  // reduction is set up, else the IPC-mapped one the peers read directly
+  if (peer_mode) { Ga = (use_mc_buf ? peers.mc_uc : peers.x[peers.rank]) + int64_t(gpar) * peers.n; Gc = Ga + da.total; }
   if (B >= 1024)                // dW levels run split-K with fp32 atomics: the gradient buffer must start at zero
     D4PG_CUDA_OK(cudaMemsetAsync(Ga, 0, size_t(da.total + dc.total) * sizeof(float), st));
   if (tcc) {
@@ -561,11 +569,15 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
   // every rank's half of this step must be complete before Adam sums them: the chain plans signal from the dW
   // kernel and wait inside the Adam kernel; the level plan (several dW launches) uses a small barrier launch
   const bool inline_sync = peer_mode && (chain || tcc);
-  // exchange shape over peer memory: "pull" = one hop, every rank sums all N halves inside Adam (N x 1.15 MB inbound);
-  // "rs" = reduce-scatter + all-gather, two hops, ~2 MB per rank whatever N.  Measured on B200s: pull wins at 2 ranks
-  // (91.8 vs 104.8 us/step), rs from 4 ranks up.  D4PG_COMM_MODE=pull|rs overrides.
-  static const int comm_mode = [] { const char* e = getenv("D4PG_COMM_MODE"); return !e ? 0 : (e[0] == 'p' ? 1 : 2); }();
-  const bool peer_rs = peer_mode && (comm_mode == 2 || (comm_mode == 0 && c.world_size >= 4));
+  // Exchange shapes (D4PG_COMM_MODE=mc|pull|rs; default: mc when the communicator set up a multicast object, else pull):
+  //   "mc"   in-switch reduction: ONE hop and 1.15 MB inbound per rank -- the Adam kernel's multimem.ld_reduce over an NVLS
+  //          multicast object returns the sum over all ranks, added by the NVSwitch;
+  //   "pull" one hop, every rank sums all N halves inside Adam (N x 1.15 MB inbound over NVLink);
+  //   "rs"   reduce-scatter + all-gather over peer memory: ~2 MB per rank whatever N, but TWO cross-rank hops (measured on
+  //          B200s it loses to "pull" even at 8 ranks: 130.7 vs 118.9 us/step; 4 ranks 112.2 vs 100.5; 2 ranks 101.0 vs 91.5).
+  static const int comm_mode = [] { const char* e = getenv("D4PG_COMM_MODE"); return !e ? 0 : (e[0] == 'p' ? 1 : (e[0] == 'r' ? 2 : 3)); }();
+  const bool peer_mc = peer_mode && peers.mc != nullptr && (comm_mode == 0 || comm_mode == 3) && inline_sync_possible;
+  const bool peer_rs = peer_mode && !peer_mc && comm_mode == 2;
   if (peer_mode && !inline_sync) RUN(comm_peer_barrier(L->comm, st));
   // reduce-scatter + all-gather over peer memory: each rank reduces its 1/N slice and pushes it to everyone
   if (peer_rs) RUN(comm_peer_reduce_scatter(L->comm, gpar, st));
@@ -581,6 +593,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
     aa.seg[0].g_out = b.grad_actor; aa.seg[0].g_off = 0;
     aa.seg[1].g_out = b.grad_critic; aa.seg[1].g_off = da.total;
     aa.my_flags = inline_sync ? peers.flag[peers.rank] : nullptr; aa.rank = peers.rank;
+    if (peer_mc) aa.mc_g = peers.mc + int64_t(gpar) * peers.n;    // NVSwitch reduces; signal 0 (every rank's dW done) is awaited in-kernel
     if (peer_rs) {                                              // the reduced gradient is local: wait for every rank's "slice pushed", then stream it
       aa.peer_reduced = 1;
       aa.seg[0].g = peers.red[peers.rank]; aa.seg[1].g = peers.red[peers.rank] + da.total;
@@ -653,7 +666,8 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   (void)debug_trace_buffer();          // allocate outside of any stream capture
   if (int rc = tcc_setup(L)) { delete L; return rc; }
   L->host_steps = 0; L->host_losses = nullptr; L->ev_in = nullptr; L->ev_out = nullptr;
-  for (int i = 0; i < 2; ++i) { L->host_u[i] = nullptr; L->host_pos[i] = nullptr; L->ev_h2d[i] = nullptr; }
+  for (int i = 0; i < 2; ++i) { L->host_u[i] = nullptr; L->host_pos[i] = nullptr; L->ev_h2d[i] = nullptr; L->loss_ring[i] = nullptr; L->ev_loss[i] = nullptr; }
+  L->loss_steps = 0;
   {
     const size_t nb = size_t(cfg->batch);
     bool ok = cudaEventCreateWithFlags(&L->ev_in, cudaEventDisableTiming) == cudaSuccess &&
@@ -661,6 +675,8 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
               cudaHostAlloc(reinterpret_cast<void**>(&L->host_losses), 4 * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i)
       ok = cudaEventCreateWithFlags(&L->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&L->ev_loss[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaHostAlloc(reinterpret_cast<void**>(&L->loss_ring[i]), 4 * sizeof(float), cudaHostAllocDefault) == cudaSuccess &&
            cudaHostAlloc(reinterpret_cast<void**>(&L->host_u[i]), nb * sizeof(double), cudaHostAllocDefault) == cudaSuccess &&
            cudaHostAlloc(reinterpret_cast<void**>(&L->host_pos[i]), nb * sizeof(int32_t), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) { set_error("d4pg_learner_create: pinned staging allocation failed"); delete L; return D4PG_ECUDA; }
@@ -691,6 +707,8 @@ extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   if (L->host_losses) cudaFreeHost(L->host_losses);
   for (int i = 0; i < 2; ++i) {
     if (L->ev_h2d[i]) cudaEventDestroy(L->ev_h2d[i]);
+    if (L->ev_loss[i]) cudaEventDestroy(L->ev_loss[i]);
+    if (L->loss_ring[i]) cudaFreeHost(L->loss_ring[i]);
     if (L->host_u[i]) cudaFreeHost(L->host_u[i]);
     if (L->host_pos[i]) cudaFreeHost(L->host_pos[i]);
   }
@@ -769,8 +787,23 @@ static int step_host_common(d4pg_learner_t* L, const double* uniforms, const uin
   }
   int rc = d4pg_learner_step(L, learner_stream);
   if (rc) return rc;
+  {                                                            // this step's result, queued for d4pg_learner_fetch_losses
+    const int slot = int(L->loss_steps & 1);
+    D4PG_CUDA_OK(cudaMemcpyAsync(L->loss_ring[slot], L->buf.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, ls));
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_loss[slot], ls));
+    ++L->loss_steps;
+  }
   D4PG_CUDA_OK(cudaEventRecord(L->ev_out, ls));
   D4PG_CUDA_OK(cudaStreamWaitEvent(cs, L->ev_out, 0));
+  return D4PG_OK;
+}
+
+extern "C" int32_t d4pg_learner_fetch_losses(d4pg_learner_t* L, int32_t lag, float* out4) {
+  D4PG_REQUIRE(L && out4 && (lag == 0 || lag == 1), D4PG_EINVAL, "d4pg_learner_fetch_losses: lag must be 0 or 1");
+  D4PG_REQUIRE(L->loss_steps > lag, D4PG_ESTATE, "d4pg_learner_fetch_losses: no such step yet");
+  const int slot = int((L->loss_steps - 1 - lag) & 1);
+  D4PG_CUDA_OK(cudaEventSynchronize(L->ev_loss[slot]));
+  for (int i = 0; i < 4; ++i) out4[i] = L->loss_ring[slot][i];
   return D4PG_OK;
 }
 

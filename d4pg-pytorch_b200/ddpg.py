@@ -116,6 +116,7 @@ class _Learner(object):
         self.step_host_mt = L.d4pg_learner_step_host_mt
         self.read_losses = L.d4pg_learner_read_losses
         self.losses_out = (C.c_float * 4)()
+        self.fresh_host_step = False          # the most recent step was a train() (its losses are in the pinned ring)
         if opt_a.step_count or (ddpg.prioritized_replay and ddpg.beta_schedule.t):
             _lib.check(L.d4pg_learner_set_counters(h, opt_a.step_count,
                                                    ddpg.beta_schedule.t if ddpg.prioritized_replay else 0,
@@ -319,6 +320,7 @@ class DDPG:
             rc = L.step_host(L.handle, None, None, _lib.raw_stream(L.dev_index), L.stream_ptr)
         if rc:
             _lib.check(rc, "d4pg_learner_step_host")
+        L.fresh_host_step = True
         if self.prioritized_replay:
             self.beta_schedule.t += 1
         for opt in (self.optimizer_global_actor, self.optimizer_global_critic):
@@ -334,15 +336,24 @@ class DDPG:
         self.replayBuffer._store.flush()
         L.stream.wait_stream(torch.cuda.current_stream())
         _lib.check(_lib.lib().d4pg_learner_run(L.handle, int(n), C.c_void_p(L.stream.cuda_stream)), "d4pg_learner_run")
+        L.fresh_host_step = False
         torch.cuda.current_stream().wait_stream(L.stream)
         if self.prioritized_replay:
             self.beta_schedule.t += n
         for opt in (self.optimizer_global_actor, self.optimizer_global_critic):
             opt.step_count += n
 
-    def last_losses(self):
-        """(critic_loss, actor_loss) of the most recent train() -- synchronises on the result."""
+    def last_losses(self, lag=0):
+        """(critic_loss, actor_loss) of the most recent train() -- waits for that step's result (a 16-byte D2H copy every
+        train() queues).  `lag=1` returns the result of the train() call BEFORE the most recent one instead, which lets a
+        training loop read every step's losses without draining the GPU: `train(); losses = last_losses(lag=1)`.
+        After train_n / profile_step (no per-step copy queued) the result is read synchronously."""
         L = self._learner
+        if L.fresh_host_step:
+            rc = _lib.lib().d4pg_learner_fetch_losses(L.handle, int(lag), L.losses_out)
+            if rc:
+                _lib.check(rc, "d4pg_learner_fetch_losses")
+            return L.losses_out[0], L.losses_out[1]
         rc = L.read_losses(L.handle, L.losses_out, L.stream_ptr)       # D2H + wait: the step's result
         if rc:
             _lib.check(rc, "d4pg_learner_read_losses")
@@ -380,6 +391,7 @@ class DDPG:
                     L.positions.copy_(torch.as_tensor(np.asarray(self.replayBuffer.sample_positions(self.batch_size), dtype=np.int32)))
             _lib.check(_lib.lib().d4pg_learner_profile_step(L.handle, C.c_void_p(L.stream.cuda_stream), cap, ms, names,
                                                             stride, C.byref(n)), "d4pg_learner_profile_step")
+        L.fresh_host_step = False
         if self.prioritized_replay:
             self.beta_schedule.t += 1
         for opt in (self.optimizer_global_actor, self.optimizer_global_critic):

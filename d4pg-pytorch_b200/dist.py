@@ -85,6 +85,101 @@ class Comm(object):
         if int(flag.item()) == 0:                  # e.g. no CUDA IPC between the ranks' containers: NCCL path on every rank
             L.d4pg_comm_peer_disable(self.handle)
             return False
+        self.multicast = bool(self.setup_multicast())
+        return True
+
+    def exchange_mode(self):
+        """How the learner sums the gradient over the ranks: "nccl" (all-reduce fallback), or over peer memory "mc"
+        (in-switch reduction, multimem.ld_reduce), "pull" (every rank sums all halves) / "rs" (reduce-scatter + all-gather)."""
+        from . import _lib
+        L = _lib.lib()
+        if self.world_size <= 1:
+            return "single"
+        if not L.d4pg_comm_peer_ready(self.handle):
+            return "nccl"
+        env = os.environ.get("D4PG_COMM_MODE", "")
+        if L.d4pg_comm_mc_ready(self.handle) and env[:1] in ("", "m"):
+            return "mc"
+        return "rs" if env[:1] == "r" else "pull"
+
+    def setup_multicast(self):
+        """In-switch reduction (NVLS): one multicast object over every rank's gradient buffer, so that the fused Adam
+        kernel reads the sum over all ranks with `multimem.ld_reduce` (one NVLink hop, the NVSwitch adds).  Collective;
+        every failure mode (no NVSwitch multicast support, descriptor passing refused, sums not bit-identical across
+        ranks) leaves every rank on the peer-memory pull.  D4PG_COMM_MC=0 skips it."""
+        import socket
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.lib()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+
+        def all_ok(ok):
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return int(t.item()) == 1
+        if not all_ok(os.environ.get("D4PG_COMM_MC", "1") != "0" and L.d4pg_comm_mc_supported(self.handle) == 1):
+            return False
+        # rank 0 creates + exports the object; the file descriptor travels over an abstract-namespace Unix socket
+        name = "\0d4pg_mc_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "0"))
+        ok, srv, fd = True, None, C.c_int32(-1)
+        if self.rank == 0:
+            ok = L.d4pg_comm_mc_create(self.handle, C.byref(fd)) == 0
+            if ok:
+                try:
+                    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                    srv.bind(name)
+                    srv.listen(self.world_size)
+                except OSError:
+                    ok = False
+        if not all_ok(ok):                         # (also the rendezvous: the socket is listening from here on)
+            if srv is not None:
+                srv.close()
+            return False
+        try:
+            if self.rank == 0:
+                srv.settimeout(60)
+                for _ in range(self.world_size - 1):
+                    conn, _ = srv.accept()
+                    socket.send_fds(conn, [b"x"], [fd.value])
+                    conn.close()
+                srv.close()
+                os.close(fd.value)
+            else:
+                cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                cli.settimeout(60)
+                cli.connect(name)
+                _, fds, _, _ = socket.recv_fds(cli, 16, 1)
+                cli.close()
+                ok = len(fds) == 1 and L.d4pg_comm_mc_import(self.handle, fds[0]) == 0
+        except OSError:
+            ok = False
+        if not all_ok(ok):
+            return False
+        if not all_ok(L.d4pg_comm_mc_add_device(self.handle) == 0):      # everyone joined the team ...
+            return False
+        if not all_ok(L.d4pg_comm_mc_bind(self.handle) == 0):            # ... before anyone binds memory
+            L.d4pg_comm_mc_disable(self.handle)
+            return False
+        # self-test: every rank must read the SAME bits (replicas have to stay identical) and the right sum
+        n = 4096
+        g = torch.Generator(device="cpu").manual_seed(1234 + self.rank)
+        mine = torch.randn(n, generator=g).cuda()
+        out = torch.empty(n, dtype=torch.float32, device="cuda")
+        ok = L.d4pg_comm_mc_selftest(self.handle, _lib.ptr(mine), None, n, _lib.stream_ptr()) == 0
+        torch.cuda.synchronize()
+        dist.barrier()
+        ok = ok and L.d4pg_comm_mc_selftest(self.handle, None, _lib.ptr(out), n, _lib.stream_ptr()) == 0
+        torch.cuda.synchronize()
+        if ok:
+            parts = [torch.empty_like(out) for _ in range(self.world_size)]
+            dist.all_gather(parts, out)
+            vals = [torch.empty_like(mine) for _ in range(self.world_size)]
+            dist.all_gather(vals, mine)
+            want = torch.stack(vals).double().sum(0)
+            ok = all(torch.equal(parts[0], p) for p in parts) and float((out.double() - want).abs().max()) < 1e-4
+        if not all_ok(ok):
+            L.d4pg_comm_mc_disable(self.handle)
+            return False
         return True
 
     def allreduce_sum_(self, flat):

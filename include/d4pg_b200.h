@@ -297,6 +297,10 @@ int32_t d4pg_learner_step_host(d4pg_learner_t* h, const double* uniforms, const 
 int32_t d4pg_learner_step_host_mt(d4pg_learner_t* h, const uint32_t* mt_words,
                                   d4pg_stream_t caller_stream, d4pg_stream_t learner_stream);
 int32_t d4pg_learner_read_losses(d4pg_learner_t* h, float* out4, d4pg_stream_t learner_stream);
+/* Every d4pg_learner_step_host* call also queues an async D2H copy of its {critic loss, actor loss, -, -} into a pinned
+ * two-slot ring.  d4pg_learner_fetch_losses waits for and returns the result of the most recent host-facing step (lag 0)
+ * or of the one before it (lag 1: usually complete already, so a caller can read step k-1 while step k runs). */
+int32_t d4pg_learner_fetch_losses(d4pg_learner_t* h, int32_t lag, float* out4);
 /* n_steps back-to-back gradient steps without returning to the caller in between (device-side
  * sampling keeps advancing; caller-supplied uniforms/positions would be reused). */
 int32_t d4pg_learner_run(d4pg_learner_t* h, int32_t n_steps, d4pg_stream_t stream);
@@ -333,6 +337,23 @@ int32_t d4pg_comm_peer_alloc(d4pg_comm_t* c, int64_t n_floats, uint8_t* handle64
 int32_t d4pg_comm_peer_open(d4pg_comm_t* c, const uint8_t* all_handles /* world x 64 bytes */);
 int32_t d4pg_comm_peer_ready(const d4pg_comm_t* c);
 int32_t d4pg_comm_peer_disable(d4pg_comm_t* c);      /* collective decision: fall back to the NCCL all-reduce */
+
+/* In-switch gradient reduction (NVLS): ONE multicast object spans every rank's [2][n] gradient buffer; the fused Adam
+ * kernel then reads the sum over all ranks with multimem.ld_reduce (the NVSwitch adds) -- one NVLink hop, n floats inbound
+ * per rank whatever the rank count.  Collective setup, driven by the host binding after d4pg_comm_peer_open:
+ *   every rank: d4pg_comm_mc_supported;  rank 0: d4pg_comm_mc_create -> POSIX file descriptor, passed to the other ranks
+ *   (SCM_RIGHTS over a Unix socket) which d4pg_comm_mc_import it;  every rank: d4pg_comm_mc_add_device;  barrier;  every
+ *   rank: d4pg_comm_mc_bind (allocates its buffer, binds it, maps the unicast and the multicast view);  barrier.
+ * d4pg_comm_mc_selftest copies `src` (n floats, device) into this rank's buffer and/or writes the switch-reduced sum over
+ * all ranks to `out`; the binding uses it to check that every rank reads bit-identical sums before enabling the path. */
+int32_t d4pg_comm_mc_supported(d4pg_comm_t* c);
+int32_t d4pg_comm_mc_create(d4pg_comm_t* c, int32_t* fd_out);
+int32_t d4pg_comm_mc_import(d4pg_comm_t* c, int32_t fd);
+int32_t d4pg_comm_mc_add_device(d4pg_comm_t* c);
+int32_t d4pg_comm_mc_bind(d4pg_comm_t* c);
+int32_t d4pg_comm_mc_ready(const d4pg_comm_t* c);
+int32_t d4pg_comm_mc_disable(d4pg_comm_t* c);
+int32_t d4pg_comm_mc_selftest(d4pg_comm_t* c, const float* src, float* out, int64_t n, d4pg_stream_t stream);
 
 /* Debug: %globaltimer (ns) phase stamps written by CTA 0 of the most recent tcgen05 GEMM launch when
  * the environment variable D4PG_TC_TRACE is set (out16 = 32 x uint64, host memory). */

@@ -207,25 +207,34 @@ def test_tree_seeded_random_matches_oracle_default_uniforms(d4pg):
 
 
 def test_tree_full_size_capacity_1m(d4pg):
-    """Config-3 size: capacity 10^6 (tree 2^20), batch 1024: invariants + oracle indices."""
-    size, B = 1_000_000, 1024
-    buf = d4pg.PrioritizedReplayBuffer(size, alpha=0.6, obs_dim=4, act_dim=2)
-    n = size
-    rng = np.random.RandomState(1)
-    buf.add_batch(np.zeros((n, 4), np.float32), np.zeros((n, 2), np.float32), np.zeros(n), np.zeros((n, 4), np.float32),
-                  np.zeros(n, bool))
+    """Config 3 AS CONFIGURED (BASELINE.json configs[2]): capacity 10^6 (tree 2^20), |s| = 376, |a| = 17 (3 GB of rows),
+    batch 1024: tree invariants, oracle indices, and the gathered 3-KB rows."""
+    size, B, S, A = 1_000_000, 1024, 376, 17
+    buf = d4pg.PrioritizedReplayBuffer(size, alpha=0.6, obs_dim=S, act_dim=A)
+    dev = torch.device("cuda")
+    step = 125_000                                     # filled from device tensors in chunks; row i carries i in column 0
+    for lo in range(0, size, step):
+        ids = torch.arange(lo, lo + step, device=dev, dtype=torch.float32)
+        obs = torch.zeros(step, S, device=dev); obs[:, 0] = ids; obs[:, S - 1] = -ids
+        obs2 = torch.zeros(step, S, device=dev); obs2[:, 1] = ids
+        act = torch.zeros(step, A, device=dev); act[:, A - 1] = ids
+        buf.add_batch(obs, act, ids.double() * 0.5, obs2, torch.zeros(step, dtype=torch.bool, device=dev))
     assert len(buf) == size
-    ob = O.PrioritizedReplayOracle(size, 0.6, 4, 2)
+    ob = O.PrioritizedReplayOracle(size, 0.6, 1, 1)    # the oracle's trees only (its row storage is not needed)
     ob.length, ob.next_idx = size, 0
     ob.sum.value[ob.capacity:ob.capacity + size] = 1.0
     ob.min.value[ob.capacity:ob.capacity + size] = 1.0
     ob.sum.rebuild(); ob.min.rebuild()
     assert np.array_equal(buf._it_sum.values(), ob.sum.value)
+    rng = np.random.RandomState(1)
     for rnd in range(3):
         us = rng.rand(B)
         out = buf.sample(B, 0.4, uniforms=us)
         idx = ob.sample_indices(us)
         assert np.array_equal(np.array(out[6]), idx)
+        fi = idx.astype(np.float32)
+        assert np.array_equal(out[0][:, 0], fi) and np.array_equal(out[0][:, S - 1], -fi) and np.array_equal(out[3][:, 1], fi)
+        assert np.array_equal(out[1][:, A - 1], fi) and np.array_equal(np.asarray(out[2]).reshape(-1), idx * 0.5)
         pr = (rng.rand(B).astype(np.float32) + np.float32(1e-6))
         buf.update_priorities(out[6], pr)
         ob.update_priorities(idx, pr)
