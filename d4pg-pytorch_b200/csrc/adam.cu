@@ -39,7 +39,7 @@ int launch_adam(const AdamArgs& a_in, cudaStream_t st) {
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   D4PG_MAX_CARVEOUT(adam_polyak_kernel);
-  const int tail = (a.clock || a.loss_out) ? 1 : 0;
+  const int tail = ((a.clock || a.loss_out) && !a.skip_tail) ? 1 : 0;
   D4PG_CUDA_OK(launch_pdl(adam_polyak_kernel, dim3(blocks, a.nseg + tail), dim3(256), 0, st, a));
   return D4PG_OK;
 }

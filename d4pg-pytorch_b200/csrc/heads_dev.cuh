@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) heads_kernel(const HeadsArgs 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * HEAD_WARPS + warp;            // warps [0, B): critic part of row g; [B, 2B): policy head of row g - B
   step_stamp(a.trace, 2);
-  if (g < a.B) heads_row<MODE, NT>(a, g, lane, ws[warp], 1);
+  if (a.only_policy) { if (g < a.B) heads_row<MODE, NT>(a, g, lane, ws[warp], 2); }
+  else if (g < a.B) heads_row<MODE, NT>(a, g, lane, ws[warp], 1);
   else if (g < 2 * a.B) heads_row<MODE, NT>(a, g - a.B, lane, ws[warp], 2);
   step_stamp(a.trace, 2 + 16);
   if (a.sampler_clock && blockIdx.x == 0 && threadIdx.x == 0) {

@@ -22,6 +22,7 @@ struct HeadsArgs {
   int ce_priority;           // 1: priority = CE_i + eps instead of |sum_j m_ij q_ij| + eps
   int pdl;                   // programmatic-dependent-launch trigger position (0/1/2)
   unsigned long long* trace;
+  int only_policy;               // 1: only the policy head (pi_rows, dlogits_pi) -- the second loss launch of the post-update-critic plan
   LearnerClock* sampler_clock;   // prefetch pipeline: thread 0 advances the sampler's counters (after sample(k), before sample(k+1))
 };
 int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st);

@@ -189,6 +189,112 @@ static int tcc_setup(d4pg_learner* L) {
   return D4PG_OK;
 }
 
+// ---- tcgen05 chain builders (mlp_tc_chain.cu) ----------------------------------------------------------------------
+struct TccCtx {
+  d4pg_learner* L; const Workspace* w; const NetDims* da; const NetDims* dc;
+  const float *Wa, *Wat, *Wc, *Wct;
+  int B, S, A, N, Sp, Ap, Np;
+};
+// T: actor_target(s') -> critic_target(s', .)   (fc1 of both networks share the resident s' chunk)     ddpg.py:205-206
+static void tcc_build_T(TccArgs& fa, int ci, const TccCtx& x) {
+  const TccImage* U = x.L->tcc_img; const Workspace& w = *x.w; const NetDims& da = *x.da; const NetDims& dc = *x.dc;
+  const int H = D4PG_HIDDEN;
+  int l, p1, p2, pa;
+  tcc_chain_x0(fa, ci, w.s2, x.Sp, x.S);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_x(fa, ci, l);
+  p1 = tcc_slot_group(fa, ci, l, U[U_AT_F1], EPI_BIAS_RELU, x.Wat + da.b_off[0], nullptr, 0, nullptr, H, 1);
+  p2 = tcc_slot_group(fa, ci, l, U[U_CT_F1], EPI_BIAS_RELU, x.Wct + dc.b_off[0], nullptr, 0, nullptr, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  p1 = tcc_slot_group(fa, ci, l, U[U_AT_F2], EPI_BIAS, x.Wat + da.b_off[1], nullptr, 0, nullptr, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  p1 = tcc_slot_group(fa, ci, l, U[U_AT_F22], EPI_BIAS_RELU, x.Wat + da.b_off[2], nullptr, 0, nullptr, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  pa = tcc_slot_group(fa, ci, l, U[U_AT_F3], EPI_BIAS_TANH, x.Wat + da.b_off[3], nullptr, 0, w.out[0], x.Ap, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p2, 8); tcc_slot_src_plane(fa, ci, l, pa, 1);
+  p1 = tcc_slot_group(fa, ci, l, U[U_CT_F2], EPI_BIAS_RELU, x.Wct + dc.b_off[1], nullptr, 0, nullptr, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  p1 = tcc_slot_group(fa, ci, l, U[U_CT_F22], EPI_BIAS_RELU, x.Wct + dc.b_off[2], nullptr, 0, nullptr, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  tcc_slot_group(fa, ci, l, U[U_CT_F3], EPI_BIAS, x.Wct + dc.b_off[3], nullptr, 0, w.out[1], x.Np, 0);
+}
+// the actor's four layers on s (outputs kept row-major for its backward pass); returns the plane of its action output
+static int tcc_build_actor(TccArgs& fa, int ci, const TccCtx& x, int* critic_h1_plane) {
+  const TccImage* U = x.L->tcc_img; const Workspace& w = *x.w; const NetDims& da = *x.da; const NetDims& dc = *x.dc;
+  const int H = D4PG_HIDDEN;
+  int l, p1;
+  tcc_chain_x0(fa, ci, w.s, x.Sp, x.S);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_x(fa, ci, l);
+  p1 = tcc_slot_group(fa, ci, l, U[U_A_F1], EPI_BIAS_RELU, x.Wa + da.b_off[0], nullptr, 0, w.h1[3], H, 1);
+  if (critic_h1_plane)       // critic fc1 on the same resident s chunk (h1 of critic(s, actor(s)); same values as chain Q's)
+    *critic_h1_plane = tcc_slot_group(fa, ci, l, U[U_C_F1], EPI_BIAS_RELU, x.Wc + dc.b_off[0], nullptr, 0, nullptr, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  p1 = tcc_slot_group(fa, ci, l, U[U_A_F2], EPI_BIAS, x.Wa + da.b_off[1], nullptr, 0, w.h2[3], H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  p1 = tcc_slot_group(fa, ci, l, U[U_A_F22], EPI_BIAS_RELU, x.Wa + da.b_off[2], nullptr, 0, w.h3[3], H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  return tcc_slot_group(fa, ci, l, U[U_A_F3], EPI_BIAS_TANH, x.Wa + da.b_off[3], nullptr, 0, w.out[3], x.Ap, 1);
+}
+// P: actor(s) -> critic(s, actor(s))                                                                     ddpg.py:236-238
+static void tcc_build_P(TccArgs& fa, int ci, const TccCtx& x) {
+  const TccImage* U = x.L->tcc_img; const Workspace& w = *x.w; const NetDims& dc = *x.dc;
+  const int H = D4PG_HIDDEN;
+  int l, p1, p2 = -1;
+  const int pa = tcc_build_actor(fa, ci, x, &p2);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p2, 8); tcc_slot_src_plane(fa, ci, l, pa, 1);
+  p1 = tcc_slot_group(fa, ci, l, U[U_C_F2], EPI_BIAS_RELU, x.Wc + dc.b_off[1], nullptr, 0, w.h2[4], H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  p1 = tcc_slot_group(fa, ci, l, U[U_C_F22], EPI_BIAS_RELU, x.Wc + dc.b_off[2], nullptr, 0, w.h3[4], H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  tcc_slot_group(fa, ci, l, U[U_C_F3], EPI_BIAS, x.Wc + dc.b_off[3], nullptr, 0, w.out[4], x.Np, 0);
+}
+// critic(s, `act`): the resident chunk holds s for fc1, then the action rows (fc2's K tail)                ddpg.py:208
+static void tcc_build_Q(TccArgs& fa, int ci, const TccCtx& x, const float* act, float* h1, float* h2, float* h3, float* logits) {
+  const TccImage* U = x.L->tcc_img; const Workspace& w = *x.w; const NetDims& dc = *x.dc;
+  const int H = D4PG_HIDDEN;
+  int l, p1;
+  tcc_chain_x0(fa, ci, w.s, x.Sp, x.S);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_x(fa, ci, l); tcc_slot_reconvert_x(fa, ci, l, act, x.Ap, x.A);
+  p1 = tcc_slot_group(fa, ci, l, U[U_C_F1], EPI_BIAS_RELU, x.Wc + dc.b_off[0], nullptr, 0, h1, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8); tcc_slot_src_x(fa, ci, l);
+  p1 = tcc_slot_group(fa, ci, l, U[U_C_F2], EPI_BIAS_RELU, x.Wc + dc.b_off[1], nullptr, 0, h2, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  p1 = tcc_slot_group(fa, ci, l, U[U_C_F22], EPI_BIAS_RELU, x.Wc + dc.b_off[2], nullptr, 0, h3, H, 1);
+  l = tcc_slot_begin(fa, ci); tcc_slot_src_plane(fa, ci, l, p1, 8);
+  tcc_slot_group(fa, ci, l, U[U_C_F3], EPI_BIAS, x.Wc + dc.b_off[3], nullptr, 0, logits, x.Np, 0);
+}
+// C: critic loss, dlogits_q -> fc3 -> fc2_2 -> fc2[:, :H]                                                  ddpg.py:230
+static void tcc_build_bwd_C(TccArgs& ba, int ci, const TccCtx& x) {
+  const TccImage* U = x.L->tcc_img; const Workspace& w = *x.w;
+  const int H = D4PG_HIDDEN;
+  int l, p1;
+  tcc_chain_pre(ba, ci, w.dlogits_q, x.Np, x.N);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_pre(ba, ci, l);
+  p1 = tcc_slot_group(ba, ci, l, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[2], H, w.c_dz22, H, 1);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_plane(ba, ci, l, p1, 8);
+  p1 = tcc_slot_group(ba, ci, l, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[2], H, w.c_dz2, H, 1);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_plane(ba, ci, l, p1, 8);
+  tcc_slot_group(ba, ci, l, U[U_C_D2H], EPI_RELU_MASK, nullptr, w.h1[2], H, w.c_dz1, H, 0);
+}
+// P: policy loss, dlogits_pi -> critic fc3 -> fc2_2 -> fc2[:, H:] (d action, tanh') -> actor fc3 -> fc2_2 -> fc2   ddpg.py:242
+static void tcc_build_bwd_P(TccArgs& ba, int ci, const TccCtx& x) {
+  const TccImage* U = x.L->tcc_img; const Workspace& w = *x.w;
+  const int H = D4PG_HIDDEN;
+  int l, p1;
+  tcc_chain_pre(ba, ci, w.dlogits_pi, x.Np, x.N);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_pre(ba, ci, l);
+  p1 = tcc_slot_group(ba, ci, l, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[4], H, nullptr, H, 1);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_plane(ba, ci, l, p1, 8);
+  p1 = tcc_slot_group(ba, ci, l, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[4], H, nullptr, H, 1);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_plane(ba, ci, l, p1, 8);
+  p1 = tcc_slot_group(ba, ci, l, U[U_C_D2A], EPI_TANH_MASK, nullptr, w.out[3], x.Ap, w.a_dz3, x.Ap, 1);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_plane(ba, ci, l, p1, 1);
+  p1 = tcc_slot_group(ba, ci, l, U[U_A_D3], EPI_RELU_MASK, nullptr, w.h3[3], H, w.a_dz22, H, 1);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_plane(ba, ci, l, p1, 8);
+  p1 = tcc_slot_group(ba, ci, l, U[U_A_D22], EPI_NONE, nullptr, nullptr, 0, w.a_dh2, H, 1);
+  l = tcc_slot_begin(ba, ci); tcc_slot_src_plane(ba, ci, l, p1, 8);
+  tcc_slot_group(ba, ci, l, U[U_A_D2], EPI_RELU_MASK, nullptr, w.h1[3], H, w.a_dz1, H, 0);
+}
+
 // idempotent launches (pure functions of their inputs) are repeated in profile mode
 constexpr int PROFILE_REPS = 16;
 
@@ -242,6 +348,11 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
   GemmBatch g;
   const int plan = step_plan(c);
   const bool tcc = plan == 1 && c.precision >= 1 && L->tcc_ok;       // tcgen05 cluster chains
+  // corrected-semantics switch (loss_flags & 4): the actor gradient goes through the critic AFTER this
+  // step's critic update (the reference uses the stale local copy, ddpg.py:229-247).  Two half steps: critic forward /
+  // loss / backward / Adam, then the policy pass through the updated critic, actor backward / Adam.
+  const bool h7 = (c.loss_flags & 4) != 0;
+  D4PG_REQUIRE(!h7 || (tcc && c.world_size <= 1), D4PG_ENOTSUP, "post-update-critic actor gradient needs the tcgen05 chain plan (precision tf32x3 / tf32, chain plan, batch <= 512) on one GPU");
   const bool chain = plan == 1 && !tcc;
   static const bool no_pre = getenv("D4PG_NO_PRE") != nullptr;          // A/B switch
   const bool pre_ok = chain && c.precision == 0 && A <= 8 && !no_pre;   // pre-layers: fp32 tile, |a| <= 8
@@ -257,51 +368,11 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
     const TccImage* U = L->tcc_img;
     TccArgs& fa = L->tcc_fwd_args;
     tcc_args_begin(fa, B, reinterpret_cast<uint8_t*>(w.xchg), c.precision == 1 ? 3 : 1); fa.step_slot = 1;
-    int l, p1, p2, pa;
-    // chain 0  T: actor_target(s') -> critic_target(s', .)   (fc1 of both networks share the resident s' chunk)
-    tcc_chain_x0(fa, 0, w.s2, Sp, S);
-    l = tcc_slot_begin(fa, 0); tcc_slot_src_x(fa, 0, l);
-    p1 = tcc_slot_group(fa, 0, l, U[U_AT_F1], EPI_BIAS_RELU, Wat + da.b_off[0], nullptr, 0, nullptr, H, 1);
-    p2 = tcc_slot_group(fa, 0, l, U[U_CT_F1], EPI_BIAS_RELU, Wct + dc.b_off[0], nullptr, 0, nullptr, H, 1);
-    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    p1 = tcc_slot_group(fa, 0, l, U[U_AT_F2], EPI_BIAS, Wat + da.b_off[1], nullptr, 0, nullptr, H, 1);
-    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    p1 = tcc_slot_group(fa, 0, l, U[U_AT_F22], EPI_BIAS_RELU, Wat + da.b_off[2], nullptr, 0, nullptr, H, 1);
-    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    pa = tcc_slot_group(fa, 0, l, U[U_AT_F3], EPI_BIAS_TANH, Wat + da.b_off[3], nullptr, 0, w.out[0], Ap, 1);
-    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p2, 8); tcc_slot_src_plane(fa, 0, l, pa, 1);
-    p1 = tcc_slot_group(fa, 0, l, U[U_CT_F2], EPI_BIAS_RELU, Wct + dc.b_off[1], nullptr, 0, nullptr, H, 1);
-    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    p1 = tcc_slot_group(fa, 0, l, U[U_CT_F22], EPI_BIAS_RELU, Wct + dc.b_off[2], nullptr, 0, nullptr, H, 1);
-    l = tcc_slot_begin(fa, 0); tcc_slot_src_plane(fa, 0, l, p1, 8);
-    tcc_slot_group(fa, 0, l, U[U_CT_F3], EPI_BIAS, Wct + dc.b_off[3], nullptr, 0, w.out[1], Np, 0);
-    // chain 1  P: actor(s) -> critic(s, actor(s))
-    tcc_chain_x0(fa, 1, w.s, Sp, S);
-    l = tcc_slot_begin(fa, 1); tcc_slot_src_x(fa, 1, l);
-    p1 = tcc_slot_group(fa, 1, l, U[U_A_F1], EPI_BIAS_RELU, Wa + da.b_off[0], nullptr, 0, w.h1[3], H, 1);
-    p2 = tcc_slot_group(fa, 1, l, U[U_C_F1], EPI_BIAS_RELU, Wc + dc.b_off[0], nullptr, 0, nullptr, H, 1);
-    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    p1 = tcc_slot_group(fa, 1, l, U[U_A_F2], EPI_BIAS, Wa + da.b_off[1], nullptr, 0, w.h2[3], H, 1);
-    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    p1 = tcc_slot_group(fa, 1, l, U[U_A_F22], EPI_BIAS_RELU, Wa + da.b_off[2], nullptr, 0, w.h3[3], H, 1);
-    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    pa = tcc_slot_group(fa, 1, l, U[U_A_F3], EPI_BIAS_TANH, Wa + da.b_off[3], nullptr, 0, w.out[3], Ap, 1);
-    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p2, 8); tcc_slot_src_plane(fa, 1, l, pa, 1);
-    p1 = tcc_slot_group(fa, 1, l, U[U_C_F2], EPI_BIAS_RELU, Wc + dc.b_off[1], nullptr, 0, w.h2[4], H, 1);
-    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    p1 = tcc_slot_group(fa, 1, l, U[U_C_F22], EPI_BIAS_RELU, Wc + dc.b_off[2], nullptr, 0, w.h3[4], H, 1);
-    l = tcc_slot_begin(fa, 1); tcc_slot_src_plane(fa, 1, l, p1, 8);
-    tcc_slot_group(fa, 1, l, U[U_C_F3], EPI_BIAS, Wc + dc.b_off[3], nullptr, 0, w.out[4], Np, 0);
-    // chain 2  Q: critic(s, a): the resident chunk holds s for fc1, then the replay actions (fc2's K tail)
-    tcc_chain_x0(fa, 2, w.s, Sp, S);
-    l = tcc_slot_begin(fa, 2); tcc_slot_src_x(fa, 2, l); tcc_slot_reconvert_x(fa, 2, l, w.a, Ap, A);
-    p1 = tcc_slot_group(fa, 2, l, U[U_C_F1], EPI_BIAS_RELU, Wc + dc.b_off[0], nullptr, 0, w.h1[2], H, 1);
-    l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8); tcc_slot_src_x(fa, 2, l);
-    p1 = tcc_slot_group(fa, 2, l, U[U_C_F2], EPI_BIAS_RELU, Wc + dc.b_off[1], nullptr, 0, w.h2[2], H, 1);
-    l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8);
-    p1 = tcc_slot_group(fa, 2, l, U[U_C_F22], EPI_BIAS_RELU, Wc + dc.b_off[2], nullptr, 0, w.h3[2], H, 1);
-    l = tcc_slot_begin(fa, 2); tcc_slot_src_plane(fa, 2, l, p1, 8);
-    tcc_slot_group(fa, 2, l, U[U_C_F3], EPI_BIAS, Wc + dc.b_off[3], nullptr, 0, w.out[2], Np, 0);
+    TccCtx cx{L, &w, &da, &dc, Wa, Wat, Wc, Wct, B, S, A, N, Sp, Ap, Np};
+    tcc_build_T(fa, 0, cx);                                      // chain 0  T: actor_target(s') -> critic_target(s', .)
+    if (h7) tcc_build_actor(fa, 1, cx, nullptr);                 // chain 1  (post-update plan) the actor alone; the critic pass follows the critic's Adam
+    else tcc_build_P(fa, 1, cx);                                 // chain 1  P: actor(s) -> critic(s, actor(s))
+    tcc_build_Q(fa, 2, cx, w.a, w.h1[2], w.h2[2], w.h3[2], w.out[2]);   // chain 2  Q: critic(s, a)
     RUN(launch_mlp_tc_chain(fa, st));
   } else if (chain) {
     // 2'. the three forward chains of the step as ONE cluster launch (mlp_chain.cu):
@@ -400,7 +471,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
 
   // 3. heads: softmaxes, projection, CE loss, td, priorities, logit gradients (ddpg.py:214-222,236-238)
   HeadsArgs ha{};
-  ha.target_logits = w.out[1]; ha.q_logits = w.out[2]; ha.pi_logits = w.out[4];
+  ha.target_logits = w.out[1]; ha.q_logits = w.out[2]; ha.pi_logits = h7 ? nullptr : w.out[4];
   ha.rewards = w.r; ha.dones = w.done; ha.B = B; ha.N = N; ha.flags = 0; ha.ld = Np;
   ha.v_min = c.v_min; ha.v_max = c.v_max; ha.delta = (c.v_max - c.v_min) / double(N - 1);
   // live projection discounts with gamma even for n_steps>1; mode 1 uses gamma**n (ddpg.py:24)
@@ -457,27 +528,9 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
     D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join2, 0));       // transposed weight images are packed
     TccArgs& ba = L->tcc_bwd_args;
     tcc_args_begin(ba, B, reinterpret_cast<uint8_t*>(w.xchg), c.precision == 1 ? 3 : 1); ba.step_slot = 5;
-    int l, p1;
-    tcc_chain_pre(ba, 0, w.dlogits_q, Np, N);                     // C: critic loss
-    l = tcc_slot_begin(ba, 0); tcc_slot_src_pre(ba, 0, l);
-    p1 = tcc_slot_group(ba, 0, l, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[2], H, w.c_dz22, H, 1);
-    l = tcc_slot_begin(ba, 0); tcc_slot_src_plane(ba, 0, l, p1, 8);
-    p1 = tcc_slot_group(ba, 0, l, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[2], H, w.c_dz2, H, 1);
-    l = tcc_slot_begin(ba, 0); tcc_slot_src_plane(ba, 0, l, p1, 8);
-    tcc_slot_group(ba, 0, l, U[U_C_D2H], EPI_RELU_MASK, nullptr, w.h1[2], H, w.c_dz1, H, 0);
-    tcc_chain_pre(ba, 1, w.dlogits_pi, Np, N);                    // P: policy loss (PRE-update critic weights)
-    l = tcc_slot_begin(ba, 1); tcc_slot_src_pre(ba, 1, l);
-    p1 = tcc_slot_group(ba, 1, l, U[U_C_D3], EPI_RELU_MASK, nullptr, w.h3[4], H, nullptr, H, 1);
-    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
-    p1 = tcc_slot_group(ba, 1, l, U[U_C_D22], EPI_RELU_MASK, nullptr, w.h2[4], H, nullptr, H, 1);
-    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
-    p1 = tcc_slot_group(ba, 1, l, U[U_C_D2A], EPI_TANH_MASK, nullptr, w.out[3], Ap, w.a_dz3, Ap, 1);
-    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 1);
-    p1 = tcc_slot_group(ba, 1, l, U[U_A_D3], EPI_RELU_MASK, nullptr, w.h3[3], H, w.a_dz22, H, 1);
-    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
-    p1 = tcc_slot_group(ba, 1, l, U[U_A_D22], EPI_NONE, nullptr, nullptr, 0, w.a_dh2, H, 1);
-    l = tcc_slot_begin(ba, 1); tcc_slot_src_plane(ba, 1, l, p1, 8);
-    tcc_slot_group(ba, 1, l, U[U_A_D2], EPI_RELU_MASK, nullptr, w.h1[3], H, w.a_dz1, H, 0);
+    TccCtx cx{L, &w, &da, &dc, Wa, Wat, Wc, Wct, B, S, A, N, Sp, Ap, Np};
+    tcc_build_bwd_C(ba, 0, cx);                                  // C: critic loss
+    if (!h7) tcc_build_bwd_P(ba, 1, cx);                         // P: policy loss (PRE-update critic weights)
     RUN(launch_mlp_tc_chain(ba, st));
   }
   if (chain) {
@@ -513,13 +566,13 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
     gemm_wide_begin(gw, peer_mode ? &sig1 : nullptr);              // its last CTA signals the peers
     gemm_wide_add(gw, gemm_dw(w.c_dz22, H, w.h2[2], H, Gc + dc.w_off[2], lc[2], Gc + dc.b_off[2], H, H, B));
     gemm_wide_add(gw, gemm_dw(w.c_dz2, H, w.h1[2], H, Gc + dc.w_off[1], lc[1], Gc + dc.b_off[1], H, H, B));
-    gemm_wide_add(gw, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], la[2], Ga + da.b_off[2], H, H, B));
-    gemm_wide_add(gw, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], la[1], Ga + da.b_off[1], H, H, B));
+    if (!h7) gemm_wide_add(gw, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], la[2], Ga + da.b_off[2], H, H, B));
+    if (!h7) gemm_wide_add(gw, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], la[1], Ga + da.b_off[1], H, H, B));
     gemm_wide_add(gw, gemm_dw(w.dlogits_q, Np, w.h3[2], H, Gc + dc.w_off[3], lc[3], Gc + dc.b_off[3], N, H, B));
     gemm_wide_add(gw, gemm_dw(w.c_dz2, H, w.a, Ap, Gc + dc.w_off[1] + H, lc[1], nullptr, H, A, B));
     gemm_wide_add(gw, gemm_dw(w.c_dz1, H, w.s, Sp, Gc + dc.w_off[0], lc[0], Gc + dc.b_off[0], H, S, B));
-    gemm_wide_add(gw, gemm_dw(w.a_dz3, Ap, w.h3[3], H, Ga + da.w_off[3], la[3], Ga + da.b_off[3], A, H, B));
-    gemm_wide_add(gw, gemm_dw(w.a_dz1, H, w.s, Sp, Ga + da.w_off[0], la[0], Ga + da.b_off[0], H, S, B));
+    if (!h7) gemm_wide_add(gw, gemm_dw(w.a_dz3, Ap, w.h3[3], H, Ga + da.w_off[3], la[3], Ga + da.b_off[3], A, H, B));
+    if (!h7) gemm_wide_add(gw, gemm_dw(w.a_dz1, H, w.s, Sp, Ga + da.w_off[0], la[0], Ga + da.b_off[0], H, S, B));
     RUN(gemm_wide_launch(gw, st));
   } else {
   // 5. backward.  "c_" = critic-loss pass, "p_" = policy pass through the critic, "a_" = actor.
@@ -620,7 +673,35 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
   aa.pipe_slot = pf ? par : -1;
   // tail slice of the same launch: reported batch-mean losses + advance the device clock
   aa.loss_rows = w.loss_rows; aa.pi_rows = w.pi_rows; aa.B = B; aa.inv_count = 1.0f / float(B); aa.loss_out = b.losses;
-  RUN(launch_adam(aa, st));
+  if (h7) {
+    // ---- post-update-critic plan, second half ---------------------------------------------------------------------
+    AdamArgs ac = aa;                                            // critic update alone (writes the critic's forward images too)
+    ac.seg[0] = aa.seg[1]; ac.nseg = 1; ac.skip_tail = 1;
+    RUN(launch_adam(ac, st));
+    RUN(launch_tcc_pack(L->tcc_pack_dx, st));                    // transposed images of the UPDATED critic for the policy backward
+    TccCtx cx{L, &w, &da, &dc, Wa, Wat, Wc, Wct, B, S, A, N, Sp, Ap, Np};
+    TccArgs& fb = L->tcc_fwd_args;
+    tcc_args_begin(fb, B, reinterpret_cast<uint8_t*>(w.xchg), c.precision == 1 ? 3 : 1); fb.step_slot = 1;
+    tcc_build_Q(fb, 0, cx, w.out[3], nullptr, w.h2[4], w.h3[4], w.out[4]);      // critic(s, actor(s)) with the new critic weights
+    RUN(launch_mlp_tc_chain(fb, st));
+    HeadsArgs hp = ha;
+    hp.pi_logits = w.out[4]; hp.only_policy = 1; hp.sampler_clock = nullptr;
+    RUN(launch_heads(hp, c.proj_mode, st));
+    TccArgs& bb = L->tcc_bwd_args;
+    tcc_args_begin(bb, B, reinterpret_cast<uint8_t*>(w.xchg), c.precision == 1 ? 3 : 1); bb.step_slot = 5;
+    tcc_build_bwd_P(bb, 0, cx);
+    RUN(launch_mlp_tc_chain(bb, st));
+    GemmWideBatch& gw = L->dw_batch;
+    gemm_wide_begin(gw, nullptr);
+    gemm_wide_add(gw, gemm_dw(w.a_dz22, H, w.h2[3], H, Ga + da.w_off[2], la[2], Ga + da.b_off[2], H, H, B));
+    gemm_wide_add(gw, gemm_dw(w.a_dh2, H, w.h1[3], H, Ga + da.w_off[1], la[1], Ga + da.b_off[1], H, H, B));
+    gemm_wide_add(gw, gemm_dw(w.a_dz3, Ap, w.h3[3], H, Ga + da.w_off[3], la[3], Ga + da.b_off[3], A, H, B));
+    gemm_wide_add(gw, gemm_dw(w.a_dz1, H, w.s, Sp, Ga + da.w_off[0], la[0], Ga + da.b_off[0], H, S, B));
+    RUN(gemm_wide_launch(gw, st));
+    AdamArgs ab = aa;                                            // actor update + the step's tail (loss means, clock)
+    ab.nseg = 1;
+    RUN(launch_adam(ab, st));
+  } else RUN(launch_adam(aa, st));
   if (c.prioritized || pf) D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_join, 0));
 #undef LEVEL
 #undef RUN
@@ -644,6 +725,9 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
                "d4pg_learner_create: precision %d unknown (0 fp32 FFMA, 1 3xTF32 tcgen05, 2 TF32 tcgen05)", cfg->precision);
   D4PG_REQUIRE(cfg->world_size <= 1 || comm, D4PG_EINVAL, "d4pg_learner_create: world_size>1 needs a communicator");
   D4PG_REQUIRE(cfg->chain == 0 || cfg->chain == 1, D4PG_EINVAL, "d4pg_learner_create: chain must be 0 or 1");
+  D4PG_REQUIRE(!(cfg->loss_flags & 4) || (tcc_shapes_ok(*cfg) && cfg->world_size <= 1), D4PG_ENOTSUP,
+               "d4pg_learner_create: loss_flags & 4 (post-update-critic actor gradient) needs the tcgen05 chain plan: precision 1/2, chain 1, "
+               "batch <= 512, obs_dim <= 32, act_dim <= 32, on one GPU");
   D4PG_REQUIRE(buf->actor && buf->actor_target && buf->critic && buf->critic_target && buf->grad_actor && buf->grad_critic &&
                buf->adam_m_actor && buf->adam_v_actor && buf->adam_m_critic && buf->adam_v_critic &&
                buf->idx && buf->prio && buf->td && buf->losses && buf->workspace, D4PG_EINVAL,

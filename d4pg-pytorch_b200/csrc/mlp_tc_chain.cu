@@ -629,7 +629,7 @@ int tcc_slot_group(TccArgs& a, int c, int slot, const TccImage& img, int epi, co
 int launch_mlp_tc_chain(TccArgs& a, cudaStream_t st) {
   D4PG_REQUIRE(a.nchains > 0 && a.nchains <= TCC_MAX_CHAINS, D4PG_EINVAL, "launch_mlp_tc_chain: %d chains", a.nchains);
   D4PG_REQUIRE(a.passes == 1 || a.passes == 3, D4PG_EINVAL, "launch_mlp_tc_chain: passes %d", a.passes);
-  static const int gmax = [] { const char* e = getenv("D4PG_TCC_GROUP"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+  static const int gmax = [] { const char* e = getenv("D4PG_TCC_GROUP"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   for (int c = 0; c < a.nchains; ++c) {
     TccChain& ch = a.chain[c];
     bool x_clobbered = false;

@@ -22,7 +22,7 @@ int launch_heads(const HeadsArgs& a_in, int mode, cudaStream_t st) {
   HeadsArgs a = a_in;
   a.pdl = pdl_mode();
   a.trace = (a.sampler_clock && debug_trace_buffer()) ? debug_trace_buffer() + STEP_TRACE_BASE : nullptr;
-  dim3 grid(cdiv((a.pi_logits ? 2 : 1) * a.B, HEAD_WARPS)), block(HEAD_WARPS * 32);   // policy heads on warps of their own
+  dim3 grid(cdiv(((a.pi_logits && !a.only_policy) ? 2 : 1) * a.B, HEAD_WARPS)), block(HEAD_WARPS * 32);   // policy heads on warps of their own
   D4PG_MAX_CARVEOUT((heads_kernel<0, 2>)); D4PG_MAX_CARVEOUT((heads_kernel<1, 2>));
   D4PG_MAX_CARVEOUT((heads_kernel<0, 4>)); D4PG_MAX_CARVEOUT((heads_kernel<1, 4>));
   // NT = atom slots per lane: 2 covers N<=64 (51 atoms), 4 covers N<=128 (101 atoms)
@@ -61,6 +61,6 @@ extern "C" int32_t d4pg_proj_loss(const float* target_logits, const float* q_log
   a.m = m; a.bins_l = bins_l; a.bins_u = bins_u; a.target_probs = target_probs; a.q_probs = q_probs;
   a.loss_rows = loss_rows; a.td = td; a.prio = prio; a.dlogits_q = dlogits_q;
   a.pi_rows = pi_rows; a.dlogits_pi = dlogits_pi;
-  a.is_weights = nullptr; a.ce_priority = 0;
+  a.is_weights = nullptr; a.ce_priority = 0; a.only_policy = 0;
   return launch_heads(a, proj_mode, as_stream(stream));
 }

@@ -70,7 +70,8 @@ class _Learner(object):
         cfg.philox_seed = int(ddpg.philox_seed)
         cfg.world_size = ddpg.comm.world_size if ddpg.comm is not None else 1
         cfg.use_graph = 1 if ddpg.use_graph else 0
-        cfg.loss_flags = (1 if ddpg.importance_weighted else 0) | (2 if ddpg.priority == "ce" else 0)
+        cfg.loss_flags = ((1 if ddpg.importance_weighted else 0) | (2 if ddpg.priority == "ce" else 0) |
+                          (4 if ddpg.actor_critic == "post_update" else 0))
         # plan 1: fp32 = FFMA chain tiles; tf32x3 / tf32 = tcgen05 chain tiles (mlp_tc_chain.cu); plan 0: one launch per level
         cfg.chain = {"levels": 0, "cluster": 1, False: 0, True: 1, 0: 0, 1: 1}[ddpg.chain]
         cfg.prefetch = 1 if (ddpg.prefetch and cfg.sample_mode == 1) else 0
@@ -157,7 +158,7 @@ class DDPG:
                  # ---- B200 build extensions (keyword-only in spirit; reference callers never pass them)
                  device=None, sampling="reference", projection="reference", precision="fp32",
                  use_graph=True, philox_seed=0, comm=None, chain="cluster", prefetch=True,
-                 importance_weighted=False, priority="reference"):
+                 importance_weighted=False, priority="reference", actor_critic="reference"):
         self.gamma = gamma
         self.n_steps = n_steps
         self.n_step_gamma = self.gamma ** self.n_steps
@@ -177,8 +178,11 @@ class DDPG:
         # device-side sampling only: step t already samples batch t+1 behind its own backward pass (identical results)
         self.prefetch = prefetch
         # corrected-semantics switches (default = the reference's behaviour)
-        assert priority in ("reference", "ce")
+        assert priority in ("reference", "ce") and actor_critic in ("reference", "post_update")
         self.importance_weighted, self.priority = bool(importance_weighted), priority
+        # "post_update": the actor gradient flows through the critic AFTER this step's critic update (corrected SURVEY.md
+        # H7); "reference": through the stale pre-update copy, as ddpg.py:229-247 does.  tcgen05 chain plan, one GPU.
+        self.actor_critic = actor_critic
 
         self.dist_type = critic_dist_info["type"]
         if self.dist_type != "categorical":

@@ -245,7 +245,9 @@ typedef struct {
   int32_t loss_flags;         /* corrected-semantics switches, 0 = reference behaviour:
                                  1 = importance-weighted critic CE (the reference samples the weights but
                                      ignores them, ddpg.py:217), 2 = priority = CE_i + eps instead of
-                                     |sum_j m_ij q_ij| + eps (ddpg.py:221-222,253) */
+                                     |sum_j m_ij q_ij| + eps (ddpg.py:221-222,253), 4 = the actor gradient flows
+                                     through the critic AFTER this step's critic update (the reference uses the stale
+                                     pre-update local copy, ddpg.py:229-247); needs the tcgen05 chain plan, one GPU */
   int32_t chain;              /* step plan of the MLP passes (batches above 512 rows always use plan 0): 0 = one grouped launch per dependency
                                  level (18 kernels/step); 1 = cluster-fused layer chains: forward passes, dX passes
                                  and all dW are ONE launch each (7 kernels/step; precision 0: FFMA tiles, bit-identical

@@ -548,11 +548,13 @@ class LearnerOracle:
         return project_nstep(target_probs, r, done, self.v_min, self.v_max,
                              self.n_atoms, self.gamma, self.n_steps).astype(F32)
 
-    def train_step(self, s, a, r, s2, done, grad_hook=None, is_weights=None, ce_priority=False):
+    def train_step(self, s, a, r, s2, done, grad_hook=None, is_weights=None, ce_priority=False, post_update_critic=False):
         """One `DDPG.train` body on a given batch.  `grad_hook(flat_grads)` lets a
         data-parallel test average gradients across ranks before Adam.
-        `is_weights` / `ce_priority` are the corrected-semantics variants of SURVEY.md section 8f.4
-        (DERIVED oracle: the reference implements neither, ddpg.py:217,221-222)."""
+        `is_weights` / `ce_priority` / `post_update_critic` are the corrected-semantics variants of SURVEY.md section
+        8f.4 (DERIVED oracle: the reference implements none of them, ddpg.py:217,221-222,229-247): with
+        `post_update_critic` the critic's Adam step runs BEFORE the policy loss is evaluated, so the actor gradient
+        flows through the updated critic (what ddpg.py would do if sync_local_global preceded line 236)."""
         s_t = torch.from_numpy(np.asarray(s, dtype=F32))
         a_t = torch.from_numpy(np.asarray(a, dtype=F32))
         s2_t = torch.from_numpy(np.asarray(s2, dtype=F32))
@@ -573,6 +575,13 @@ class LearnerOracle:
         loss_c.backward()                                          # ddpg.py:230
         g_c = {k: cw[k].grad.detach().clone() for k in PARAM_ORDER}
 
+        if post_update_critic:                                     # derived variant: critic first
+            if grad_hook is not None:
+                raise ValueError("post_update_critic and grad_hook are not combined")
+            self.step_c += 1
+            for k in PARAM_ORDER:
+                adam_step(self.critic[k], g_c[k], self.m_c[k], self.v_c[k], self.step_c,
+                          self.lr, self.betas[0], self.betas[1], self.eps)
         # actor loss through the PRE-update critic   ddpg.py:236-242
         aw = {k: v.clone().requires_grad_(True) for k, v in self.actor.items()}
         qp = critic_forward(self.critic, s_t, actor_forward(aw, s_t))
@@ -583,10 +592,11 @@ class LearnerOracle:
         if grad_hook is not None:
             grad_hook(g_a, g_c)
 
-        self.step_c += 1                                           # ddpg.py:232
-        for k in PARAM_ORDER:
-            adam_step(self.critic[k], g_c[k], self.m_c[k], self.v_c[k], self.step_c,
-                      self.lr, self.betas[0], self.betas[1], self.eps)
+        if not post_update_critic:
+            self.step_c += 1                                       # ddpg.py:232
+            for k in PARAM_ORDER:
+                adam_step(self.critic[k], g_c[k], self.m_c[k], self.v_c[k], self.step_c,
+                          self.lr, self.betas[0], self.betas[1], self.eps)
         self.step_a += 1                                           # ddpg.py:244
         for k in PARAM_ORDER:
             adam_step(self.actor[k], g_a[k], self.m_a[k], self.v_a[k], self.step_a,

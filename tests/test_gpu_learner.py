@@ -451,3 +451,42 @@ def test_config5_full_size_nstep_b4096_vs_oracle():
         for k in H.NAMES:
             gk = net.named_grad_views()[k].cpu()
             assert (gk - grads[k]).abs().max().item() <= TOL, (k, (gk - grads[k]).abs().max().item())
+
+
+def test_post_update_critic_switch_vs_derived_oracle():
+    """Corrected-semantics switch for SURVEY.md H7: actor_critic="post_update" runs the critic's Adam step first and
+    sends the policy gradient through the UPDATED critic.  Derived oracle (the reference has no such mode): losses,
+    gradients and parameters over 3 steps; and the default mode must differ from it (the switch does something)."""
+    import d4pg_b200 as d4pg
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": 51}
+    B, n = 64, 1024
+    rng = np.random.RandomState(16)
+    S = rng.randn(n, 17).astype(np.float32); A = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+    R = -3 * rng.rand(n); S2 = rng.randn(n, 17).astype(np.float32); D = rng.rand(n) < 0.05
+    results = {}
+    for mode in ("post_update", "reference"):
+        torch.manual_seed(14); random.seed(14)
+        dd = d4pg.DDPG(17, 6, memory_size=n, batch_size=B, critic_dist_info=info, precision="tf32x3", actor_critic=mode)
+        dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters()), d4pg.SharedAdam(dd.critic.parameters()))
+        dd.replayBuffer.add_batch(S, A, R, S2, D)
+        lo = O.LearnerOracle(17, 6, info, actor_w={k: v.cpu().clone() for k, v in dd.actor.state_dict().items()},
+                             critic_w={k: v.cpu().clone() for k, v in dd.critic.state_dict().items()})
+        for t in range(3):
+            random.seed(90 + t)
+            dd.train()
+            idx = dd.last_batch_info()["idx"].cpu().numpy()
+            out = lo.train_step(S[idx], A[idx], R[idx], S2[idx], D[idx], post_update_critic=(mode == "post_update"))
+            lc, la = dd.last_losses()
+            assert abs(lc - float(out["loss_critic"])) <= TOL and abs(la - float(out["loss_actor"])) <= TOL * max(1.0, abs(la)), (mode, t)
+            for net, grads in ((dd.actor, out["grads_actor"]), (dd.critic, out["grads_critic"])):
+                for k in H.NAMES:
+                    gk = net.named_grad_views()[k].cpu()
+                    assert (gk - grads[k]).abs().max().item() <= TOL, (mode, t, k)
+            st = dd.replayBuffer._store                         # trees: adopt the device's own priorities in the next sample
+        for k in H.NAMES:
+            for mine, ref in ((dd.actor.state_dict()[k], lo.actor[k]), (dd.critic.state_dict()[k], lo.critic[k]),
+                              (dd.actor_target.state_dict()[k], lo.actor_target[k])):
+                err = (mine.cpu() - ref).abs()
+                assert err.max().item() <= 2.5e-4 and (err > TOL).float().mean().item() <= 0.1, (mode, k)
+        results[mode] = dd.actor.flat_params().cpu().clone()
+    assert not torch.equal(results["post_update"], results["reference"])
