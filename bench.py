@@ -422,7 +422,9 @@ def gpu_main(args):
                                                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                                                      "how": "per step: add_batch of 256 new transitions from pinned host memory (H2D), train() with host-drawn "
                                                             "MT19937 uniforms (H2D), its losses copied D2H; the host reads step k-1's losses while step k runs "
-                                                            "(DDPG.last_losses(lag=1)), the final step's before the clock stops"},
+                                                            "(DDPG.last_losses(lag=1)), the final step's before the clock stops.  Host pipeline: add(k) and "
+                                                            "sample(k) run on the learner's ingest stream behind step k-1's priority write-back, overlapping its "
+                                                            "backward pass / dW / Adam (tree order update(k-1) -> add(k) -> sample(k) as in the reference)"},
                 "gpu_launches": kernels * args.steps, "kernels_per_step": kernels,
                 "roofline": roofline, "roofline_step": step_roof, "launch_us_per_step": launch_breakdown,
                 "cpu_baseline": cpu, "losses": [lc, la]}

@@ -108,6 +108,9 @@ _PROTOS = {
     "d4pg_learner_tensor": (C.c_int32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "d4pg_learner_profile_step": (C.c_int32, [_P, _P, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "d4pg_learner_steps_done": (C.c_int64, [_P]),
+    "d4pg_learner_ingest_stream": (_P, [_P]),
+    "d4pg_learner_weights_changed": (C.c_int32, [_P]),
+    "d4pg_replay_order_after": (C.c_int32, [_P, _P, _P]),
     "d4pg_learner_kernels_per_step": (C.c_int32, [_P]),
     "d4pg_learner_set_counters": (C.c_int32, [_P, C.c_int64, C.c_int64, _P]),
     "d4pg_debug_tc_trace": (C.c_int32, [_P]),

@@ -27,13 +27,23 @@ struct HeadsArgs {
 };
 int launch_heads(const HeadsArgs& a, int mode, cudaStream_t st);
 
+constexpr int SAMPLE_ROWS = 32;      // batch rows per CTA of the sample + gather kernel (replay_dev.cuh)
+
 // sample for the learner: per-step scalars come from device memory (graph replay safe)
 int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
                    uint64_t seed, LearnerClock* clock, const ClockParams& cp,
                    int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
-                   int ld_obs, int ld_act, int pipe_slot, cudaStream_t st);
-int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st);
+                   int ld_obs, int ld_act, int pipe_slot, cudaStream_t st, bool dependent = false,
+                   unsigned long long* done_epoch = nullptr);
+// gate != nullptr: *gate is bumped (release) once the trees are complete -- by the update kernel itself when it can
+int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st, unsigned long long* gate = nullptr);
 int64_t replay_generation(const d4pg_replay* h);
+// ingest gate (host pipeline): every gated learner step bumps the buffer's flag once (launch_gate_signal) and arms the
+// gate after its launch; the next add / presample on the ingest stream first waits for flag >= number of armed steps
+unsigned long long* replay_gate_flag(d4pg_replay* h);
+void replay_arm_gate(d4pg_replay* h);
+int replay_gate_consume(d4pg_replay* h, cudaStream_t st);
+int launch_gate_signal(unsigned long long* flag, cudaStream_t st);
 void trace_set_side_stream(cudaStream_t s);     // changes whenever the caller mutates the buffer
 int comm_allreduce(d4pg_comm* c, float* buf, int64_t n, cudaStream_t st);
 // fused all-reduce over IPC-mapped peer memory (comm.cu): x[r] = rank r's [2][n] gradient halves

@@ -39,6 +39,7 @@ struct Workspace {
   float *c_dz22, *c_dz2, *c_dz1, *p_dz22, *p_dz2, *a_dz3, *a_dz22, *a_dh2, *a_dz1;
   LearnerClock* clock;
   float* xchg;                     // exchange planes of the cluster-fused chain kernels (chain mode)
+  unsigned long long* pipe_epoch;  // host pipeline: per-CTA completion epochs of the presample kernel (polled by the forward chains)
   // prefetch pipeline: the second half of the double-buffered batch, and the sampler's own index / weight buffers
   float *s_b, *a_b, *s2_b; double* r_b; uint8_t* done_b;
   int32_t* idx2[2]; float* wts2[2];
@@ -70,6 +71,7 @@ static Workspace carve(float* base, int B, int S, int A, int N, bool chain, bool
   w.a_dz1 = take(int64_t(B) * H);
   w.clock = reinterpret_cast<LearnerClock*>(take(sizeof(LearnerClock) / 4 + 4));
   w.xchg = chain ? take(std::max(chain_xchg_floats(B), tcc_xchg_floats(B))) : nullptr;
+  w.pipe_epoch = reinterpret_cast<unsigned long long*>(take(2 * int64_t((B + SAMPLE_ROWS - 1) / SAMPLE_ROWS)));
   if (prefetch) {
     w.s_b = take(int64_t(B) * Sp); w.a_b = take(int64_t(B) * Ap); w.s2_b = take(int64_t(B) * Sp);
     w.r_b = reinterpret_cast<double*>(take(int64_t(B) * 2));
@@ -112,11 +114,15 @@ struct d4pg_learner {
   GemmWideBatch dw_batch;
   // host-facing step: library-owned pinned staging, double-buffered by step parity (a buffer is rewritten only after
   // the H2D copy out of it, two steps earlier, has completed)
-  double* host_u[2]; int32_t* host_pos[2]; float* host_losses; cudaEvent_t ev_in, ev_out, ev_h2d[2];
+  double* host_u[4]; int32_t* host_pos[4]; float* host_losses; cudaEvent_t ev_in, ev_out, ev_h2d[4];
   int64_t host_steps;
   // results of the host-facing steps: {critic loss, actor loss, -, -} of step k land in ring slot k & 1 (async D2H queued
   // by the step itself), so a caller can read step k-1 while step k runs
   float* loss_ring[2]; cudaEvent_t ev_loss[2]; int64_t loss_steps;
+  // host pipeline: library-owned ingest stream (adds + the presample of the next batch), the gate flag the step's
+  // priority write-back bumps, how many gated steps were launched
+  cudaStream_t ing; cudaEvent_t ev_ing; unsigned long long* gate_flag;
+  bool images_dirty;               // parameters were written outside the library since the forward weight images were last current
   bool profiling;
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> ev_name;
@@ -130,6 +136,15 @@ struct d4pg_learner {
 static int step_plan(const d4pg_learner_config_t& c) { return c.batch > 512 ? 0 : c.chain; }
 // prefetch pipeline: batch t+1 is sampled on a side branch of step t (device-side sampling only)
 static bool prefetching(const d4pg_learner_config_t& c) { return c.prefetch != 0 && c.sample_mode == 1; }
+// host pipeline (host-drawn uniforms / positions, cfg.prefetch): the host-facing step samples batch k on the library's
+// ingest stream -- behind the caller's add(k), gated on step k-1's priority write-back -- while step k-1's backward
+// pass, dW and Adam still run on the learner stream; the step graph then starts from the sampled batch.  Same double
+// buffers and clock slots as the device prefetch pipeline; the order of tree operations is the reference's
+// (update_priorities(k-1) -> add(k) -> sample(k), main.py / ddpg.py:200-255).
+static bool host_pipe(const d4pg_learner_config_t& c) { return c.prefetch != 0 && c.sample_mode == 0 && c.use_graph != 0; }
+static bool piped(const d4pg_learner_config_t& c) { return prefetching(c) || host_pipe(c); }
+struct d4pg_learner;
+static bool inline_wait(const d4pg_learner* L);     // the warm host-pipeline graph polls the sampler's epochs itself (tcgen05 chain plan)
 
 // weight matrices as the tcgen05 chains consume them (F = forward image, D = transposed image for dX)
 enum { U_A_F1, U_A_F2, U_A_F22, U_A_F3, U_A_D3, U_A_D22, U_A_D2, U_AT_F1, U_AT_F2, U_AT_F22, U_AT_F3,
@@ -305,7 +320,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
   const d4pg_learner_config_t& c = L->cfg;
   const d4pg_learner_buffers_t& b = L->buf;
   Workspace w = L->ws;                               // local copy: the batch pointers follow `par`
-  const bool pf = prefetching(c);
+  const bool pf = piped(c);
   int32_t* bidx = b.idx; float* bwts = b.weights;
   if (pf) {
     if (par) { w.s = w.s_b; w.a = w.a_b; w.s2 = w.s2_b; w.r = w.r_b; w.done = w.done_b; }
@@ -373,6 +388,12 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
     if (h7) tcc_build_actor(fa, 1, cx, nullptr);                 // chain 1  (post-update plan) the actor alone; the critic pass follows the critic's Adam
     else tcc_build_P(fa, 1, cx);                                 // chain 1  P: actor(s) -> critic(s, actor(s))
     tcc_build_Q(fa, 2, cx, w.a, w.h1[2], w.h2[2], w.h3[2], w.out[2]);   // chain 2  Q: critic(s, a)
+    if (host_pipe(c) && !cold && inline_wait(L)) {
+      // warm host-pipeline variant: the batch comes from the ingest stream's sample kernel; instead of a stream event
+      // (event + graph start: ~6 us after the sample ends) every CTA polls the epochs that kernel publishes
+      fa.wait_epoch = w.pipe_epoch; fa.wait_clock = reinterpret_cast<const long long*>(&w.clock->steps_done);
+      fa.wait_n = cdiv(B, SAMPLE_ROWS);
+    }
     RUN(launch_mlp_tc_chain(fa, st));
   } else if (chain) {
     // 2'. the three forward chains of the step as ONE cluster launch (mlp_chain.cu):
@@ -490,13 +511,17 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
   if (c.prioritized || pf) {
     D4PG_CUDA_OK(cudaEventRecord(L->ev_fork, st));
     D4PG_CUDA_OK(cudaStreamWaitEvent(L->side, L->ev_fork, 0));
-    if (pf) {                                          // the caller-visible copies of this step's indices / IS weights
+    static const bool copy_first = getenv("D4PG_PIPE_COPY_FIRST") != nullptr;      // A/B switch
+    if (pf && copy_first) {
       D4PG_CUDA_OK(cudaMemcpyAsync(b.idx, bidx, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToDevice, L->side));
       if (b.weights && c.prioritized)
         D4PG_CUDA_OK(cudaMemcpyAsync(b.weights, bwts, size_t(B) * sizeof(float), cudaMemcpyDeviceToDevice, L->side));
     }
-    if (c.prioritized) RUN(launch_tree_update(L->replay, B, bidx, b.prio, L->side));
-    if (pf) {
+    // host pipeline: the write-back also opens the ingest gate of step k+1 (its tree add / presample wait for this step's
+    // loss kernel -- which advanced the sampler clock -- and for the priorities)
+    if (c.prioritized) RUN(launch_tree_update(L->replay, B, bidx, b.prio, L->side, host_pipe(c) ? L->gate_flag : nullptr));
+    else if (host_pipe(c)) RUN(launch_gate_signal(L->gate_flag, L->side));
+    if (prefetching(c)) {
       // 4'. the NEXT step's batch, sampled from the just-updated trees into the other half of the batch buffers
       // while this step's backward pass, dW and Adam run (it needs the trees, not the weights)
       const int q = par ^ 1;
@@ -504,6 +529,12 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
       RUN(learner_sample(L->replay, B, c.prioritized, nullptr, nullptr, c.philox_seed, w.clock, cp, o.idx2[q], o.wts2[q],
                          q ? o.s_b : o.s, q ? o.a_b : o.a, q ? o.r_b : o.r, q ? o.s2_b : o.s2, q ? o.done_b : o.done,
                          Sp, Ap, q, L->side));
+    }
+    if (pf && !copy_first) {                           // the caller-visible copies of this step's indices / IS weights (off the
+      // path to the next batch: after the write-back and the prefetch)
+      D4PG_CUDA_OK(cudaMemcpyAsync(b.idx, bidx, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToDevice, L->side));
+      if (b.weights && c.prioritized)
+        D4PG_CUDA_OK(cudaMemcpyAsync(b.weights, bwts, size_t(B) * sizeof(float), cudaMemcpyDeviceToDevice, L->side));
     }
     D4PG_CUDA_OK(cudaEventRecord(L->ev_join, L->side));
   }
@@ -711,7 +742,7 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
 
 extern "C" int64_t d4pg_learner_workspace_floats(const d4pg_learner_config_t* cfg) {
   if (!cfg) return -1;
-  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1, prefetching(*cfg)).total;
+  return carve(nullptr, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1, piped(*cfg)).total;
 }
 
 extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d4pg_learner_buffers_t* buf,
@@ -741,7 +772,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
     set_error("d4pg_learner_create: grad_critic must equal grad_actor + P_a (one flat gradient buffer)");
     delete L; return D4PG_EINVAL;
   }
-  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1, prefetching(*cfg));
+  L->ws = carve(buf->workspace, cfg->batch, cfg->obs_dim, cfg->act_dim, cfg->n_atoms, step_plan(*cfg) == 1, piped(*cfg));
   for (int i = 0; i < 4; ++i) { L->graph_exec[i] = nullptr; L->graph_ready[i] = false; }
   for (int i = 0; i < 2; ++i) { L->multi_exec[i] = nullptr; L->multi_ready[i] = false; }
   L->pipe_par = 0; L->last_par = 0; L->prefetch_valid = false; L->seen_gen = -1;
@@ -750,19 +781,30 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   (void)debug_trace_buffer();          // allocate outside of any stream capture
   if (int rc = tcc_setup(L)) { delete L; return rc; }
   L->host_steps = 0; L->host_losses = nullptr; L->ev_in = nullptr; L->ev_out = nullptr;
-  for (int i = 0; i < 2; ++i) { L->host_u[i] = nullptr; L->host_pos[i] = nullptr; L->ev_h2d[i] = nullptr; L->loss_ring[i] = nullptr; L->ev_loss[i] = nullptr; }
+  for (int i = 0; i < 4; ++i) { L->host_u[i] = nullptr; L->host_pos[i] = nullptr; L->ev_h2d[i] = nullptr; }
+  for (int i = 0; i < 2; ++i) { L->loss_ring[i] = nullptr; L->ev_loss[i] = nullptr; }
   L->loss_steps = 0;
+  L->ing = nullptr; L->ev_ing = nullptr; L->gate_flag = nullptr; L->images_dirty = true;
+  if (host_pipe(*cfg)) {
+    L->gate_flag = replay_gate_flag(replay);
+    const bool ok = L->gate_flag && cudaStreamCreateWithFlags(&L->ing, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&L->ev_ing, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      set_error("d4pg_learner_create: ingest stream setup failed"); delete L; return D4PG_ECUDA;
+    }
+  }
   {
     const size_t nb = size_t(cfg->batch);
     bool ok = cudaEventCreateWithFlags(&L->ev_in, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&L->ev_out, cudaEventDisableTiming) == cudaSuccess &&
               cudaHostAlloc(reinterpret_cast<void**>(&L->host_losses), 4 * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&L->ev_loss[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaHostAlloc(reinterpret_cast<void**>(&L->loss_ring[i]), 4 * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i)
       ok = cudaEventCreateWithFlags(&L->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&L->ev_loss[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaHostAlloc(reinterpret_cast<void**>(&L->loss_ring[i]), 4 * sizeof(float), cudaHostAllocDefault) == cudaSuccess &&
-           cudaHostAlloc(reinterpret_cast<void**>(&L->host_u[i]), nb * sizeof(double), cudaHostAllocDefault) == cudaSuccess &&
-           cudaHostAlloc(reinterpret_cast<void**>(&L->host_pos[i]), nb * sizeof(int32_t), cudaHostAllocDefault) == cudaSuccess;
+           cudaHostAlloc(reinterpret_cast<void**>(&L->host_u[i]), nb * sizeof(double), cudaHostAllocMapped) == cudaSuccess &&
+           cudaHostAlloc(reinterpret_cast<void**>(&L->host_pos[i]), nb * sizeof(int32_t), cudaHostAllocMapped) == cudaSuccess;
     if (!ok) { set_error("d4pg_learner_create: pinned staging allocation failed"); delete L; return D4PG_ECUDA; }
   }
   if (cudaStreamCreateWithFlags(&L->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -774,6 +816,7 @@ extern "C" int32_t d4pg_learner_create(const d4pg_learner_config_t* cfg, const d
   }
   trace_set_side_stream(L->side);
   cudaError_t e = cudaMemset(L->ws.clock, 0, sizeof(LearnerClock));
+  if (e == cudaSuccess) e = cudaMemset(L->ws.pipe_epoch, 0, sizeof(unsigned long long) * size_t(cdiv(cfg->batch, SAMPLE_ROWS)));
   if (e != cudaSuccess) { set_error("d4pg_learner_create: %s", cudaGetErrorString(e)); delete L; return D4PG_ECUDA; }
   *out = L;
   return D4PG_OK;
@@ -786,13 +829,17 @@ extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
   cudaEventDestroy(L->ev_fork); cudaEventDestroy(L->ev_join); cudaEventDestroy(L->ev_fork2); cudaEventDestroy(L->ev_join2);
   cudaStreamDestroy(L->side);
   if (L->tcc_images) cudaFree(L->tcc_images);
+  if (L->ing) { cudaStreamSynchronize(L->ing); cudaStreamDestroy(L->ing); }
+  if (L->ev_ing) cudaEventDestroy(L->ev_ing);
   if (L->ev_in) cudaEventDestroy(L->ev_in);
   if (L->ev_out) cudaEventDestroy(L->ev_out);
   if (L->host_losses) cudaFreeHost(L->host_losses);
   for (int i = 0; i < 2; ++i) {
-    if (L->ev_h2d[i]) cudaEventDestroy(L->ev_h2d[i]);
     if (L->ev_loss[i]) cudaEventDestroy(L->ev_loss[i]);
     if (L->loss_ring[i]) cudaFreeHost(L->loss_ring[i]);
+  }
+  for (int i = 0; i < 4; ++i) {
+    if (L->ev_h2d[i]) cudaEventDestroy(L->ev_h2d[i]);
     if (L->host_u[i]) cudaFreeHost(L->host_u[i]);
     if (L->host_pos[i]) cudaFreeHost(L->host_pos[i]);
   }
@@ -802,33 +849,48 @@ extern "C" int32_t d4pg_learner_destroy(d4pg_learner_t* L) {
 
 // which half of the batch buffers the next step uses, and whether it has to sample it first
 static void next_variant(d4pg_learner* L, int* par, bool* cold) {
-  if (!prefetching(L->cfg)) { *par = 0; *cold = true; return; }
+  if (!piped(L->cfg)) { *par = 0; *cold = true; return; }
   *par = L->pipe_par;
-  *cold = !L->prefetch_valid || replay_generation(L->replay) != L->seen_gen;
+  // host pipeline: a direct d4pg_learner_step samples in the graph; d4pg_learner_step_host presamples on the ingest stream
+  *cold = host_pipe(L->cfg) || !L->prefetch_valid || replay_generation(L->replay) != L->seen_gen;
 }
 static void commit_variant(d4pg_learner* L, int par) {
   ++L->steps_done;
-  if (!prefetching(L->cfg)) return;
+  if (!piped(L->cfg)) return;
   L->last_par = par; L->pipe_par = par ^ 1; L->prefetch_valid = true; L->seen_gen = replay_generation(L->replay);
 }
+
+static int launch_variant(d4pg_learner* L, cudaStream_t st, int par, bool cold);
 
 extern "C" int32_t d4pg_learner_step(d4pg_learner_t* L, d4pg_stream_t stream) {
   D4PG_REQUIRE(L, D4PG_EINVAL, "d4pg_learner_step: null handle");
   cudaStream_t st = as_stream(stream);
   int par; bool cold;
   next_variant(L, &par, &cold);
+  if (L->ing) {                                      // adds issued on the ingest stream come first
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_ing, L->ing));
+    D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_ing, 0));
+  }
+  return launch_variant(L, st, par, cold);
+}
+
+// the step graph of variant (par, cold) on `st` (captured on first use); arms the ingest gate of the next step
+static int launch_variant(d4pg_learner* L, cudaStream_t st, int par, bool cold) {
+  auto arm_gate = [&] { if (L->ing) replay_arm_gate(L->replay); };
   if (!L->cfg.use_graph) {
-    int rc = enqueue_step(L, st, par, cold);
-    if (rc == D4PG_OK) commit_variant(L, par);
+    int rc = enqueue_step(L, st, par, cold, !(host_pipe(L->cfg) && !cold));
+    if (rc == D4PG_OK) { commit_variant(L, par); arm_gate(); }
     return rc;
   }
   // without the prefetch pipeline the only per-step variation is the gradient half of the peer exchange
-  const int v = prefetching(L->cfg) ? par * 2 + (cold ? 1 : 0) : int(L->steps_done & 1);
+  const int v = piped(L->cfg) ? par * 2 + (cold ? 1 : 0) : int(L->steps_done & 1);
   if (!L->graph_ready[v]) {
     D4PG_REQUIRE(st != nullptr, D4PG_EINVAL, "d4pg_learner_step: graph capture needs a non-default stream");
     cudaGraph_t graph = nullptr;
     D4PG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(L, st, par, cold);
+    // warm host-pipeline variants start from a sampled batch AND packed forward images (d4pg_learner_step_host packs
+    // eagerly on the learner stream while the ingest stream still samples)
+    int rc = enqueue_step(L, st, par, cold, !(host_pipe(L->cfg) && !cold));
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     if (rc != D4PG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) { set_error("d4pg_learner_step: end capture: %s", cudaGetErrorString(e)); return D4PG_ECUDA; }
@@ -839,7 +901,26 @@ extern "C" int32_t d4pg_learner_step(d4pg_learner_t* L, d4pg_stream_t stream) {
   }
   D4PG_CUDA_OK(cudaGraphLaunch(L->graph_exec[v], st));
   commit_variant(L, par);
+  arm_gate();
   return D4PG_OK;
+}
+
+static bool inline_wait(const d4pg_learner* L) {
+  static const bool off = getenv("D4PG_PIPE_EVENT") != nullptr;      // A/B switch: stream event instead
+  return !off && step_plan(L->cfg) == 1 && L->cfg.precision >= 1 && L->tcc_ok && cdiv(L->cfg.batch, SAMPLE_ROWS) <= TCC_THREADS;
+}
+
+// host pipeline: sample + gather batch `par` from the device copy of this step's uniforms / positions (the launch the
+// cold graph variant starts with, issued on the ingest stream instead)
+static int presample(d4pg_learner* L, int par, const double* uniforms, const int32_t* positions, cudaStream_t st) {
+  const d4pg_learner_config_t& c = L->cfg; const d4pg_learner_buffers_t& b = L->buf; const Workspace& o = L->ws;
+  const ClockParams cp{c.lr_actor, c.lr_critic, c.beta1, c.beta2, c.per_beta0, c.per_beta_final,
+                       c.per_beta_iters > 0 ? c.per_beta_iters : 1};
+  (void)b;
+  return learner_sample(L->replay, c.batch, c.prioritized, uniforms, !c.prioritized ? positions : nullptr, c.philox_seed,
+                        o.clock, cp, o.idx2[par], o.wts2[par], par ? o.s_b : o.s, par ? o.a_b : o.a, par ? o.r_b : o.r,
+                        par ? o.s2_b : o.s2, par ? o.done_b : o.done, pitch4(c.obs_dim), pitch4(c.act_dim), par, st,
+                        getenv("D4PG_PIPE_NO_PDL") == nullptr, o.pipe_epoch);
 }
 
 // The host-facing step: stage this step's host inputs in pinned memory, H2D, the step, order the caller after it.
@@ -847,29 +928,61 @@ static int step_host_common(d4pg_learner_t* L, const double* uniforms, const uin
                             d4pg_stream_t caller_stream, d4pg_stream_t learner_stream) {
   cudaStream_t cs = as_stream(caller_stream), ls = as_stream(learner_stream);
   const int B = L->cfg.batch;
-  const int par = int(L->host_steps & 1);
   D4PG_CUDA_OK(cudaEventRecord(L->ev_in, cs));                 // adds / weight loads issued by the caller
   D4PG_CUDA_OK(cudaStreamWaitEvent(ls, L->ev_in, 0));
+  const bool pipe = L->ing != nullptr && (uniforms || mt_words || positions);
+  // piped: the sample kernel reads this step's uniforms / positions (2 KB) straight out of the pinned staging slot over
+  // PCIe -- no copy node between the caller's add and the sample on the ingest stream -- so the slots form a ring of 4.
+  // (The caller's replay operations on caller_stream are NOT waited for before sampling: the host mirror orders them
+  // explicitly with d4pg_replay_order_after, see d4pg_learner_ingest_stream in the header.)
+  const int par = int(L->host_steps & (pipe ? 3 : 1));
+  double* du = L->buf.uniforms;
+  int32_t* dpos = L->buf.positions;
   if (uniforms || mt_words || positions) {
-    if (L->host_steps >= 2) D4PG_CUDA_OK(cudaEventSynchronize(L->ev_h2d[par]));   // the copy out of this buffer, two steps ago
+    if (L->host_steps >= (pipe ? 4 : 2)) D4PG_CUDA_OK(cudaEventSynchronize(L->ev_h2d[par]));   // the last reader of this slot
     if (uniforms || mt_words) {
-      D4PG_REQUIRE(L->buf.uniforms, D4PG_ESTATE, "d4pg_learner_step_host: no device uniforms buffer");
+      D4PG_REQUIRE(du, D4PG_ESTATE, "d4pg_learner_step_host: no device uniforms buffer");
       double* u = L->host_u[par];
       if (uniforms) memcpy(u, uniforms, size_t(B) * sizeof(double));
       else                                                     // CPython random.random(): (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53
         for (int i = 0; i < B; ++i)
           u[i] = (double(mt_words[2 * i] >> 5) * 67108864.0 + double(mt_words[2 * i + 1] >> 6)) * (1.0 / 9007199254740992.0);
-      D4PG_CUDA_OK(cudaMemcpyAsync(L->buf.uniforms, u, size_t(B) * sizeof(double), cudaMemcpyHostToDevice, ls));
+      if (pipe) D4PG_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&du), u, 0));
+      else D4PG_CUDA_OK(cudaMemcpyAsync(du, u, size_t(B) * sizeof(double), cudaMemcpyHostToDevice, ls));
     }
     if (positions) {
-      D4PG_REQUIRE(L->buf.positions, D4PG_ESTATE, "d4pg_learner_step_host: no device positions buffer");
+      D4PG_REQUIRE(dpos, D4PG_ESTATE, "d4pg_learner_step_host: no device positions buffer");
       memcpy(L->host_pos[par], positions, size_t(B) * sizeof(int32_t));
-      D4PG_CUDA_OK(cudaMemcpyAsync(L->buf.positions, L->host_pos[par], size_t(B) * sizeof(int32_t), cudaMemcpyHostToDevice, ls));
+      if (pipe) D4PG_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dpos), L->host_pos[par], 0));
+      else D4PG_CUDA_OK(cudaMemcpyAsync(dpos, L->host_pos[par], size_t(B) * sizeof(int32_t), cudaMemcpyHostToDevice, ls));
     }
-    D4PG_CUDA_OK(cudaEventRecord(L->ev_h2d[par], ls));
+    if (!pipe) D4PG_CUDA_OK(cudaEventRecord(L->ev_h2d[par], ls));
     ++L->host_steps;
   }
-  int rc = d4pg_learner_step(L, learner_stream);
+  int rc;
+  if (pipe) {
+    // batch k on the ingest stream: behind the caller's add(k) (same stream) and the gate of step k-1, while step k-1's
+    // backward pass / dW / Adam still run on the learner stream; the step graph starts from the sampled batch
+    int bpar; bool cold_unused;
+    next_variant(L, &bpar, &cold_unused);
+    rc = replay_gate_consume(L->replay, L->ing);
+    if (rc) return rc;
+    rc = presample(L, bpar, du, dpos, L->ing);
+    if (rc) return rc;
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_h2d[par], L->ing));      // the staging slot has been read
+    D4PG_CUDA_OK(cudaEventRecord(L->ev_ing, L->ing));
+    // forward weight images: the Adam kernel keeps them current, so they are re-packed only after the caller reported a
+    // parameter write of its own (d4pg_learner_weights_changed) -- behind Adam(k-1), beside the ingest stream's tail
+    if (L->images_dirty && step_plan(L->cfg) == 1 && L->cfg.precision >= 1 && L->tcc_ok) {
+      rc = launch_tcc_pack(L->tcc_pack_fwd, ls);
+      if (rc) return rc;
+    }
+    L->images_dirty = false;
+    if (!inline_wait(L)) D4PG_CUDA_OK(cudaStreamWaitEvent(ls, L->ev_ing, 0));
+    rc = launch_variant(L, ls, bpar, false);
+  } else {
+    rc = d4pg_learner_step(L, learner_stream);
+  }
   if (rc) return rc;
   {                                                            // this step's result, queued for d4pg_learner_fetch_losses
     const int slot = int(L->loss_steps & 1);
@@ -955,9 +1068,10 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
   L->profiling = true; L->ev.clear(); L->ev_name.clear(); L->ev_reps.clear();
   int par; bool cold;
   next_variant(L, &par, &cold);
+  if (L->ing) { D4PG_CUDA_OK(cudaEventRecord(L->ev_ing, L->ing)); D4PG_CUDA_OK(cudaStreamWaitEvent(st, L->ev_ing, 0)); }
   int rc = enqueue_step(L, st, par, cold);
   L->profiling = false;
-  if (rc == D4PG_OK) commit_variant(L, par);
+  if (rc == D4PG_OK) { commit_variant(L, par); if (L->ing) replay_arm_gate(L->replay); }
   cudaError_t e = cudaStreamSynchronize(st);
   const int n = int(L->ev_name.size());
   *n_out = n < max_launches ? n : max_launches;
@@ -979,6 +1093,12 @@ extern "C" int32_t d4pg_learner_profile_step(d4pg_learner_t* L, d4pg_stream_t st
   return rc;
 }
 
+extern "C" int32_t d4pg_learner_weights_changed(d4pg_learner_t* L) {
+  D4PG_REQUIRE(L, D4PG_EINVAL, "d4pg_learner_weights_changed: null handle");
+  L->images_dirty = true;
+  return D4PG_OK;
+}
+extern "C" void* d4pg_learner_ingest_stream(const d4pg_learner_t* L) { return L ? static_cast<void*>(L->ing) : nullptr; }
 extern "C" int64_t d4pg_learner_steps_done(const d4pg_learner_t* L) { return L ? L->steps_done : -1; }
 extern "C" int32_t d4pg_learner_kernels_per_step(const d4pg_learner_t* L) { return L ? L->kernels_per_step : -1; }
 
@@ -988,6 +1108,7 @@ extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_ste
   c.adam_step = adam_step; c.beta_t = beta_t; c.steps_done = adam_step;
   c.s_adam_step = adam_step; c.s_beta_t = beta_t; c.s_steps_done = adam_step;
   L->prefetch_valid = false;                          // a prefetched batch was drawn with the old counters
+  D4PG_CUDA_OK(cudaMemsetAsync(L->ws.pipe_epoch, 0, sizeof(unsigned long long) * size_t(cdiv(L->cfg.batch, SAMPLE_ROWS)), as_stream(stream)));
   D4PG_CUDA_OK(cudaMemcpyAsync(L->ws.clock, &c, sizeof(c), cudaMemcpyHostToDevice, as_stream(stream)));
   D4PG_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
   return D4PG_OK;
@@ -996,7 +1117,7 @@ extern "C" int32_t d4pg_learner_set_counters(d4pg_learner_t* L, int64_t adam_ste
 extern "C" int32_t d4pg_learner_tensor(d4pg_learner_t* L, const char* name, void** ptr, int64_t* count, int32_t* ld) {
   D4PG_REQUIRE(L && name && ptr && count && ld, D4PG_EINVAL, "d4pg_learner_tensor: null argument");
   Workspace w = L->ws;
-  if (prefetching(L->cfg) && L->last_par) { w.s = w.s_b; w.a = w.a_b; w.s2 = w.s2_b; w.r = w.r_b; w.done = w.done_b; }
+  if (piped(L->cfg) && L->last_par) { w.s = w.s_b; w.a = w.a_b; w.s2 = w.s2_b; w.r = w.r_b; w.done = w.done_b; }
   const int64_t B = L->cfg.batch;
   const int Sp = pitch4(L->cfg.obs_dim), Ap = pitch4(L->cfg.act_dim), Np = pitch4(L->cfg.n_atoms);
   struct E { const char* n; void* p; int64_t c; int ld; };

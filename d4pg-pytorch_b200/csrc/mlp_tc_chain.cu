@@ -198,6 +198,14 @@ mlp_tc_chain_kernel(const __grid_constant__ TccArgs args) {
   const int npre = CH.pre ? (CH.precols + TCC_KC - 1) / TCC_KC : 0;
   const int passes = args.passes;
   unsigned long long* tr0 = (args.trace && int(blockIdx.x) == args.trace_cta) ? args.trace : nullptr;
+  if (args.wait_epoch) {                 // host pipeline: the sample kernel of this step publishes per-CTA epochs
+    if (tid < args.wait_n) {
+      const unsigned long long target = (unsigned long long)(*reinterpret_cast<const volatile long long*>(args.wait_clock) + 1);
+      unsigned long long v;
+      do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(args.wait_epoch + tid) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+  }
   step_stamp(args.step_trace, args.step_slot);
 
   if (tid == 0) {

@@ -28,10 +28,19 @@ struct d4pg_replay {
   int pristine;
   int64_t gen;            // bumped by every external mutation (add / set / update): a learner's prefetched batch is stale
   // host ingest staging (caller-owned buffers registered by d4pg_replay_set_staging)
-  uint8_t* stage_host; uint8_t* stage_dev; int64_t stage_bytes; cudaEvent_t stage_ev; bool stage_busy;
+  // two slots (halves of the registered buffers) so the host can stage add k+1 while add k still waits on the device
+  uint8_t* stage_host; uint8_t* stage_dev; int64_t stage_bytes; cudaEvent_t stage_ev[2]; bool stage_busy[2]; int stage_slot;
+  // ingest gate (learner host pipeline): the next kernel that touches the store / trees on the ingest stream first waits
+  // until *gate_flag >= gate_target (the priority write-back of the last launched learner step)
+  // The flag lives with the buffer (learners come and go); every gated step bumps it once and arms target = #armed.
+  unsigned long long* gate_flag; unsigned long long gate_target; bool gate_pending;
+  cudaEvent_t order_ev;
 };
 
 namespace d4pg {
+// step timeline (D4PG_TC_TRACE, tools/e2e_timeline.py): ingest kernels stamp slots 10 (gate), 11 (ring write), 12 (tree add)
+static unsigned long long* step_trace() { unsigned long long* p = debug_trace_buffer(); return p ? p + STEP_TRACE_BASE : nullptr; }
+
 
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const SampleArgs a) {
   __shared__ SampleSmem sm;
@@ -39,6 +48,14 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_gather_kernel(const Sam
   pdl_wait();
   step_stamp(a.trace, a.trace_slot);
   sample_body(a, blockIdx.x, sm);
+  if (a.done_epoch) {                          // the forward chains of the step poll these instead of a stream event
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long e = (unsigned long long)(a.clock->s_steps_done + 1);
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.done_epoch + blockIdx.x), "l"(e) : "memory");
+    }
+  }
   step_stamp(a.trace, a.trace_slot + 16);
   pdl_trigger_end(a.pdl);
 }
@@ -102,10 +119,22 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_add_range_kernel(float* sum
 constexpr int TREE_ADD_FAST_MAX = 2048;
 __global__ void __launch_bounds__(TREE_THREADS) tree_add_range_fast_kernel(float* sum, float* mn, int64_t cap, int log2cap,
                                                                            int64_t start, int64_t n, const ReplayState* state,
-                                                                           float alpha_f32) {
+                                                                           float alpha_f32, unsigned long long* trace,
+                                                                           const unsigned long long* gate_flag,
+                                                                           unsigned long long gate_target) {
   __shared__ float vs[2][TREE_ADD_FAST_MAX], vm[2][TREE_ADD_FAST_MAX];
   __shared__ float old_s[2][32], old_m[2][32];                         // [left / right edge][level]
   const int t = threadIdx.x;
+  step_stamp(trace, 10);
+  if (gate_flag) {                                                     // ingest gate, fused: saves a kernel boundary
+    if (t == 0) {
+      unsigned long long v;
+      do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(gate_flag) : "memory"); } while (v < gate_target);
+    }
+    __syncthreads();
+  }
+  pdl_trigger_raw();      // a programmatically dependent sample kernel (host pipeline) may become resident now; it still waits for this grid's end
+  step_stamp(trace, 12);
   const float leaf = pow_alpha(state->max_priority, alpha_f32);       // :255-256
   if (t < 2 * log2cap) {
     const int lvl = (t >> 1) + 1, side = t & 1;                        // the outside child needed by level `lvl`
@@ -134,6 +163,7 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_add_range_fast_kernel(float
     }
     __syncthreads();
   }
+  step_stamp(trace, 12 + 16);
 }
 
 // bulk path for large adds: grid-wide leaf fill, then one launch per level
@@ -158,8 +188,9 @@ __global__ void ring_write_kernel(float* obs, float* act, double* rew, float* ob
                                   const float* s, const float* a, const double* r, const float* s2,
                                   const uint8_t* d, int64_t n, int obs_dim, int act_dim,
                                   int64_t size, int64_t ring_start, ReplayState* state,
-                                  int64_t new_len, int64_t new_next) {
+                                  int64_t new_len, int64_t new_next, unsigned long long* trace) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x, t0 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  step_stamp(trace, 11);
   if (t0 == 0) { state->len = new_len; state->next_idx = new_next; }
   for (int64_t e = t0; e < n * obs_dim; e += stride) {
     const int64_t i = e / obs_dim, c = e - i * obs_dim, p = (ring_start + i) % size;
@@ -174,6 +205,7 @@ __global__ void ring_write_kernel(float* obs, float* act, double* rew, float* ob
     const int64_t p = (ring_start + i) % size;
     rew[p] = r[i]; done[p] = d[i];
   }
+  step_stamp(trace, 11 + 16);
 }
 
 __global__ void tree_init_kernel(float* sum, float* mn, int32_t* scratch, ReplayState* state, int64_t cap) {
@@ -251,7 +283,7 @@ __global__ void find_prefix_kernel(const float* sum, int64_t cap, int n, const d
 static cudaStream_t g_side_stream = nullptr;          // trace only: which launches are the prefetching sampler's
 void trace_set_side_stream(cudaStream_t s) { g_side_stream = s; }
 static bool st_is_side(cudaStream_t st) { return g_side_stream != nullptr && st == g_side_stream; }
-int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
+int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st, bool dependent = false) {
   a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.state = reinterpret_cast<const ReplayState*>(h->state);
   a.obs = h->obs; a.act = h->act; a.rew = h->rew; a.obs2 = h->obs2; a.done = h->done;
   a.obs_dim = h->obs_dim; a.act_dim = h->act_dim;
@@ -259,6 +291,18 @@ int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
   a.trace = (a.clock && debug_trace_buffer()) ? debug_trace_buffer() + STEP_TRACE_BASE : nullptr;
   a.trace_slot = a.pipe_slot >= 0 && a.uniforms == nullptr && st_is_side(st) ? 4 : 0;
   D4PG_MAX_CARVEOUT(sample_gather_kernel);
+  if (dependent) {
+    // programmatic dependent launch behind the previous kernel of the stream (the host pipeline's tree add): the grid is
+    // resident when that kernel ends, griddepcontrol.wait at the top of the kernel holds it until its writes are visible
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cdiv(a.B, SAMPLE_ROWS)); cfg.blockDim = dim3(SAMPLE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    D4PG_CUDA_OK(cudaLaunchKernelEx(&cfg, sample_gather_kernel, a));
+    return D4PG_OK;
+  }
   D4PG_CUDA_OK(launch_pdl(sample_gather_kernel, dim3(cdiv(a.B, SAMPLE_ROWS)), dim3(SAMPLE_THREADS), 0, st, a));
   return D4PG_OK;
 }
@@ -266,14 +310,15 @@ int launch_sample(const d4pg_replay* h, SampleArgs& a, cudaStream_t st) {
 int learner_sample(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
                    uint64_t seed, LearnerClock* clock, const ClockParams& cp,
                    int32_t* idx, float* weights, float* s, float* a, double* r, float* s2, uint8_t* d,
-                   int ld_obs, int ld_act, int pipe_slot, cudaStream_t st) {
+                   int ld_obs, int ld_act, int pipe_slot, cudaStream_t st, bool dependent, unsigned long long* done_epoch) {
   SampleArgs sa{};
+  sa.done_epoch = done_epoch;
   sa.ld_obs = ld_obs; sa.ld_act = ld_act; sa.pipe_slot = pipe_slot;
   sa.uniforms = uniforms; sa.seed = seed; sa.counter = 0; sa.clock = clock; sa.clock_params = cp;
   sa.beta = 1.f; sa.B = B; sa.idx = idx; sa.weights = prioritized ? weights : nullptr;
   sa.s = s; sa.a = a; sa.r = r; sa.s2 = s2; sa.d = d;
   if (!prioritized) { sa.idx_in = positions; sa.uniform_mode = positions ? 0 : 1; }
-  return launch_sample(h, sa, st);
+  return launch_sample(h, sa, st, dependent);
 }
 
 void learner_sample_args(d4pg_replay* h, int B, int prioritized, const double* uniforms, const int32_t* positions,
@@ -300,7 +345,8 @@ void tree_update_args(d4pg_replay* h, int B, const int32_t* idx, const float* pr
 
 int64_t replay_generation(const d4pg_replay* h) { return h->gen; }
 
-int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st) {
+int launch_gate_signal(unsigned long long* flag, cudaStream_t st);
+int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* prio, cudaStream_t st, unsigned long long* gate) {
   TreeArgs a{};
   a.sum = h->sum; a.mn = h->mn; a.cap = h->cap; a.log2cap = h->log2cap; a.size = h->size;
   a.n = B; a.idx = idx; a.v0 = prio; a.alpha_f32 = h->alpha_f32; a.scratch = h->scratch; a.state = reinterpret_cast<ReplayState*>(h->state);
@@ -313,12 +359,15 @@ int launch_tree_update(d4pg_replay* h, int B, const int32_t* idx, const float* p
     const size_t smem = size_t(hs) * 2 * (sizeof(int) + sizeof(float2));     // 12 KB at B = 512
     D4PG_MAX_CARVEOUT(tree_update_fast_kernel);
     const int D = std::min(4, h->log2cap);                     // 2^D CTAs, one per top-level subtree
+    static const bool sig_kernel = getenv("D4PG_PIPE_SIGNAL_KERNEL") != nullptr;      // A/B switch: separate signal kernel
+    if (D > 0 && !sig_kernel) { a.gate = gate; gate = nullptr; }   // the last CTA opens the gate itself
     tree_update_fast_kernel<<<1 << D, threads, smem, st>>>(a, hs, D);
   } else {
     D4PG_MAX_CARVEOUT(tree_write_kernel<TREE_UPDATE>);
     tree_write_kernel<TREE_UPDATE><<<1, TREE_THREADS, 0, st>>>(a);
   }
   D4PG_LAUNCH_OK();
+  if (gate) { int rc = launch_gate_signal(gate, st); if (rc) return rc; }
   h->pristine = 0;
   return D4PG_OK;
 }
@@ -351,7 +400,9 @@ extern "C" int32_t d4pg_replay_create(int64_t size, int32_t obs_dim, int32_t act
   h->obs_dim = obs_dim; h->act_dim = act_dim; h->alpha = alpha; h->alpha_f32 = float(alpha);
   h->sum = sum_tree; h->mn = min_tree; h->obs = obs; h->act = act; h->rew = rew; h->obs2 = obs2; h->done = done;
   h->scratch = scratch; h->state = state; h->len = 0; h->next_idx = 0; h->pristine = 1;
-  h->stage_host = nullptr; h->stage_dev = nullptr; h->stage_bytes = 0; h->stage_ev = nullptr; h->stage_busy = false;
+  h->stage_host = nullptr; h->stage_dev = nullptr; h->stage_bytes = 0; h->stage_slot = 0;
+  for (int i = 0; i < 2; ++i) { h->stage_ev[i] = nullptr; h->stage_busy[i] = false; }
+  h->gate_flag = nullptr; h->gate_target = 0; h->gate_pending = false; h->order_ev = nullptr;
   tree_init_kernel<<<296, 256, 0, as_stream(stream)>>>(h->sum, h->mn, h->scratch,
                                                         reinterpret_cast<ReplayState*>(h->state), h->cap);
   cudaError_t e = cudaGetLastError();
@@ -361,7 +412,11 @@ extern "C" int32_t d4pg_replay_create(int64_t size, int32_t obs_dim, int32_t act
 }
 
 extern "C" int32_t d4pg_replay_destroy(d4pg_replay_t* h) {
-  if (h && h->stage_ev) cudaEventDestroy(h->stage_ev);
+  if (h) {
+    for (int i = 0; i < 2; ++i) if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
+    if (h->gate_flag) { cudaDeviceSynchronize(); cudaFree(h->gate_flag); }
+  }
   delete h;
   return D4PG_OK;
 }
@@ -380,14 +435,18 @@ PackLayout pack_layout(const d4pg_replay* h, int64_t n) {
 }  // namespace
 
 extern "C" int64_t d4pg_replay_staging_bytes(const d4pg_replay_t* h, int64_t rows) {
-  return (h && rows > 0) ? pack_layout(h, rows).total : -1;
+  return (h && rows > 0) ? 2 * pack_layout(h, rows).total : -1;      // two staging slots
 }
 
 extern "C" int32_t d4pg_replay_set_staging(d4pg_replay_t* h, void* pinned_host, void* device, int64_t bytes) {
   D4PG_REQUIRE(h && pinned_host && device && bytes > 0, D4PG_EINVAL, "d4pg_replay_set_staging: bad arguments");
-  h->stage_host = static_cast<uint8_t*>(pinned_host); h->stage_dev = static_cast<uint8_t*>(device); h->stage_bytes = bytes;
-  if (!h->stage_ev) D4PG_CUDA_OK(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
-  h->stage_busy = false;
+  h->stage_host = static_cast<uint8_t*>(pinned_host); h->stage_dev = static_cast<uint8_t*>(device);
+  h->stage_bytes = (bytes / 2) & ~int64_t(15);                        // per slot
+  for (int i = 0; i < 2; ++i) {
+    if (!h->stage_ev[i]) D4PG_CUDA_OK(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+    h->stage_busy[i] = false;
+  }
+  h->stage_slot = 0;
   return D4PG_OK;
 }
 
@@ -505,21 +564,66 @@ extern "C" int32_t d4pg_replay_add_host(d4pg_replay_t* h, int64_t n, const float
   D4PG_REQUIRE(h->stage_host, D4PG_ESTATE, "d4pg_replay_add_host: call d4pg_replay_set_staging first");
   const PackLayout p = pack_layout(h, n);
   D4PG_REQUIRE(p.total <= h->stage_bytes, D4PG_EINVAL, "d4pg_replay_add_host: %lld rows do not fit the staging buffer", (long long)n);
-  if (h->stage_busy) D4PG_CUDA_OK(cudaEventSynchronize(h->stage_ev));       // previous copy has left the pinned buffer
-  uint8_t* hp = h->stage_host;
+  const int slot = h->stage_slot; h->stage_slot ^= 1;
+  if (h->stage_busy[slot]) D4PG_CUDA_OK(cudaEventSynchronize(h->stage_ev[slot]));   // the add that used this slot has consumed it
+  uint8_t* hp = h->stage_host + size_t(slot) * h->stage_bytes;
+  uint8_t* d = h->stage_dev + size_t(slot) * h->stage_bytes;
   memcpy(hp + p.obs, obs, size_t(n) * h->obs_dim * 4);
   memcpy(hp + p.obs2, obs2, size_t(n) * h->obs_dim * 4);
   memcpy(hp + p.act, act, size_t(n) * h->act_dim * 4);
   memcpy(hp + p.rew, rew, size_t(n) * 8);
   memcpy(hp + p.done, done, size_t(n));
   cudaStream_t st = as_stream(stream);
-  D4PG_CUDA_OK(cudaMemcpyAsync(h->stage_dev, hp, size_t(p.total), cudaMemcpyHostToDevice, st));
-  D4PG_CUDA_OK(cudaEventRecord(h->stage_ev, st));
-  h->stage_busy = true;
-  uint8_t* d = h->stage_dev;
-  return d4pg_replay_add(h, n, reinterpret_cast<const float*>(d + p.obs), reinterpret_cast<const float*>(d + p.act),
-                         reinterpret_cast<const double*>(d + p.rew), reinterpret_cast<const float*>(d + p.obs2),
-                         d + p.done, prioritized, stream);
+  D4PG_CUDA_OK(cudaMemcpyAsync(d, hp, size_t(p.total), cudaMemcpyHostToDevice, st));   // ahead of the ingest gate
+  int rc = d4pg_replay_add(h, n, reinterpret_cast<const float*>(d + p.obs), reinterpret_cast<const float*>(d + p.act),
+                           reinterpret_cast<const double*>(d + p.rew), reinterpret_cast<const float*>(d + p.obs2),
+                           d + p.done, prioritized, stream);
+  D4PG_CUDA_OK(cudaEventRecord(h->stage_ev[slot], st));               // device slot read by the ring write
+  h->stage_busy[slot] = true;
+  return rc;
+}
+
+// ---- ingest gate + stream ordering (learner host pipeline, learner.cu) ------------------------------------------
+namespace d4pg {
+__global__ void gate_wait_kernel(const unsigned long long* flag, unsigned long long target, unsigned long long* trace) {
+  unsigned long long v;
+  step_stamp(trace, 10);
+  do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory"); } while (v < target);
+  step_stamp(trace, 10 + 16);
+}
+__global__ void gate_signal_kernel(unsigned long long* flag) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(flag), "l"(v + 1) : "memory");
+}
+unsigned long long* replay_gate_flag(d4pg_replay* h) {
+  if (!h->gate_flag) {
+    if (cudaMalloc(reinterpret_cast<void**>(&h->gate_flag), 16) != cudaSuccess || cudaMemset(h->gate_flag, 0, 16) != cudaSuccess) return nullptr;
+  }
+  return h->gate_flag;
+}
+void replay_arm_gate(d4pg_replay* h) { ++h->gate_target; h->gate_pending = true; }
+int replay_gate_consume(d4pg_replay* h, cudaStream_t st) {
+  if (!h->gate_pending) return D4PG_OK;
+  gate_wait_kernel<<<1, 1, 0, st>>>(h->gate_flag, h->gate_target, step_trace());
+  D4PG_LAUNCH_OK();
+  h->gate_pending = false;
+  return D4PG_OK;
+}
+int launch_gate_signal(unsigned long long* flag, cudaStream_t st) {
+  gate_signal_kernel<<<1, 1, 0, st>>>(flag);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+}  // namespace d4pg
+
+extern "C" int32_t d4pg_replay_order_after(d4pg_replay_t* h, d4pg_stream_t first, d4pg_stream_t then) {
+  D4PG_REQUIRE(h, D4PG_EINVAL, "d4pg_replay_order_after: null handle");
+  if (as_stream(first) == as_stream(then)) return D4PG_OK;
+  if (!h->order_ev) D4PG_CUDA_OK(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+  D4PG_CUDA_OK(cudaEventRecord(h->order_ev, as_stream(first)));
+  D4PG_CUDA_OK(cudaStreamWaitEvent(as_stream(then), h->order_ev, 0));
+  return D4PG_OK;
 }
 extern "C" int64_t d4pg_replay_len(const d4pg_replay_t* h) { return h ? h->len : -1; }
 extern "C" int64_t d4pg_replay_next_idx(const d4pg_replay_t* h) { return h ? h->next_idx : -1; }
@@ -547,16 +651,29 @@ extern "C" int32_t d4pg_replay_add(d4pg_replay_t* h, int64_t n, const float* obs
   const int blocks = int(std::min<int64_t>(148 * 4, (n * h->obs_dim + 255) / 256));
   ring_write_kernel<<<blocks, 256, 0, st>>>(h->obs, h->act, h->rew, h->obs2, h->done, obs, act, rew, obs2, done,
                                              n, h->obs_dim, h->act_dim, h->size, start,
-                                             reinterpret_cast<ReplayState*>(h->state), new_len, new_next);
+                                             reinterpret_cast<ReplayState*>(h->state), new_len, new_next, step_trace());
   D4PG_LAUNCH_OK();
   if (prioritized) {
+    // ingest gate (host pipeline): the rows above only had to follow the previous gather (stream order); the trees wait for
+    // the last launched learner step's priority write-back -- inside the first tree kernel when that is the 1-CTA fast one
+    const int64_t n1g = std::min<int64_t>(n, h->size - start);
+    const unsigned long long* gflag = nullptr; unsigned long long gtarget = 0;
+    static const bool gate_kernel = getenv("D4PG_PIPE_GATE_KERNEL") != nullptr;      // A/B switch: separate 1-thread gate kernel
+    if (h->gate_pending && !gate_kernel && n <= 65536 && n1g <= TREE_ADD_FAST_MAX && h->log2cap < 32) {
+      gflag = h->gate_flag; gtarget = h->gate_target; h->gate_pending = false;
+    } else {
+      int grc = replay_gate_consume(h, st); if (grc) return grc;
+    }
     if (n <= 65536) {
       // split a wrapping add into its two contiguous pieces
       const int64_t n1 = std::min<int64_t>(n, h->size - start);
       auto add_range = [&](int64_t s0, int64_t cnt) {
-        if (cnt <= TREE_ADD_FAST_MAX && h->log2cap < 32)
+        if (cnt <= TREE_ADD_FAST_MAX && h->log2cap < 32) {
           tree_add_range_fast_kernel<<<1, TREE_THREADS, 0, st>>>(h->sum, h->mn, h->cap, h->log2cap, s0, cnt,
-                                                                 reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);
+                                                                 reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32, step_trace(),
+                                                                 gflag, gtarget);
+          gflag = nullptr;
+        }
         else
           tree_add_range_kernel<<<1, TREE_THREADS, 0, st>>>(h->sum, h->mn, h->cap, h->log2cap, s0, cnt,
                                                             reinterpret_cast<const ReplayState*>(h->state), h->alpha_f32);

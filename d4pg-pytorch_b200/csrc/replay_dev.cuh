@@ -71,9 +71,9 @@ struct SampleArgs {
   int pdl;                          // programmatic-dependent-launch trigger position (0/1/2)
   int pipe_slot;                    // >= 0 (prefetch pipeline): use the sampler's own counters, derive into this slot
   unsigned long long* trace; int trace_slot;
+  unsigned long long* done_epoch;   // host pipeline: CTA b publishes (release) s_steps_done + 1 in [b] when its rows are gathered
 };
 
-constexpr int SAMPLE_ROWS = 32;      // rows per CTA
 constexpr int SAMPLE_THREADS = 256;
 constexpr int TOP_LEVELS = 11;       // tree levels 0..10 (nodes 1..2047) are staged in shared memory
 
@@ -236,6 +236,7 @@ struct TreeArgs {
   int64_t ring_start;                                              // ADD: positions (ring_start+i) % size
   float alpha_f32; int32_t* scratch; ReplayState* state;
   unsigned long long* trace;
+  unsigned long long* gate;     // non-null (host pipeline): bumped once, with release order, when every node is written
 };
 constexpr int TREE_THREADS = 1024;
 
@@ -417,6 +418,15 @@ __device__ __forceinline__ void tree_update_fast_body(const TreeArgs& a, unsigne
       }
       __threadfence_block();
       __syncwarp();
+    }
+    if (a.gate) {                                             // the ingest gate opens: the trees are complete
+      __threadfence();
+      __syncwarp();
+      if (t == 0) {
+        unsigned long long v;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.gate) : "memory");
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.gate), "l"(v + 1) : "memory");
+      }
     }
   }
 }

@@ -74,7 +74,10 @@ class _Learner(object):
                           (4 if ddpg.actor_critic == "post_update" else 0))
         # plan 1: fp32 = FFMA chain tiles; tf32x3 / tf32 = tcgen05 chain tiles (mlp_tc_chain.cu); plan 0: one launch per level
         cfg.chain = {"levels": 0, "cluster": 1, False: 0, True: 1, 0: 0, 1: 1}[ddpg.chain]
-        cfg.prefetch = 1 if (ddpg.prefetch and cfg.sample_mode == 1) else 0
+        # device sampling: step t samples batch t+1 on a side branch; reference sampling (host-drawn uniforms): the host
+        # pipeline -- train() samples batch k on the learner's ingest stream, behind the add()s issued there, while step
+        # k-1 still runs (needs the CUDA-graph step)
+        cfg.prefetch = 1 if (ddpg.prefetch and (cfg.sample_mode == 1 or ddpg.use_graph)) else 0
         self.cfg = cfg
         nws = L.d4pg_learner_workspace_floats(C.byref(cfg))
         f32 = torch.float32
@@ -118,6 +121,14 @@ class _Learner(object):
         self.read_losses = L.d4pg_learner_read_losses
         self.losses_out = (C.c_float * 4)()
         self.fresh_host_step = False          # the most recent step was a train() (its losses are in the pinned ring)
+        self._store = store
+        # parameter writes torch can see (load_state_dict, hard_update, optimizer steps: in-place ops bump the version counter
+        # the views share with the flat buffer) are reported to the library by train(); see DDPG.weights_changed
+        self._flats = (g.actor.flat_params(), g.critic.flat_params(), ddpg.actor_target.flat_params(), ddpg.critic_target.flat_params())
+        self.seen_versions = None
+        self.weights_changed = L.d4pg_learner_weights_changed
+        ing = L.d4pg_learner_ingest_stream(h)
+        store.attach_ingest_stream(int(ing) if ing else None)   # host pipeline: add_batch_host goes to the ingest stream
         if opt_a.step_count or (ddpg.prioritized_replay and ddpg.beta_schedule.t):
             _lib.check(L.d4pg_learner_set_counters(h, opt_a.step_count,
                                                    ddpg.beta_schedule.t if ddpg.prioritized_replay else 0,
@@ -139,6 +150,9 @@ class _Learner(object):
 
     def close(self):
         if self.handle is not None:
+            if getattr(self, "_store", None) is not None:
+                self._store.attach_ingest_stream(None)            # joins the ingest stream first
+                self._store = None
             _lib.lib().d4pg_learner_destroy(self.handle)
             self.handle = None
 
@@ -157,7 +171,7 @@ class DDPG:
                  critic_dist_info=None, n_steps=1,
                  # ---- B200 build extensions (keyword-only in spirit; reference callers never pass them)
                  device=None, sampling="reference", projection="reference", precision="fp32",
-                 use_graph=True, philox_seed=0, comm=None, chain="cluster", prefetch=True,
+                 use_graph=True, philox_seed=0, comm=None, chain="cluster", prefetch=True, track_weights=True,
                  importance_weighted=False, priority="reference", actor_critic="reference"):
         self.gamma = gamma
         self.n_steps = n_steps
@@ -177,6 +191,7 @@ class DDPG:
         self.chain = chain
         # device-side sampling only: step t already samples batch t+1 behind its own backward pass (identical results)
         self.prefetch = prefetch
+        self.track_weights = track_weights
         # corrected-semantics switches (default = the reference's behaviour)
         assert priority in ("reference", "ce") and actor_critic in ("reference", "post_update")
         self.importance_weighted, self.priority = bool(importance_weighted), priority
@@ -241,8 +256,17 @@ class DDPG:
         model_global._flat_grad = model_local.flat_grads()
         model_global._bind_grads()
 
+    def weights_changed(self):
+        """Report a parameter write the learner cannot see.  train() notices every in-place torch operation on actor /
+        critic / target parameters (load_state_dict, hard_update, sync_local_global, `with torch.no_grad(): p.copy_(..)`)
+        through the tensors' version counters; writes through `p.data` or raw pointers bypass those counters -- call this
+        after them (or construct with track_weights=False: the weight images are then rebuilt on every step)."""
+        if self._learner is not None and self._learner.handle is not None:
+            self._learner.seen_versions = None
+
     def update_target_parameters(self):                                                      # ddpg.py:110-116
         _lib.require_cuda()
+        self.weights_changed()
         for tgt, src in ((self.actor_target, self.actor), (self.critic_target, self.critic)):
             _lib.check(_lib.lib().d4pg_polyak(_lib.ptr(tgt.flat_params()), _lib.ptr(src.flat_params()),
                                               tgt._total, float(self.tau), _lib.stream_ptr()), "d4pg_polyak")
@@ -310,6 +334,11 @@ class DDPG:
         store = self.replayBuffer._store
         if store._n_staged:
             store.flush()
+        f = L._flats
+        v = (f[0]._version, f[1]._version, f[2]._version, f[3]._version) if self.track_weights else None
+        if v != L.seen_versions or v is None:
+            L.weights_changed(L.handle)
+            L.seen_versions = v
         B = self.batch_size
         # one library call: order after the caller's stream, H2D of this step's host inputs, the step's
         # CUDA graph on the learner stream, order the caller's stream after it

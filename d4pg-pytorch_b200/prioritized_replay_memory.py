@@ -56,6 +56,11 @@ class _DeviceReplay(object):
         self._n_staged = 0
         self._len = 0
         self._next_idx = 0
+        # host pipeline (a learner's ingest stream, ddpg.py): add_batch_host is issued there; every other device
+        # operation runs on the caller's stream -- the two are kept in program order by events, only when they interleave
+        self._ingest_stream = None
+        self._ing_dirty = False
+        self._cs_dirty = False
         if obs_dim is not None and act_dim is not None and torch.cuda.is_available():
             self._allocate(obs_dim, act_dim)
 
@@ -100,9 +105,41 @@ class _DeviceReplay(object):
     def __del__(self):
         try:
             if self.handle is not None:
-                _lib.lib().d4pg_replay_destroy(self.handle)
+                h, self.handle = self.handle, None       # a learner collected later (reference cycles) must not touch it
+                self._ingest_stream = None
+                _lib.lib().d4pg_replay_destroy(h)
         except Exception:
             pass
+
+    # -- streams -----------------------------------------------------------------------
+    def attach_ingest_stream(self, raw_stream):
+        """raw cudaStream_t (int) of the learner's ingest stream, or None to detach (joins it first)."""
+        if self._ingest_stream is not None and self.handle is not None:
+            self._join_ingest()
+        self._ingest_stream = raw_stream
+        self._ing_dirty = False
+        self._cs_dirty = raw_stream is not None          # whatever the caller's stream did so far comes first
+
+    def _join_ingest(self):
+        """The caller's stream is about to touch the buffer: order it after the ingest stream's adds."""
+        if self._ingest_stream is not None and self.handle is not None:
+            if self._ing_dirty:
+                _lib.check(_lib.lib().d4pg_replay_order_after(self.handle, C.c_void_p(self._ingest_stream), _lib.stream_ptr()),
+                           "d4pg_replay_order_after")
+                self._ing_dirty = False
+            self._cs_dirty = True
+
+    def _ingest_ptr(self):
+        """Stream of a host add: the ingest stream when attached (ordered after the caller's earlier buffer operations)."""
+        ing = self._ingest_stream
+        if ing is None:
+            return _lib.raw_stream()
+        if self._cs_dirty:
+            _lib.check(_lib.lib().d4pg_replay_order_after(self.handle, _lib.stream_ptr(), C.c_void_p(ing)),
+                       "d4pg_replay_order_after")
+            self._cs_dirty = False
+        self._ing_dirty = True
+        return ing
 
     # -- ingest ------------------------------------------------------------------------
     def add(self, s, a, r, s2, done):
@@ -146,7 +183,7 @@ class _DeviceReplay(object):
             # host tensors of the right types (e.g. slices of a pinned rollout buffer): no numpy round trip
             n = s.shape[0]
             rc = _lib.lib().d4pg_replay_add_host(self.handle, n, s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr(),
-                                                 done.data_ptr(), 1 if self.prioritized else 0, _lib.raw_stream())
+                                                 done.data_ptr(), 1 if self.prioritized else 0, self._ingest_ptr())
             if rc:
                 _lib.check(rc, "d4pg_replay_add_host")
             self._next_idx = (self._next_idx + n) % self.size
@@ -174,7 +211,7 @@ class _DeviceReplay(object):
         if d.dtype != np.uint8:
             d = d.astype(np.uint8)
         rc = L.d4pg_replay_add_host(self.handle, n, s.ctypes.data, a.ctypes.data, r.ctypes.data, s2.ctypes.data,
-                                    d.ctypes.data, 1 if self.prioritized else 0, _lib.raw_stream())
+                                    d.ctypes.data, 1 if self.prioritized else 0, self._ingest_ptr())
         if rc:
             _lib.check(rc, "d4pg_replay_add_host")
         self._next_idx = (self._next_idx + n) % self.size
@@ -284,6 +321,7 @@ class _DeviceReplay(object):
         self._next_idx = int(_lib.lib().d4pg_replay_next_idx(self.handle))
 
     def flush(self):
+        self._join_ingest()
         n = self._n_staged
         if n == 0:
             return

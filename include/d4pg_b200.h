@@ -130,12 +130,17 @@ int32_t d4pg_replay_add(d4pg_replay_t* h, int64_t n, const float* obs, const flo
 /* Host-side ingest: register a caller-owned PINNED host staging buffer and a device staging buffer
  * of `bytes` each (>= d4pg_replay_staging_bytes(rows)), then add() n <= rows transitions straight from
  * ordinary host arrays: the five arrays are packed into the pinned buffer, moved with ONE async H2D
- * copy and unpacked by the ring-write kernel.  Stream-ordered; the pinned buffer is re-used only after
- * the previous copy out of it has completed. */
+ * copy and unpacked by the ring-write kernel.  Stream-ordered.  The buffers are used as TWO slots of bytes/2
+ * (d4pg_replay_staging_bytes already counts both), alternating per call, so the host can stage add k+1 while
+ * add k still waits on the device; a slot is re-used only after the add that read it has completed. */
 int64_t d4pg_replay_staging_bytes(const d4pg_replay_t* h, int64_t rows);
 int32_t d4pg_replay_set_staging(d4pg_replay_t* h, void* pinned_host, void* device, int64_t bytes);
 int32_t d4pg_replay_add_host(d4pg_replay_t* h, int64_t n, const float* obs, const float* act, const double* rew,
                              const float* obs2, const uint8_t* done, int32_t prioritized, d4pg_stream_t stream);
+/* Order stream `then` after everything enqueued so far on stream `first` (event record + wait; no-op if equal).  The
+ * host mirror uses it to keep buffer operations issued on the caller's stream and on a learner's ingest stream
+ * (d4pg_learner_ingest_stream) in program order. */
+int32_t d4pg_replay_order_after(d4pg_replay_t* h, d4pg_stream_t first, d4pg_stream_t then);
 
 /* Device-side ingest with n-step return accumulation at insert (replay_memory.py:38-45).  The arrays hold ONE episode
  * of T consecutive steps, resident on the device; transition i = (s_i, a_i, sum_{k<n} gamma^k r_{i+k}, s'_{i+n-1},
@@ -256,7 +261,13 @@ typedef struct {
                                  priorities are in the trees, while its backward pass and Adam still run.  Same
                                  Philox counters and the same trees as sampling at the start of step t+1, so results
                                  are identical; any replay mutation by the caller (add / set / update) between two
-                                 steps discards the prefetched batch and step t+1 samples again at its start */
+                                 steps discards the prefetched batch and step t+1 samples again at its start.
+                                 With sample_mode 0 (host-drawn uniforms / positions) and use_graph: the HOST pipeline --
+                                 d4pg_learner_step_host* samples batch k on the library's ingest stream
+                                 (d4pg_learner_ingest_stream), behind the add()s the caller issued on that stream and
+                                 gated on step k-1's priority write-back, while step k-1's backward pass, dW and Adam
+                                 still run.  Tree operations keep the reference's order update(k-1) -> add(k) ->
+                                 sample(k) (ddpg.py:200-255 + main.py's add loop): results are identical */
 } d4pg_learner_config_t;
 
 /* Caller-owned device buffers.  P_a / P_c = d4pg_*_layout().total. */
@@ -316,6 +327,18 @@ int32_t d4pg_learner_tensor(d4pg_learner_t* h, const char* name, void** ptr, int
 int32_t d4pg_learner_profile_step(d4pg_learner_t* h, d4pg_stream_t stream, int32_t max_launches,
                                   float* ms_out, char* names_out, int32_t name_stride, int32_t* n_out);
 int64_t d4pg_learner_steps_done(const d4pg_learner_t* h);
+/* host pipeline (cfg.prefetch with sample_mode 0): the stream buffer adds should be issued on so they overlap the
+ * running step (NULL when the pipeline is off).  Owned by the learner.  With the pipeline on, d4pg_learner_step_host*
+ * samples on this stream and does NOT wait for caller_stream first (that stream is ordered after the whole previous
+ * step, which would serialise the pipeline): a caller that touched the buffer on another stream (add, update_priorities,
+ * set_leaves ...) calls d4pg_replay_order_after(replay, that_stream, ingest_stream) before the next step. */
+void* d4pg_learner_ingest_stream(const d4pg_learner_t* h);
+/* The tcgen05 plans consume pre-split hi/lo weight IMAGES that the library's Adam / Polyak kernel keeps current.  Every
+ * CUDA-graph step that samples in the graph re-packs them from the fp32 parameters first (any external write is picked
+ * up); the host pipeline's steps (above) re-pack only after this call -- make it whenever actor / critic / target
+ * parameters were written from outside the library (state_dict load, hard update, manual edits) since the last step.
+ * A new learner starts "changed". */
+int32_t d4pg_learner_weights_changed(d4pg_learner_t* h);
 int32_t d4pg_learner_kernels_per_step(const d4pg_learner_t* h);
 /* restore the optimiser step counters / beta-schedule clock (checkpoint resume) */
 int32_t d4pg_learner_set_counters(d4pg_learner_t* h, int64_t adam_step, int64_t beta_t, d4pg_stream_t stream);

@@ -490,3 +490,83 @@ def test_post_update_critic_switch_vs_derived_oracle():
                 assert err.max().item() <= 2.5e-4 and (err > TOL).float().mean().item() <= 0.1, (mode, k)
         results[mode] = dd.actor.flat_params().cpu().clone()
     assert not torch.equal(results["post_update"], results["reference"])
+
+
+@pytest.mark.parametrize("prioritized,precision", [(True, "fp32"), (True, "tf32x3"), (False, "fp32")])
+def test_host_pipeline_adds_interleaved_with_steps_vs_oracle(prioritized, precision):
+    """The end-to-end loop of bench.py / main.py: add_batch of new transitions, train(), read the loss one step late.
+    With host-drawn uniforms the step is the HOST pipeline (add + sample of batch k on the learner's ingest stream while
+    step k-1 still runs).  Tree operations must keep the reference's order update(k-1) -> add(k) -> sample(k): sampled
+    indices bit-exact against the oracle on every step, also across a caller-stream update_priorities and a small ring
+    that wraps."""
+    import d4pg_b200 as d4pg
+    B, mem, n_fill, n_new, steps = 64, 1024, 512, 96, 9
+    info = {"type": "categorical", "v_min": -50.0, "v_max": 0.0, "n_atoms": 51}
+    torch.manual_seed(11); np.random.seed(11); random.seed(11)
+    dd = d4pg.DDPG(17, 6, memory_size=mem, batch_size=B, critic_dist_info=info, prioritized_replay=prioritized, precision=precision)
+    dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3), d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
+    rng = np.random.RandomState(12)
+
+    def rows(n):
+        return (rng.randn(n, 17).astype(np.float32), rng.uniform(-1, 1, (n, 6)).astype(np.float32),
+                (-3 * rng.rand(n)).astype(np.float32).astype(np.float64), rng.randn(n, 17).astype(np.float32), rng.rand(n) < 0.05)
+    first = rows(n_fill)
+    dd.replayBuffer.add_batch(*first)
+    lo = O.LearnerOracle(17, 6, info, actor_w={k: v.cpu().clone() for k, v in dd.actor.state_dict().items()},
+                         critic_w={k: v.cpu().clone() for k, v in dd.critic.state_dict().items()})
+    ob = O.PrioritizedReplayOracle(mem, 0.6, 17, 6)          # uniform replay: the same ring storage, positions drawn uniformly
+    ob.add_batch(*first)
+    sched = O.LinearScheduleOracle(100000, 1.0, 0.4)
+    pin = None
+    expected = []
+    for t in range(steps):
+        new = rows(n_new)
+        pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in new]      # host tensors: the fast ingest path
+        dd.replayBuffer.add_batch(*pin)
+        ob.add_batch(*new)
+        random.seed(700 + t)
+        st = random.getstate()
+        if prioritized:
+            us = [random.random() for _ in range(B)]
+            batch = ob.sample(B, sched.value(), us)
+        else:
+            pos = np.asarray(O.uniform_sample_positions(random, len(ob), B))                 # replay_memory.py:67
+            batch = (ob.obs[pos], ob.act[pos], ob.rew[pos], ob.obs2[pos], ob.done[pos])
+        random.setstate(st)
+        dd.train()
+        if t < 4 or t == steps - 1:       # the steps in between run without any host synchronisation: the pipeline is really ahead
+            idx = dd.last_batch_info()["idx"].cpu().numpy()
+            assert np.array_equal(idx, batch[6] if prioritized else pos), "step %d: sampled indices differ from the oracle" % t
+        out = lo.train_step(*batch[:5])
+        if prioritized:
+            ob.update_priorities(batch[6], out["prio"])
+        expected.append(float(out["loss_critic"]))
+        if t >= 1:
+            lc_prev, _ = dd.last_losses(lag=1)
+            assert abs(lc_prev - expected[t - 1]) <= (TOL if precision == "fp32" else 5e-5), (t, lc_prev, expected[t - 1])
+        if t == 5:
+            # parameter writes between two pipelined steps: the library's weight images must follow.  load_state_dict is seen
+            # through the tensors' version counters; a write through .data is not and is reported with weights_changed()
+            dd.actor.load_state_dict({k: v * 0.9 for k, v in dd.actor.state_dict().items()})
+            for k in H.NAMES:
+                lo.actor[k] = lo.actor[k] * 0.9
+        if t == 6:
+            for prm in dd.critic.parameters():
+                prm.data.mul_(0.95)
+            dd.weights_changed()
+            for k in H.NAMES:
+                lo.critic[k] = lo.critic[k] * 0.95
+        if prioritized and t == 4:
+            # a caller-stream tree write between two steps: ordered before the next ingest-stream add
+            ii = np.arange(10, dtype=np.int32); pp = np.linspace(0.5, 2.0, 10).astype(np.float32)
+            dd.replayBuffer.update_priorities(ii, pp)
+            ob.update_priorities(ii, pp)
+    lc, la = dd.last_losses()
+    assert abs(lc - expected[-1]) <= (TOL if precision == "fp32" else 5e-5)
+    tol_w = 2.5e-4 if precision == "fp32" else 3e-3      # 3xTF32 rounding flips a few ReLU masks over 9 Adam steps (lr 1e-3)
+    for k in H.NAMES:
+        for mine, ref in ((dd.actor.state_dict()[k], lo.actor[k]), (dd.critic.state_dict()[k], lo.critic[k])):
+            err = (mine.cpu() - ref).abs()
+            assert err.max().item() <= tol_w, (k, err.max().item())
+    if prioritized:
+        assert np.allclose(dd.replayBuffer._it_sum.values()[1], ob.sum.value[1], rtol=1e-5)

@@ -9,6 +9,7 @@ cfg = bench.CFG["c2"]
 info = {"type": "categorical", "v_min": cfg["v_min"], "v_max": cfg["v_max"], "n_atoms": cfg["atoms"]}
 B, cap = cfg["batch"], cfg["cap"]
 sampling = os.environ.get("SAMPLING", "reference")
+LAG = int(os.environ.get("LAG", "1"))
 dd = d4pg.DDPG(cfg["obs"], cfg["act"], memory_size=cap, batch_size=B, critic_dist_info=info, sampling=sampling)
 dd.assign_global_optimizer(d4pg.SharedAdam(dd.actor.parameters(), lr=1e-3), d4pg.SharedAdam(dd.critic.parameters(), lr=1e-3))
 dd.replayBuffer.add_batch(*bench.synth(cfg, cap, seed=0))
@@ -22,15 +23,18 @@ def step(i, acc=True):
     b = time.perf_counter()
     dd.train()
     c = time.perf_counter()
-    dd.last_losses()
+    if LAG and i > 0: dd.last_losses(lag=1)
+    elif not LAG: dd.last_losses()
     d = time.perf_counter()
     if acc:
         t["add"] += b - a; t["train"] += c - b; t["loss"] += d - c
 for i in range(50): step(i, False)
+dd.last_losses()
 torch.cuda.synchronize()
 N = 2000
 t0 = time.perf_counter()
 for i in range(N): step(i)
+dd.last_losses()
 tot = time.perf_counter() - t0
 print("sampling=%s  %.1f us/step: add_batch %.1f  train %.1f  last_losses(sync) %.1f" % (sampling, tot / N * 1e6, t["add"] / N * 1e6, t["train"] / N * 1e6, t["loss"] / N * 1e6))
 pr = cProfile.Profile(); pr.enable()
