@@ -72,8 +72,9 @@ __device__ __forceinline__ void peer_signal_last_cta(const PeerSignal& s, unsign
     f[2] = 0ull;
     const unsigned long long v = f[1] + 1ull;
     f[1] = v;
-    __threadfence_system();
-    for (int p = 0; p < s.world; ++p) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(s.inbox[p]), "l"(v) : "memory");
+    __threadfence_system();                    // ONE system-scope fence, then relaxed stores: fence + relaxed store = release;
+    // (st.release.sys per peer put a MEMBAR.ALL.SYS in front of every one of the N flag stores)
+    for (int p = 0; p < s.world; ++p) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(s.inbox[p]), "l"(v) : "memory");
   }
 }
 // threads 0..world-1 of a CTA poll the LOCAL inbox until every rank published >= this rank's own count; then __syncthreads

@@ -167,6 +167,44 @@ int comm_peer_reduce_scatter(d4pg_comm* c, int parity, cudaStream_t st) {
   return D4PG_OK;
 }
 
+// ---- two-phase in-switch reduction (NVLS) ------------------------------------------------------------------------
+// Rank r owns slice r: ONE multimem.ld_reduce per element returns the sum over all ranks (added by the NVSwitch), ONE
+// multimem.st broadcasts it into slice r of every rank's reduced buffer.  Per GPU 2 x 1.15 MB cross the links instead of
+// N x 1.15 MB when every rank ld_reduces everything; the price is a second flag hop (signal 1) before Adam.
+struct PeerMC2Args {
+  int world; int64_t lo4, hi4;
+  const float* mc_half; float* mc_red;          // multicast addresses: this step's gradient half, the reduced buffer
+  const unsigned long long* my_f1;              // local inbox of signal 0: every rank's dW is done
+  d4pg::PeerSignal sig2;                        // signal 1: my slice is reduced and broadcast
+};
+__global__ void __launch_bounds__(256) mc_reduce_bcast_kernel(const PeerMC2Args a) {
+  d4pg::peer_wait_all(a.my_f1, a.world);
+  for (int64_t i = a.lo4 + int64_t(blockIdx.x) * 256 + threadIdx.x; i < a.hi4; i += int64_t(gridDim.x) * 256) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(reinterpret_cast<const float4*>(a.mc_half) + i) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(reinterpret_cast<float4*>(a.mc_red) + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence_system(); d4pg::peer_signal_last_cta(a.sig2, gridDim.x); }
+}
+int comm_mc_reduce_bcast(d4pg_comm* c, int parity, cudaStream_t st) {
+  PeerInfo info{};
+  D4PG_REQUIRE(comm_peer_info(c, &info) && info.mc, D4PG_ESTATE, "comm_mc_reduce_bcast: multicast is not set up");
+  PeerMC2Args a{};
+  a.world = info.world;
+  const int64_t n4 = info.n >> 2, per = (n4 + info.world - 1) / info.world;
+  a.lo4 = std::min<int64_t>(n4, per * info.rank); a.hi4 = std::min<int64_t>(n4, a.lo4 + per);
+  a.mc_half = info.mc + int64_t(parity) * info.n;
+  a.mc_red = const_cast<float*>(info.mc) + 2 * info.n;
+  a.my_f1 = info.flag[info.rank]; a.sig2 = comm_peer_signal(info, 1);
+  const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(296, (a.hi4 - a.lo4 + 255) / 256)));
+  mc_reduce_bcast_kernel<<<blocks, 256, 0, st>>>(a);
+  D4PG_LAUNCH_OK();
+  return D4PG_OK;
+}
+
 int comm_allreduce(d4pg_comm* c, float* buf, int64_t n, cudaStream_t st) {
   D4PG_REQUIRE(c && buf && n > 0, D4PG_EINVAL, "comm_allreduce: bad arguments");
   NCCL_OK(g_nccl.AllReduce(buf, buf, size_t(n), ncclFloat32, ncclSum, c->comm, st));
@@ -338,9 +376,10 @@ static int mc_size_for(d4pg_comm* c, size_t* out) {
   D4PG_REQUIRE(c->xn > 0, D4PG_ESTATE, "d4pg_comm_mc_*: call d4pg_comm_peer_alloc first (the exchange length comes from it)");
   CUmulticastObjectProp p = mc_prop(c->world, 0);
   size_t gran = 0;
-  p.size = size_t(2 * c->xn) * sizeof(float);
+  // [2][n] gradient halves + [n] reduced gradient (two-phase mode: every rank broadcasts its reduced slice into it)
+  p.size = size_t(3 * c->xn) * sizeof(float);
   DRV_OK(g_drv.MulticastGetGranularity(&gran, &p, CU_MULTICAST_GRANULARITY_RECOMMENDED));
-  *out = ((size_t(2 * c->xn) * sizeof(float) + gran - 1) / gran) * gran;
+  *out = ((size_t(3 * c->xn) * sizeof(float) + gran - 1) / gran) * gran;
   return D4PG_OK;
 }
 /* rank 0: create the multicast object for [2][n] floats per rank and export it; *fd_out is a POSIX file descriptor */

@@ -53,5 +53,8 @@ int comm_peer_barrier(d4pg_comm* c, cudaStream_t st);
 // reduce-scatter + all-gather of the step's gradient over peer memory: this rank sums ITS slice of every rank's half
 // `parity` (rank order) and pushes the result into every rank's reduced buffer; publishes flag2 when done
 int comm_peer_reduce_scatter(d4pg_comm* c, int parity, cudaStream_t st);
+// two-phase in-switch form: multimem.ld_reduce of this rank's slice, multimem.st into every rank's reduced buffer
+// (mc_uc + 2n on each rank), then flag2
+int comm_mc_reduce_bcast(d4pg_comm* c, int parity, cudaStream_t st);
 
 }  // namespace d4pg

@@ -546,8 +546,24 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
   const bool peer_mode = c.world_size > 1 && comm_peer_info(L->comm, &peers);
   const int gpar = pf ? par : int(L->steps_done & 1);
   const bool inline_sync_possible = chain || tcc;
-  static const bool mc_off = [] { const char* e = getenv("D4PG_COMM_MODE"); return e && e[0] != 'm'; }();
-  const bool use_mc_buf = peer_mode && peers.mc != nullptr && !mc_off && inline_sync_possible;
+  // Exchange shapes (D4PG_COMM_MODE=mc|mc2|pull|rs; default: "mc" from D4PG_COMM_MC_FROM = 3 ranks up when the communicator
+  // set up a multicast object, else "pull"):
+  //   "mc"   in-switch reduction: ONE hop and 1.15 MB inbound per rank -- the Adam kernel's multimem.ld_reduce over an NVLS
+  //          multicast object returns the sum over all ranks, added by the NVSwitch (8 ranks: 101.6 us/step);
+  //   "mc2"  its two-phase form: every rank ld_reduces its 1/N slice and multimem.st's it to everyone (2 x 1.15 MB per GPU
+  //          whatever N), then a second flag hop (8 ranks: 100.9 us; 2 ranks: 98.9 vs 90.5 for "mc");
+  //   "pull" one hop, every rank sums all N halves inside Adam (N x 1.15 MB inbound over NVLink; 2 ranks 89.2 us -- the
+  //          fastest there -- 8 ranks 111.9);
+  //   "rs"   reduce-scatter + all-gather over peer memory: TWO hops of 16-B remote accesses (loses everywhere: 130.7 us at 8).
+  static const int comm_mode = [] { const char* e = getenv("D4PG_COMM_MODE");
+                                    return !e ? 0 : (e[0] == 'p' ? 1 : (e[0] == 'r' ? 2 : (e[0] == 'm' && e[1] == 'c' && e[2] == '2' ? 4 : 3))); }();
+  static const int mc_from = [] { const char* e = getenv("D4PG_COMM_MC_FROM"); return e ? atoi(e) : 3; }();
+  static const int mc2_from = [] { const char* e = getenv("D4PG_COMM_MC2_FROM"); return e ? atoi(e) : 1000; }();
+  const bool mc_avail = peer_mode && peers.mc != nullptr && inline_sync_possible;
+  const bool peer_mc2 = mc_avail && (comm_mode == 4 || (comm_mode == 0 && peers.world >= mc2_from));
+  const bool peer_mc = mc_avail && !peer_mc2 && (comm_mode == 3 || (comm_mode == 0 && peers.world >= mc_from));
+  const bool peer_rs = peer_mode && !peer_mc && !peer_mc2 && comm_mode == 2;
+  const bool use_mc_buf = peer_mc || peer_mc2;
   // this step's gradients go into this rank's half of the exchange buffer: the multicast-bound one when the in-switch
   // reduction is set up, else the IPC-mapped one the peers read directly
   if (peer_mode) { Ga = (use_mc_buf ? peers.mc_uc : peers.x[peers.rank]) + int64_t(gpar) * peers.n; Gc = Ga + da.total; }
@@ -653,18 +669,10 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
   // every rank's half of this step must be complete before Adam sums them: the chain plans signal from the dW
   // kernel and wait inside the Adam kernel; the level plan (several dW launches) uses a small barrier launch
   const bool inline_sync = peer_mode && (chain || tcc);
-  // Exchange shapes (D4PG_COMM_MODE=mc|pull|rs; default: mc when the communicator set up a multicast object, else pull):
-  //   "mc"   in-switch reduction: ONE hop and 1.15 MB inbound per rank -- the Adam kernel's multimem.ld_reduce over an NVLS
-  //          multicast object returns the sum over all ranks, added by the NVSwitch;
-  //   "pull" one hop, every rank sums all N halves inside Adam (N x 1.15 MB inbound over NVLink);
-  //   "rs"   reduce-scatter + all-gather over peer memory: ~2 MB per rank whatever N, but TWO cross-rank hops (measured on
-  //          B200s it loses to "pull" even at 8 ranks: 130.7 vs 118.9 us/step; 4 ranks 112.2 vs 100.5; 2 ranks 101.0 vs 91.5).
-  static const int comm_mode = [] { const char* e = getenv("D4PG_COMM_MODE"); return !e ? 0 : (e[0] == 'p' ? 1 : (e[0] == 'r' ? 2 : 3)); }();
-  const bool peer_mc = peer_mode && peers.mc != nullptr && (comm_mode == 0 || comm_mode == 3) && inline_sync_possible;
-  const bool peer_rs = peer_mode && !peer_mc && comm_mode == 2;
   if (peer_mode && !inline_sync) RUN(comm_peer_barrier(L->comm, st));
   // reduce-scatter + all-gather over peer memory: each rank reduces its 1/N slice and pushes it to everyone
-  if (peer_rs) RUN(comm_peer_reduce_scatter(L->comm, gpar, st));
+  if (peer_mc2) RUN(comm_mc_reduce_bcast(L->comm, gpar, st));
+  else if (peer_rs) RUN(comm_peer_reduce_scatter(L->comm, gpar, st));
   else if (!peer_mode && c.world_size > 1) RUN(comm_allreduce(L->comm, Ga, da.total + dc.total, st));
 
   // 7. Adam (actor + critic), sync (identity), Polyak -- one launch, two segments
@@ -678,6 +686,11 @@ static int enqueue_step(d4pg_learner* L, cudaStream_t st, int par, bool cold, bo
     aa.seg[1].g_out = b.grad_critic; aa.seg[1].g_off = da.total;
     aa.my_flags = inline_sync ? peers.flag[peers.rank] : nullptr; aa.rank = peers.rank;
     if (peer_mc) aa.mc_g = peers.mc + int64_t(gpar) * peers.n;    // NVSwitch reduces; signal 0 (every rank's dW done) is awaited in-kernel
+    if (peer_mc2) {                                             // the reduced gradient was broadcast into the local multicast-bound buffer
+      aa.peer_reduced = 1;
+      aa.seg[0].g = peers.mc_uc + 2 * peers.n; aa.seg[1].g = peers.mc_uc + 2 * peers.n + da.total;
+      aa.my_flags = peers.flag2[peers.rank];
+    }
     if (peer_rs) {                                              // the reduced gradient is local: wait for every rank's "slice pushed", then stream it
       aa.peer_reduced = 1;
       aa.seg[0].g = peers.red[peers.rank]; aa.seg[1].g = peers.red[peers.rank] + da.total;

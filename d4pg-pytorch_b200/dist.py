@@ -90,7 +90,7 @@ class Comm(object):
 
     def exchange_mode(self):
         """How the learner sums the gradient over the ranks: "nccl" (all-reduce fallback), or over peer memory "mc"
-        (in-switch reduction, multimem.ld_reduce), "pull" (every rank sums all halves) / "rs" (reduce-scatter + all-gather)."""
+        (in-switch reduction, multimem.ld_reduce; "mc2" = its two-phase form: reduce 1/N, multimem.st broadcast), "pull" (every rank sums all halves) / "rs" (reduce-scatter + all-gather)."""
         from . import _lib
         L = _lib.lib()
         if self.world_size <= 1:
@@ -98,8 +98,11 @@ class Comm(object):
         if not L.d4pg_comm_peer_ready(self.handle):
             return "nccl"
         env = os.environ.get("D4PG_COMM_MODE", "")
-        if L.d4pg_comm_mc_ready(self.handle) and env[:1] in ("", "m"):
-            return "mc"
+        if L.d4pg_comm_mc_ready(self.handle) and env[:1] in ("", "m"):       # same selection as learner.cu
+            if env[:3] == "mc2" or (env == "" and self.world_size >= int(os.environ.get("D4PG_COMM_MC2_FROM", "1000"))):
+                return "mc2"
+            if env[:1] == "m" or self.world_size >= int(os.environ.get("D4PG_COMM_MC_FROM", "3")):
+                return "mc"
         return "rs" if env[:1] == "r" else "pull"
 
     def setup_multicast(self):
