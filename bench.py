@@ -412,7 +412,7 @@ def gpu_main(args):
                 "timing": {"regions_ms": [round(x, 4) for x in regions], "reported": "median region", "steps_per_region": args.steps,
                            "graph_capture_steps_before_warmup": capture_steps, "warmup_steps": max(args.warmup, 3)},
                 "replicas_identical": replicas_identical,
-                "implementation": {"step_plan": {1: "cluster chains", 0: "levels"}[args.chain],
+                "implementation": {"step_plan": "levels (one launch per dependency level; the library's plan above 512 rows)" if (B > 512 or not args.chain) else "cluster chains",
                            "gradient_exchange": exchange,
                            "precision": {"fp32": "exact fp32 FFMA tiles", "tf32x3": "3xTF32 on tcgen05 tensor cores (hi/lo split, fp32 accumulate in TMEM; meets the 1e-5 parity bar)", "tf32": "one TF32 tcgen05 pass (not parity-grade)"}[args.precision],
                            "l2": "inputs larger than L2: replay store %.0f MB + trees %.0f MB per GPU, rows sampled at "
